@@ -1,0 +1,566 @@
+// Segment-boundary kernels: time-dilation vector, extended Gram, CholeskyQR2 small
+// algebra, tangent update / next-ensemble construction.
+//
+// K3-K6 and K9 of SURVEY.md 2.3.  Reference: fds/timedilation.py:14-82 (dxdt,
+// contribution, project), fds/lsstan.py:20-34 (checkpoint: QR, b, v update),
+// fds/segment.py:43-51 (perturbed initial conditions), :74-79 (FD tangents).
+//
+// Tangents are rows of T[site][m+1] (j < m homogeneous, j = m inhomogeneous) or,
+// right after a segment, implicit in the ensemble: t_j = (E[.][j+1] - E[.][0]) / eps.
+// Everything at a boundary is linear in X_i = [t_0 .. t_m, d_i] (MX = m+2 values per
+// site), so it reduces to (1) the Gram X^T X, one pass, (2) tiny dense algebra on that
+// Gram in one CTA, (3) out_i = A X_i with a constant (m+1) x (m+2) matrix, one pass.
+#include <algorithm>
+#include "kernels.h"
+#include "common.cuh"
+
+namespace fds {
+
+// ------------------------------ elementwise bits ----------------------------- //
+__global__ void extract_col0_kernel(const double* __restrict__ E, int M, double* __restrict__ P, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) P[i] = E[i * M];
+}
+cudaError_t launch_extract_col0(const double* E, int M, double* P, long long n, cudaStream_t st, LaunchStats* ls) {
+    extract_col0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, M, P, n);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// d = ((c0*u0 + c1*u1) + c2*u2) + c3*u3, each product and sum rounded
+// (fds/timedilation.py:20: Python sum() of c[i]*u[i], left to right)
+__global__ void dxdt_kernel(const double* __restrict__ P0, const double* __restrict__ P1,
+                            const double* __restrict__ P2, const double* __restrict__ P3,
+                            const double* __restrict__ c, double* __restrict__ d, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = __dmul_rn(c[0], P0[i]);
+    acc = __dadd_rn(acc, __dmul_rn(c[1], P1[i]));
+    acc = __dadd_rn(acc, __dmul_rn(c[2], P2[i]));
+    acc = __dadd_rn(acc, __dmul_rn(c[3], P3[i]));
+    d[i] = acc;
+}
+cudaError_t launch_dxdt(const double* P0, const double* P1, const double* P2, const double* P3,
+                        const double* c, double* d, long long n, cudaStream_t st, LaunchStats* ls) {
+    dxdt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P0, P1, P2, P3, c, d, n);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// T[i][j] = (E[i][j+1] - E[i][0]) / eps   (fds/segment.py:74,77; true IEEE division)
+__global__ void diff_tangents_kernel(const double* __restrict__ E, int M, double eps, double* __restrict__ T,
+                                     long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int MO = M - 1;
+    const long long i = idx / MO;
+    const int j = (int)(idx % MO);
+    T[idx] = __ddiv_rn(__dsub_rn(E[i * M + j + 1], E[i * M]), eps);
+}
+cudaError_t launch_diff_tangents(const double* E, int M, double eps, double* T, long long n, cudaStream_t st,
+                                 LaunchStats* ls) {
+    const long long total = n * (M - 1);
+    diff_tangents_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(E, M, eps, T, total);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// E[i][0] = u_i ; E[i][j+1] = u_i + T[i][j]*eps   (fds/segment.py:43,49; mul then add)
+__global__ void make_ensemble_kernel(const double* __restrict__ u, const double* __restrict__ T, int M, double eps,
+                                     double* __restrict__ E, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long i = idx / M;
+    const int k = (int)(idx % M);
+    const double ui = u[i];
+    E[idx] = k == 0 ? ui : __dadd_rn(ui, __dmul_rn(T[i * (M - 1) + k - 1], eps));
+}
+cudaError_t launch_make_ensemble(const double* u, const double* T, int M, double eps, double* E, long long n,
+                                 cudaStream_t st, LaunchStats* ls) {
+    const long long total = n * M;
+    make_ensemble_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(u, T, M, eps, E, total);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// tiled transposes between device [rows][cols] and host-order [cols][ld]
+__global__ void transpose_kernel(const double* __restrict__ in, long long rows, int cols, double* __restrict__ out,
+                                 long long ld_out) {
+    __shared__ double tile[32][33];
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const long long r = r0 + y;
+        const int c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[y][threadIdx.x] = in[r * cols + c];
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int c = c0 + y;
+        const long long r = r0 + threadIdx.x;
+        if (r < rows && c < cols) out[(long long)c * ld_out + r] = tile[threadIdx.x][y];
+    }
+}
+cudaError_t launch_transpose(const double* in, long long rows, int cols, double* out, long long ld_out,
+                             cudaStream_t st, LaunchStats* ls) {
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
+    transpose_kernel<<<grid, block, 0, st>>>(in, rows, cols, out, ld_out);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+__global__ void transpose_back_kernel(const double* __restrict__ in, long long ld_in, long long rows, int cols,
+                                      double* __restrict__ out) {
+    __shared__ double tile[32][33];
+    const long long r0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int c = c0 + y;
+        const long long r = r0 + threadIdx.x;
+        if (r < rows && c < cols) tile[y][threadIdx.x] = in[(long long)c * ld_in + r];
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const long long r = r0 + y;
+        const int c = c0 + threadIdx.x;
+        if (r < rows && c < cols) out[r * cols + c] = tile[threadIdx.x][y];
+    }
+}
+cudaError_t launch_transpose_back(const double* in, long long ld_in, long long rows, int cols, double* out,
+                                  cudaStream_t st, LaunchStats* ls) {
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), block(32, 8);
+    transpose_back_kernel<<<grid, block, 0, st>>>(in, ld_in, rows, cols, out);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// uniform [0,1) tangents from a counter-based generator keyed on the GLOBAL (row, site)
+// index, so the field does not depend on how sites are sharded (pascal.random, fds/fds.py:23)
+FDS_D uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void fill_random_kernel(double* __restrict__ T, long long n, int MO, int m, long long site_offset,
+                                   long long n_global, uint64_t seed) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * MO) return;
+    const long long i = idx / MO;
+    const int j = (int)(idx % MO);
+    if (j >= m) { T[idx] = 0.0; return; }
+    const uint64_t ctr = (uint64_t)j * (uint64_t)n_global + (uint64_t)(site_offset + i);
+    const uint64_t h = splitmix64(splitmix64(seed) ^ splitmix64(ctr));
+    T[idx] = (double)(h >> 11) * (1.0 / 9007199254740992.0);
+}
+cudaError_t launch_fill_random(double* T, long long n, int MO, int m, long long site_offset, long long n_global,
+                               uint64_t seed, cudaStream_t st, LaunchStats* ls) {
+    const long long total = n * MO;
+    fill_random_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(T, n, MO, m, site_offset, n_global, seed);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// -------------------------------- Gram kernel -------------------------------- //
+// 4x4 register blocks over the upper triangle of the (padded) MXP x MXP Gram.
+// CTA = NG site-groups x GS lanes; lane l of a group owns block pair (bi[l], bj[l]);
+// group g handles sites g, g+NG, ... of each staged tile.
+constexpr int kGramTile = 32;   // sites staged per iteration
+
+template <int SRC>
+__global__ void __launch_bounds__(1024) gram_kernel(const double* __restrict__ E, const double* __restrict__ T,
+                                                    const double* __restrict__ d, int m, double inv_eps, long long n,
+                                                    int MXP, int nb, int GS, int NG, double* __restrict__ part) {
+    extern __shared__ __align__(16) double sm[];      // Xs[kGramTile][MXP], then reduction scratch
+    const int MX = m + 2, M = m + 2, MO = m + 1;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int grp = tid / GS, lane = tid % GS;
+    const int npair = nb * (nb + 1) / 2;
+    int bi = 0, bj = 0;
+    if (lane < npair) {                                // decode upper-triangular pair index
+        int rem = lane;
+        while (rem >= nb - bi) { rem -= nb - bi; ++bi; }
+        bj = bi + rem;
+    }
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+
+    const long long ntiles = (n + kGramTile - 1) / kGramTile;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * kGramTile;
+        // stage X for kGramTile sites
+        for (int e = tid; e < kGramTile * MXP; e += nthr) {
+            const int s = e / MXP, l = e - s * MXP;
+            const long long i = s0 + s;
+            double v = 0.0;
+            if (i < n) {
+                if (l < MO) {
+                    if (SRC == SRC_ENSEMBLE) v = (E[i * M + l + 1] - E[i * M]) * inv_eps;
+                    else v = T[i * MO + l];
+                } else if (l == MO) {
+                    v = d[i];
+                }
+            }
+            sm[e] = v;
+        }
+        __syncthreads();
+        if (lane < npair && grp < NG) {
+            for (int s = grp; s < kGramTile; s += NG) {
+                const double* row = sm + s * MXP;
+                const double2 a01 = *reinterpret_cast<const double2*>(row + 4 * bi);
+                const double2 a23 = *reinterpret_cast<const double2*>(row + 4 * bi + 2);
+                const double2 b01 = *reinterpret_cast<const double2*>(row + 4 * bj);
+                const double2 b23 = *reinterpret_cast<const double2*>(row + 4 * bj + 2);
+                const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+                const double bv[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], bv[b], acc[a][b]);
+            }
+        }
+        __syncthreads();
+    }
+    // fixed-order reduction over the site groups, then scatter into the full symmetric matrix
+    double* red = sm;                                  // [NG][npair][16]
+    if (lane < npair && grp < NG) {
+        double* dst = red + ((size_t)grp * npair + lane) * 16;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) dst[a * 4 + b] = acc[a][b];
+    }
+    __syncthreads();
+    double* out = part + (size_t)blockIdx.x * MX * MX;
+    for (int e = tid; e < npair * 16; e += nthr) {
+        const int pr = e / 16, ab = e % 16, a = ab / 4, b = ab % 4;
+        int pi = 0, rem = pr;
+        while (rem >= nb - pi) { rem -= nb - pi; ++pi; }
+        const int pj = pi + rem;
+        double s = 0.0;
+        for (int g = 0; g < NG; ++g) s += red[((size_t)g * npair + pr) * 16 + ab];
+        const int row = 4 * pi + a, col = 4 * pj + b;
+        if (row < MX && col < MX) {
+            out[row * MX + col] = s;
+            out[col * MX + row] = s;
+        }
+    }
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ part, int nparts, int len, double* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    double s = 0.0;
+    for (int p = 0; p < nparts; ++p) s += part[(size_t)p * len + e];
+    out[e] = s;
+}
+
+cudaError_t launch_gram(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
+                        long long n, double* part, int max_part, double* out, int num_sms, cudaStream_t st,
+                        LaunchStats* ls) {
+    const int MX = m + 2;
+    const int MXP = (MX + 3) / 4 * 4;
+    const int nb = MXP / 4;
+    const int npair = nb * (nb + 1) / 2;
+    const int GS = (npair + 31) / 32 * 32;
+    if (GS > 1024) return cudaErrorInvalidValue;
+    int NG = std::max(1, std::min(8, 512 / GS));
+    const int block = GS * NG;
+    const long long ntiles = (n + kGramTile - 1) / kGramTile;
+    int grid = (int)std::min<long long>(ntiles, std::min(max_part, 2 * num_sms));
+    if (grid < 1) grid = 1;
+    const size_t smem = sizeof(double) * std::max((size_t)kGramTile * MXP, (size_t)NG * npair * 16);
+    cudaError_t e;
+    if (src == SRC_ENSEMBLE) {
+        e = cudaFuncSetAttribute(gram_kernel<SRC_ENSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gram_kernel<SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, T, d, m, inv_eps, n, MXP, nb, GS, NG, part);
+    } else {
+        e = cudaFuncSetAttribute(gram_kernel<SRC_TANGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        gram_kernel<SRC_TANGENT><<<grid, block, smem, st>>>(E, T, d, m, inv_eps, n, MXP, nb, GS, NG, part);
+    }
+    if (ls) ls->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int len = MX * MX;
+    sum_partials_kernel<<<(len + 255) / 256, 256, 0, st>>>(part, grid, len, out);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// -------------------------------- apply kernel ------------------------------- //
+// out[i][o] = sum_l A[o][l] X_i[l];  4 sites x 4 outputs per thread, operands staged
+// transposed in shared memory (Xt[l][S], At[l][MOP]) so both are read as 128-bit vectors.
+constexpr int kApplyTile = 64;
+
+template <int SRC>
+__global__ void __launch_bounds__(512) apply_kernel(const double* __restrict__ E, const double* Tin,
+                                                    const double* __restrict__ d, const double* __restrict__ A, int m,
+                                                    double inv_eps, long long n, double* Tout, double* E_out,
+                                                    const double* __restrict__ u, double eps, int MOP) {
+    extern __shared__ __align__(16) double sm[];
+    const int MX = m + 2, M = m + 2, MO = m + 1;
+    double* At = sm;                         // [MX][MOP]
+    double* Xt = sm + (size_t)MX * MOP;      // [MX][kApplyTile]
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int e = tid; e < MX * MOP; e += nthr) {
+        const int l = e / MOP, o = e - l * MOP;
+        At[e] = o < MO ? A[o * MX + l] : 0.0;
+    }
+    const int nob = MOP / 4;                 // output blocks
+    const int nsb = kApplyTile / 4;          // site blocks
+    const int ob = tid % nob, sb = tid / nob;
+    const long long ntiles = (n + kApplyTile - 1) / kApplyTile;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * kApplyTile;
+        __syncthreads();
+        for (int e = tid; e < kApplyTile * MX; e += nthr) {
+            const int s = e / MX, l = e - s * MX;
+            const long long i = s0 + s;
+            double v = 0.0;
+            if (i < n) {
+                if (l < MO) {
+                    if (SRC == SRC_ENSEMBLE) v = (E[i * M + l + 1] - E[i * M]) * inv_eps;
+                    else v = Tin[i * MO + l];
+                } else {
+                    v = d != nullptr ? d[i] : 0.0;
+                }
+            }
+            Xt[l * kApplyTile + s] = v;
+        }
+        __syncthreads();
+        if (sb < nsb) {
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+            for (int l = 0; l < MX; ++l) {
+                const double2 x01 = *reinterpret_cast<const double2*>(Xt + l * kApplyTile + 4 * sb);
+                const double2 x23 = *reinterpret_cast<const double2*>(Xt + l * kApplyTile + 4 * sb + 2);
+                const double2 a01 = *reinterpret_cast<const double2*>(At + l * MOP + 4 * ob);
+                const double2 a23 = *reinterpret_cast<const double2*>(At + l * MOP + 4 * ob + 2);
+                const double xv[4] = {x01.x, x01.y, x23.x, x23.y};
+                const double av[4] = {a01.x, a01.y, a23.x, a23.y};
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(xv[a], av[b], acc[a][b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const long long i = s0 + 4 * sb + a;
+                if (i >= n) continue;
+                const double ui = E_out != nullptr ? u[i] : 0.0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int o = 4 * ob + b;
+                    if (o >= MO) continue;
+                    Tout[i * MO + o] = acc[a][b];
+                    if (E_out != nullptr) E_out[i * M + o + 1] = __dadd_rn(ui, __dmul_rn(acc[a][b], eps));
+                }
+                if (E_out != nullptr && ob == 0) E_out[i * M] = ui;
+            }
+        }
+    }
+}
+
+cudaError_t launch_apply(int src, const double* E, const double* Tin, const double* d, const double* A, int m,
+                         double inv_eps, long long n, double* Tout, double* E_out, const double* u, double eps,
+                         cudaStream_t st, LaunchStats* ls) {
+    const int MX = m + 2, MO = m + 1;
+    const int MOP = (MO + 3) / 4 * 4;
+    const int nob = MOP / 4, nsb = kApplyTile / 4;
+    int block = (nob * nsb + 31) / 32 * 32;
+    if (block > 512) return cudaErrorInvalidValue;
+    const long long ntiles = (n + kApplyTile - 1) / kApplyTile;
+    const int grid = (int)std::min<long long>(ntiles, 148 * 8);
+    const size_t smem = sizeof(double) * ((size_t)MX * MOP + (size_t)MX * kApplyTile);
+    cudaError_t e;
+    if (src == SRC_ENSEMBLE) {
+        e = cudaFuncSetAttribute(apply_kernel<SRC_ENSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        apply_kernel<SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, Tin, d, A, m, inv_eps, n, Tout, E_out, u, eps, MOP);
+    } else {
+        e = cudaFuncSetAttribute(apply_kernel<SRC_TANGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        apply_kernel<SRC_TANGENT><<<grid, block, smem, st>>>(E, Tin, d, A, m, inv_eps, n, Tout, E_out, u, eps, MOP);
+    }
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------ small algebra (1 CTA) ------------------------ //
+// In-place Cholesky G = L L^T of the leading mm x mm block of a matrix with row stride ld
+// (lower triangle holds L on exit).  Returns via *fail the 1-based failing column, else 0.
+__device__ void cta_cholesky(double* G, int ld, int mm, int* fail) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int j = 0; j < mm; ++j) {
+        __syncthreads();
+        const double piv = G[j * ld + j];
+        if (!(piv > 0.0)) { if (tid == 0 && *fail == 0) *fail = j + 1; }
+        const double ljj = sqrt(piv > 0.0 ? piv : 1.0);
+        __syncthreads();
+        if (tid == 0) G[j * ld + j] = ljj;
+        for (int i = j + 1 + tid; i < mm; i += nthr) G[i * ld + j] /= ljj;
+        __syncthreads();
+        const int rem = mm - j - 1;
+        for (int e = tid; e < rem * rem; e += nthr) {
+            const int i = j + 1 + e / rem, k = j + 1 + e % rem;
+            if (k <= i) G[i * ld + k] -= G[i * ld + j] * G[k * ld + j];
+        }
+    }
+    __syncthreads();
+}
+
+// Linv = L^{-1} for lower-triangular L (row stride ld); Linv is mm x mm, row stride mm, full storage
+__device__ void cta_tri_inverse(const double* L, int ld, int mm, double* Linv) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int e = tid; e < mm * mm; e += nthr) Linv[e] = 0.0;
+    __syncthreads();
+    for (int c = tid; c < mm; c += nthr) {          // column c of the inverse by forward substitution
+        for (int i = c; i < mm; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int k = c; k < i; ++k) s -= L[i * ld + k] * Linv[k * mm + c];
+            Linv[i * mm + c] = s / L[i * ld + i];
+        }
+    }
+    __syncthreads();
+}
+
+size_t small_smem_bytes(int m) {
+    const int MX = m + 2;
+    return sizeof(double) * ((size_t)MX * MX + 2 * (size_t)m * m + 2 * MX) + 16;
+}
+
+// pass 1: G_dil/g_dil, projection, (optionally) first Cholesky factor; builds A1
+__global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use_d, int do_qr) {
+    extern __shared__ __align__(16) double sm[];
+    const int MX = m + 2, MO = m + 1, D = m + 1;
+    double* G = sm;                      // MX*MX
+    double* Gp = G + MX * MX;            // m*m
+    double* Li = Gp + m * m;             // m*m
+    double* c = Li + m * m;              // MX
+    __shared__ int fail;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) fail = 0;
+    for (int e = tid; e < MX * MX; e += nthr) G[e] = B.gram[e];
+    __syncthreads();
+    const double dd = G[D * MX + D];
+    for (int k = tid; k < MO; k += nthr) {
+        const double ck = use_d ? G[k * MX + D] / dd : 0.0;   // <t_k,d>/<d,d>: contribution AND projection coefficient
+        c[k] = ck;
+        B.gdil[k] = ck;
+    }
+    __syncthreads();
+    if (!do_qr) {
+        for (int e = tid; e < MO * MX; e += nthr) {
+            const int o = e / MX, l = e % MX;
+            B.A[e] = l == D ? -c[o] : (l == o ? 1.0 : 0.0);
+        }
+        if (tid == 0) *B.status = 0;
+        return;
+    }
+    // Gram of the projected homogeneous tangents
+    for (int e = tid; e < m * m; e += nthr) {
+        const int j = e / m, l = e % m;
+        Gp[e] = use_d ? G[j * MX + l] - c[j] * G[l * MX + D] : G[j * MX + l];
+    }
+    __syncthreads();
+    cta_cholesky(Gp, m, m, &fail);
+    cta_tri_inverse(Gp, m, m, Li);
+    for (int e = tid; e < m * m; e += nthr) {
+        const int i = e / m, k = e % m;
+        B.L1[e] = k <= i ? Gp[e] : 0.0;
+    }
+    for (int e = tid; e < MO * MX; e += nthr) {
+        const int o = e / MX, l = e % MX;
+        double v;
+        if (o < m) {
+            if (l < m) v = l <= o ? Li[o * m + l] : 0.0;
+            else if (l == m) v = 0.0;
+            else {                                    // d column: -(Linv c)_o
+                double s = 0.0;
+                for (int k = 0; k <= o; ++k) s += Li[o * m + k] * c[k];
+                v = -s;
+            }
+        } else {                                      // inhomogeneous row: projection only
+            v = l == m ? 1.0 : (l == D ? -c[m] : 0.0);
+        }
+        B.A[e] = v;
+    }
+    __syncthreads();
+    if (tid == 0) *B.status = fail;
+}
+
+// pass 2: second Cholesky factor on the Gram of [Q1; p_w], b, R = (L1 L2)^T; builds A2
+__global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m) {
+    extern __shared__ __align__(16) double sm[];
+    const int MX = m + 2, MO = m + 1, D = m + 1;
+    double* G = sm;                      // MX*MX
+    double* L2 = G + MX * MX;            // m*m
+    double* Li = L2 + m * m;             // m*m
+    double* bb = Li + m * m;             // m
+    __shared__ int fail;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) fail = 0;
+    for (int e = tid; e < MX * MX; e += nthr) G[e] = B.gram[e];
+    __syncthreads();
+    for (int e = tid; e < m * m; e += nthr) L2[e] = G[(e / m) * MX + e % m];
+    __syncthreads();
+    cta_cholesky(L2, m, m, &fail);
+    cta_tri_inverse(L2, m, m, Li);
+    for (int j = tid; j < m; j += nthr) {            // b = L2^{-1} (Q1 . p_w)
+        double s = 0.0;
+        for (int l = 0; l <= j; ++l) s += Li[j * m + l] * G[l * MX + m];
+        bb[j] = s;
+        B.b[j] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * m; e += nthr) {        // R[a][b] = sum_k L1[b][k] L2[k][a]  (upper triangular)
+        const int a = e / m, b = e % m;
+        double s = 0.0;
+        if (b >= a)
+            for (int k = a; k <= b; ++k) s += B.L1[b * m + k] * L2[k * m + a];
+        B.R[e] = s;
+    }
+    for (int e = tid; e < MO * MX; e += nthr) {
+        const int o = e / MX, l = e % MX;
+        double v = 0.0;
+        if (o < m) {
+            if (l < m && l <= o) v = Li[o * m + l];
+        } else {
+            if (l < m) {                              // -(b^T L2^{-1})_l
+                double s = 0.0;
+                for (int j = l; j < m; ++j) s += bb[j] * Li[j * m + l];
+                v = -s;
+            } else if (l == m) v = 1.0;
+        }
+        B.A[e] = v;
+    }
+    (void)D;
+    __syncthreads();
+    if (tid == 0) *B.status = fail;
+}
+
+cudaError_t launch_small1(const SmallBufs& B, int m, int use_d, int do_qr, cudaStream_t st, LaunchStats* ls) {
+    const size_t smem = small_smem_bytes(m);
+    cudaError_t e = cudaFuncSetAttribute(small1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    small1_kernel<<<1, 256, smem, st>>>(B, m, use_d, do_qr);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+cudaError_t launch_small2(const SmallBufs& B, int m, cudaStream_t st, LaunchStats* ls) {
+    const size_t smem = small_smem_bytes(m);
+    cudaError_t e = cudaFuncSetAttribute(small2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    small2_kernel<<<1, 256, smem, st>>>(B, m);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace fds

@@ -1,0 +1,570 @@
+// Context + C ABI of libfds_b200 (see include/fds_b200.h for the contract and the
+// reference interfaces each entry point replaces).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fds_b200.h"
+#include "kernels.h"
+
+using namespace fds;
+
+struct fds_ctx {
+    fds_config cfg;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int m = 0, M = 0, MO = 0, MX = 0;
+    long long n = 0;
+    long long H = 1;               // halo capacity in steps
+    long long alo = 0, ahi = 0;    // allocated site range of ensemble / primal arrays
+    double* Ebase[2] = {nullptr, nullptr};
+    int cur = 0;
+    double* Pbase[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* T = nullptr;
+    double* d = nullptr;
+    double* gram_part = nullptr;
+    int max_part = 0;
+    double* small_block = nullptr;
+    SmallBufs small{};
+    double* c4 = nullptr;
+    double* jpart = nullptr;
+    double* jscratch = nullptr;
+    double* jsum = nullptr;
+    long long jsum_cap = 0;        // steps
+    long long nleaf = 0;
+    double* stage = nullptr;
+    long long stage_sites = 0;
+    // state machine
+    bool state_in_ensemble = false;   // newest primal state is column 0 of the ensemble
+    bool tangents_implicit = false;   // newest tangents are (E_k - E_0)/eps_last
+    bool time_dilation = true;
+    double eps_last = 0.0;
+    long long ens_halo_valid = 0, pri_halo_valid = 0;
+    LaunchStats ls;
+    std::string err;
+
+    double* E(int which) const { return Ebase[which] + (-alo) * M; }
+    double* Ecur() const { return E(cur); }
+    double* P(int j) const { return Pbase[j] + (-alo); }
+};
+
+static std::string g_create_err;
+
+#define FDS_CK(ctx, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                  \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+static int fail(fds_ctx* c, const std::string& msg) { c->err = msg; return 2; }
+
+static int check_small_status(fds_ctx* c, const char* what) {
+    int st = 0;
+    FDS_CK(c, cudaMemcpyAsync(&st, c->small.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    if (st != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(st) +
+                                    " (tangent block numerically rank deficient)");
+    return 0;
+}
+
+extern "C" {
+
+const char* fds_version(void) { return "fds_b200 0.1 (sm_100a)"; }
+
+const char* fds_last_error(const fds_ctx* c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
+    *out = nullptr;
+    if (!cfg || cfg->m < 1 || cfg->n_local < 4 || cfg->world < 1) { g_create_err = "bad config"; return 2; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_err = std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                       " -- fds_b200 has no CPU fallback";
+        return 3;
+    }
+    fds_ctx* c = new fds_ctx();
+    c->cfg = *cfg;
+    if (c->cfg.dt == 0.0) c->cfg.dt = 0.01;
+    if (c->cfg.n_global == 0) c->cfg.n_global = cfg->n_local;
+    c->m = cfg->m; c->M = cfg->m + 2; c->MO = cfg->m + 1; c->MX = cfg->m + 2;
+    c->n = cfg->n_local;
+#define CK0(call)                                                                \
+    do {                                                                         \
+        cudaError_t e__ = (call);                                                \
+        if (e__ != cudaSuccess) {                                                \
+            g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__);  \
+            fds_ctx_destroy(c);                                                  \
+            return 1;                                                            \
+        }                                                                        \
+    } while (0)
+    CK0(cudaSetDevice(cfg->device));
+    CK0(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
+    if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+    else { CK0(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+
+    long long H = cfg->max_halo_steps > 0 ? cfg->max_halo_steps : std::min<long long>(128, std::max<long long>(1, c->n / 64));
+    if (H < 3) H = 3;                                   // the time-dilation look-ahead needs 3 steps
+    if (cfg->world > 1 && 8 * H > c->n) {
+        g_create_err = "n_local too small for the halo width (need 8*halo_steps <= n_local)";
+        fds_ctx_destroy(c);
+        return 2;
+    }
+    c->H = H;
+    c->alo = -(8 * H + 12);
+    c->ahi = (c->n + 4 * H + 4 + 7) / 8 * 8 + 4;
+    const size_t sites = (size_t)(c->ahi - c->alo);
+    for (int j = 0; j < 2; ++j) {
+        CK0(cudaMalloc(&c->Ebase[j], sites * c->M * sizeof(double)));
+        CK0(cudaMemsetAsync(c->Ebase[j], 0, sites * c->M * sizeof(double), c->stream));
+    }
+    for (int j = 0; j < 4; ++j) {
+        CK0(cudaMalloc(&c->Pbase[j], sites * sizeof(double)));
+        CK0(cudaMemsetAsync(c->Pbase[j], 0, sites * sizeof(double), c->stream));
+    }
+    CK0(cudaMalloc(&c->T, (size_t)c->n * c->MO * sizeof(double)));
+    CK0(cudaMemsetAsync(c->T, 0, (size_t)c->n * c->MO * sizeof(double), c->stream));
+    CK0(cudaMalloc(&c->d, (size_t)c->n * sizeof(double)));
+    CK0(cudaMemsetAsync(c->d, 0, (size_t)c->n * sizeof(double), c->stream));
+    c->max_part = 2 * c->num_sms;
+    CK0(cudaMalloc(&c->gram_part, (size_t)c->max_part * c->MX * c->MX * sizeof(double)));
+    {   // small matrices in one block
+        const size_t mm = (size_t)c->m * c->m;
+        const size_t tot = (size_t)c->MX * c->MX + (size_t)c->MO * c->MX + 2 * mm + c->m + c->MO + 4;
+        CK0(cudaMalloc(&c->small_block, tot * sizeof(double)));
+        CK0(cudaMemsetAsync(c->small_block, 0, tot * sizeof(double), c->stream));
+        double* p = c->small_block;
+        c->small.gram = p; p += (size_t)c->MX * c->MX;
+        c->small.A = p;    p += (size_t)c->MO * c->MX;
+        c->small.L1 = p;   p += mm;
+        c->small.R = p;    p += mm;
+        c->small.b = p;    p += c->m;
+        c->small.gdil = p; p += c->MO;
+        c->small.status = reinterpret_cast<int*>(p);
+    }
+    CK0(cudaMalloc(&c->c4, 4 * sizeof(double)));
+    {
+        const double w[4] = {-11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0};
+        CK0(cudaMemcpyAsync(c->c4, w, sizeof(w), cudaMemcpyHostToDevice, c->stream));
+        CK0(cudaStreamSynchronize(c->stream));
+    }
+    c->nleaf = (c->n + 63) / 64;
+    CK0(cudaMalloc(&c->jpart, (size_t)c->nleaf * c->M * 2 * sizeof(double)));
+    CK0(cudaMalloc(&c->jscratch, (size_t)2 * ((c->nleaf + 255) / 256) * c->M * 2 * sizeof(double)));
+    if (small_smem_bytes(c->m) > 220 * 1024 || lss_smem_bytes(c->m) > 220 * 1024) {
+        g_create_err = "subspace dimension too large for the single-CTA kernels (m <= 80)";
+        fds_ctx_destroy(c);
+        return 2;
+    }
+    CK0(cudaStreamSynchronize(c->stream));
+#undef CK0
+    *out = c;
+    return 0;
+}
+
+void fds_ctx_destroy(fds_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int j = 0; j < 2; ++j) cudaFree(c->Ebase[j]);
+    for (int j = 0; j < 4; ++j) cudaFree(c->Pbase[j]);
+    cudaFree(c->T); cudaFree(c->d); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
+    cudaFree(c->jpart); cudaFree(c->jscratch); cudaFree(c->jsum); cudaFree(c->stage);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int fds_sync(fds_ctx* c) {
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int64_t fds_kernel_launches(const fds_ctx* c) { return c->ls.launches; }
+
+void* fds_buffer_ptr(const fds_ctx* c, int which) {
+    switch (which) {
+        case FDS_BUF_ENSEMBLE: return c->Ecur();
+        case FDS_BUF_PRIMAL: return c->P(0);
+        case FDS_BUF_GRAM: return c->small.gram;
+        case FDS_BUF_JSUM: return c->jsum;
+        case FDS_BUF_TANGENT: return c->T;
+        case FDS_BUF_DXDT: return c->d;
+    }
+    return nullptr;
+}
+
+int fds_set_dxdt_weights(fds_ctx* c, const double w[4]) {
+    FDS_CK(c, cudaMemcpyAsync(c->c4, w, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fds_set_time_dilation(fds_ctx* c, int enabled) { c->time_dilation = enabled != 0; return 0; }
+
+// ------------------------------- state in / out ------------------------------ //
+static int sync_primal_from_ensemble(fds_ctx* c) {
+    if (c->state_in_ensemble) {
+        FDS_CK(c, launch_extract_col0(c->Ecur(), c->M, c->P(0), c->n, c->stream, &c->ls));
+        c->state_in_ensemble = false;
+        c->pri_halo_valid = 0;
+    }
+    return 0;
+}
+
+int fds_set_state(fds_ctx* c, const double* u) {
+    FDS_CK(c, cudaMemcpyAsync(c->P(0), u, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    c->state_in_ensemble = false;
+    c->pri_halo_valid = 0;
+    return 0;
+}
+
+int fds_get_state(fds_ctx* c, double* u) {
+    if (int r = sync_primal_from_ensemble(c)) return r;
+    FDS_CK(c, cudaMemcpyAsync(u, c->P(0), (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int ensure_stage(fds_ctx* c) {
+    if (c->stage) return 0;
+    c->stage_sites = std::min<long long>(c->n, 1LL << 20);
+    FDS_CK(c, cudaMalloc(&c->stage, (size_t)c->stage_sites * c->MO * sizeof(double)));
+    return 0;
+}
+
+static int materialize_tangents(fds_ctx* c) {
+    if (c->tangents_implicit) {
+        FDS_CK(c, launch_diff_tangents(c->Ecur(), c->M, c->eps_last, c->T, c->n, c->stream, &c->ls));
+        c->tangents_implicit = false;
+    }
+    return 0;
+}
+
+int fds_set_tangents(fds_ctx* c, const double* V, const double* v) {
+    if (int r = ensure_stage(c)) return r;
+    for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites) {
+        const long long cnt = std::min(c->stage_sites, c->n - s0);
+        // stage[j][0..cnt) <- V[j][s0..s0+cnt), row m <- v
+        FDS_CK(c, cudaMemcpy2DAsync(c->stage, (size_t)c->stage_sites * sizeof(double), V + s0,
+                                    (size_t)c->n * sizeof(double), (size_t)cnt * sizeof(double), c->m,
+                                    cudaMemcpyHostToDevice, c->stream));
+        if (v) FDS_CK(c, cudaMemcpyAsync(c->stage + (size_t)c->m * c->stage_sites, v + s0, (size_t)cnt * sizeof(double),
+                                         cudaMemcpyHostToDevice, c->stream));
+        else FDS_CK(c, cudaMemsetAsync(c->stage + (size_t)c->m * c->stage_sites, 0, (size_t)cnt * sizeof(double), c->stream));
+        FDS_CK(c, launch_transpose_back(c->stage, c->stage_sites, cnt, c->MO, c->T + (size_t)s0 * c->MO, c->stream, &c->ls));
+        FDS_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    c->tangents_implicit = false;
+    return 0;
+}
+
+int fds_get_tangents(fds_ctx* c, double* V, double* v) {
+    if (int r = materialize_tangents(c)) return r;
+    if (int r = ensure_stage(c)) return r;
+    for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites) {
+        const long long cnt = std::min(c->stage_sites, c->n - s0);
+        FDS_CK(c, launch_transpose(c->T + (size_t)s0 * c->MO, cnt, c->MO, c->stage, c->stage_sites, c->stream, &c->ls));
+        if (V) FDS_CK(c, cudaMemcpy2DAsync(V + s0, (size_t)c->n * sizeof(double), c->stage,
+                                           (size_t)c->stage_sites * sizeof(double), (size_t)cnt * sizeof(double), c->m,
+                                           cudaMemcpyDeviceToHost, c->stream));
+        if (v) FDS_CK(c, cudaMemcpyAsync(v + s0, c->stage + (size_t)c->m * c->stage_sites, (size_t)cnt * sizeof(double),
+                                         cudaMemcpyDeviceToHost, c->stream));
+        FDS_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int fds_random_tangents(fds_ctx* c, uint64_t seed) {
+    FDS_CK(c, launch_fill_random(c->T, c->n, c->MO, c->m, c->cfg.site_offset, c->cfg.n_global, seed, c->stream, &c->ls));
+    c->tangents_implicit = false;
+    return 0;
+}
+
+// ----------------------------------- halos ----------------------------------- //
+int64_t fds_halo_steps(const fds_ctx* c, int64_t steps) { return std::min<long long>(steps, c->H); }
+
+int fds_halo_wrap_ensemble(fds_ctx* c, int64_t hs) {
+    if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_ensemble: world > 1, exchange halos between ranks instead");
+    if (hs < 1 || hs > c->H) return fail(c, "halo_steps out of range");
+    FDS_CK(c, launch_halo_wrap(c->Ecur(), c->M, c->n, 8 * hs, 4 * hs, c->stream, &c->ls));
+    c->ens_halo_valid = hs;
+    return 0;
+}
+
+int fds_halo_wrap_primal(fds_ctx* c, int64_t hs) {
+    if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_primal: world > 1, exchange halos between ranks instead");
+    if (hs < 1 || hs > c->H) return fail(c, "halo_steps out of range");
+    FDS_CK(c, launch_halo_wrap(c->P(0), 1, c->n, 8 * hs, 4 * hs, c->stream, &c->ls));
+    c->pri_halo_valid = hs;
+    return 0;
+}
+
+int fds_halo_mark_valid(fds_ctx* c, int which, int64_t hs) {
+    if (hs < 0 || hs > c->H) return fail(c, "halo_steps out of range");
+    if (which == FDS_BUF_ENSEMBLE) c->ens_halo_valid = hs;
+    else if (which == FDS_BUF_PRIMAL) c->pri_halo_valid = hs;
+    else return fail(c, "fds_halo_mark_valid: buffer has no halo");
+    return 0;
+}
+
+int fds_halo_layout(const fds_ctx* c, int which, int64_t hs, int64_t off[4], int64_t cnt[4]) {
+    const long long W = which == FDS_BUF_ENSEMBLE ? c->M : 1;
+    if (which != FDS_BUF_ENSEMBLE && which != FDS_BUF_PRIMAL) return 2;
+    if (hs < 1 || hs > c->H || 8 * hs > c->n) return 2;
+    const long long gl = 8 * hs, gr = 4 * hs;
+    off[0] = (c->n - gl) * W; cnt[0] = gl * W;   // send to right neighbour (its left ghost)
+    off[1] = 0;               cnt[1] = gr * W;   // send to left neighbour (its right ghost)
+    off[2] = -gl * W;         cnt[2] = gl * W;   // receive from left neighbour
+    off[3] = c->n * W;        cnt[3] = gr * W;   // receive from right neighbour
+    return 0;
+}
+
+// ---------------------------------- stepping --------------------------------- //
+static int ensure_jsum(fds_ctx* c, long long steps) {
+    if (steps <= c->jsum_cap) return 0;
+    double* nj = nullptr;
+    const long long cap = std::max<long long>(steps, 2 * c->jsum_cap);
+    FDS_CK(c, cudaMalloc(&nj, (size_t)cap * c->M * 2 * sizeof(double)));
+    FDS_CK(c, cudaMemsetAsync(nj, 0, (size_t)cap * c->M * 2 * sizeof(double), c->stream));
+    if (c->jsum) {
+        FDS_CK(c, cudaMemcpyAsync(nj, c->jsum, (size_t)c->jsum_cap * c->M * 2 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        FDS_CK(c, cudaStreamSynchronize(c->stream));
+        cudaFree(c->jsum);
+    }
+    c->jsum = nj;
+    c->jsum_cap = cap;
+    return 0;
+}
+
+// one step of `M_` columns X -> Y with `valid` halo steps left; optional objective sums
+static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, double Flast, long long valid,
+                    double* jsum_slot) {
+    StepArgs a;
+    a.X = X; a.Y = Y; a.M = M_; a.n = c->n;
+    a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
+    a.alo = c->alo; a.ahi = c->ahi;
+    a.F0 = F0; a.Flast = Flast; a.dt = c->cfg.dt; a.exact = c->cfg.math == FDS_MATH_EXACT;
+    a.jpart = jsum_slot ? c->jpart : nullptr;
+    a.nleaf = c->nleaf;
+    const bool euler = c->cfg.system == FDS_SYS_L96_EULER;
+    const bool stream_ok = !euler && !(c->cfg.flags & FDS_FLAG_SIMPLE_KERNELS) && M_ <= 576;
+    if (stream_ok) {
+        FDS_CK(c, launch_l96_rk4_stream(a, c->num_sms, c->stream, &c->ls));
+    } else {
+        FDS_CK(c, launch_l96_simple(a, euler ? 1 : 0, c->stream, &c->ls));
+        if (jsum_slot) FDS_CK(c, launch_stats_leaf(Y, M_, c->n, c->jpart, c->nleaf, c->stream, &c->ls));
+    }
+    if (jsum_slot) FDS_CK(c, launch_tree_reduce(c->jpart, c->nleaf, 2 * M_, jsum_slot, c->jscratch, c->stream, &c->ls));
+    return 0;
+}
+
+int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int record) {
+    if (int r = sync_primal_from_ensemble(c)) return r;
+    if (record) if (int r = ensure_jsum(c, step0 + nsteps)) return r;
+    const double F = s + 8.0;
+    for (long long j = 0; j < nsteps; ++j) {
+        if (c->pri_halo_valid < 1) return fail(c, "fds_primal_advance: primal halo exhausted; refresh it first");
+        // primal stepping uses the one-thread-per-element kernel (single column)
+        StepArgs a;
+        a.X = c->P(0); a.Y = c->P(1); a.M = 1; a.n = c->n;
+        a.lo = -8 * (c->pri_halo_valid - 1); a.hi = c->n + 4 * (c->pri_halo_valid - 1);
+        a.alo = c->alo; a.ahi = c->ahi; a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
+        a.exact = c->cfg.math == FDS_MATH_EXACT; a.jpart = nullptr; a.nleaf = c->nleaf;
+        FDS_CK(c, launch_l96_simple(a, c->cfg.system == FDS_SYS_L96_EULER, c->stream, &c->ls));
+        if (record) {
+            FDS_CK(c, launch_stats_leaf(c->P(1), 1, c->n, c->jpart, c->nleaf, c->stream, &c->ls));
+            FDS_CK(c, launch_tree_reduce(c->jpart, c->nleaf, 2, c->jsum + (size_t)(step0 + j) * 2, c->jscratch, c->stream, &c->ls));
+        }
+        std::swap(c->Pbase[0], c->Pbase[1]);
+        c->pri_halo_valid--;
+    }
+    return 0;
+}
+
+int fds_run(fds_ctx* c, double s, int64_t steps, double* Jsum_host) {
+    if (c->cfg.world != 1) return fail(c, "fds_run: world > 1, drive fds_primal_advance with halo exchanges");
+    if (int r = sync_primal_from_ensemble(c)) return r;
+    for (long long t = 0; t < steps;) {
+        const long long hs = std::min<long long>(c->H, steps - t);
+        if (int r = fds_halo_wrap_primal(c, hs)) return r;
+        if (int r = fds_primal_advance(c, s, t, hs, Jsum_host != nullptr)) return r;
+        t += hs;
+    }
+    if (Jsum_host && steps > 0)
+        FDS_CK(c, cudaMemcpyAsync(Jsum_host, c->jsum, (size_t)steps * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t nsteps) {
+    if (int r = ensure_jsum(c, step0 + nsteps)) return r;
+    const double F0 = s + 8.0, Flast = (s + eps) + 8.0;   // fds/segment.py:64: parameter + epsilon
+    for (long long j = 0; j < nsteps; ++j) {
+        if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
+        double* slot = c->jsum + (size_t)(step0 + j) * c->M * 2;
+        if (int r = one_step(c, c->Ecur(), c->E(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, slot)) return r;
+        c->cur ^= 1;
+        c->ens_halo_valid--;
+    }
+    c->state_in_ensemble = true;
+    c->tangents_implicit = true;
+    c->eps_last = eps;
+    return 0;
+}
+
+int fds_segment_jsums(fds_ctx* c, int64_t steps, double* out) {
+    if (steps > c->jsum_cap) return fail(c, "fds_segment_jsums: more steps than were run");
+    FDS_CK(c, cudaMemcpyAsync(out, c->jsum, (size_t)steps * c->M * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fds_segment(fds_ctx* c, double s, double eps, int64_t steps, double* Jsum_host) {
+    if (c->cfg.world != 1) return fail(c, "fds_segment: world > 1, drive fds_segment_advance with halo exchanges");
+    for (long long t = 0; t < steps;) {
+        const long long hs = std::min<long long>(c->H, steps - t);
+        if (int r = fds_halo_wrap_ensemble(c, hs)) return r;
+        if (int r = fds_segment_advance(c, s, eps, t, hs)) return r;
+        t += hs;
+    }
+    if (Jsum_host) return fds_segment_jsums(c, steps, Jsum_host);
+    return 0;
+}
+
+// ---------------------------------- boundary --------------------------------- //
+int fds_boundary_begin(fds_ctx* c, int from_ensemble) {
+    if (from_ensemble) {
+        c->state_in_ensemble = true;   // column 0 of the ensemble is the state of record
+        if (int r = sync_primal_from_ensemble(c)) return r;
+    } else if (c->state_in_ensemble) {
+        if (int r = sync_primal_from_ensemble(c)) return r;
+    }
+    return 0;
+}
+
+int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
+    if (c->time_dilation) {
+        if (c->pri_halo_valid < 3) return fail(c, "fds_boundary_dxdt: primal halo must be valid for 3 steps");
+        const double F = s + 8.0;
+        long long valid = 3;
+        for (int j = 1; j <= 3; ++j) {
+            StepArgs a;
+            a.X = c->P(j - 1); a.Y = c->P(j); a.M = 1; a.n = c->n;
+            a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
+            a.alo = c->alo; a.ahi = c->ahi; a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
+            a.exact = c->cfg.math == FDS_MATH_EXACT; a.jpart = nullptr; a.nleaf = c->nleaf;
+            FDS_CK(c, launch_l96_simple(a, c->cfg.system == FDS_SYS_L96_EULER, c->stream, &c->ls));
+            --valid;
+        }
+        c->pri_halo_valid = 0;
+        FDS_CK(c, launch_dxdt(c->P(0), c->P(1), c->P(2), c->P(3), c->c4, c->d, c->n, c->stream, &c->ls));
+    } else {
+        FDS_CK(c, cudaMemsetAsync(c->d, 0, (size_t)c->n * sizeof(double), c->stream));
+    }
+    const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
+    if (!from_ensemble) if (int r = materialize_tangents(c)) return r;
+    FDS_CK(c, launch_gram(src, c->Ecur(), c->T, c->d, c->m, from_ensemble ? 1.0 / eps : 0.0, c->n, c->gram_part,
+                          c->max_part, c->small.gram, c->num_sms, c->stream, &c->ls));
+    return 0;
+}
+
+int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
+    FDS_CK(c, launch_small1(c->small, c->m, c->time_dilation ? 1 : 0, do_qr, c->stream, &c->ls));
+    if (do_qr) if (int r = check_small_status(c, "CholeskyQR pass 1")) return r;
+    const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
+    FDS_CK(c, launch_apply(src, c->Ecur(), c->T, c->d, c->small.A, c->m, from_ensemble ? 1.0 / eps : 0.0, c->n, c->T,
+                           nullptr, nullptr, 0.0, c->stream, &c->ls));
+    c->tangents_implicit = false;
+    if (do_qr)
+        FDS_CK(c, launch_gram(SRC_TANGENT, nullptr, c->T, c->d, c->m, 0.0, c->n, c->gram_part, c->max_part,
+                              c->small.gram, c->num_sms, c->stream, &c->ls));
+    return 0;
+}
+
+int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
+    if (do_qr) {
+        FDS_CK(c, launch_small2(c->small, c->m, c->stream, &c->ls));
+        if (int r = check_small_status(c, "CholeskyQR pass 2")) return r;
+        FDS_CK(c, launch_apply(SRC_TANGENT, nullptr, c->T, c->d, c->small.A, c->m, 0.0, c->n, c->T,
+                               build ? c->Ecur() : nullptr, c->P(0), eps, c->stream, &c->ls));
+    } else if (build) {
+        FDS_CK(c, launch_make_ensemble(c->P(0), c->T, c->M, eps, c->Ecur(), c->n, c->stream, &c->ls));
+    }
+    if (build) { c->ens_halo_valid = 0; c->eps_last = eps; }
+    c->state_in_ensemble = false;
+    c->tangents_implicit = false;
+    return 0;
+}
+
+int fds_boundary_results(fds_ctx* c, double* R, double* b, double* G_dil, double* g_dil) {
+    if (R) FDS_CK(c, cudaMemcpyAsync(R, c->small.R, (size_t)c->m * c->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (b) FDS_CK(c, cudaMemcpyAsync(b, c->small.b, (size_t)c->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (G_dil) FDS_CK(c, cudaMemcpyAsync(G_dil, c->small.gdil, (size_t)c->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (g_dil) FDS_CK(c, cudaMemcpyAsync(g_dil, c->small.gdil + c->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fds_boundary(fds_ctx* c, double s, double eps, int from_ensemble, int do_qr, int build, int64_t halo_steps,
+                 double* R, double* b, double* G_dil, double* g_dil) {
+    if (c->cfg.world != 1) return fail(c, "fds_boundary: world > 1, drive the phases with reductions in between");
+    if (int r = fds_boundary_begin(c, from_ensemble)) return r;
+    if (c->time_dilation) if (int r = fds_halo_wrap_primal(c, 3)) return r;
+    if (int r = fds_boundary_dxdt(c, s, from_ensemble, eps)) return r;
+    if (int r = fds_boundary_factor(c, do_qr, from_ensemble, eps)) return r;
+    if (int r = fds_boundary_finish(c, do_qr, eps, build)) return r;
+    if (build && halo_steps > 0) if (int r = fds_halo_wrap_ensemble(c, halo_steps)) return r;
+    return fds_boundary_results(c, do_qr ? R : nullptr, do_qr ? b : nullptr, G_dil, g_dil);
+}
+
+int fds_run_segment_host(fds_ctx* c, double* u, double* V, double* v, double s, double eps, int64_t steps,
+                         double* Jsum_host) {
+    if (c->cfg.world != 1) return fail(c, "fds_run_segment_host: world == 1 only");
+    if (int r = fds_set_state(c, u)) return r;
+    if (int r = fds_set_tangents(c, V, v)) return r;
+    FDS_CK(c, launch_make_ensemble(c->P(0), c->T, c->M, eps, c->Ecur(), c->n, c->stream, &c->ls));
+    c->eps_last = eps;
+    if (int r = fds_segment(c, s, eps, steps, Jsum_host)) return r;
+    if (int r = fds_get_state(c, u)) return r;
+    return fds_get_tangents(c, V, v);
+}
+
+// ---------------------------------- LSS solve -------------------------------- //
+int fds_lss_solve(int device, const double* R, const double* b, int64_t K, int m, double* alpha) {
+    if (K < 1 || m < 1 || lss_smem_bytes(m) > 220 * 1024) { g_create_err = "fds_lss_solve: bad K or m"; return 2; }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { g_create_err = std::string("fds_lss_solve: ") + cudaGetErrorString(e) + " -- no CPU fallback"; return 3; }
+    const size_t mm = (size_t)m * m;
+    double *dR = nullptr, *db = nullptr, *da = nullptr, *dw = nullptr;
+    int* dst = nullptr;
+    int rc = 0, st = 0;
+#define CKL(call)                                                                          \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__); rc = 1; goto done; } \
+    } while (0)
+    CKL(cudaMalloc(&dR, K * mm * sizeof(double)));
+    CKL(cudaMalloc(&db, (size_t)K * m * sizeof(double)));
+    CKL(cudaMalloc(&da, (size_t)K * m * sizeof(double)));
+    CKL(cudaMalloc(&dw, ((size_t)2 * K * mm + (size_t)2 * K * m) * sizeof(double)));
+    CKL(cudaMalloc(&dst, sizeof(int)));
+    CKL(cudaMemcpy(dR, R, K * mm * sizeof(double), cudaMemcpyHostToDevice));
+    CKL(cudaMemcpy(db, b, (size_t)K * m * sizeof(double), cudaMemcpyHostToDevice));
+    CKL(launch_lss_solve(dR, db, K, m, da, dw, dst, nullptr, nullptr));
+    CKL(cudaMemcpy(alpha, da, (size_t)K * m * sizeof(double), cudaMemcpyDeviceToHost));
+    CKL(cudaMemcpy(&st, dst, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st != 0) { g_create_err = "fds_lss_solve: Schur complement not positive definite at row " + std::to_string(st); rc = 4; }
+done:
+    cudaFree(dR); cudaFree(db); cudaFree(da); cudaFree(dw); cudaFree(dst);
+    return rc;
+#undef CKL
+}
+
+}  // extern "C"

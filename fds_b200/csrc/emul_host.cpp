@@ -1,0 +1,92 @@
+// Host emulation of the streaming RK4 step kernel's per-thread control flow.
+// Built with g++ -ffp-contract=off into tests/_emul.so and compared bit for bit
+// with the numpy oracle on the CPU (tests/test_emulation.py).  It executes the
+// same headers (l96_core.cuh, l96_march.cuh) as the CUDA kernel; only the IO
+// policy (plain arrays instead of a TMA-fed shared-memory ring) differs.
+#include <vector>
+#include "l96_march.cuh"
+
+using namespace fds;
+
+namespace {
+struct HostIO {
+    const double* X;   // base of site 0 of the padded input, [site][M]
+    double* Y;
+    double* jpart;     // [nleaf][M][2]
+    long long nleaf;
+    long long a;
+    int M, k;
+    long long alo, ahi;  // allocated site range (loads are clamped like the producer does)
+    void acquire(int) {}
+    void release(int) {}
+    double load(int b, int p) const {
+        long long cs = a + 8LL * b + 4;           // chunk start (as the TMA producer computes it)
+        if (cs < alo) cs = alo;
+        if (cs + 8 > ahi) cs = ahi - 8;
+        return X[(cs + p) * M + k];
+    }
+    void store(long long i, double v) { Y[i * M + k] = v; }
+    void emit_leaf(long long leaf, double s1, double s2) {
+        if (leaf >= 0 && leaf < nleaf) {
+            jpart[(leaf * M + k) * 2 + 0] = s1;
+            jpart[(leaf * M + k) * 2 + 1] = s2;
+        }
+    }
+};
+}  // namespace
+
+extern "C" {
+
+// X, Y: pointers to site 0 of padded [site][M] arrays allocated for sites [alo, ahi)
+int emul_l96_rk4_step(const double* X, double* Y, int M, long long n, long long lo, long long hi,
+                      long long alo, long long ahi, const double* F /*[M]*/, double dt, int exact,
+                      long long max_strips, double* jpart, long long* plan_out) {
+    StripPlan plan = make_strip_plan(lo, hi, max_strips);
+    if (plan_out) { plan_out[0] = plan.a0; plan_out[1] = plan.ls; plan_out[2] = plan.nstrips; }
+    Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+    long long nleaf = (n + kLeafSites - 1) / kLeafSites;
+    for (long long s = 0; s < plan.nstrips; ++s) {
+        for (int k = 0; k < M; ++k) {
+            HostIO io{X, Y, jpart, nleaf, plan.a0 + s * plan.ls, M, k, alo, ahi};
+            MarchGeom g{io.a, lo, hi, n, plan.nblk, jpart != nullptr};
+            if (exact) l96_rk4_march<ExactMath>(io, g, F[k], c);
+            else       l96_rk4_march<FastMath>(io, g, F[k], c);
+        }
+    }
+    return 0;
+}
+
+// simple-kernel math: one site from its 13-point cone
+int emul_l96_rk4_point(const double* X, double* Y, int M, long long lo, long long hi,
+                       const double* F, double dt, int exact) {
+    Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+    for (long long i = lo; i < hi; ++i)
+        for (int k = 0; k < M; ++k) {
+            double x[13];
+            for (int j = 0; j < 13; ++j) x[j] = X[(i - 8 + j) * M + k];
+            Y[i * M + k] = exact ? l96_rk4_point<ExactMath>(x, F[k], c) : l96_rk4_point<FastMath>(x, F[k], c);
+        }
+    return 0;
+}
+
+int emul_l96_euler_point(const double* X, double* Y, int M, long long lo, long long hi,
+                         const double* F, double dt, int exact) {
+    for (long long i = lo; i < hi; ++i)
+        for (int k = 0; k < M; ++k) {
+            double x[4];
+            for (int j = 0; j < 4; ++j) x[j] = X[(i - 2 + j) * M + k];
+            Y[i * M + k] = exact ? l96_euler_point<ExactMath>(x, F[k], dt) : l96_euler_point<FastMath>(x, F[k], dt);
+        }
+    return 0;
+}
+
+// canonical tree over `count` leaf partials (padded with zeros to a power of two)
+double emul_tree_reduce(const double* v, long long count, long long stride) {
+    long long p = 1; int L = 0;
+    while (p < count) { p *= 2; ++L; }
+    TreeAcc<40> acc; acc.reset();
+    for (long long j = 0; j < p; ++j) acc.push(j < count ? v[j * stride] : 0.0);
+    return acc.result(L);
+}
+
+}  // extern "C"

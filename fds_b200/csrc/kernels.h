@@ -1,0 +1,87 @@
+// Internal launch API of the fds_b200 CUDA kernels (C++; the C ABI is in ctx.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace fds {
+
+struct LaunchStats { long long launches = 0; };
+
+// ---- l96_step.cu ------------------------------------------------------------ //
+struct StepArgs {
+    const double* X;       // input, pointer to site 0, layout [site][M]
+    double* Y;             // output, same layout
+    int M;                 // columns
+    long long n;           // owned sites (objective sums cover [0, n))
+    long long lo, hi;      // output range of this step
+    long long alo, ahi;    // allocated site range of X (both == 4 mod 8)
+    double F0, Flast;      // forcing of columns < M-1 and of column M-1
+    double dt;
+    int exact;             // FDS_MATH_EXACT / FAST
+    double* jpart;         // [nleaf][M][2] 64-site partial sums, or nullptr
+    long long nleaf;
+};
+
+// streaming TMA-fed kernel (RK4 only)
+cudaError_t launch_l96_rk4_stream(const StepArgs& a, int num_sms, cudaStream_t st, LaunchStats* ls);
+// one thread per element, global loads (RK4 or Euler); no objective sums
+cudaError_t launch_l96_simple(const StepArgs& a, int euler, cudaStream_t st, LaunchStats* ls);
+// 64-site leaf partials of an array: jpart[leaf][M][2]
+cudaError_t launch_stats_leaf(const double* Y, int M, long long n, double* jpart, long long nleaf,
+                              cudaStream_t st, LaunchStats* ls);
+// canonical tree over the leading axis of in[n_in][C] -> out[C]; scratch holds 2 * ceil(n_in/256) * C
+cudaError_t launch_tree_reduce(const double* in, long long n_in, int C, double* out, double* scratch,
+                               cudaStream_t st, LaunchStats* ls);
+// periodic ghosts: A[g][:] = A[g mod n][:] for g in [-gl,0) U [n, n+gr)
+cudaError_t launch_halo_wrap(double* A, int M, long long n, long long gl, long long gr,
+                             cudaStream_t st, LaunchStats* ls);
+
+// ---- boundary.cu ------------------------------------------------------------ //
+cudaError_t launch_extract_col0(const double* E, int M, double* P, long long n, cudaStream_t, LaunchStats*);
+cudaError_t launch_dxdt(const double* P0, const double* P1, const double* P2, const double* P3,
+                        const double* c4_dev, double* d, long long n, cudaStream_t, LaunchStats*);
+cudaError_t launch_diff_tangents(const double* E, int M, double eps, double* T, long long n,
+                                 cudaStream_t, LaunchStats*);
+cudaError_t launch_make_ensemble(const double* u, const double* T, int M, double eps, double* E,
+                                 long long n, cudaStream_t, LaunchStats*);
+// in[rows][cols] -> out[cols][ld_out] (first `rows` entries of each output row)
+cudaError_t launch_transpose(const double* in, long long rows, int cols, double* out, long long ld_out,
+                             cudaStream_t, LaunchStats*);
+// in[cols][ld_in] -> out[rows][cols]
+cudaError_t launch_transpose_back(const double* in, long long ld_in, long long rows, int cols, double* out,
+                                  cudaStream_t, LaunchStats*);
+cudaError_t launch_fill_random(double* T, long long n, int MO, int m, long long site_offset,
+                               long long n_global, uint64_t seed, cudaStream_t, LaunchStats*);
+
+enum { SRC_ENSEMBLE = 0, SRC_TANGENT = 1 };
+// Gram of X_i = [t_0..t_m, d_i]  (MX = m+2), t from the ensemble ((E_k - E_0) * inv_eps) or from T.
+// part: [grid][MX*MX] scratch; out: MX*MX (deterministic fixed-order sum of the partials)
+cudaError_t launch_gram(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
+                        long long n, double* part, int max_part, double* out, int num_sms,
+                        cudaStream_t, LaunchStats*);
+// out_i = A . X_i  (A: (m+1) x (m+2) row-major on device); writes T (may alias the source T) and,
+// if E_out != nullptr, the next ensemble E_out[i] = [u_i, u_i + eps*out_i]
+cudaError_t launch_apply(int src, const double* E, const double* Tin, const double* d, const double* A,
+                         int m, double inv_eps, long long n, double* Tout, double* E_out, const double* u,
+                         double eps, cudaStream_t, LaunchStats*);
+
+struct SmallBufs {          // all device pointers
+    double* gram;           // (m+2)^2
+    double* A;              // (m+1)(m+2)
+    double* L1;             // m*m
+    double* R;              // m*m
+    double* b;              // m
+    double* gdil;           // m+1  (G_dil[0..m-1], g_dil)
+    int* status;            // 0 ok, >0 Cholesky pivot failure (1-based column)
+};
+cudaError_t launch_small1(const SmallBufs&, int m, int use_d, int do_qr, cudaStream_t, LaunchStats*);
+cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*);
+size_t small_smem_bytes(int m);
+
+// ---- lss.cu ----------------------------------------------------------------- //
+// R[K][m][m], b[K][m] (device) -> alpha[K][m] (device); work: (2*m*m + 2*m) * K doubles
+cudaError_t launch_lss_solve(const double* R, const double* b, long long K, int m, double* alpha,
+                             double* work, int* status, cudaStream_t, LaunchStats*);
+size_t lss_smem_bytes(int m);
+
+}  // namespace fds

@@ -1,0 +1,212 @@
+// Lorenz-96 arithmetic shared by the CUDA kernels and the host emulation harness.
+//
+// Operation order is the contract with oracle/plugins.py (l96_rhs_factored,
+// l96_rhs_fun3d, l96_rk4_step, l96_euler_step, tree_sum): in ExactMath mode every
+// value below is bit-identical to the numpy oracle.
+#pragma once
+#include "common.cuh"
+
+namespace fds {
+
+// dx_i = ((x_{i+1} - x_{i-2}) * x_{i-1} - x_i) + F      (RK4 plugin; reference
+// tests/solvers/Lorenz96/Lorenz96.f90:20)
+template <class MP>
+FDS_HD double l96_rhs(double xm2, double xm1, double x0, double xp1, double F) {
+    if (MP::kExact) {
+        double t = MP::sub(xp1, xm2);
+        t = MP::mul(t, xm1);
+        t = MP::sub(t, x0);
+        return MP::add(t, F);
+    } else {
+        double t = xp1 - xm2;
+        t = MP::fma_(t, xm1, -x0);
+        return t + F;
+    }
+}
+
+// dx_i = (((-x_{i-2}) * x_{i-1} + x_{i-1} * x_{i+1}) - x_i) + F   (Euler plugin;
+// reference tests/solvers/mock_fun3d/fun3d:54)
+template <class MP>
+FDS_HD double l96_rhs_fun3d(double xm2, double xm1, double x0, double xp1, double F) {
+    if (MP::kExact) {
+        double a = MP::mul(-xm2, xm1);
+        double b = MP::mul(xm1, xp1);
+        double t = MP::add(a, b);
+        t = MP::sub(t, x0);
+        return MP::add(t, F);
+    } else {
+        double b = xm1 * xp1;
+        double t = MP::fma_(-xm2, xm1, b);
+        return (t - x0) + F;
+    }
+}
+
+struct Rk4Coef {
+    double h2;  // 0.5*dt
+    double h;   // dt
+    double h6;  // dt/6.0
+};
+
+// --------------------------------------------------------------------------- //
+// Software-pipelined RK4 along one column: push x[i+4], get x'[i].
+// Rings hold x on sites i..i+4 (mod 8) and the stage inputs y2 (i..i+3),
+// y3 (i-1..i+2), y4 (i-2..i+1) and the running k1+2k2+2k3 (i..i+3) (mod 4).
+// P = i mod 8 is a template parameter so that every ring index is a constant
+// and the rings live in registers.
+// --------------------------------------------------------------------------- //
+template <class MP>
+struct Rk4Pipe {
+    double X[8], Y2[4], Y3[4], Y4[4], A[4];
+
+    FDS_HD void reset() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) X[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { Y2[j] = 0.0; Y3[j] = 0.0; Y4[j] = 0.0; A[j] = 0.0; }
+    }
+
+    template <int P>
+    FDS_HD double push(double xn, double F, const Rk4Coef& c) {
+        X[(P + 4) & 7] = xn;
+        // stage 1 at site i+3
+        const double k1 = l96_rhs<MP>(X[(P + 1) & 7], X[(P + 2) & 7], X[(P + 3) & 7], X[(P + 4) & 7], F);
+        A[(P + 3) & 3] = k1;
+        Y2[(P + 3) & 3] = MP::muladd(c.h2, k1, X[(P + 3) & 7]);
+        // stage 2 at site i+2
+        const double k2 = l96_rhs<MP>(Y2[P & 3], Y2[(P + 1) & 3], Y2[(P + 2) & 3], Y2[(P + 3) & 3], F);
+        A[(P + 2) & 3] = MP::twice_plus(k2, A[(P + 2) & 3]);
+        Y3[(P + 2) & 3] = MP::muladd(c.h2, k2, X[(P + 2) & 7]);
+        // stage 3 at site i+1
+        const double k3 = l96_rhs<MP>(Y3[(P + 3) & 3], Y3[P & 3], Y3[(P + 1) & 3], Y3[(P + 2) & 3], F);
+        A[(P + 1) & 3] = MP::twice_plus(k3, A[(P + 1) & 3]);
+        Y4[(P + 1) & 3] = MP::muladd(c.h, k3, X[(P + 1) & 7]);
+        // stage 4 at site i
+        const double k4 = l96_rhs<MP>(Y4[(P + 2) & 3], Y4[(P + 3) & 3], Y4[P & 3], Y4[(P + 1) & 3], F);
+        const double s = MP::add(A[P & 3], k4);
+        return MP::muladd(c.h6, s, X[P & 7]);
+    }
+};
+
+// One RK4 step at a single site from its 13-point dependency cone
+// x[0..12] = x_{i-8} .. x_{i+4}  (straightforward form; used by the simple kernel).
+template <class MP>
+FDS_HD double l96_rk4_point(const double* x, double F, const Rk4Coef& c) {
+    double k1[10], y2[10];           // sites i-6 .. i+3   (x index j+2)
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        k1[j] = l96_rhs<MP>(x[j], x[j + 1], x[j + 2], x[j + 3], F);
+        y2[j] = MP::muladd(c.h2, k1[j], x[j + 2]);
+    }
+    double k2[7], y3[7];             // sites i-4 .. i+2   (x index j+4)
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        k2[j] = l96_rhs<MP>(y2[j], y2[j + 1], y2[j + 2], y2[j + 3], F);
+        y3[j] = MP::muladd(c.h2, k2[j], x[j + 4]);
+    }
+    double k3[4], y4[4];             // sites i-2 .. i+1   (x index j+6)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        k3[j] = l96_rhs<MP>(y3[j], y3[j + 1], y3[j + 2], y3[j + 3], F);
+        y4[j] = MP::muladd(c.h, k3[j], x[j + 6]);
+    }
+    const double k4 = l96_rhs<MP>(y4[0], y4[1], y4[2], y4[3], F);
+    double s = MP::twice_plus(k2[4], k1[6]);
+    s = MP::twice_plus(k3[2], s);
+    s = MP::add(s, k4);
+    return MP::muladd(c.h6, s, x[8]);
+}
+
+// forward Euler at a single site, x[0..3] = x_{i-2} .. x_{i+1}
+template <class MP>
+FDS_HD double l96_euler_point(const double* x, double F, double dt) {
+    const double k = l96_rhs_fun3d<MP>(x[0], x[1], x[2], x[3], F);
+    return MP::muladd(dt, k, x[2]);
+}
+
+// --------------------------------------------------------------------------- //
+// Specified reduction tree (oracle/plugins.py: tree_sum): balanced binary tree
+// over adjacent sites.  Tree8 folds 8 consecutive values; LeafStack folds 8
+// consecutive Tree8 results into a 64-site leaf; TreeAcc is the generic
+// binary-counter form.  Left operand is always the lower-index partial.
+// --------------------------------------------------------------------------- //
+struct Tree8 {
+    double t1, t2, t4;
+    template <int P>
+    FDS_HD double push(double v) {   // returns the 8-sum when P == 7
+        if (P == 0) { t1 = v; }
+        else if (P == 1) { t2 = t1 + v; }
+        else if (P == 2) { t1 = v; }
+        else if (P == 3) { t4 = t2 + (t1 + v); }
+        else if (P == 4) { t1 = v; }
+        else if (P == 5) { t2 = t1 + v; }
+        else if (P == 6) { t1 = v; }
+        else { return t4 + (t2 + (t1 + v)); }
+        return 0.0;
+    }
+};
+
+struct LeafStack {
+    double s0, s1, s2;
+    // b = index of the 8-block inside its 64-site leaf; true when the leaf is complete
+    FDS_HD bool push(double p, int b, double& leaf) {
+        if ((b & 1) == 0) { s0 = p; return false; }
+        p = s0 + p;
+        if ((b & 2) == 0) { s1 = p; return false; }
+        p = s1 + p;
+        if ((b & 4) == 0) { s2 = p; return false; }
+        leaf = s2 + p;
+        return true;
+    }
+};
+
+template <int MAXL>
+struct TreeAcc {
+    double st[MAXL + 1];
+    unsigned cnt;
+    FDS_HD void reset() { cnt = 0; }
+    FDS_HD void push(double v) {
+        int l = 0;
+#pragma unroll 1
+        while ((cnt >> l) & 1u) { v = st[l] + v; ++l; }
+        st[l] = v;
+        ++cnt;
+    }
+    // valid after exactly 2^L pushes
+    FDS_HD double result(int L) const { return st[L]; }
+};
+
+constexpr int kLeafSites = 64;   // sites per leaf of the objective partials
+constexpr int kLeafShift = 6;
+
+// --------------------------------------------------------------------------- //
+// Strip decomposition of the streaming step kernel.  Output sites [lo, hi) are cut
+// into strips of `ls` sites (a multiple of 64) anchored at a multiple of 64,
+// so that every 8-block and every 64-site leaf is aligned to global site 0.
+// --------------------------------------------------------------------------- //
+struct StripPlan {
+    long long a0;       // first strip starts here (multiple of 64, <= lo)
+    long long ls;       // strip length
+    long long nstrips;  // strips needed to reach hi
+    int nblk;           // 8-blocks per strip
+};
+
+inline long long floor_div(long long a, long long b) {
+    long long q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+inline StripPlan make_strip_plan(long long lo, long long hi, long long max_strips) {
+    StripPlan p;
+    if (max_strips < 1) max_strips = 1;
+    const long long a0 = floor_div(lo, kLeafSites) * kLeafSites;
+    const long long span = hi - a0;
+    long long ls = ((span + max_strips - 1) / max_strips + kLeafSites - 1) / kLeafSites * kLeafSites;
+    if (ls < kLeafSites) ls = kLeafSites;
+    p.a0 = a0;
+    p.ls = ls;
+    p.nstrips = (span + ls - 1) / ls;
+    p.nblk = (int)(ls / 8);
+    return p;
+}
+
+}  // namespace fds

@@ -1,0 +1,362 @@
+// Lorenz-96 ensemble time-step kernels for sm_100a.
+//
+// K2 of SURVEY.md 2.3: replaces the m+2 pooled solver runs of one segment
+// (reference fds/segment.py:56-64; solver body tests/solvers/mock_fun3d/fun3d:48-57).
+//
+// l96_rk4_stream_kernel  -- the hot kernel.  Site-major ensemble [site][M] in HBM.
+//   Each CTA owns R strips of consecutive sites; thread (r, k) marches along strip r
+//   for ensemble column k with the whole 4-stage RK4 software-pipelined in registers
+//   (l96_march.cuh), so a site is read once and written once per step (16 B per
+//   trajectory-site-step) and no intermediate stage ever touches shared or global
+//   memory.  Input arrives through a ring of shared-memory stages filled by 1-D TMA
+//   bulk copies (cp.async.bulk + mbarrier complete_tx) issued by a producer warp;
+//   every strip is a contiguous chunk of the site-major array, so each copy is one
+//   contiguous 8*M*8-byte transfer.  Output goes straight from registers to HBM,
+//   coalesced across the columns of a site.  Objective sums (sum x, sum x^2 per
+//   column) are accumulated on the fly in a specified binary tree.
+#include <algorithm>
+#include "kernels.h"
+#include "l96_march.cuh"
+
+namespace fds {
+
+// ------------------------------- PTX wrappers -------------------------------- //
+FDS_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FDS_D void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+FDS_D void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+FDS_D void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+FDS_D bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+FDS_D void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {}
+}
+FDS_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------ streaming kernel ----------------------------- //
+struct StreamParams {
+    const double* X;
+    double* Y;
+    double* jpart;
+    long long nleaf;
+    long long a0, ls, nstrips;
+    long long lo, hi, n, alo, ahi;
+    int nblk;
+    int M, R, run_stride, nstages, nconsumer;  // nconsumer = R*M
+    double F0, Flast;
+    Rk4Coef c;
+};
+
+constexpr int kMaxStages = 8;
+
+struct StreamIO {
+    const double* sdata;     // this thread's (run, column) slot in stage 0
+    int stage_stride;        // doubles per stage
+    int M;
+    int nstages;
+    uint64_t* full;
+    uint64_t* empty;
+    double* Y;               // site 0, already offset by column
+    double* jp;              // leaf 0, already offset by column (or nullptr)
+    long long nleaf;
+    int lane;
+    // ring position
+    int st;
+    uint32_t par;
+    const double* cur;
+
+    FDS_D void acquire(int) {
+        mbar_wait(&full[st], par);
+        cur = sdata + (size_t)st * stage_stride;
+    }
+    FDS_D double load(int, int p) const { return cur[p * M]; }
+    FDS_D void release(int) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (++st == nstages) { st = 0; par ^= 1u; }
+    }
+    FDS_D void store(long long i, double v) { Y[i * M] = v; }
+    FDS_D void emit_leaf(long long leaf, double s1, double s2) {
+        if (jp != nullptr && leaf >= 0 && leaf < nleaf)
+            *reinterpret_cast<double2*>(jp + leaf * (2LL * M)) = make_double2(s1, s2);
+    }
+};
+
+template <class MP>
+__global__ void __launch_bounds__(608, 1) l96_rk4_stream_kernel(const StreamParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + kMaxStages;
+    double* sdata = reinterpret_cast<double*>(smem_raw + 128);
+
+    const int tid = threadIdx.x;
+    const int ncw = (p.nconsumer + 31) >> 5;          // consumer warps
+    const int warp = tid >> 5, lane = tid & 31;
+    const int stage_stride = p.R * p.run_stride;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.nstages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], ncw);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int nit = p.nblk + 2;                        // blocks b = -2 .. nblk-1
+    if (warp == ncw) {
+        // ---------------- producer warp: one lane issues the bulk copies ------- //
+        if (lane == 0) {
+            const uint32_t chunk_bytes = (uint32_t)(8 * p.M * sizeof(double));
+            int st = 0;
+            uint32_t par = 0;
+            for (int it = 0; it < nit; ++it) {
+                if (it >= p.nstages) mbar_wait(&empty[st], par ^ 1u);
+                mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)p.R);
+                double* dst = sdata + (size_t)st * stage_stride;
+                const long long boff = 8LL * (it - 2) + 4;
+                for (int r = 0; r < p.R; ++r) {
+                    long long strip = (long long)blockIdx.x * p.R + r;
+                    long long cs = p.a0 + strip * p.ls + boff;
+                    cs = cs < p.alo ? p.alo : cs;
+                    cs = cs + 8 > p.ahi ? p.ahi - 8 : cs;
+                    bulk_g2s(dst + r * p.run_stride, p.X + cs * p.M, chunk_bytes, &full[st]);
+                }
+                if (++st == p.nstages) { st = 0; par ^= 1u; }
+            }
+        }
+        return;
+    }
+    // -------------------- consumer threads: (run r, column k) ------------------ //
+    const bool active = tid < p.nconsumer;
+    const int t = active ? tid : p.nconsumer - 1;       // idle lanes shadow the last thread
+    const int r = t / p.M, k = t - r * p.M;
+    const long long strip = (long long)blockIdx.x * p.R + r;
+
+    StreamIO io;
+    io.sdata = sdata + r * p.run_stride + k;
+    io.stage_stride = stage_stride;
+    io.M = p.M;
+    io.nstages = p.nstages;
+    io.full = full;
+    io.empty = empty;
+    io.Y = p.Y + k;
+    io.jp = (p.jpart != nullptr && active) ? p.jpart + 2 * k : nullptr;
+    io.nleaf = p.nleaf;
+    io.lane = lane;
+    io.st = 0;
+    io.par = 0;
+    io.cur = io.sdata;
+
+    MarchGeom g;
+    g.a = p.a0 + strip * p.ls;
+    g.lo = active ? p.lo : 0;
+    g.hi = active ? (g.a + p.ls < p.hi ? g.a + p.ls : p.hi) : 0;   // idle lanes store nothing
+    g.n = p.n;
+    g.nblk = p.nblk;
+    g.stats = p.jpart != nullptr;
+    const double F = (k == p.M - 1) ? p.Flast : p.F0;
+    l96_rk4_march<MP>(io, g, F, p.c);
+}
+
+static int pick_runs(int M) {
+    int R = 1;
+    while (R * 2 * M <= 576 && R < 512) R *= 2;
+    return R;
+}
+
+cudaError_t launch_l96_rk4_stream(const StepArgs& a, int num_sms, cudaStream_t st, LaunchStats* ls) {
+    StreamParams p;
+    p.X = a.X; p.Y = a.Y; p.jpart = a.jpart; p.nleaf = a.nleaf;
+    p.lo = a.lo; p.hi = a.hi; p.n = a.n; p.alo = a.alo; p.ahi = a.ahi;
+    p.M = a.M;
+    p.R = pick_runs(a.M);
+    if (p.R * a.M > 576) return cudaErrorInvalidValue;   // M too large for this kernel
+    p.nconsumer = p.R * a.M;
+    int pad = (16 - (7 * a.M) % 16) % 16;
+    if (pad & 1) pad += 1;
+    p.run_stride = 8 * a.M + pad;
+    const size_t stage_bytes = (size_t)p.R * p.run_stride * sizeof(double);
+    int nst = (int)std::min<size_t>(kMaxStages, (200 * 1024) / stage_bytes);
+    if (nst < 2) return cudaErrorInvalidValue;
+    p.nstages = nst;
+    StripPlan plan = make_strip_plan(a.lo, a.hi, (long long)num_sms * p.R);
+    p.a0 = plan.a0; p.ls = plan.ls; p.nstrips = plan.nstrips; p.nblk = plan.nblk;
+    p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
+    p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
+    const int grid = (int)((plan.nstrips + p.R - 1) / p.R);
+    const int block = ((p.nconsumer + 31) / 32) * 32 + 32;
+    const size_t smem = 128 + stage_bytes * nst;
+    cudaError_t e;
+    if (a.exact) {
+        e = cudaFuncSetAttribute(l96_rk4_stream_kernel<ExactMath>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        l96_rk4_stream_kernel<ExactMath><<<grid, block, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(l96_rk4_stream_kernel<FastMath>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        l96_rk4_stream_kernel<FastMath><<<grid, block, smem, st>>>(p);
+    }
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------- simple kernel ------------------------------- //
+template <class MP, int EULER>
+__global__ void __launch_bounds__(256) l96_simple_kernel(const double* __restrict__ X, double* __restrict__ Y,
+                                                         int M, long long lo, long long count, double F0,
+                                                         double Flast, Rk4Coef c) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= count) return;
+    const long long i = lo + idx / M;
+    const int k = (int)(idx % M);
+    const double F = (k == M - 1) ? Flast : F0;
+    if (EULER) {
+        double x[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = X[(i - 2 + j) * M + k];
+        Y[i * M + k] = l96_euler_point<MP>(x, F, c.h);
+    } else {
+        double x[13];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) x[j] = X[(i - 8 + j) * M + k];
+        Y[i * M + k] = l96_rk4_point<MP>(x, F, c);
+    }
+}
+
+cudaError_t launch_l96_simple(const StepArgs& a, int euler, cudaStream_t st, LaunchStats* ls) {
+    const long long count = (a.hi - a.lo) * a.M;
+    if (count <= 0) return cudaSuccess;
+    const int block = 256;
+    const long long grid = (count + block - 1) / block;
+    Rk4Coef c{0.5 * a.dt, a.dt, a.dt / 6.0};
+    const double Fl = a.M > 1 ? a.Flast : a.F0;
+#define FDS_LAUNCH_SIMPLE(MP, E) \
+    l96_simple_kernel<MP, E><<<(unsigned)grid, block, 0, st>>>(a.X, a.Y, a.M, a.lo, count, a.F0, Fl, c)
+    if (a.exact) { if (euler) FDS_LAUNCH_SIMPLE(ExactMath, 1); else FDS_LAUNCH_SIMPLE(ExactMath, 0); }
+    else         { if (euler) FDS_LAUNCH_SIMPLE(FastMath, 1);  else FDS_LAUNCH_SIMPLE(FastMath, 0); }
+#undef FDS_LAUNCH_SIMPLE
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// ------------------------------ objective sums ------------------------------- //
+__global__ void __launch_bounds__(256) stats_leaf_kernel(const double* __restrict__ Y, int M, long long n,
+                                                         double* __restrict__ jpart, long long nleaf) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nleaf * M) return;
+    const long long leaf = idx / M;
+    const int k = (int)(idx % M);
+    TreeAcc<kLeafShift> a1, a2;
+    a1.reset(); a2.reset();
+    const long long i0 = leaf * kLeafSites;
+    for (int j = 0; j < kLeafSites; ++j) {
+        const long long i = i0 + j;
+        const double v = i < n ? Y[i * M + k] : 0.0;
+        a1.push(v);
+        a2.push(__dmul_rn(v, v));
+    }
+    reinterpret_cast<double2*>(jpart)[idx] = make_double2(a1.result(kLeafShift), a2.result(kLeafShift));
+}
+
+cudaError_t launch_stats_leaf(const double* Y, int M, long long n, double* jpart, long long nleaf,
+                              cudaStream_t st, LaunchStats* ls) {
+    const long long total = nleaf * M;
+    stats_leaf_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Y, M, n, jpart, nleaf);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// One level of the canonical tree: out[g][c] = tree(in[g*LG .. g*LG+LG-1][c]), zero padded.
+constexpr int kLG = 256;
+__global__ void __launch_bounds__(1024) tree_level_kernel(const double* __restrict__ in, long long n_in, int C,
+                                                          int Q, double* __restrict__ out) {
+    extern __shared__ double sm[];                 // [Q][C]
+    const int c = threadIdx.x % C, q = threadIdx.x / C;
+    const long long g = blockIdx.x;
+    if (q < Q) {
+        const int per = kLG / Q;                   // power of two
+        int L = 0;
+        while ((1 << L) < per) ++L;
+        TreeAcc<8> acc;
+        acc.reset();
+        const long long e0 = g * kLG + (long long)q * per;
+        for (int j = 0; j < per; ++j) {
+            const long long e = e0 + j;
+            acc.push(e < n_in ? in[e * C + c] : 0.0);
+        }
+        sm[q * C + c] = acc.result(L);
+    }
+    __syncthreads();
+    for (int s = 1; s < Q; s <<= 1) {
+        if (q < Q && (q % (2 * s)) == 0) sm[q * C + c] = sm[q * C + c] + sm[(q + s) * C + c];
+        __syncthreads();
+    }
+    if (q == 0) out[g * C + c] = sm[c];
+}
+
+cudaError_t launch_tree_reduce(const double* in, long long n_in, int C, double* out, double* scratch,
+                               cudaStream_t st, LaunchStats* ls) {
+    int Q = 1;
+    while (Q * 2 * C <= 1024 && Q * 2 <= kLG) Q *= 2;
+    if (C > 1024) return cudaErrorInvalidValue;
+    const long long cap = (n_in + kLG - 1) / kLG;   // size of one scratch half, in rows
+    const double* src = in;
+    long long n = n_in;
+    int flip = 0;
+    for (;;) {
+        const long long n_out = (n + kLG - 1) / kLG;
+        double* dst = (n_out == 1) ? out : scratch + (size_t)flip * cap * C;
+        tree_level_kernel<<<(unsigned)n_out, Q * C, (size_t)Q * C * sizeof(double), st>>>(src, n, C, Q, dst);
+        if (ls) ls->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        if (n_out == 1) break;
+        src = dst; n = n_out; flip ^= 1;
+    }
+    return cudaSuccess;
+}
+
+// --------------------------------- halo wrap --------------------------------- //
+__global__ void __launch_bounds__(256) halo_wrap_kernel(double* __restrict__ A, int M, long long n,
+                                                        long long gl, long long gr) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (gl + gr) * M;
+    if (idx >= total) return;
+    const long long s = idx / M;
+    const int k = (int)(idx % M);
+    const long long g = s < gl ? s - gl : n + (s - gl);     // ghost site index
+    long long src = g % n;
+    if (src < 0) src += n;
+    A[g * M + k] = A[src * M + k];
+}
+
+cudaError_t launch_halo_wrap(double* A, int M, long long n, long long gl, long long gr, cudaStream_t st,
+                             LaunchStats* ls) {
+    const long long total = (gl + gr) * M;
+    if (total <= 0) return cudaSuccess;
+    halo_wrap_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, M, n, gl, gr);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace fds

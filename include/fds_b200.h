@@ -1,0 +1,162 @@
+/*
+ * fds_b200 -- C ABI of the B200-native finite-difference-shadowing hot path.
+ *
+ * One context per GPU (one process per GPU).  The context owns the
+ * device-resident state of the shadowing segment loop of qiqi/fds:
+ *
+ *   ensemble  E[site][col]   site-major ("interleaved SoA"), col 0 = primal u,
+ *                            cols 1..m = u + eps*W_j, col m+1 = u + eps*w
+ *   tangents  T[site][j]     j < m homogeneous (W), j = m inhomogeneous (w)
+ *   d[site]                  per-step du/dt estimate (time dilation)
+ *
+ * All host buffers are caller-owned row-major float64; all device memory is
+ * library-owned.  Every function returns 0 on success, non-zero on failure;
+ * fds_last_error() gives the message.  One host thread per context; no global
+ * state; do not fork() after fds_ctx_create().
+ *
+ * Each entry point cites the reference (qiqi/fds) interface it replaces.
+ */
+#ifndef FDS_B200_H
+#define FDS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct fds_ctx fds_ctx;
+
+/* solver "systems" (the plugin on the far side of run(), fds/fds.py:184-200) */
+enum {
+    FDS_SYS_L96_RK4   = 0, /* Lorenz-96, classical RK4, dt, F = s + 8            */
+    FDS_SYS_L96_EULER = 1  /* Lorenz-96, forward Euler: tests/solvers/mock_fun3d/fun3d:48-57 */
+};
+
+/* arithmetic modes */
+enum {
+    FDS_MATH_EXACT = 0,    /* FMA-free, numpy operation order: bit-identical state */
+    FDS_MATH_FAST  = 1     /* FMA contraction allowed (statistically equivalent)   */
+};
+
+/* context flags */
+enum {
+    FDS_FLAG_SIMPLE_KERNELS = 1  /* use the one-thread-per-element step kernel (cross-check path) */
+};
+
+/* device buffers a multi-GPU host may need to address (halo exchange, reductions) */
+enum {
+    FDS_BUF_ENSEMBLE = 0,  /* current ensemble, base of site 0, [.][M]             */
+    FDS_BUF_PRIMAL   = 1,  /* primal work array P0, base of site 0, [.]            */
+    FDS_BUF_GRAM     = 2,  /* extended Gram (m+2)^2, to be sum-reduced over ranks  */
+    FDS_BUF_JSUM     = 3,  /* objective sums [steps][M][2] of the last segment     */
+    FDS_BUF_TANGENT  = 4,  /* explicit tangents [n_local][m+1]                     */
+    FDS_BUF_DXDT     = 5   /* d[n_local]                                           */
+};
+
+typedef struct fds_config {
+    int32_t device;        /* CUDA device ordinal                                  */
+    int32_t system;        /* FDS_SYS_*                                            */
+    int32_t math;          /* FDS_MATH_*                                           */
+    int32_t m;             /* subspace dimension (number of homogeneous tangents)  */
+    int64_t n_local;       /* sites owned by this rank                             */
+    int64_t n_global;      /* sites of the whole ring                              */
+    int64_t site_offset;   /* global index of local site 0                         */
+    int32_t rank, world;   /* position in the ring of ranks                        */
+    int32_t max_halo_steps;/* steps between halo refreshes (0 = library default)   */
+    int32_t flags;         /* FDS_FLAG_*                                           */
+    double  dt;            /* time step (0 = 0.01)                                 */
+    void*   stream;        /* cudaStream_t to launch on (NULL = own stream)        */
+} fds_config;
+
+/* ---- life cycle ------------------------------------------------------------- */
+int  fds_ctx_create(const fds_config* cfg, fds_ctx** out);
+void fds_ctx_destroy(fds_ctx* ctx);
+const char* fds_last_error(const fds_ctx* ctx);   /* ctx may be NULL: creation error */
+const char* fds_version(void);
+
+/* ---- state in / out (reference: Checkpoint.u0/V/v, fds/checkpoint.py:6) ------- */
+int fds_set_state(fds_ctx*, const double* u_host);                 /* [n_local]      */
+int fds_get_state(fds_ctx*, double* u_host);
+int fds_set_tangents(fds_ctx*, const double* V_host, const double* v_host); /* [m][n_local], [n_local] */
+int fds_get_tangents(fds_ctx*, double* V_host, double* v_host);
+int fds_random_tangents(fds_ctx*, uint64_t seed);  /* uniform[0,1) V (pascal.random, fds/fds.py:23), v = 0 */
+
+/* FD stencil weights of the time-dilation derivative (fds/timedilation.py:16-19 gets them
+ * from np.linalg.solve; pass those 4 doubles for bit parity).  Default: -11/6, 3, -3/2, 1/3 */
+int fds_set_dxdt_weights(fds_ctx*, const double c[4]);
+/* run_ddt=0 of the reference (fds/timedilation.py:59-61): no time dilation at boundaries   */
+int fds_set_time_dilation(fds_ctx*, int enabled);
+
+/* ---- the solver plugin itself: u1, J = run(u0, s, steps), fds/fds.py:184-200 -- */
+/* single trajectory on the context's primal array (world == 1; halos wrapped inside);
+ * Jsum_host is [steps][2] = [sum x, sum x^2] (divide by n_global for J) or NULL      */
+int fds_run(fds_ctx*, double s, int64_t steps, double* Jsum_host);
+/* the same in chunks for world > 1: the host refreshes the primal halo (valid for
+ * fds_halo_steps() steps) before each chunk; sums land in FDS_BUF_JSUM[step0+j][1][2] */
+int fds_primal_advance(fds_ctx*, double s, int64_t step0, int64_t nsteps, int record);
+/* tell the library the host has refreshed a halo itself (world > 1)                   */
+int fds_halo_mark_valid(fds_ctx*, int which_buf, int64_t halo_steps);
+
+/* ---- halo handling ----------------------------------------------------------- */
+/* world == 1: periodic wrap on the device.  world > 1: the host exchanges the
+ * regions described by fds_halo_layout() between ring neighbours (NCCL send/recv)
+ * INSTEAD of calling these.  (reference: tests/solvers/mock_fun3d/fun3d:29-37)    */
+int fds_halo_wrap_ensemble(fds_ctx*, int64_t halo_steps);
+int fds_halo_wrap_primal(fds_ctx*, int64_t halo_steps);
+/* element offsets (in doubles, relative to the FDS_BUF_* base) and counts of the
+ * four contiguous regions: send_to_right, send_to_left, recv_from_left, recv_from_right */
+int fds_halo_layout(const fds_ctx*, int which_buf, int64_t halo_steps, int64_t off[4], int64_t cnt[4]);
+
+/* ---- one segment boundary, split at its reduction points ---------------------- */
+/* reference: TimeDilation.__init__/contribution/project (fds/timedilation.py:37-82),
+ * LssTangent.checkpoint (fds/lsstan.py:20-34), perturbed ICs (fds/segment.py:43-51).
+ *
+ *  fds_boundary_begin   : primal <- ensemble col 0 (or the state set by fds_set_state)
+ *        [halo: primal, 3 steps]
+ *  fds_boundary_dxdt    : u1,u2,u3, d = sum c_i u_i ; Gram of [tangents ; d] -> FDS_BUF_GRAM
+ *        [sum-reduce FDS_BUF_GRAM over ranks]
+ *  fds_boundary_factor  : G_dil, g_dil, projection (+ CholeskyQR pass 1 if do_qr); applies it;
+ *                         if do_qr: Gram of the result -> FDS_BUF_GRAM
+ *        [if do_qr: sum-reduce FDS_BUF_GRAM over ranks]
+ *  fds_boundary_finish  : (CholeskyQR pass 2 if do_qr) R, b; explicit tangents; next ensemble
+ *        [halo: ensemble, halo_steps]
+ */
+int fds_boundary_begin(fds_ctx*, int from_ensemble);
+int fds_boundary_dxdt(fds_ctx*, double s, int from_ensemble, double eps);
+int fds_boundary_factor(fds_ctx*, int do_qr, int from_ensemble, double eps);
+int fds_boundary_finish(fds_ctx*, int do_qr, double eps, int build_ensemble);
+/* small results of the last boundary: R[m][m], b[m], G_dil[m], g_dil[1]; any may be NULL */
+int fds_boundary_results(fds_ctx*, double* R, double* b, double* G_dil, double* g_dil);
+
+/* ---- one segment: advance all m+2 trajectories `steps` steps ------------------ */
+/* reference: run_segment's m+2 solver calls (fds/segment.py:56-64).  The host
+ * refreshes halos every fds_halo_steps() steps: call fds_segment_advance() in
+ * chunks (step0 = index of the first step of the chunk within the segment).       */
+int64_t fds_halo_steps(const fds_ctx*, int64_t steps);
+int fds_segment_advance(fds_ctx*, double s, double eps, int64_t step0, int64_t nsteps);
+/* objective sums of the last segment, J_host[steps][m+2][2] = [sum x, sum x^2]    */
+int fds_segment_jsums(fds_ctx*, int64_t steps, double* Jsum_host);
+
+/* ---- convenience for world == 1 (all phases + halos inside) ------------------- */
+int fds_boundary(fds_ctx*, double s, double eps, int from_ensemble, int do_qr, int build_ensemble,
+                 int64_t halo_steps, double* R, double* b, double* G_dil, double* g_dil);
+int fds_segment(fds_ctx*, double s, double eps, int64_t steps, double* Jsum_host);
+/* host-buffer form of one reference run_segment call (fds/segment.py:14-82):
+ * u, V, v in -> advanced u, V, v out, Jsum[steps][m+2][2]; H2D and D2H inside     */
+int fds_run_segment_host(fds_ctx*, double* u, double* V, double* v, double s, double eps,
+                         int64_t steps, double* Jsum_host);
+
+/* ---- LssTangent.solve (fds/lsstan.py:36-50): min |a|^2 s.t. a_{i+1}=R_i a_i+b_i */
+/* R[K][m][m], b[K][m] -> alpha[K][m]; single-CTA block-tridiagonal Cholesky       */
+int fds_lss_solve(int device, const double* R, const double* b, int64_t K, int m, double* alpha);
+
+/* ---- introspection ------------------------------------------------------------ */
+void*   fds_buffer_ptr(const fds_ctx*, int which_buf);   /* device pointer of site/elem 0 */
+int64_t fds_kernel_launches(const fds_ctx*);              /* kernels launched so far        */
+int     fds_sync(fds_ctx*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDS_B200_H */
