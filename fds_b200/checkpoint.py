@@ -1,0 +1,57 @@
+"""Checkpoint carrier between ``shadowing`` and ``continue_shadowing``.
+
+Same 9-field order, file naming (``m{m}_segment{K}``) and load-latest semantics as
+the reference ``fds/checkpoint.py`` (:6-52).  Unlike the reference (which pickles
+un-evaluated lazy graphs with dill), ``u0``, ``V``, ``v`` here are plain numpy
+arrays fetched from the device, so the standard pickle is enough.
+"""
+import os
+import pickle
+from collections import namedtuple
+
+Checkpoint = namedtuple('Checkpoint', 'u0 V v lss G_lss g_lss J G_dil g_dil')
+
+
+def _filename(cp):
+    return 'm{0}_segment{1}'.format(cp.lss.m_modes(), cp.lss.K_segments())
+
+
+def save_checkpoint(checkpoint_path, cp):
+    with open(os.path.join(checkpoint_path, _filename(cp)), 'wb') as f:
+        pickle.dump(cp, f)
+
+
+def load_checkpoint(checkpoint_file):
+    with open(checkpoint_file, 'rb') as f:
+        return pickle.load(f)
+
+
+def verify_checkpoint(cp):
+    """All per-segment histories have one entry per finished segment
+    (reference fds/checkpoint.py:20-26)."""
+    k = cp.lss.K_segments()
+    return all(len(h) == k for h in (cp.G_lss, cp.g_lss, cp.J, cp.G_dil, cp.g_dil))
+
+
+def _parse(filename):
+    """(m, K) of a file named m{m}_segment{K}, else None (garbage names are ignored,
+    reference tests/test_restart.py:46-50)."""
+    head, sep, tail = filename.partition('_segment')
+    if not sep or not head.startswith('m'):
+        return None
+    try:
+        return int(head[1:]), int(tail)
+    except ValueError:
+        return None
+
+
+def load_last_checkpoint(checkpoint_path, m):
+    """The checkpoint with the largest segment count among those written for
+    subspace dimension ``m``; None if there is none (fds/checkpoint.py:28-52)."""
+    best = None
+    for name in os.listdir(checkpoint_path):
+        mk = _parse(name)
+        if mk is not None and mk[0] == m and (best is None or mk[1] > best[0]):
+            best = (mk[1], name)
+    if best is not None:
+        return load_checkpoint(os.path.join(checkpoint_path, best[1]))

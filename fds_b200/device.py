@@ -1,0 +1,201 @@
+"""Device context: thin object wrapper over the C ABI (include/fds_b200.h).
+
+One ``Context`` owns the device-resident state of one shard of the shadowing
+segment loop (ensemble, tangents, dxdt, objective sums, small matrices).  All
+arrays crossing this boundary are host numpy float64; nothing here computes on
+the CPU -- every method is one or more calls into libfds_b200.so and raises
+``FdsError`` if the library or a CUDA device is missing.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import FdsError, dptr
+
+SYSTEMS = {'rk4': _lib.FDS_SYS_L96_RK4, 'euler': _lib.FDS_SYS_L96_EULER}
+MATH = {'exact': _lib.FDS_MATH_EXACT, 'fast': _lib.FDS_MATH_FAST}
+
+
+class Context:
+    """Device-resident Lorenz-96 shadowing state for ``n_local`` sites x (m+2) trajectories."""
+
+    def __init__(self, n_local, m, scheme='rk4', math='exact', dt=0.01, device=0,
+                 n_global=None, site_offset=0, rank=0, world=1, max_halo_steps=0,
+                 simple_kernels=False, stream=None):
+        self.lib = _lib.load()
+        self.n = int(n_local)
+        self.m = int(m)
+        self.M = self.m + 2
+        self.n_global = int(n_global if n_global is not None else n_local)
+        self.rank, self.world = int(rank), int(world)
+        cfg = _lib.FdsConfig(device=device, system=SYSTEMS[scheme], math=MATH[math], m=self.m,
+                             n_local=self.n, n_global=self.n_global, site_offset=int(site_offset),
+                             rank=self.rank, world=self.world, max_halo_steps=int(max_halo_steps),
+                             flags=_lib.FDS_FLAG_SIMPLE_KERNELS if simple_kernels else 0,
+                             dt=float(dt), stream=stream)
+        h = ctypes.c_void_p()
+        rc = self.lib.fds_ctx_create(ctypes.byref(cfg), ctypes.byref(h))
+        if rc != 0:
+            raise FdsError('fds_ctx_create failed (%d): %s'
+                           % (rc, self.lib.fds_last_error(None).decode()))
+        self.h = h
+
+    # -- plumbing ------------------------------------------------------------ #
+    def _ck(self, rc):
+        if rc != 0:
+            raise FdsError(self.lib.fds_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, 'h', None):
+            self.lib.fds_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._ck(self.lib.fds_sync(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.fds_kernel_launches(self.h))
+
+    def buffer_ptr(self, which):
+        return self.lib.fds_buffer_ptr(self.h, which)
+
+    # -- state --------------------------------------------------------------- #
+    def set_state(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.shape == (self.n,)
+        self._ck(self.lib.fds_set_state(self.h, dptr(u)))
+
+    def get_state(self):
+        u = np.empty(self.n)
+        self._ck(self.lib.fds_get_state(self.h, dptr(u)))
+        return u
+
+    def set_tangents(self, V, v=None):
+        V = np.ascontiguousarray(V, dtype=np.float64)
+        assert V.shape == (self.m, self.n)
+        if v is not None:
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            assert v.shape == (self.n,)
+        self._ck(self.lib.fds_set_tangents(self.h, dptr(V), dptr(v)))
+
+    def get_tangents(self):
+        V, v = np.empty((self.m, self.n)), np.empty(self.n)
+        self._ck(self.lib.fds_get_tangents(self.h, dptr(V), dptr(v)))
+        return V, v
+
+    def random_tangents(self, seed):
+        self._ck(self.lib.fds_random_tangents(self.h, ctypes.c_uint64(int(seed) & (2 ** 64 - 1))))
+
+    def set_dxdt_weights(self, c):
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        assert c.shape == (4,)
+        self._ck(self.lib.fds_set_dxdt_weights(self.h, dptr(c)))
+
+    def set_time_dilation(self, enabled):
+        self._ck(self.lib.fds_set_time_dilation(self.h, int(bool(enabled))))
+
+    # -- solver plugin ------------------------------------------------------- #
+    def run(self, s, steps, want_J=True):
+        """Advance the primal ``steps`` steps; returns objective SUMS [steps][2] (or None)."""
+        J = np.empty((int(steps), 2)) if want_J and steps > 0 else None
+        self._ck(self.lib.fds_run(self.h, float(s), int(steps), dptr(J)))
+        return J
+
+    # -- halos / phases (world > 1 drives these itself) ---------------------- #
+    def halo_steps(self, steps):
+        return int(self.lib.fds_halo_steps(self.h, int(steps)))
+
+    def halo_layout(self, which, hs):
+        off, cnt = (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
+        if self.lib.fds_halo_layout(self.h, which, int(hs), off, cnt) != 0:
+            raise FdsError('fds_halo_layout: bad arguments')
+        return list(off), list(cnt)
+
+    def halo_wrap_ensemble(self, hs):
+        self._ck(self.lib.fds_halo_wrap_ensemble(self.h, int(hs)))
+
+    def halo_wrap_primal(self, hs):
+        self._ck(self.lib.fds_halo_wrap_primal(self.h, int(hs)))
+
+    def halo_mark_valid(self, which, hs):
+        self._ck(self.lib.fds_halo_mark_valid(self.h, which, int(hs)))
+
+    def primal_advance(self, s, step0, nsteps, record):
+        self._ck(self.lib.fds_primal_advance(self.h, float(s), int(step0), int(nsteps), int(record)))
+
+    def boundary_begin(self, from_ensemble):
+        self._ck(self.lib.fds_boundary_begin(self.h, int(from_ensemble)))
+
+    def boundary_dxdt(self, s, from_ensemble, eps):
+        self._ck(self.lib.fds_boundary_dxdt(self.h, float(s), int(from_ensemble), float(eps)))
+
+    def boundary_factor(self, do_qr, from_ensemble, eps):
+        self._ck(self.lib.fds_boundary_factor(self.h, int(do_qr), int(from_ensemble), float(eps)))
+
+    def boundary_finish(self, do_qr, eps, build):
+        self._ck(self.lib.fds_boundary_finish(self.h, int(do_qr), float(eps), int(build)))
+
+    def boundary_results(self, do_qr):
+        m = self.m
+        R = np.empty((m, m)) if do_qr else None
+        b = np.empty(m) if do_qr else None
+        Gd, gd = np.empty(m), np.empty(1)
+        self._ck(self.lib.fds_boundary_results(self.h, dptr(R), dptr(b), dptr(Gd), dptr(gd)))
+        return R, b, Gd, float(gd[0])
+
+    def segment_advance(self, s, eps, step0, nsteps):
+        self._ck(self.lib.fds_segment_advance(self.h, float(s), float(eps), int(step0), int(nsteps)))
+
+    def segment_jsums(self, steps):
+        J = np.empty((int(steps), self.M, 2))
+        self._ck(self.lib.fds_segment_jsums(self.h, int(steps), dptr(J)))
+        return J
+
+    # -- world == 1 conveniences --------------------------------------------- #
+    def boundary(self, s, eps, from_ensemble, do_qr, build, halo_steps=0):
+        """One segment boundary; returns (R, b, G_dil, g_dil) (R, b None unless do_qr)."""
+        m = self.m
+        R = np.empty((m, m)) if do_qr else None
+        b = np.empty(m) if do_qr else None
+        Gd, gd = np.empty(m), np.empty(1)
+        self._ck(self.lib.fds_boundary(self.h, float(s), float(eps), int(from_ensemble), int(do_qr),
+                                       int(build), int(halo_steps), dptr(R), dptr(b), dptr(Gd), dptr(gd)))
+        return R, b, Gd, float(gd[0])
+
+    def segment(self, s, eps, steps, want_J=True):
+        """Advance all m+2 trajectories ``steps`` steps; objective SUMS [steps][m+2][2]."""
+        J = np.empty((int(steps), self.M, 2)) if want_J else None
+        self._ck(self.lib.fds_segment(self.h, float(s), float(eps), int(steps), dptr(J)))
+        return J
+
+    def run_segment_host(self, u, V, v, s, eps, steps):
+        """Host-buffer form of the reference's run_segment (fds/segment.py:14-82)."""
+        u = np.array(u, dtype=np.float64)
+        V = np.array(V, dtype=np.float64)
+        v = np.array(v, dtype=np.float64)
+        J = np.empty((int(steps), self.M, 2))
+        self._ck(self.lib.fds_run_segment_host(self.h, dptr(u), dptr(V), dptr(v), float(s), float(eps),
+                                               int(steps), dptr(J)))
+        return u, V, v, J
+
+
+def lss_solve(R, b, device=0):
+    """LssTangent.solve on the device (reference fds/lsstan.py:36-50)."""
+    lib = _lib.load()
+    R = np.ascontiguousarray(R, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    K, m = b.shape
+    assert R.shape == (K, m, m)
+    alpha = np.empty((K, m))
+    rc = lib.fds_lss_solve(int(device), dptr(R), dptr(b), K, m, dptr(alpha))
+    if rc != 0:
+        raise FdsError(lib.fds_last_error(None).decode())
+    return alpha

@@ -1,0 +1,187 @@
+"""Driver of one shard's device context through a segment boundary / a segment.
+
+The C library splits a boundary at its reduction points (include/fds_b200.h);
+this module is the host side that fills those points: periodic wrap on one GPU,
+``Ring`` halo exchange + all-reduce when the state is sharded over ranks.  The
+sequence is the reference's per-segment algorithm (SURVEY.md appendix A;
+fds/fds.py:128-170, fds/timedilation.py:63-82, fds/lsstan.py:20-34,
+fds/segment.py:43-79).
+"""
+import numpy as np
+
+from . import _lib
+from .device import Context
+from .ring import Ring, shard_range
+
+
+class _DevView:
+    """Expose a span of a library-owned device buffer through __cuda_array_interface__."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {'shape': (int(count),), 'typestr': '<f8',
+                                         'data': (int(ptr), False), 'version': 2}
+
+
+class Engine:
+    def __init__(self, n_global, m, scheme='rk4', math='exact', dt=0.01, device=None,
+                 group=None, distributed=None, max_halo_steps=0, simple_kernels=False):
+        self.n_global = int(n_global)
+        self.m = int(m)
+        self.M = self.m + 2
+        self.ring = None
+        self.torch = None
+        stream = None
+        if distributed is None:
+            try:
+                import torch.distributed as dist
+                distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+            except ImportError:
+                distributed = False
+        if distributed:
+            import torch
+            self.torch = torch
+            self.ring = Ring(group)
+            if device is None:
+                device = torch.cuda.current_device()
+            torch.cuda.set_device(device)
+            stream = torch.cuda.current_stream().cuda_stream
+        if device is None:
+            device = 0
+        self.device = int(device)
+        rank, world = (self.ring.rank, self.ring.world) if self.ring else (0, 1)
+        self.lo, self.hi = shard_range(self.n_global, rank, world)
+        self.ctx = Context(self.hi - self.lo, m, scheme=scheme, math=math, dt=dt, device=self.device,
+                           n_global=self.n_global, site_offset=self.lo, rank=rank, world=world,
+                           max_halo_steps=max_halo_steps, simple_kernels=simple_kernels, stream=stream)
+        self.time_dilation = True
+
+    # -- sharding of host arrays --------------------------------------------- #
+    def local(self, a):
+        """Slice the trailing (site) axis of a global host array to this shard."""
+        a = np.asarray(a, dtype=np.float64)
+        if a.shape[-1] == self.n_global and self.ring is not None:
+            return np.ascontiguousarray(a[..., self.lo:self.hi])
+        return a
+
+    def gather_sites(self, a):
+        """Concatenate per-rank host arrays along the site axis (all ranks get the result)."""
+        if self.ring is None:
+            return a
+        parts = [None] * self.ring.world
+        self.ring.dist.all_gather_object(parts, a, group=self.ring.group)
+        return np.concatenate(parts, axis=-1)
+
+    # -- device views / exchanges --------------------------------------------- #
+    def _view(self, which, off, cnt):
+        base = self.ctx.buffer_ptr(which)
+        return self.torch.as_tensor(_DevView(base + 8 * off, cnt), device='cuda:%d' % self.device)
+
+    def _halo(self, which, hs):
+        if self.ring is None:
+            (self.ctx.halo_wrap_ensemble if which == _lib.FDS_BUF_ENSEMBLE else self.ctx.halo_wrap_primal)(hs)
+            return
+        off, cnt = self.ctx.halo_layout(which, hs)
+        v = [self._view(which, o, c) for o, c in zip(off, cnt)]
+        self.ring.exchange_halo(v[0], v[1], v[2], v[3])
+        self.ctx.halo_mark_valid(which, hs)
+
+    def _reduce_gram(self):
+        if self.ring is not None:
+            self.ring.allreduce_sum(self._view(_lib.FDS_BUF_GRAM, 0, (self.m + 2) ** 2))
+
+    # -- the solver plugin on the primal --------------------------------------- #
+    def set_time_dilation(self, enabled):
+        self.time_dilation = bool(enabled)
+        self.ctx.set_time_dilation(enabled)
+
+    def run(self, s, steps, want_J=True):
+        """Advance the primal; returns J (steps, 2) = [mean x, mean x^2] or None."""
+        steps = int(steps)
+        if self.ring is None:
+            Js = self.ctx.run(s, steps, want_J)
+        else:
+            self.ctx.boundary_begin(0)
+            t = 0
+            while t < steps:
+                hs = self.ctx.halo_steps(steps - t)
+                self._halo(_lib.FDS_BUF_PRIMAL, hs)
+                self.ctx.primal_advance(s, t, hs, want_J)
+                t += hs
+            Js = None
+            if want_J and steps > 0:
+                part = self._view(_lib.FDS_BUF_JSUM, 0, steps * 2).clone()
+                Js = self.ring.ordered_sum(part).reshape(steps, 2)
+        return None if Js is None else Js / self.n_global
+
+    # -- one boundary ----------------------------------------------------------- #
+    def boundary(self, s, eps, from_ensemble, do_qr, build):
+        """Time dilation + projection (+ QR) at the current state; optionally builds the
+        next perturbed ensemble.  Returns (R, b, G_dil, g_dil)."""
+        c = self.ctx
+        c.boundary_begin(from_ensemble)
+        if self.time_dilation:
+            self._halo(_lib.FDS_BUF_PRIMAL, 3)
+        c.boundary_dxdt(s, from_ensemble, eps)
+        self._reduce_gram()
+        c.boundary_factor(do_qr, from_ensemble, eps)
+        if do_qr:
+            self._reduce_gram()
+        c.boundary_finish(do_qr, eps, build)
+        return c.boundary_results(do_qr)
+
+    # -- one segment ------------------------------------------------------------ #
+    def segment(self, s, eps, steps):
+        """Advance the m+2 trajectories; returns J (steps, m+2, 2)."""
+        steps = int(steps)
+        t = 0
+        while t < steps:
+            hs = self.ctx.halo_steps(steps - t)
+            self._halo(_lib.FDS_BUF_ENSEMBLE, hs)
+            self.ctx.segment_advance(s, eps, t, hs)
+            t += hs
+        if self.ring is None:
+            Js = self.ctx.segment_jsums(steps)
+        else:
+            part = self._view(_lib.FDS_BUF_JSUM, 0, steps * self.M * 2).clone()
+            Js = self.ring.ordered_sum(part).reshape(steps, self.M, 2)
+        return Js / self.n_global
+
+    # -- state in / out (global host arrays) ------------------------------------ #
+    def set_state(self, u):
+        self.ctx.set_state(self.local(u))
+
+    def get_state(self):
+        return self.gather_sites(self.ctx.get_state())
+
+    def set_tangents(self, V, v):
+        self.ctx.set_tangents(self.local(V), None if v is None else self.local(v))
+
+    def get_tangents(self):
+        V, v = self.ctx.get_tangents()
+        return self.gather_sites(V), self.gather_sites(v)
+
+    def orthonormal_random_tangents(self, seed=None, host_rng=None):
+        """V = Q of the thin QR of a uniform [0,1) (m, N) block, v = 0
+        (reference fds/fds.py:21-27).  ``host_rng`` draws the block on the host with
+        numpy (small N; honours np.random.seed like the reference); otherwise a
+        counter-based device generator keyed on the global (row, site) index."""
+        if host_rng is not None:
+            W = host_rng.rand(self.m, self.n_global)
+            self.ctx.set_tangents(self.local(W), None)
+        else:
+            self.ctx.random_tangents(seed)
+        td = self.time_dilation
+        self.ctx.set_time_dilation(False)
+        try:
+            c = self.ctx
+            c.boundary_begin(0)
+            c.boundary_dxdt(0.0, 0, 1.0)
+            self._reduce_gram()
+            c.boundary_factor(1, 0, 1.0)
+            self._reduce_gram()
+            c.boundary_finish(1, 1.0, 0)
+        finally:
+            self.ctx.set_time_dilation(td)
+
+    def close(self):
+        self.ctx.close()

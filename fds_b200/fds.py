@@ -1,0 +1,143 @@
+"""Public API of the shadowing hot path: ``shadowing``, ``continue_shadowing``,
+``lss_gradient`` -- same signatures, argument meaning and return values as the
+reference ``fds/fds.py`` (:29-51, :92-176, :178-220).
+
+``run`` must be a device plugin (``fds_b200.L96``).  The whole segment loop --
+ensemble time stepping, finite-difference tangents, time dilation, projection,
+QR, next perturbed ensemble -- runs in CUDA kernels on device-resident state;
+per segment only KBs (R, b, G_dil, g_dil, the objective sums) come back to the
+host.  There is no CPU fallback: an arbitrary Python ``run`` raises TypeError.
+"""
+import sys
+from copy import deepcopy
+
+import numpy as np
+
+from .checkpoint import Checkpoint, verify_checkpoint, save_checkpoint
+from .lsstan import LssTangent
+from .segment import trapez_mean, sensitivities
+from .timedilation import stencil_weights
+from .timeseries import windowed_mean
+
+# host <-> device random-tangent switch: below this many elements the (m, N) block is
+# drawn on the host with np.random.rand like the reference (fds/compute.py:38-42)
+HOST_RNG_MAX_ELEMS = 1 << 22
+
+
+def _engine_of(run, m):
+    eng = getattr(run, 'engine', None)
+    if eng is None:
+        raise TypeError('fds_b200.shadowing needs a device plugin (e.g. fds_b200.L96); '
+                        'arbitrary Python solvers are not supported -- there is no CPU path')
+    return eng(m)
+
+
+def lss_gradient_series(checkpoint, segment_range=None):
+    """Per-segment series (grad_lss, grad_dil) whose means add up to dJ/ds."""
+    _, _, _, lss, G_lss, g_lss, J, G_dil, g_dil = checkpoint
+    if segment_range is not None:
+        sl = slice(segment_range) if isinstance(segment_range, int) else slice(*segment_range)
+        lss = deepcopy(lss)
+        lss.Rs, lss.bs = lss.Rs[sl], lss.bs[sl]
+        G_lss, g_lss, J, G_dil, g_dil = G_lss[sl], g_lss[sl], J[sl], G_dil[sl], g_dil[sl]
+    alpha = lss.solve()
+    grad_lss = (alpha[:, :, np.newaxis] * np.array(G_lss)).sum(1) + np.array(g_lss)
+    J = np.array(J)
+    dJ = trapez_mean(J.mean(0), 0) - J[:, -1]
+    dil = ((alpha * np.array(G_dil)).sum(1) + np.array(g_dil)) / J.shape[1]
+    return grad_lss, dil[:, np.newaxis] * dJ
+
+
+def lss_gradient(checkpoint, segment_range=None):
+    """dJ/ds from the histories in a checkpoint (reference fds/fds.py:29-51)."""
+    grad_lss, grad_dil = lss_gradient_series(checkpoint, segment_range)
+    return windowed_mean(grad_lss) + windowed_mean(grad_dil)
+
+
+def continue_shadowing(run, parameter, checkpoint, num_segments, steps_per_segment,
+                       epsilon=1E-6, checkpoint_path=None, checkpoint_interval=1,
+                       simultaneous_runs=None, run_ddt=None, return_checkpoint=False,
+                       get_host_dir=None, spawn_compute_job=None, verbose=False):
+    """Run segments K0 .. num_segments-1 (K0 = segments already in ``checkpoint``);
+    ``num_segments`` is the TOTAL target (reference fds/fds.py:92-176).
+    ``run_ddt=0`` switches time dilation off (fds/timedilation.py:59-61); other
+    non-None values are the reference's broken analytic path and are rejected.
+    ``simultaneous_runs``, ``get_host_dir``, ``spawn_compute_job`` are inert."""
+    assert verify_checkpoint(checkpoint)
+    u0, V, v, lss, G_lss, g_lss, J_hist, G_dil, g_dil = checkpoint
+    if run_ddt is not None and run_ddt != 0:
+        raise NotImplementedError('run_ddt: only None (finite-difference time dilation) or 0 (off)')
+    V = np.asarray(V)
+    eng = _engine_of(run, V.shape[0])
+    eng.set_time_dilation(run_ddt is None)
+    eng.ctx.set_dxdt_weights(stencil_weights(3))
+    eng.set_state(u0)
+    eng.set_tangents(V, v)
+    return _segment_loop(eng, parameter, lss, G_lss, g_lss, J_hist, G_dil, g_dil, num_segments,
+                         steps_per_segment, epsilon, checkpoint_path, checkpoint_interval,
+                         return_checkpoint, verbose)
+
+
+def _segment_loop(eng, parameter, lss, G_lss, g_lss, J_hist, G_dil, g_dil, num_segments,
+                  steps, epsilon, checkpoint_path, checkpoint_interval, return_checkpoint, verbose):
+    def record_segment():
+        J0, G, g = sensitivities(eng.segment(parameter, epsilon, steps), epsilon)
+        J_hist.append(J0), G_lss.append(G), g_lss.append(g)
+
+    def snapshot():
+        V, v = eng.get_tangents()
+        return Checkpoint(eng.get_state(), V, v, lss, G_lss, g_lss, J_hist, G_dil, g_dil)
+
+    # first boundary of this call: time dilation + projection only (fds/fds.py:113-126)
+    eng.boundary(parameter, epsilon, from_ensemble=0, do_qr=0, build=1)
+    record_segment()
+    for i in range(lss.K_segments() + 1, num_segments + 1):
+        last = i == num_segments
+        R, b, Gd, gd = eng.boundary(parameter, epsilon, from_ensemble=1, do_qr=1, build=not last)
+        lss.append(R, b)
+        G_dil.append(Gd), g_dil.append(gd)
+        if verbose:
+            print(lss_gradient(Checkpoint(None, None, None, lss, G_lss, g_lss, J_hist, G_dil, g_dil)))
+            sys.stdout.flush()
+        if checkpoint_path and i % checkpoint_interval == 0:
+            save_checkpoint(checkpoint_path, snapshot())
+        if not last:
+            record_segment()
+    if return_checkpoint:
+        return snapshot()
+    cp = Checkpoint(None, None, None, lss, G_lss, g_lss, J_hist, G_dil, g_dil)
+    return np.array(J_hist).mean((0, 1)), lss_gradient(cp)
+
+
+def shadowing(run, u0, parameter, subspace_dimension, num_segments, steps_per_segment, runup_steps,
+              epsilon=1E-6, checkpoint_path=None, checkpoint_interval=1, simultaneous_runs=None,
+              run_ddt=None, return_checkpoint=False, get_host_dir=None, spawn_compute_job=None,
+              verbose=False, tangent_seed=None):
+    """dJ/ds of the long-time average J of a chaotic system by finite-difference
+    non-intrusive least-squares shadowing (reference fds/fds.py:178-220).
+
+    run                 device plugin (``fds_b200.L96``)
+    u0                  initial state, flat (N,)
+    parameter           the scalar s
+    subspace_dimension  m, number of homogeneous tangents (> number of positive Lyapunov exponents)
+    num_segments, steps_per_segment, runup_steps, epsilon   as in the reference
+    returns             (time-averaged J (n_qoi,), dJ/ds (n_qoi,)) or the Checkpoint
+    """
+    m = int(subspace_dimension)
+    if run_ddt is not None and run_ddt != 0:
+        raise NotImplementedError('run_ddt: only None (finite-difference time dilation) or 0 (off)')
+    eng = _engine_of(run, m)
+    eng.set_time_dilation(run_ddt is None)
+    eng.ctx.set_dxdt_weights(stencil_weights(3))
+    eng.set_state(u0)
+    if runup_steps > 0:
+        eng.run(parameter, runup_steps, want_J=False)
+    # random orthonormal tangents, v = 0 (fds/fds.py:21-27)
+    if tangent_seed is None and m * eng.n_global <= HOST_RNG_MAX_ELEMS:
+        eng.orthonormal_random_tangents(host_rng=np.random)
+    else:
+        seed = np.random.randint(2 ** 31 - 1) if tangent_seed is None else tangent_seed
+        eng.orthonormal_random_tangents(seed=seed)
+    return _segment_loop(eng, parameter, LssTangent(device_ordinal=eng.device), [], [], [], [], [],
+                         num_segments, steps_per_segment, epsilon, checkpoint_path,
+                         checkpoint_interval, return_checkpoint, verbose)

@@ -1,0 +1,53 @@
+"""Built-in device solver plugins obeying the reference's ``run`` contract.
+
+``u1, J = run(u0, parameter, steps[, run_id][, interprocess])`` (reference
+fds/fds.py:184-200): ``u0`` flat float64 (N,), ``J`` (steps, n_qoi), the state is
+advanced one step and then the objective recorded.  An ``L96`` instance is such a
+callable (host numpy in / out, computed on the GPU), so the REFERENCE driver can run
+it unchanged; handed to ``fds_b200.shadowing`` it is recognised as device-resident
+and the whole segment loop stays on the GPU.
+"""
+import numpy as np
+
+from .engine import Engine
+
+
+class L96:
+    """Lorenz-96 ring, ``dx_i/dt = (x_{i+1} - x_{i-2}) x_{i-1} - x_i + F``, ``F = s + 8``,
+    ``J = [mean x, mean x^2]`` -- the reference's own Lorenz-96 test solver
+    (tests/solvers/mock_fun3d/fun3d:39-57) with ``scheme='euler'``, and the classical
+    RK4 integrator of the north-star configuration with ``scheme='rk4'``.
+
+    math='exact': FMA-free, numpy operation order (bit-identical to oracle/plugins.py);
+    math='fast' : FMA contraction allowed.
+    """
+    n_qoi = 2
+
+    def __init__(self, N, scheme='rk4', dt=0.01, math='exact', device=None, group=None,
+                 max_halo_steps=0, simple_kernels=False):
+        self.N = int(N)
+        self.kw = dict(scheme=scheme, math=math, dt=dt, device=device, group=group,
+                       max_halo_steps=max_halo_steps, simple_kernels=simple_kernels)
+        self._engines = {}
+
+    def engine(self, m):
+        """The device engine holding an (m+2)-trajectory ensemble (cached per m)."""
+        if m not in self._engines:
+            self._engines[m] = Engine(self.N, m, **self.kw)
+        return self._engines[m]
+
+    def __call__(self, u0, parameter, steps, run_id=None, interprocess=None):
+        eng = self.engine(1)
+        eng.set_state(u0)
+        J = eng.run(parameter, steps, want_J=True)
+        if J is None:
+            J = np.empty((0, 2))
+        return eng.get_state(), J
+
+    def __getstate__(self):          # picklable, as the reference's pool requires
+        return {'N': self.N, 'kw': self.kw, '_engines': {}}
+
+    def close(self):
+        for e in self._engines.values():
+            e.close()
+        self._engines = {}
