@@ -33,7 +33,7 @@ FDS_HD void march_site(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, double& 
     if (g.stats) {
         const double v = (i >= 0 && i < g.n) ? xo : 0.0;
         const double r1 = t1.template push<P>(v);
-        const double r2 = t2.template push<P>(v * v);
+        const double r2 = t2.template push<P>(MP::mul(v, v));   // never contracted into the tree's add
         if (P == 7) { b1 = r1; b2 = r2; }
     }
 }

@@ -178,9 +178,9 @@ class Context:
 
     def run_segment_host(self, u, V, v, s, eps, steps):
         """Host-buffer form of the reference's run_segment (fds/segment.py:14-82)."""
-        u = np.array(u, dtype=np.float64)
-        V = np.array(V, dtype=np.float64)
-        v = np.array(v, dtype=np.float64)
+        u = np.array(u, dtype=np.float64, order='C')
+        V = np.array(V, dtype=np.float64, order='C')
+        v = np.array(v, dtype=np.float64, order='C')
         J = np.empty((int(steps), self.M, 2))
         self._ck(self.lib.fds_run_segment_host(self.h, dptr(u), dptr(V), dptr(v), float(s), float(eps),
                                                int(steps), dptr(J)))
