@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""Benchmark of the shadowing segment loop (BASELINE.json metric) on 1..8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3]): Lorenz-96, F = 8, RK4 dt = 0.01,
+N = 2^24 sites PER GPU (weak scaling, state sharded along N with halo exchange),
+m = 32 homogeneous tangents -> 34 trajectories, 100 time steps per segment,
+epsilon = 1e-6 sqrt(N), synthetic data (u0 = RandomState(0).rand(N) + run-up).
+
+One bench "step" = one shadowing segment: the boundary (time dilation, projection,
+CholeskyQR2, next perturbed ensemble) + 100 ensemble time steps + the objective
+sums / sensitivities brought back to the host.  metric = state-updates/s =
+N_total * (m+1) * steps_per_segment * K / time.
+
+`value`   device-resident loop (inputs in HBM when the clock starts).
+`e2e`     the public API call continue_shadowing(run, s, checkpoint, ...) on HOST
+          numpy buffers: u0/V/v uploaded, K segments, u0/V/v + histories downloaded.
+`roofline` the ensemble step kernel: algorithmic bytes 16 B * N_local * (m+2) per
+          launch / mean launch duration (CUDA events around every launch in the
+          timed region) vs the measured HBM copy peak (MEASURED_PEAKS.json).
+`cpu_baseline` / --impl reference: the numpy restatement of the reference's loop
+          (oracle/shadowing_port.py, pinned against /root/reference by
+          oracle/gen_golden.py) on the host cores, process pool of os.cpu_count()
+          workers like the reference (fds/segment.py:37), on a bounded sample.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'L96 shadowing state-updates/s (N*(m+1)*steps*K / time)'
+UNIT = 'state-updates/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5, help='timed segments')
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--logn', type=int, default=24, help='log2 of sites per GPU')
+    ap.add_argument('--m', type=int, default=32)
+    ap.add_argument('--seg-steps', type=int, default=100)
+    ap.add_argument('--math', default='exact', choices=['exact', 'fast'])
+    ap.add_argument('--cpu-logn', type=int, default=20, help='log2 N of the CPU-baseline sample')
+    ap.add_argument('--cpu-seg-steps', type=int, default=10)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------- #
+# CPU leg: the oracle port (the only place bench.py executes oracle/)
+# --------------------------------------------------------------------------- #
+def cpu_port_run(logn, m, seg_steps, K):
+    from oracle import plugins, shadowing_port as port
+    N = 1 << logn
+    cores = os.cpu_count() or 1
+    u0 = np.random.RandomState(0).rand(N)
+    u0 = plugins.run_l96_rk4(u0, 0.0, 20)[0]
+    np.random.seed(0)
+    t0 = time.perf_counter()
+    port.shadowing(plugins.run_l96_rk4, u0, 0.0, m, K, seg_steps, 0,
+                   epsilon=1e-6 * np.sqrt(N), workers=cores)
+    dt = time.perf_counter() - t0
+    return N * (m + 1) * seg_steps * K / dt, dt, cores
+
+
+def cpu_baseline(args):
+    K = 2
+    v, dt, cores = cpu_port_run(args.cpu_logn, args.m, args.cpu_seg_steps, K)
+    return {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': 'oracle/shadowing_port.py shadowing(), L96-RK4 N=2^%d m=%d, %d segments x %d steps, '
+                      'pool of %d processes, %.1f s' % (args.cpu_logn, args.m, K, args.cpu_seg_steps, cores, dt)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (numpy port; the Python reference
+    itself cannot travel to the GPU box) on the host cores, same metric."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    K = 2
+    vals, times = [], []
+    for it in range(args.warmup + args.steps):
+        v, dt, cores = cpu_port_run(args.cpu_logn, args.m, args.cpu_seg_steps, K)
+        if it >= args.warmup:
+            vals.append(v), times.append(dt)
+    value = float(np.mean(vals))
+    sample = ('bounded sample of the workload: N=2^%d (not 2^%d) m=%d, %d segments x %d steps per bench step, '
+              'pool of %d processes' % (args.cpu_logn, args.logn, args.m, K, args.cpu_seg_steps, cores))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(times) * 1e3),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': workload_config(args),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {'workload': 'Lorenz-96 F=8 RK4 dt=0.01 shadowing, N=2^%d sites per GPU, m=%d (%d trajectories), '
+                        '%d steps/segment, eps=1e-6*sqrt(N)' % (args.logn, args.m, args.m + 2, args.seg_steps),
+            'N_per_gpu': 1 << args.logn, 'm': args.m, 'steps_per_segment': args.seg_steps, 'math': args.math,
+            'bench_step': 'one segment = boundary (time dilation + projection + CholeskyQR2 + next ensemble) '
+                          '+ %d ensemble time steps' % args.seg_steps,
+            'l2': 'ensemble %.1f GB per GPU >> 126 MB L2 (no flush needed)'
+                  % ((1 << args.logn) * (args.m + 2) * 8 / 1e9),
+            'parallelism': 'N-sharded ring, %d GPU(s)' % args.gpus}
+
+
+# --------------------------------------------------------------------------- #
+# clocks
+# --------------------------------------------------------------------------- #
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {'hw_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwSlowdown', 0x8),
+                 'hw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonHwThermalSlowdown', 0x40),
+                 'sw_thermal_slowdown': getattr(nv, 'nvmlClocksThrottleReasonSwThermalSlowdown', 0x20),
+                 'sw_power_cap': getattr(nv, 'nvmlClocksThrottleReasonSwPowerCap', 0x4)}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=1.0)
+        return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------- #
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import fds_b200
+    from fds_b200.segment import sensitivities
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    assert world == args.gpus, 'launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus)
+
+    n_local = 1 << args.logn
+    N = n_local * world
+    m, M, S = args.m, args.m + 2, args.seg_steps
+    eps = 1e-6 * np.sqrt(N)
+    s = 0.0
+    stream = torch.cuda.current_stream().cuda_stream
+    run = fds_b200.L96(N, math=args.math, device=local_rank, stream=stream)
+    eng = run.engine(m)
+    lo, hi = eng.lo, eng.hi
+
+    # synthetic initial state on the attractor; random orthonormal tangents (device RNG)
+    eng.ctx.set_state(np.random.RandomState(rank).rand(n_local))
+    eng.run(s, 200, want_J=False)
+    eng.orthonormal_random_tangents(seed=1)
+    eng.boundary(s, eps, from_ensemble=0, do_qr=0, build=1)
+    eng.segment(s, eps, S)
+
+    def one_segment():
+        R, b, Gd, gd = eng.boundary(s, eps, from_ensemble=1, do_qr=1, build=1)
+        J0, G, g = sensitivities(eng.segment(s, eps, S), eps)
+        return R, b, Gd, gd, J0, G, g
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_segment()
+    sampler = ClockSampler(local_rank)
+    eng.ctx.profile_enable(True)
+    l0 = eng.ctx.launches
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hist = [one_segment() for _ in range(args.steps)]
+    e1.record()
+    barrier()
+    clocks = sampler.result()
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+    launches = torch.tensor([eng.ctx.launches - l0], device='cuda', dtype=torch.float64)
+    kern_ms, kern_n = eng.ctx.profile_read()
+    eng.ctx.profile_enable(False)
+    kern = torch.tensor([kern_ms / max(kern_n, 1)], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    value = N * (m + 1) * S * args.steps / (total_ms * 1e-3)
+
+    # sanity of what was computed inside the timed region
+    R = hist[-1][0]
+    assert np.isfinite(R).all() and (np.diag(R) > 0).all()
+    assert np.isfinite(hist[-1][4]).all()
+
+    # ---- end to end through the public API on host buffers ----------------- #
+    e2e = None
+    if not args.no_e2e:
+        from fds_b200.lsstan import LssTangent
+        from fds_b200.checkpoint import Checkpoint
+        V, v = eng.ctx.get_tangents()
+        u = eng.ctx.get_state()
+        # pinned host buffers (global arrays are sliced per rank inside the API)
+        def pinned(a):
+            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = a
+            return t.numpy()
+        cp = Checkpoint(pinned(u), pinned(V), pinned(v), LssTangent(), [], [], [], [], [])
+        barrier()
+        t0 = time.perf_counter()
+        out = fds_b200.continue_shadowing(_LocalShardPlugin(run, eng), s, cp, args.steps, S, epsilon=eps,
+                                          return_checkpoint=True)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        assert out.lss.K_segments() == args.steps and np.isfinite(out.V).all()
+        bytes_in = (M * n_local * 8) * world
+        small = args.steps * (m * m + m + m + 1 + S * M * 2) * 8
+        e2e = {'value': N * (m + 1) * S * args.steps / dt, 'unit': UNIT,
+               'h2d_bytes_per_step': bytes_in / args.steps, 'd2h_bytes_per_step': (bytes_in + small) / args.steps,
+               'call': 'continue_shadowing(run, s, checkpoint(host u0,V,v), %d segments, return_checkpoint=True); '
+                       'one call = %d bench steps, %.3f s' % (args.steps, args.steps, dt)}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        except Exception:
+            pass
+        peak = float(peaks.get('hbm_gbs', 6650.0))
+        kms = float(kern.item())
+        alg_bytes = 16.0 * n_local * M
+        achieved = alg_bytes / (kms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')))['dram_bytes_per_launch']
+        except Exception:
+            pass
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': workload_config(args),
+                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                             'frac': achieved / peak, 'traffic': traffic,
+                             'kernel': 'l96_rk4_stream_kernel', 'kernel_ms': kms,
+                             'algorithmic_bytes_per_launch': alg_bytes,
+                             'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s',
+                             'frac_of_nominal_8TBs': achieved / 8000.0,
+                             'step_kernel_share_of_time': kms * S * args.steps / total_ms},
+                'clocks': clocks, 'gpu_launches': int(launches.item())}
+        if e2e is not None:
+            line['e2e'] = e2e
+        if not args.no_cpu and world == 1:
+            line['cpu_baseline'] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+class _LocalShardPlugin:
+    """Hands the already-built engine to continue_shadowing (per-rank shard arrays in, out)."""
+
+    def __init__(self, run, eng):
+        self.run, self.eng = run, eng
+
+    def engine(self, m):
+        assert m == self.eng.m
+        return _LocalEngine(self.eng)
+
+
+class _LocalEngine:
+    """Engine view whose host arrays are per-rank shards (no global gather of 4.6 GB blocks)."""
+
+    def __init__(self, eng):
+        self.__dict__['e'] = eng
+
+    def __getattr__(self, k):
+        return getattr(self.e, k)
+
+    def get_state(self):
+        return self.e.ctx.get_state()
+
+    def get_tangents(self):
+        return self.e.ctx.get_tangents()
+
+    def set_state(self, u):
+        self.e.ctx.set_state(u)
+
+    def set_tangents(self, V, v):
+        self.e.ctx.set_tangents(V, v)
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

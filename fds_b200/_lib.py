@@ -63,6 +63,8 @@ SIGNATURES = {
     'fds_buffer_ptr': (ctypes.c_void_p, [_CTX, _I32]),
     'fds_kernel_launches': (_I64, [_CTX]),
     'fds_sync': (_I32, [_CTX]),
+    'fds_profile_enable': (_I32, [_CTX, _I32]),
+    'fds_profile_read': (_I32, [_CTX, c_double_p, c_int64_p]),
 }
 
 _lib = None

@@ -20,6 +20,8 @@ struct fds_ctx {
     long long n = 0;
     long long H = 1;               // halo capacity in steps
     long long alo = 0, ahi = 0;    // allocated site range of ensemble / primal arrays
+    StripPlan plan{};              // fixed strip decomposition of the ensemble step kernel
+    bool stream_ok = false;
     double* Ebase[2] = {nullptr, nullptr};
     int cur = 0;
     double* Pbase[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -45,6 +47,10 @@ struct fds_ctx {
     long long ens_halo_valid = 0, pri_halo_valid = 0;
     LaunchStats ls;
     std::string err;
+    // optional per-launch timing of the step kernel (fds_profile_*)
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
 
     double* E(int which) const { return Ebase[which] + (-alo) * M; }
     double* Ecur() const { return E(cur); }
@@ -117,8 +123,13 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         return 2;
     }
     c->H = H;
-    c->alo = -(8 * H + 12);
-    c->ahi = (c->n + 4 * H + 4 + 7) / 8 * 8 + 4;
+    {
+        const int R = stream_runs_per_cta(c->M);
+        c->stream_ok = R >= 1 && cfg->system == FDS_SYS_L96_RK4 && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS);
+        c->plan = make_strip_plan(c->n, H, (long long)c->num_sms * (R >= 1 ? R : 1));
+        c->alo = c->plan.alo;
+        c->ahi = c->plan.ahi;
+    }
     const size_t sites = (size_t)(c->ahi - c->alo);
     for (int j = 0; j < 2; ++j) {
         CK0(cudaMalloc(&c->Ebase[j], sites * c->M * sizeof(double)));
@@ -176,6 +187,7 @@ void fds_ctx_destroy(fds_ctx* c) {
     for (int j = 0; j < 4; ++j) cudaFree(c->Pbase[j]);
     cudaFree(c->T); cudaFree(c->d); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
     cudaFree(c->jpart); cudaFree(c->jscratch); cudaFree(c->jsum); cudaFree(c->stage);
+    for (auto& pe : c->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -186,6 +198,26 @@ int fds_sync(fds_ctx* c) {
 }
 
 int64_t fds_kernel_launches(const fds_ctx* c) { return c->ls.launches; }
+
+int fds_profile_enable(fds_ctx* c, int enabled) {
+    c->profiling = enabled != 0;
+    c->prof_used = 0;
+    return 0;
+}
+
+int fds_profile_read(fds_ctx* c, double* total_ms, int64_t* launches) {
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    for (size_t j = 0; j < c->prof_used; ++j) {
+        float ms = 0.f;
+        FDS_CK(c, cudaEventElapsedTime(&ms, c->prof_events[j].first, c->prof_events[j].second));
+        tot += ms;
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = (int64_t)c->prof_used;
+    c->prof_used = 0;
+    return 0;
+}
 
 void* fds_buffer_ptr(const fds_ctx* c, int which) {
     switch (which) {
@@ -349,14 +381,25 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
     StepArgs a;
     a.X = X; a.Y = Y; a.M = M_; a.n = c->n;
     a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
-    a.alo = c->alo; a.ahi = c->ahi;
     a.F0 = F0; a.Flast = Flast; a.dt = c->cfg.dt; a.exact = c->cfg.math == FDS_MATH_EXACT;
     a.jpart = jsum_slot ? c->jpart : nullptr;
     a.nleaf = c->nleaf;
     const bool euler = c->cfg.system == FDS_SYS_L96_EULER;
-    const bool stream_ok = !euler && !(c->cfg.flags & FDS_FLAG_SIMPLE_KERNELS) && M_ <= 576;
-    if (stream_ok) {
-        FDS_CK(c, launch_l96_rk4_stream(a, c->num_sms, c->stream, &c->ls));
+    if (c->stream_ok && M_ == c->M) {
+        cudaEvent_t e1 = nullptr;
+        if (c->profiling) {
+            if (c->prof_used == c->prof_events.size()) {
+                cudaEvent_t a0, a1;
+                FDS_CK(c, cudaEventCreate(&a0));
+                FDS_CK(c, cudaEventCreate(&a1));
+                c->prof_events.emplace_back(a0, a1);
+            }
+            FDS_CK(c, cudaEventRecord(c->prof_events[c->prof_used].first, c->stream));
+            e1 = c->prof_events[c->prof_used].second;
+            c->prof_used++;
+        }
+        FDS_CK(c, launch_l96_rk4_stream(a, c->plan, c->stream, &c->ls));
+        if (e1) FDS_CK(c, cudaEventRecord(e1, c->stream));
     } else {
         FDS_CK(c, launch_l96_simple(a, euler ? 1 : 0, c->stream, &c->ls));
         if (jsum_slot) FDS_CK(c, launch_stats_leaf(Y, M_, c->n, c->jpart, c->nleaf, c->stream, &c->ls));
@@ -375,7 +418,7 @@ int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int 
         StepArgs a;
         a.X = c->P(0); a.Y = c->P(1); a.M = 1; a.n = c->n;
         a.lo = -8 * (c->pri_halo_valid - 1); a.hi = c->n + 4 * (c->pri_halo_valid - 1);
-        a.alo = c->alo; a.ahi = c->ahi; a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
+        a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
         a.exact = c->cfg.math == FDS_MATH_EXACT; a.jpart = nullptr; a.nleaf = c->nleaf;
         FDS_CK(c, launch_l96_simple(a, c->cfg.system == FDS_SYS_L96_EULER, c->stream, &c->ls));
         if (record) {
@@ -458,7 +501,7 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
             StepArgs a;
             a.X = c->P(j - 1); a.Y = c->P(j); a.M = 1; a.n = c->n;
             a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
-            a.alo = c->alo; a.ahi = c->ahi; a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
+            a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
             a.exact = c->cfg.math == FDS_MATH_EXACT; a.jpart = nullptr; a.nleaf = c->nleaf;
             FDS_CK(c, launch_l96_simple(a, c->cfg.system == FDS_SYS_L96_EULER, c->stream, &c->ls));
             --valid;

@@ -16,39 +16,45 @@ struct HostIO {
     long long nleaf;
     long long a;
     int M, k;
-    long long alo, ahi;  // allocated site range (loads are clamped like the producer does)
-    void acquire(int) {}
-    void release(int) {}
-    double load(int b, int p) const {
-        long long cs = a + 8LL * b + 4;           // chunk start (as the TMA producer computes it)
-        if (cs < alo) cs = alo;
-        if (cs + 8 > ahi) cs = ahi - 8;
-        return X[(cs + p) * M + k];
+    long long cs = 0;     // first input site of the current block
+    long long j0 = 0;     // first output site of the current block
+    void begin_block(int b) {
+        cs = a + 8LL * b + 4;
+        j0 = a + 8LL * b - 3;
     }
-    void store(long long i, double v) { Y[i * M + k] = v; }
+    void end_block(int) {}
+    double load(int p) const { return X[(cs + p) * M + k]; }
+    void store(int p, double v) { Y[(j0 + p) * M + k] = v; }
     void emit_leaf(long long leaf, double s1, double s2) {
         if (leaf >= 0 && leaf < nleaf) {
             jpart[(leaf * M + k) * 2 + 0] = s1;
             jpart[(leaf * M + k) * 2 + 1] = s2;
         }
     }
+    bool all(bool v) const { return v; }
 };
 }  // namespace
 
 extern "C" {
 
-// X, Y: pointers to site 0 of padded [site][M] arrays allocated for sites [alo, ahi)
-int emul_l96_rk4_step(const double* X, double* Y, int M, long long n, long long lo, long long hi,
-                      long long alo, long long ahi, const double* F /*[M]*/, double dt, int exact,
-                      long long max_strips, double* jpart, long long* plan_out) {
-    StripPlan plan = make_strip_plan(lo, hi, max_strips);
-    if (plan_out) { plan_out[0] = plan.a0; plan_out[1] = plan.ls; plan_out[2] = plan.nstrips; }
+// the fixed strip plan of a context: out = {a0, ls, nstrips, nblk, alo, ahi}
+int emul_plan(long long n, long long H, long long max_strips, long long* out) {
+    StripPlan p = make_strip_plan(n, H, max_strips);
+    out[0] = p.a0; out[1] = p.ls; out[2] = p.nstrips; out[3] = p.nblk; out[4] = p.alo; out[5] = p.ahi;
+    return 0;
+}
+
+// One step over the whole span of the plan.  X, Y: pointers to site 0 of padded [site][M]
+// arrays allocated for sites [alo, ahi) of the plan.
+int emul_l96_rk4_step(const double* X, double* Y, int M, long long n, long long H,
+                      const double* F /*[M]*/, double dt, int exact, long long max_strips, double* jpart) {
+    StripPlan plan = make_strip_plan(n, H, max_strips);
     Rk4Coef c{0.5 * dt, dt, dt / 6.0};
     long long nleaf = (n + kLeafSites - 1) / kLeafSites;
     for (long long s = 0; s < plan.nstrips; ++s) {
         for (int k = 0; k < M; ++k) {
-            HostIO io{X, Y, jpart, nleaf, plan.a0 + s * plan.ls, M, k, alo, ahi};
-            MarchGeom g{io.a, lo, hi, n, plan.nblk, jpart != nullptr};
+            HostIO io{X, Y, jpart, nleaf, plan.a0 + s * plan.ls, M, k};
+            MarchGeom g{io.a, n, plan.nblk, jpart != nullptr};
             if (exact) l96_rk4_march<ExactMath>(io, g, F[k], c);
             else       l96_rk4_march<FastMath>(io, g, F[k], c);
         }

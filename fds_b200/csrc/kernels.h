@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "l96_core.cuh"
 
 namespace fds {
 
@@ -13,8 +14,8 @@ struct StepArgs {
     double* Y;             // output, same layout
     int M;                 // columns
     long long n;           // owned sites (objective sums cover [0, n))
-    long long lo, hi;      // output range of this step
-    long long alo, ahi;    // allocated site range of X (both == 4 mod 8)
+    long long lo, hi;      // output range of this step (simple kernels only; the streaming
+                           // kernel always computes the whole span of its fixed StripPlan)
     double F0, Flast;      // forcing of columns < M-1 and of column M-1
     double dt;
     int exact;             // FDS_MATH_EXACT / FAST
@@ -22,8 +23,10 @@ struct StepArgs {
     long long nleaf;
 };
 
-// streaming TMA-fed kernel (RK4 only)
-cudaError_t launch_l96_rk4_stream(const StepArgs& a, int num_sms, cudaStream_t st, LaunchStats* ls);
+// streaming TMA-fed kernel (RK4 only); `plan` = make_strip_plan(n, H, num_sms * stream_runs_per_cta(M)),
+// X and Y allocated for sites [plan.alo, plan.ahi)
+int stream_runs_per_cta(int M);
+cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls);
 // one thread per element, global loads (RK4 or Euler); no objective sums
 cudaError_t launch_l96_simple(const StepArgs& a, int euler, cudaStream_t st, LaunchStats* ls);
 // 64-site leaf partials of an array: jpart[leaf][M][2]

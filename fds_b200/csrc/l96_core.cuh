@@ -48,42 +48,49 @@ struct Rk4Coef {
 };
 
 // --------------------------------------------------------------------------- //
-// Software-pipelined RK4 along one column: push x[i+4], get x'[i].
-// Rings hold x on sites i..i+4 (mod 8) and the stage inputs y2 (i..i+3),
-// y3 (i-1..i+2), y4 (i-2..i+1) and the running k1+2k2+2k3 (i..i+3) (mod 4).
-// P = i mod 8 is a template parameter so that every ring index is a constant
-// and the rings live in registers.
+// Software-pipelined RK4 along one column as a SKEWED wavefront: push x[i+4], get
+// x'[i-3].  The four stages of one push work on different sites,
+//     stage 1 at i+3 : k1 from x       -> y2[i+3], acc[i+3]  = k1
+//     stage 2 at i+1 : k2 from y2      -> y3[i+1], acc[i+1] += 2 k2
+//     stage 3 at i-1 : k3 from y3      -> y4[i-1], acc[i-1] += 2 k3
+//     stage 4 at i-3 : k4 from y4      -> x'[i-3] = x + h6 (acc + k4)
+// and each reads only values produced by EARLIER pushes, so the four dependency
+// chains are independent and the FP64 pipe sees 4-way instruction-level
+// parallelism per thread.  Rings are indexed by (site mod 8); P = i mod 8 is a
+// template parameter, so every ring index is a constant and the rings live in
+// registers (only the live entries: 8 + 5 + 5 + 5 + 7 doubles).
 // --------------------------------------------------------------------------- //
 template <class MP>
 struct Rk4Pipe {
-    double X[8], Y2[4], Y3[4], Y4[4], A[4];
+    double X[8], Y2[8], Y3[8], Y4[8], A[8];
+    static constexpr int kLag = 3;      // output site = push site - kLag
 
     FDS_HD void reset() {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) X[j] = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { Y2[j] = 0.0; Y3[j] = 0.0; Y4[j] = 0.0; A[j] = 0.0; }
+        for (int j = 0; j < 8; ++j) { X[j] = 0.0; Y2[j] = 0.0; Y3[j] = 0.0; Y4[j] = 0.0; A[j] = 0.0; }
     }
 
     template <int P>
     FDS_HD double push(double xn, double F, const Rk4Coef& c) {
-        X[(P + 4) & 7] = xn;
+#define FDS_SLOT(o) ((P + (o) + 16) & 7)
+        X[FDS_SLOT(4)] = xn;
+        // stage 4 at site i-3
+        const double k4 = l96_rhs<MP>(Y4[FDS_SLOT(-5)], Y4[FDS_SLOT(-4)], Y4[FDS_SLOT(-3)], Y4[FDS_SLOT(-2)], F);
+        const double out = MP::muladd(c.h6, MP::add(A[FDS_SLOT(-3)], k4), X[FDS_SLOT(-3)]);
+        // stage 3 at site i-1
+        const double k3 = l96_rhs<MP>(Y3[FDS_SLOT(-3)], Y3[FDS_SLOT(-2)], Y3[FDS_SLOT(-1)], Y3[FDS_SLOT(0)], F);
+        A[FDS_SLOT(-1)] = MP::twice_plus(k3, A[FDS_SLOT(-1)]);
+        Y4[FDS_SLOT(-1)] = MP::muladd(c.h, k3, X[FDS_SLOT(-1)]);
+        // stage 2 at site i+1
+        const double k2 = l96_rhs<MP>(Y2[FDS_SLOT(-1)], Y2[FDS_SLOT(0)], Y2[FDS_SLOT(1)], Y2[FDS_SLOT(2)], F);
+        A[FDS_SLOT(1)] = MP::twice_plus(k2, A[FDS_SLOT(1)]);
+        Y3[FDS_SLOT(1)] = MP::muladd(c.h2, k2, X[FDS_SLOT(1)]);
         // stage 1 at site i+3
-        const double k1 = l96_rhs<MP>(X[(P + 1) & 7], X[(P + 2) & 7], X[(P + 3) & 7], X[(P + 4) & 7], F);
-        A[(P + 3) & 3] = k1;
-        Y2[(P + 3) & 3] = MP::muladd(c.h2, k1, X[(P + 3) & 7]);
-        // stage 2 at site i+2
-        const double k2 = l96_rhs<MP>(Y2[P & 3], Y2[(P + 1) & 3], Y2[(P + 2) & 3], Y2[(P + 3) & 3], F);
-        A[(P + 2) & 3] = MP::twice_plus(k2, A[(P + 2) & 3]);
-        Y3[(P + 2) & 3] = MP::muladd(c.h2, k2, X[(P + 2) & 7]);
-        // stage 3 at site i+1
-        const double k3 = l96_rhs<MP>(Y3[(P + 3) & 3], Y3[P & 3], Y3[(P + 1) & 3], Y3[(P + 2) & 3], F);
-        A[(P + 1) & 3] = MP::twice_plus(k3, A[(P + 1) & 3]);
-        Y4[(P + 1) & 3] = MP::muladd(c.h, k3, X[(P + 1) & 7]);
-        // stage 4 at site i
-        const double k4 = l96_rhs<MP>(Y4[(P + 2) & 3], Y4[(P + 3) & 3], Y4[P & 3], Y4[(P + 1) & 3], F);
-        const double s = MP::add(A[P & 3], k4);
-        return MP::muladd(c.h6, s, X[P & 7]);
+        const double k1 = l96_rhs<MP>(X[FDS_SLOT(1)], X[FDS_SLOT(2)], X[FDS_SLOT(3)], X[FDS_SLOT(4)], F);
+        A[FDS_SLOT(3)] = k1;
+        Y2[FDS_SLOT(3)] = MP::muladd(c.h2, k1, X[FDS_SLOT(3)]);
+#undef FDS_SLOT
+        return out;
     }
 };
 
@@ -179,15 +186,21 @@ constexpr int kLeafSites = 64;   // sites per leaf of the objective partials
 constexpr int kLeafShift = 6;
 
 // --------------------------------------------------------------------------- //
-// Strip decomposition of the streaming step kernel.  Output sites [lo, hi) are cut
-// into strips of `ls` sites (a multiple of 64) anchored at a multiple of 64,
-// so that every 8-block and every 64-site leaf is aligned to global site 0.
+// Strip decomposition of the streaming step kernel.  FIXED per context: the widest
+// output range a step can have, [-8(H-1), n + 4(H-1)) for a halo valid for H steps,
+// is cut into strips of `ls` sites (a multiple of 64) anchored at a multiple of 64,
+// so that every 8-block and every 64-site leaf is aligned to global site 0.  Every
+// step computes the whole span (cells outside the still-valid halo receive values
+// that are never used), so the kernel needs no range checks, and the arrays are
+// allocated for sites [alo, ahi) = [a0 - 12, a0 + nstrips*ls + 12): exactly the
+// input chunks the strips read (both bounds == 4 mod 8).
 // --------------------------------------------------------------------------- //
 struct StripPlan {
-    long long a0;       // first strip starts here (multiple of 64, <= lo)
+    long long a0;       // first strip starts here (multiple of 64)
     long long ls;       // strip length
-    long long nstrips;  // strips needed to reach hi
+    long long nstrips;  // strips needed to cover the span
     int nblk;           // 8-blocks per strip
+    long long alo, ahi; // allocated site range
 };
 
 inline long long floor_div(long long a, long long b) {
@@ -195,9 +208,10 @@ inline long long floor_div(long long a, long long b) {
     return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 
-inline StripPlan make_strip_plan(long long lo, long long hi, long long max_strips) {
+inline StripPlan make_strip_plan(long long n, long long H, long long max_strips) {
     StripPlan p;
     if (max_strips < 1) max_strips = 1;
+    const long long lo = -8 * (H - 1), hi = n + 4 * (H - 1);
     const long long a0 = floor_div(lo, kLeafSites) * kLeafSites;
     const long long span = hi - a0;
     long long ls = ((span + max_strips - 1) / max_strips + kLeafSites - 1) / kLeafSites * kLeafSites;
@@ -206,6 +220,8 @@ inline StripPlan make_strip_plan(long long lo, long long hi, long long max_strip
     p.ls = ls;
     p.nstrips = (span + ls - 1) / ls;
     p.nblk = (int)(ls / 8);
+    p.alo = a0 - 12;
+    p.ahi = a0 + p.nstrips * ls + 12;
     return p;
 }
 

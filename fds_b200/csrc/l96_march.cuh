@@ -3,12 +3,19 @@
 // CUDA kernel (shared-memory ring fed by TMA bulk copies) and the host emulation
 // harness (plain arrays) execute literally the same code.
 //
+// Block b of a strip that starts at site a consumes the 8 input sites
+// a + 8b + 4 .. a + 8b + 11 and produces the 8 output sites a + 8b - 3 .. a + 8b + 4
+// (the pipeline lags 3 sites behind the push index, l96_core.cuh).
+//
 // IO policy:
-//   void   acquire(int b)                 block b's 8 input sites are readable
-//   double load(int b, int p)             x[a + 8b + p + 4]
-//   void   release(int b)                 done reading block b
-//   void   store(long long i, double v)   x'[i]
+//   void   begin_block(int b)             block b's 8 input sites are readable; position the
+//                                         output cursor at site a + 8b - 3
+//   double load(int p)                    x[a + 8b + 4 + p]
+//   void   store(int p, double v)         x'[a + 8b - 3 + p]
+//   void   end_block(int b)               done with block b
 //   void   emit_leaf(long long leaf, double s1, double s2)   64-site partial sums
+//   bool   all(bool)                      warp-wide AND (the CUDA kernel keeps a warp on ONE
+//                                         of the two code paths; true for a single thread)
 #pragma once
 #include "l96_core.cuh"
 
@@ -16,27 +23,65 @@ namespace fds {
 
 struct MarchGeom {
     long long a;      // first output site of this strip (multiple of 64)
-    long long lo, hi; // outputs are stored for sites in [lo, hi)
     long long n;      // objective sums cover sites in [0, n)
-    int nblk;         // 8-blocks in the strip
+    int nblk;         // 8-blocks in the strip; the strip stores sites [a, a + 8*nblk)
     int stats;        // accumulate the objective partials?
 };
 
-template <class MP, int P, class IO>
+// One site of one block.  FAST: the whole block lies inside the store range and the
+// objective range, so no per-site checks are needed.
+template <class MP, int P, bool FAST, class IO>
 FDS_HD void march_site(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, double& b1, double& b2,
-                       const MarchGeom& g, int b, long long i0, double F, const Rk4Coef& c,
-                       bool live) {
-    const double xn = io.load(b, P);
-    const double xo = pipe.template push<P>(xn, F, c);
-    const long long i = i0 + P;
-    if (live && i >= g.lo && i < g.hi) io.store(i, xo);
-    if (g.stats) {
-        const double v = (i >= 0 && i < g.n) ? xo : 0.0;
-        const double r1 = t1.template push<P>(v);
-        const double r2 = t2.template push<P>(MP::mul(v, v));   // never contracted into the tree's add
-        if (P == 7) { b1 = r1; b2 = r2; }
+                       long long j0, long long slo, long long shi, long long jlo, long long jhi,
+                       bool stats, double F, const Rk4Coef& c) {
+    constexpr int Q = (P + 8 - Rk4Pipe<MP>::kLag) & 7;   // output site mod 8
+    const double xo = pipe.template push<P>(io.load(P), F, c);
+    if (FAST) {
+        io.store(P, xo);
+        if (stats) {
+            const double r1 = t1.template push<Q>(xo);
+            const double r2 = t2.template push<Q>(MP::mul(xo, xo));   // never contracted into the tree's add
+            if (Q == 7) { b1 = r1; b2 = r2; }
+        }
+    } else {
+        const long long j = j0 + P;
+        if (j >= slo && j < shi) io.store(P, xo);
+        if (stats) {
+            const double v = (j >= jlo && j < jhi) ? xo : 0.0;
+            const double r1 = t1.template push<Q>(v);
+            const double r2 = t2.template push<Q>(MP::mul(v, v));
+            if (Q == 7) { b1 = r1; b2 = r2; }
+        }
     }
 }
+
+template <class MP, bool FAST, class IO>
+FDS_HD void march_block(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, LeafStack& l1, LeafStack& l2,
+                        const MarchGeom& g, int b, long long slo, long long shi, long long jlo, long long jhi,
+                        double F, const Rk4Coef& c) {
+    const long long j0 = g.a + 8LL * b - Rk4Pipe<MP>::kLag;
+    const bool stats = g.stats != 0;
+    double b1 = 0.0, b2 = 0.0;
+    march_site<MP, 0, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
+    march_site<MP, 1, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
+    march_site<MP, 2, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
+    // sites a+8(b-1) .. a+8b-1 are complete here: 8-block (b-1) of the strip
+    if (stats && b >= 1) {
+        double s1, s2;
+        const bool d1 = l1.push(b1, (b - 1) & 7, s1);
+        const bool d2 = l2.push(b2, (b - 1) & 7, s2);
+        if (d1 && d2) io.emit_leaf((g.a + 8LL * (b - 1)) >> kLeafShift, s1, s2);
+    }
+    march_site<MP, 3, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
+    march_site<MP, 4, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
+    march_site<MP, 5, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
+    march_site<MP, 6, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
+    march_site<MP, 7, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
+}
+
+// number of blocks a strip of nblk 8-blocks runs through: two warm-up blocks fill the
+// stage pipeline, one trailing block drains the 3-site lag
+FDS_HD int march_iterations(int nblk) { return nblk + 3; }
 
 template <class MP, class IO>
 FDS_HD void l96_rk4_march(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
@@ -46,29 +91,25 @@ FDS_HD void l96_rk4_march(IO& io, const MarchGeom& g, double F, const Rk4Coef& c
     LeafStack l1, l2;
     t1.t1 = t1.t2 = t1.t4 = 0.0; t2 = t1;
     l1.s0 = l1.s1 = l1.s2 = 0.0; l2 = l1;
-    // two warm-up blocks fill the stage pipeline (their outputs belong to the
-    // previous strip and are discarded)
+    // this strip stores sites [slo, shi) and counts sites [jlo, jhi) in the objective
+    const long long slo = g.a, shi = g.a + 8LL * g.nblk;
+    const long long jlo = slo > 0 ? slo : 0;
+    const long long jhi = g.n < shi ? g.n : shi;
+    // Only the 64-site leaf that contains site n (if n is not a multiple of 64) needs its
+    // objective terms masked: leaves wholly outside [0, n) are dropped by emit_leaf.
+    const long long nfl = g.n & ~(long long)(kLeafSites - 1);
+    const long long ncl = (g.n + kLeafSites - 1) & ~(long long)(kLeafSites - 1);
 #pragma unroll 1
-    for (int b = -2; b < g.nblk; ++b) {
-        const long long i0 = g.a + 8LL * b;
-        const bool live = b >= 0;
-        double b1 = 0.0, b2 = 0.0;
-        io.acquire(b);
-        march_site<MP, 0>(io, pipe, t1, t2, b1, b2, g, b, i0, F, c, live);
-        march_site<MP, 1>(io, pipe, t1, t2, b1, b2, g, b, i0, F, c, live);
-        march_site<MP, 2>(io, pipe, t1, t2, b1, b2, g, b, i0, F, c, live);
-        march_site<MP, 3>(io, pipe, t1, t2, b1, b2, g, b, i0, F, c, live);
-        march_site<MP, 4>(io, pipe, t1, t2, b1, b2, g, b, i0, F, c, live);
-        march_site<MP, 5>(io, pipe, t1, t2, b1, b2, g, b, i0, F, c, live);
-        march_site<MP, 6>(io, pipe, t1, t2, b1, b2, g, b, i0, F, c, live);
-        march_site<MP, 7>(io, pipe, t1, t2, b1, b2, g, b, i0, F, c, live);
-        io.release(b);
-        if (g.stats && live) {
-            double s1, s2;
-            const bool d1 = l1.push(b1, b & 7, s1);
-            const bool d2 = l2.push(b2, b & 7, s2);
-            if (d1 && d2) io.emit_leaf(i0 >> kLeafShift, s1, s2);
-        }
+    for (int b = -2; b <= g.nblk; ++b) {
+        const long long j0 = g.a + 8LL * b - Rk4Pipe<MP>::kLag;
+        io.begin_block(b);
+        // unchecked path: all 8 outputs belong to this strip and none lies in the partial leaf
+        const bool fast = j0 >= slo && j0 + 8 <= shi && (j0 + 8 <= nfl || j0 >= ncl);
+        if (io.all(fast))
+            march_block<MP, true>(io, pipe, t1, t2, l1, l2, g, b, slo, shi, jlo, jhi, F, c);
+        else
+            march_block<MP, false>(io, pipe, t1, t2, l1, l2, g, b, slo, shi, jlo, jhi, F, c);
+        io.end_block(b);
     }
 }
 

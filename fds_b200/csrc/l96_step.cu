@@ -59,7 +59,7 @@ struct StreamParams {
     double* jpart;
     long long nleaf;
     long long a0, ls, nstrips;
-    long long lo, hi, n, alo, ahi;
+    long long n;
     int nblk;
     int M, R, run_stride, nstages, nconsumer;  // nconsumer = R*M
     double F0, Flast;
@@ -75,7 +75,7 @@ struct StreamIO {
     int nstages;
     uint64_t* full;
     uint64_t* empty;
-    double* Y;               // site 0, already offset by column
+    double* yrow;            // output cursor: site a + 8b - 3 of this thread's column
     double* jp;              // leaf 0, already offset by column (or nullptr)
     long long nleaf;
     int lane;
@@ -84,25 +84,27 @@ struct StreamIO {
     uint32_t par;
     const double* cur;
 
-    FDS_D void acquire(int) {
+    FDS_D void begin_block(int) {
         mbar_wait(&full[st], par);
         cur = sdata + (size_t)st * stage_stride;
     }
-    FDS_D double load(int, int p) const { return cur[p * M]; }
-    FDS_D void release(int) {
+    FDS_D double load(int p) const { return cur[p * M]; }
+    FDS_D void store(int p, double v) { yrow[p * M] = v; }
+    FDS_D void end_block(int) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
         if (++st == nstages) { st = 0; par ^= 1u; }
+        yrow += 8 * M;
     }
-    FDS_D void store(long long i, double v) { Y[i * M] = v; }
     FDS_D void emit_leaf(long long leaf, double s1, double s2) {
         if (jp != nullptr && leaf >= 0 && leaf < nleaf)
             *reinterpret_cast<double2*>(jp + leaf * (2LL * M)) = make_double2(s1, s2);
     }
+    FDS_D bool all(bool v) const { return __all_sync(0xffffffffu, v); }
 };
 
 template <class MP>
-__global__ void __launch_bounds__(608, 1) l96_rk4_stream_kernel(const StreamParams p) {
+__global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
@@ -122,35 +124,44 @@ __global__ void __launch_bounds__(608, 1) l96_rk4_stream_kernel(const StreamPara
     }
     __syncthreads();
 
-    const int nit = p.nblk + 2;                        // blocks b = -2 .. nblk-1
+    // strips past the end of the plan (last CTA only) mirror the last strip: same loads,
+    // same arithmetic, same stores of the same values -- no thread ever takes its own path
+    const long long last_strip = p.nstrips - 1;
+    const int nit = march_iterations(p.nblk);          // blocks b = -2 .. nblk
     if (warp == ncw) {
-        // ---------------- producer warp: one lane issues the bulk copies ------- //
-        if (lane == 0) {
-            const uint32_t chunk_bytes = (uint32_t)(8 * p.M * sizeof(double));
-            int st = 0;
-            uint32_t par = 0;
-            for (int it = 0; it < nit; ++it) {
-                if (it >= p.nstages) mbar_wait(&empty[st], par ^ 1u);
-                mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)p.R);
-                double* dst = sdata + (size_t)st * stage_stride;
-                const long long boff = 8LL * (it - 2) + 4;
-                for (int r = 0; r < p.R; ++r) {
-                    long long strip = (long long)blockIdx.x * p.R + r;
-                    long long cs = p.a0 + strip * p.ls + boff;
-                    cs = cs < p.alo ? p.alo : cs;
-                    cs = cs + 8 > p.ahi ? p.ahi - 8 : cs;
-                    bulk_g2s(dst + r * p.run_stride, p.X + cs * p.M, chunk_bytes, &full[st]);
-                }
-                if (++st == p.nstages) { st = 0; par ^= 1u; }
+        // ------- producer warp: lane r issues the bulk copy of strip r (r, r+32, ...) ------- //
+        const uint32_t chunk_bytes = (uint32_t)(8 * p.M * sizeof(double));
+        int st = 0;
+        uint32_t par = 0;
+        for (int it = 0; it < nit; ++it) {
+            if (it >= p.nstages) mbar_wait(&empty[st], par ^ 1u);
+            if (lane == 0) mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)p.R);
+            __syncwarp();
+            double* dst = sdata + (size_t)st * stage_stride;
+            for (int r = lane; r < p.R; r += 32) {
+                long long strip = (long long)blockIdx.x * p.R + r;
+                strip = strip < last_strip ? strip : last_strip;
+                // input chunk of block b = it - 2: sites a + 8b + 4 .. a + 8b + 11 (inside the allocation
+                // by construction of the plan, l96_core.cuh)
+                const long long cs = p.a0 + strip * p.ls + 8LL * it - 12;
+                bulk_g2s(dst + r * p.run_stride, p.X + cs * p.M, chunk_bytes, &full[st]);
             }
+            if (++st == p.nstages) { st = 0; par ^= 1u; }
         }
         return;
     }
     // -------------------- consumer threads: (run r, column k) ------------------ //
-    const bool active = tid < p.nconsumer;
-    const int t = active ? tid : p.nconsumer - 1;       // idle lanes shadow the last thread
+    // idle lanes of the last consumer warp mirror the last thread
+    const int t = tid < p.nconsumer ? tid : p.nconsumer - 1;
     const int r = t / p.M, k = t - r * p.M;
-    const long long strip = (long long)blockIdx.x * p.R + r;
+    long long strip = (long long)blockIdx.x * p.R + r;
+    strip = strip < last_strip ? strip : last_strip;
+
+    MarchGeom g;
+    g.a = p.a0 + strip * p.ls;
+    g.n = p.n;
+    g.nblk = p.nblk;
+    g.stats = p.jpart != nullptr;
 
     StreamIO io;
     io.sdata = sdata + r * p.run_stride + k;
@@ -159,38 +170,30 @@ __global__ void __launch_bounds__(608, 1) l96_rk4_stream_kernel(const StreamPara
     io.nstages = p.nstages;
     io.full = full;
     io.empty = empty;
-    io.Y = p.Y + k;
-    io.jp = (p.jpart != nullptr && active) ? p.jpart + 2 * k : nullptr;
+    io.yrow = p.Y + (g.a - 8 * 2 - Rk4Pipe<MP>::kLag) * p.M + k;   // block b = -2
+    io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
     io.nleaf = p.nleaf;
     io.lane = lane;
     io.st = 0;
     io.par = 0;
     io.cur = io.sdata;
 
-    MarchGeom g;
-    g.a = p.a0 + strip * p.ls;
-    g.lo = active ? p.lo : 0;
-    g.hi = active ? (g.a + p.ls < p.hi ? g.a + p.ls : p.hi) : 0;   // idle lanes store nothing
-    g.n = p.n;
-    g.nblk = p.nblk;
-    g.stats = p.jpart != nullptr;
     const double F = (k == p.M - 1) ? p.Flast : p.F0;
     l96_rk4_march<MP>(io, g, F, p.c);
 }
 
-static int pick_runs(int M) {
-    int R = 1;
-    while (R * 2 * M <= 576 && R < 512) R *= 2;
-    return R;
-}
+// 16 warps per CTA (4 per scheduler, so each thread can hold up to 128 registers):
+// 15 consumer warps + the producer warp.  R strips x M columns <= 480 consumer threads.
+constexpr int kMaxConsumers = 480;
+int stream_runs_per_cta(int M) { return M <= kMaxConsumers ? kMaxConsumers / M : 0; }
 
-cudaError_t launch_l96_rk4_stream(const StepArgs& a, int num_sms, cudaStream_t st, LaunchStats* ls) {
+cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls) {
     StreamParams p;
     p.X = a.X; p.Y = a.Y; p.jpart = a.jpart; p.nleaf = a.nleaf;
-    p.lo = a.lo; p.hi = a.hi; p.n = a.n; p.alo = a.alo; p.ahi = a.ahi;
+    p.n = a.n;
     p.M = a.M;
-    p.R = pick_runs(a.M);
-    if (p.R * a.M > 576) return cudaErrorInvalidValue;   // M too large for this kernel
+    p.R = stream_runs_per_cta(a.M);
+    if (p.R < 1) return cudaErrorInvalidValue;            // M too large for this kernel
     p.nconsumer = p.R * a.M;
     int pad = (16 - (7 * a.M) % 16) % 16;
     if (pad & 1) pad += 1;
@@ -199,7 +202,6 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, int num_sms, cudaStream_t s
     int nst = (int)std::min<size_t>(kMaxStages, (200 * 1024) / stage_bytes);
     if (nst < 2) return cudaErrorInvalidValue;
     p.nstages = nst;
-    StripPlan plan = make_strip_plan(a.lo, a.hi, (long long)num_sms * p.R);
     p.a0 = plan.a0; p.ls = plan.ls; p.nstrips = plan.nstrips; p.nblk = plan.nblk;
     p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};

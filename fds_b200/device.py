@@ -64,6 +64,16 @@ class Context:
     def launches(self):
         return int(self.lib.fds_kernel_launches(self.h))
 
+    def profile_enable(self, enabled=True):
+        """Time every launch of the ensemble step kernel with CUDA events on the context's stream."""
+        self._ck(self.lib.fds_profile_enable(self.h, int(bool(enabled))))
+
+    def profile_read(self):
+        """(summed device milliseconds, launches) of the step kernel since profile_enable()."""
+        ms, cnt = ctypes.c_double(), ctypes.c_int64()
+        self._ck(self.lib.fds_profile_read(self.h, ctypes.byref(ms), ctypes.byref(cnt)))
+        return ms.value, cnt.value
+
     def buffer_ptr(self, which):
         return self.lib.fds_buffer_ptr(self.h, which)
 

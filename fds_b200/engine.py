@@ -24,13 +24,12 @@ class _DevView:
 
 class Engine:
     def __init__(self, n_global, m, scheme='rk4', math='exact', dt=0.01, device=None,
-                 group=None, distributed=None, max_halo_steps=0, simple_kernels=False):
+                 group=None, distributed=None, max_halo_steps=0, simple_kernels=False, stream=None):
         self.n_global = int(n_global)
         self.m = int(m)
         self.M = self.m + 2
         self.ring = None
         self.torch = None
-        stream = None
         if distributed is None:
             try:
                 import torch.distributed as dist
@@ -44,7 +43,8 @@ class Engine:
             if device is None:
                 device = torch.cuda.current_device()
             torch.cuda.set_device(device)
-            stream = torch.cuda.current_stream().cuda_stream
+            if stream is None:
+                stream = torch.cuda.current_stream().cuda_stream
         if device is None:
             device = 0
         self.device = int(device)

@@ -24,10 +24,10 @@ class L96:
     n_qoi = 2
 
     def __init__(self, N, scheme='rk4', dt=0.01, math='exact', device=None, group=None,
-                 max_halo_steps=0, simple_kernels=False):
+                 max_halo_steps=0, simple_kernels=False, stream=None):
         self.N = int(N)
         self.kw = dict(scheme=scheme, math=math, dt=dt, device=device, group=group,
-                       max_halo_steps=max_halo_steps, simple_kernels=simple_kernels)
+                       max_halo_steps=max_halo_steps, simple_kernels=simple_kernels, stream=stream)
         self._engines = {}
 
     def engine(self, m):

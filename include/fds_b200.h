@@ -155,6 +155,10 @@ int fds_lss_solve(int device, const double* R, const double* b, int64_t K, int m
 void*   fds_buffer_ptr(const fds_ctx*, int which_buf);   /* device pointer of site/elem 0 */
 int64_t fds_kernel_launches(const fds_ctx*);              /* kernels launched so far        */
 int     fds_sync(fds_ctx*);
+/* per-launch device timing of the ensemble step kernel (CUDA events on the context's stream):
+ * enable, run, then read the summed duration and the number of launches since enabling   */
+int     fds_profile_enable(fds_ctx*, int enabled);
+int     fds_profile_read(fds_ctx*, double* total_ms, int64_t* launches);
 
 #ifdef __cplusplus
 }

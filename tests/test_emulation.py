@@ -33,44 +33,55 @@ def ptr(a, off=0):
     return ctypes.cast(a.ctypes.data + 8 * off, c_dp)
 
 
-def padded(U, H):
-    """[site][M] array for sites [alo, ahi) with periodic ghosts; returns (buf, alo, ahi)."""
+LL = ctypes.c_longlong
+
+
+def plan_of(emul, N, H, max_strips):
+    out = (LL * 6)()
+    emul.emul_plan(LL(N), LL(H), LL(max_strips), out)
+    return dict(zip(('a0', 'ls', 'nstrips', 'nblk', 'alo', 'ahi'), out))
+
+
+def padded(U, alo, ahi, ghost_l, ghost_r):
+    """[site][M] array for sites [alo, ahi): owned sites + periodic ghosts [-ghost_l, 0) and
+    [N, N + ghost_r); everything else NaN, as cells outside the valid halo may hold anything."""
     M, N = U.shape
-    alo = -(8 * H + 12)
-    ahi = (N + 4 * H + 4 + 7) // 8 * 8 + 4
-    buf = np.zeros((ahi - alo, M))
-    idx = np.arange(alo, ahi) % N
-    buf[:] = U.T[idx]
-    return buf, alo, ahi
+    buf = np.full((ahi - alo, M), np.nan)
+    for g in range(-ghost_l, N + ghost_r):
+        buf[g - alo] = U[:, g % N]
+    return buf
 
 
 @pytest.mark.parametrize('N,M,H,max_strips,exact', [
     (200, 5, 3, 7, 1), (40, 18, 1, 4, 1), (37, 3, 2, 64, 1), (1024, 4, 4, 16, 1),
-    (4096, 2, 2, 37, 1), (333, 1, 3, 1, 1), (200, 5, 3, 7, 0)])
+    (4096, 2, 2, 37, 1), (333, 1, 3, 1, 1), (200, 5, 3, 7, 0), (4, 2, 3, 5, 1), (640, 3, 5, 3, 1)])
 def test_streaming_march_matches_oracle(emul, N, M, H, max_strips, exact):
     rng = np.random.RandomState(N + M)
     U = rng.rand(M, N) * 6 - 1
     F = 8.0 + np.r_[np.zeros(M - 1), 1e-4] if M > 1 else np.array([8.1])
-    bufA, alo, ahi = padded(U, H)
-    bufB = np.zeros_like(bufA)
+    pl = plan_of(emul, N, H, max_strips)
+    alo, ahi = pl['alo'], pl['ahi']
+    assert pl['nstrips'] <= max_strips and pl['ls'] % 64 == 0 and pl['a0'] % 64 == 0
+    assert alo <= -8 * H and ahi >= N + 4 * H and alo % 8 == 4 and ahi % 8 == 4
+    assert pl['a0'] + pl['nstrips'] * pl['ls'] >= N + 4 * (H - 1)
+    bufA = padded(U, alo, ahi, 8 * H, 4 * H)
+    bufB = np.full_like(bufA, np.nan)
     nleaf = (N + 63) // 64
     Xo, Jo = plugins.run_l96_ensemble(plugins.l96_rk4_step, U, F, H)
-    plan = (ctypes.c_longlong * 3)()
     for j in range(H):
-        lo, hi = -8 * (H - 1 - j), N + 4 * (H - 1 - j)
         jpart = np.full((nleaf, M, 2), np.nan)
-        emul.emul_l96_rk4_step(ptr(bufA, -alo * M), ptr(bufB, -alo * M), M,
-                               ctypes.c_longlong(N), ctypes.c_longlong(lo), ctypes.c_longlong(hi),
-                               ctypes.c_longlong(alo), ctypes.c_longlong(ahi), ptr(F),
-                               ctypes.c_double(0.01), exact, ctypes.c_longlong(max_strips),
-                               ptr(jpart), plan)
-        assert plan[2] <= max_strips and plan[1] % 64 == 0 and plan[0] % 64 == 0
+        with np.errstate(all='ignore'):
+            emul.emul_l96_rk4_step(ptr(bufA, -alo * M), ptr(bufB, -alo * M), M, LL(N), LL(H), ptr(F),
+                                   ctypes.c_double(0.01), exact, LL(max_strips), ptr(jpart))
         assert not np.isnan(jpart).any()
+        # still-valid range after step j+1: [-8(H-1-j), N + 4(H-1-j))
+        lo, hi = -8 * (H - 1 - j), N + 4 * (H - 1 - j)
+        assert not np.isnan(bufB[lo - alo:hi - alo]).any()
         if exact:
             for k in range(M):
                 for q in range(2):
                     col = np.ascontiguousarray(jpart[:, k, q])
-                    got = emul.emul_tree_reduce(ptr(col), ctypes.c_longlong(nleaf), ctypes.c_longlong(1))
+                    got = emul.emul_tree_reduce(ptr(col), LL(nleaf), LL(1))
                     assert got / N == Jo[j, k, q]
         bufA, bufB = bufB, bufA
     got = bufA[-alo:-alo + N].T
@@ -85,7 +96,8 @@ def test_point_forms_match_oracle(emul):
     N, M = 64, 3
     U = rng.rand(M, N) * 6 - 1
     F = np.array([8.0, 8.0, 8.0001])
-    buf, alo, ahi = padded(U, 1)
+    alo, ahi = -12, N + 12
+    buf = padded(U, alo, ahi, 8, 4)
     out = np.zeros_like(buf)
     emul.emul_l96_rk4_point(ptr(buf, -alo * M), ptr(out, -alo * M), M, ctypes.c_longlong(0),
                             ctypes.c_longlong(N), ptr(F), ctypes.c_double(0.01), 1)
