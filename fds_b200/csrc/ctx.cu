@@ -36,6 +36,8 @@ struct fds_ctx {
     double* jscratch = nullptr;
     double* jsum = nullptr;
     long long jsum_cap = 0;        // steps
+    double* jnode = nullptr;       // [jsum_cap][plan.nnode][M][2] node partials of the streaming kernel
+    double* jnode_scratch = nullptr;
     long long nleaf = 0;
     double* stage = nullptr;
     long long stage_sites = 0;
@@ -187,6 +189,7 @@ void fds_ctx_destroy(fds_ctx* c) {
     for (int j = 0; j < 4; ++j) cudaFree(c->Pbase[j]);
     cudaFree(c->T); cudaFree(c->d); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
     cudaFree(c->jpart); cudaFree(c->jscratch); cudaFree(c->jsum); cudaFree(c->stage);
+    cudaFree(c->jnode); cudaFree(c->jnode_scratch);
     for (auto& pe : c->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -372,12 +375,23 @@ static int ensure_jsum(fds_ctx* c, long long steps) {
     }
     c->jsum = nj;
     c->jsum_cap = cap;
+    if (c->stream_ok) {
+        cudaFree(c->jnode); cudaFree(c->jnode_scratch);
+        c->jnode = c->jnode_scratch = nullptr;
+        const size_t row = (size_t)c->plan.nnode * c->M * 2;
+        FDS_CK(c, cudaMalloc(&c->jnode, (size_t)cap * row * sizeof(double)));
+        FDS_CK(c, cudaMalloc(&c->jnode_scratch,
+                             (size_t)2 * cap * ((c->plan.nnode + 255) / 256) * c->M * 2 * sizeof(double)));
+    }
     return 0;
 }
 
-// one step of `M_` columns X -> Y with `valid` halo steps left; optional objective sums
+// one step of `M_` columns X -> Y with `valid` halo steps left; objective sums of step `jstep`
+// (streaming kernel: node partials into jnode[jstep], reduced later in one batch by
+// reduce_nodes(); simple kernels: reduced right away into jsum[jstep])
 static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, double Flast, long long valid,
-                    double* jsum_slot) {
+                    long long jstep) {
+    double* jsum_slot = c->jsum + (size_t)jstep * M_ * 2;
     StepArgs a;
     a.X = X; a.Y = Y; a.M = M_; a.n = c->n;
     a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
@@ -386,6 +400,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
     a.nleaf = c->nleaf;
     const bool euler = c->cfg.system == FDS_SYS_L96_EULER;
     if (c->stream_ok && M_ == c->M) {
+        a.jpart = c->jnode + (size_t)jstep * c->plan.nnode * c->M * 2;
         cudaEvent_t e1 = nullptr;
         if (c->profiling) {
             if (c->prof_used == c->prof_events.size()) {
@@ -402,9 +417,18 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
         if (e1) FDS_CK(c, cudaEventRecord(e1, c->stream));
     } else {
         FDS_CK(c, launch_l96_simple(a, euler ? 1 : 0, c->stream, &c->ls));
-        if (jsum_slot) FDS_CK(c, launch_stats_leaf(Y, M_, c->n, c->jpart, c->nleaf, c->stream, &c->ls));
+        FDS_CK(c, launch_stats_leaf(Y, M_, c->n, c->jpart, c->nleaf, c->stream, &c->ls));
+        FDS_CK(c, launch_tree_reduce(c->jpart, c->nleaf, 2 * M_, jsum_slot, c->jscratch, c->stream, &c->ls));
     }
-    if (jsum_slot) FDS_CK(c, launch_tree_reduce(c->jpart, c->nleaf, 2 * M_, jsum_slot, c->jscratch, c->stream, &c->ls));
+    return 0;
+}
+
+// node partials of steps [step0, step0 + nsteps) -> jsum, one batched canonical-tree reduction
+static int reduce_nodes(fds_ctx* c, long long step0, long long nsteps) {
+    if (!c->stream_ok || nsteps < 1) return 0;
+    const size_t row = (size_t)c->plan.nnode * c->M * 2;
+    FDS_CK(c, launch_tree_reduce_batched(c->jnode + (size_t)step0 * row, c->plan.nnode, 2 * c->M, nsteps,
+                                         c->jsum + (size_t)step0 * c->M * 2, c->jnode_scratch, c->stream, &c->ls));
     return 0;
 }
 
@@ -451,11 +475,11 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
     const double F0 = s + 8.0, Flast = (s + eps) + 8.0;   // fds/segment.py:64: parameter + epsilon
     for (long long j = 0; j < nsteps; ++j) {
         if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
-        double* slot = c->jsum + (size_t)(step0 + j) * c->M * 2;
-        if (int r = one_step(c, c->Ecur(), c->E(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, slot)) return r;
+        if (int r = one_step(c, c->Ecur(), c->E(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, step0 + j)) return r;
         c->cur ^= 1;
         c->ens_halo_valid--;
     }
+    if (int r = reduce_nodes(c, step0, nsteps)) return r;
     c->state_in_ensemble = true;
     c->tangents_implicit = true;
     c->eps_last = eps;

@@ -12,8 +12,8 @@ namespace {
 struct HostIO {
     const double* X;   // base of site 0 of the padded input, [site][M]
     double* Y;
-    double* jpart;     // [nleaf][M][2]
-    long long nleaf;
+    double* jpart;     // [nnode][M][2]
+    long long nleaf;   // = nnode
     long long a;
     int M, k;
     long long cs = 0;     // first input site of the current block
@@ -25,22 +25,26 @@ struct HostIO {
     void end_block(int) {}
     double load(int p) const { return X[(cs + p) * M + k]; }
     void store(int p, double v) { Y[(j0 + p) * M + k] = v; }
-    void emit_leaf(long long leaf, double s1, double s2) {
-        if (leaf >= 0 && leaf < nleaf) {
-            jpart[(leaf * M + k) * 2 + 0] = s1;
-            jpart[(leaf * M + k) * 2 + 1] = s2;
+    void emit_node(long long node, double s1, double s2) {
+        if (node >= 0 && node < nleaf) {
+            jpart[(node * M + k) * 2 + 0] = s1;
+            jpart[(node * M + k) * 2 + 1] = s2;
         }
     }
     bool all(bool v) const { return v; }
+    double ns[kMaxNodeLevels + 1][2];
+    double ns_get(int l, int q) const { return ns[l][q]; }
+    void ns_put(int l, int q, double v) { ns[l][q] = v; }
 };
 }  // namespace
 
 extern "C" {
 
-// the fixed strip plan of a context: out = {a0, ls, nstrips, nblk, alo, ahi}
+// the fixed strip plan of a context: out = {a0, ls, nstrips, nblk, alo, ahi, node_shift, nnode}
 int emul_plan(long long n, long long H, long long max_strips, long long* out) {
     StripPlan p = make_strip_plan(n, H, max_strips);
     out[0] = p.a0; out[1] = p.ls; out[2] = p.nstrips; out[3] = p.nblk; out[4] = p.alo; out[5] = p.ahi;
+    out[6] = p.node_shift; out[7] = p.nnode;
     return 0;
 }
 
@@ -50,11 +54,10 @@ int emul_l96_rk4_step(const double* X, double* Y, int M, long long n, long long 
                       const double* F /*[M]*/, double dt, int exact, long long max_strips, double* jpart) {
     StripPlan plan = make_strip_plan(n, H, max_strips);
     Rk4Coef c{0.5 * dt, dt, dt / 6.0};
-    long long nleaf = (n + kLeafSites - 1) / kLeafSites;
     for (long long s = 0; s < plan.nstrips; ++s) {
         for (int k = 0; k < M; ++k) {
-            HostIO io{X, Y, jpart, nleaf, plan.a0 + s * plan.ls, M, k};
-            MarchGeom g{io.a, n, plan.nblk, jpart != nullptr};
+            HostIO io{X, Y, jpart, plan.nnode, plan.a0 + s * plan.ls, M, k};
+            MarchGeom g{io.a, n, plan.nblk, jpart != nullptr, plan.node_shift};
             if (exact) l96_rk4_march<ExactMath>(io, g, F[k], c);
             else       l96_rk4_march<FastMath>(io, g, F[k], c);
         }

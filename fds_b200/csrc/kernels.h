@@ -19,7 +19,8 @@ struct StepArgs {
     double F0, Flast;      // forcing of columns < M-1 and of column M-1
     double dt;
     int exact;             // FDS_MATH_EXACT / FAST
-    double* jpart;         // [nleaf][M][2] 64-site partial sums, or nullptr
+    double* jpart;         // simple kernels: [nleaf][M][2] 64-site partial sums; streaming kernel:
+                           // [plan.nnode][M][2] node partial sums; or nullptr
     long long nleaf;
 };
 
@@ -35,6 +36,9 @@ cudaError_t launch_stats_leaf(const double* Y, int M, long long n, double* jpart
 // canonical tree over the leading axis of in[n_in][C] -> out[C]; scratch holds 2 * ceil(n_in/256) * C
 cudaError_t launch_tree_reduce(const double* in, long long n_in, int C, double* out, double* scratch,
                                cudaStream_t st, LaunchStats* ls);
+// batch of independent reductions: in[batch][n_in][C] -> out[batch][C]; scratch: 2 * batch * ceil(n_in/256) * C
+cudaError_t launch_tree_reduce_batched(const double* in, long long n_in, int C, long long batch, double* out,
+                                       double* scratch, cudaStream_t st, LaunchStats* ls);
 // periodic ghosts: A[g][:] = A[g mod n][:] for g in [-gl,0) U [n, n+gr)
 cudaError_t launch_halo_wrap(double* A, int M, long long n, long long gl, long long gr,
                              cudaStream_t st, LaunchStats* ls);

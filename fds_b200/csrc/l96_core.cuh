@@ -184,6 +184,28 @@ struct TreeAcc {
 
 constexpr int kLeafSites = 64;   // sites per leaf of the objective partials
 constexpr int kLeafShift = 6;
+constexpr int kMaxNodeLevels = 7;    // a node of the emitted partials spans at most 64 * 2^7 = 8192 sites
+
+// Continuation of the tree from 64-site leaves up to nodes of 2^(6 + levels) sites, for the two
+// objective sums at once: a binary counter whose pending partials live in storage provided by
+// the IO policy (shared memory in the CUDA kernel -- it is touched once per 64 sites and
+// indexed dynamically, so registers and local memory are both the wrong place).
+//   double ns_get(int level, int which)      void ns_put(int level, int which, double v)
+struct NodeCounter {
+    unsigned cnt;
+    FDS_HD void reset() { cnt = 0; }
+    // push one leaf; true when a node of 2^levels leaves is complete (its sums in a, b)
+    template <class IO>
+    FDS_HD bool push(IO& io, double& a, double& b, int levels) {
+        int l = 0;
+#pragma unroll 1
+        while ((cnt >> l) & 1u) { a = io.ns_get(l, 0) + a; b = io.ns_get(l, 1) + b; ++l; }
+        ++cnt;
+        if (l == levels) { cnt = 0; return true; }
+        io.ns_put(l, 0, a); io.ns_put(l, 1, b);
+        return false;
+    }
+};
 
 // --------------------------------------------------------------------------- //
 // Strip decomposition of the streaming step kernel.  FIXED per context: the widest
@@ -196,11 +218,13 @@ constexpr int kLeafShift = 6;
 // input chunks the strips read (both bounds == 4 mod 8).
 // --------------------------------------------------------------------------- //
 struct StripPlan {
-    long long a0;       // first strip starts here (multiple of 64)
-    long long ls;       // strip length
+    long long a0;       // first strip starts here (multiple of the node size)
+    long long ls;       // strip length (multiple of the node size)
     long long nstrips;  // strips needed to cover the span
     int nblk;           // 8-blocks per strip
     long long alo, ahi; // allocated site range
+    int node_shift;     // objective partials are emitted per node of 2^node_shift sites (>= 6)
+    long long nnode;    // nodes covering [0, n)
 };
 
 inline long long floor_div(long long a, long long b) {
@@ -212,16 +236,33 @@ inline StripPlan make_strip_plan(long long n, long long H, long long max_strips)
     StripPlan p;
     if (max_strips < 1) max_strips = 1;
     const long long lo = -8 * (H - 1), hi = n + 4 * (H - 1);
-    const long long a0 = floor_div(lo, kLeafSites) * kLeafSites;
-    const long long span = hi - a0;
-    long long ls = ((span + max_strips - 1) / max_strips + kLeafSites - 1) / kLeafSites * kLeafSites;
-    if (ls < kLeafSites) ls = kLeafSites;
-    p.a0 = a0;
-    p.ls = ls;
-    p.nstrips = (span + ls - 1) / ls;
-    p.nblk = (int)(ls / 8);
-    p.alo = a0 - 12;
-    p.ahi = a0 + p.nstrips * ls + 12;
+    // the coarsest node (fewest partials to reduce afterwards) that lengthens a strip by <= 2 %
+    long long ls6 = 0;
+    for (int e = kLeafShift + kMaxNodeLevels; e >= kLeafShift; --e) {
+        const long long g = 1LL << e;
+        const long long a0 = floor_div(lo, g) * g;
+        const long long span = hi - a0;
+        long long ls = ((span + max_strips - 1) / max_strips + g - 1) / g * g;
+        if (ls < g) ls = g;
+        if (e > kLeafShift) {
+            if (ls6 == 0) {   // reference length at the finest granularity
+                const long long a6 = floor_div(lo, kLeafSites) * kLeafSites;
+                const long long s6 = hi - a6;
+                ls6 = ((s6 + max_strips - 1) / max_strips + kLeafSites - 1) / kLeafSites * kLeafSites;
+                if (ls6 < kLeafSites) ls6 = kLeafSites;
+            }
+            if (ls * 50 > ls6 * 51) continue;
+        }
+        p.a0 = a0;
+        p.ls = ls;
+        p.nstrips = (span + ls - 1) / ls;
+        p.node_shift = e;
+        break;
+    }
+    p.nblk = (int)(p.ls / 8);
+    p.alo = p.a0 - 12;
+    p.ahi = p.a0 + p.nstrips * p.ls + 12;
+    p.nnode = (n + (1LL << p.node_shift) - 1) >> p.node_shift;
     return p;
 }
 

@@ -13,7 +13,9 @@
 //   double load(int p)                    x[a + 8b + 4 + p]
 //   void   store(int p, double v)         x'[a + 8b - 3 + p]
 //   void   end_block(int b)               done with block b
-//   void   emit_leaf(long long leaf, double s1, double s2)   64-site partial sums
+//   void   emit_node(long long node, double s1, double s2)   partial sums of one node (2^node_shift sites)
+//   double ns_get(int level, int which) / void ns_put(int level, int which, double v)
+//                                         per-thread storage of the node counter (l96_core.cuh)
 //   bool   all(bool)                      warp-wide AND (the CUDA kernel keeps a warp on ONE
 //                                         of the two code paths; true for a single thread)
 #pragma once
@@ -26,6 +28,7 @@ struct MarchGeom {
     long long n;      // objective sums cover sites in [0, n)
     int nblk;         // 8-blocks in the strip; the strip stores sites [a, a + 8*nblk)
     int stats;        // accumulate the objective partials?
+    int node_shift;   // partials are emitted per node of 2^node_shift sites (a, 8*nblk multiples of it)
 };
 
 // One site of one block.  FAST: the whole block lies inside the store range and the
@@ -57,7 +60,7 @@ FDS_HD void march_site(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, double& 
 
 template <class MP, bool FAST, class IO>
 FDS_HD void march_block(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, LeafStack& l1, LeafStack& l2,
-                        const MarchGeom& g, int b, long long slo, long long shi, long long jlo, long long jhi,
+                        NodeCounter& ns, const MarchGeom& g, int b, long long slo, long long shi, long long jlo, long long jhi,
                         double F, const Rk4Coef& c) {
     const long long j0 = g.a + 8LL * b - Rk4Pipe<MP>::kLag;
     const bool stats = g.stats != 0;
@@ -70,7 +73,12 @@ FDS_HD void march_block(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, LeafSta
         double s1, s2;
         const bool d1 = l1.push(b1, (b - 1) & 7, s1);
         const bool d2 = l2.push(b2, (b - 1) & 7, s2);
-        if (d1 && d2) io.emit_leaf((g.a + 8LL * (b - 1)) >> kLeafShift, s1, s2);
+        if (d1 && d2) {
+            // leaves outside [0, n) hold unused cells: they enter the tree as exact zeros
+            const long long leaf = (g.a + 8LL * (b - 1)) >> kLeafShift;
+            if (leaf < 0 || leaf * kLeafSites >= g.n) { s1 = 0.0; s2 = 0.0; }
+            if (ns.push(io, s1, s2, g.node_shift - kLeafShift)) io.emit_node(leaf >> (g.node_shift - kLeafShift), s1, s2);
+        }
     }
     march_site<MP, 3, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
     march_site<MP, 4, FAST>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, stats, F, c);
@@ -91,12 +99,14 @@ FDS_HD void l96_rk4_march(IO& io, const MarchGeom& g, double F, const Rk4Coef& c
     LeafStack l1, l2;
     t1.t1 = t1.t2 = t1.t4 = 0.0; t2 = t1;
     l1.s0 = l1.s1 = l1.s2 = 0.0; l2 = l1;
+    NodeCounter ns;
+    ns.reset();
     // this strip stores sites [slo, shi) and counts sites [jlo, jhi) in the objective
     const long long slo = g.a, shi = g.a + 8LL * g.nblk;
     const long long jlo = slo > 0 ? slo : 0;
     const long long jhi = g.n < shi ? g.n : shi;
     // Only the 64-site leaf that contains site n (if n is not a multiple of 64) needs its
-    // objective terms masked: leaves wholly outside [0, n) are dropped by emit_leaf.
+    // objective terms masked: leaves wholly outside [0, n) are zeroed as a whole (march_block).
     const long long nfl = g.n & ~(long long)(kLeafSites - 1);
     const long long ncl = (g.n + kLeafSites - 1) & ~(long long)(kLeafSites - 1);
 #pragma unroll 1
@@ -106,9 +116,9 @@ FDS_HD void l96_rk4_march(IO& io, const MarchGeom& g, double F, const Rk4Coef& c
         // unchecked path: all 8 outputs belong to this strip and none lies in the partial leaf
         const bool fast = j0 >= slo && j0 + 8 <= shi && (j0 + 8 <= nfl || j0 >= ncl);
         if (io.all(fast))
-            march_block<MP, true>(io, pipe, t1, t2, l1, l2, g, b, slo, shi, jlo, jhi, F, c);
+            march_block<MP, true>(io, pipe, t1, t2, l1, l2, ns, g, b, slo, shi, jlo, jhi, F, c);
         else
-            march_block<MP, false>(io, pipe, t1, t2, l1, l2, g, b, slo, shi, jlo, jhi, F, c);
+            march_block<MP, false>(io, pipe, t1, t2, l1, l2, ns, g, b, slo, shi, jlo, jhi, F, c);
         io.end_block(b);
     }
 }

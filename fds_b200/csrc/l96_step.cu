@@ -57,16 +57,52 @@ struct StreamParams {
     const double* X;
     double* Y;
     double* jpart;
-    long long nleaf;
+    long long nnode;
     long long a0, ls, nstrips;
     long long n;
-    int nblk;
+    int nblk, node_shift;
     int M, R, run_stride, nstages, nconsumer;  // nconsumer = R*M
+    int dedicated;                             // 1: the last warp only produces; 0: warp 0 produces in between its blocks
     double F0, Flast;
     Rk4Coef c;
 };
 
 constexpr int kMaxStages = 8;
+
+// The TMA producer role, carried by warp 0 in between its own blocks: after releasing block
+// `it`, it refills the stage released one block earlier (by then every warp has let go of it)
+// with block it + nstages - 1.  Lane r issues the bulk copy of strip r (r, r+32, ...).
+struct StreamProducer {
+    const double* X;
+    double* sdata;
+    uint64_t* full;
+    uint64_t* empty;
+    long long a0, ls, last_strip;
+    int M, R, run_stride, stage_stride, nstages, nit;
+    uint32_t chunk_bytes;
+    int lane;
+    int it, st;
+    uint32_t par;
+
+    FDS_D void issue_next() {
+        if (it >= nit) return;
+        if (it >= nstages) mbar_wait(&empty[st], par ^ 1u);
+        if (lane == 0) mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)R);
+        __syncwarp();
+        double* dst = sdata + (size_t)st * stage_stride;
+        for (int r = lane; r < R; r += 32) {
+            // strips past the end of the plan (last CTA only) mirror the last strip
+            long long strip = (long long)blockIdx.x * R + r;
+            strip = strip < last_strip ? strip : last_strip;
+            // input chunk of block b = it - 2: sites a + 8b + 4 .. a + 8b + 11 (inside the allocation
+            // by construction of the plan, l96_core.cuh)
+            const long long cs = a0 + strip * ls + 8LL * it - 12;
+            bulk_g2s(dst + r * run_stride, X + cs * M, chunk_bytes, &full[st]);
+        }
+        ++it;
+        if (++st == nstages) { st = 0; par ^= 1u; }
+    }
+};
 
 struct StreamIO {
     const double* sdata;     // this thread's (run, column) slot in stage 0
@@ -76,9 +112,12 @@ struct StreamIO {
     uint64_t* full;
     uint64_t* empty;
     double* yrow;            // output cursor: site a + 8b - 3 of this thread's column
-    double* jp;              // leaf 0, already offset by column (or nullptr)
-    long long nleaf;
+    double* jp;              // node 0, already offset by column (or nullptr)
+    long long nnode;
+    double* nsm;             // node-counter storage of this thread: nsm[(2*level + which) * nthr]
+    int nthr;
     int lane;
+    StreamProducer* prod;    // non-null in warp 0
     // ring position
     int st;
     uint32_t par;
@@ -93,13 +132,16 @@ struct StreamIO {
     FDS_D void end_block(int) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
+        if (prod != nullptr) prod->issue_next();
         if (++st == nstages) { st = 0; par ^= 1u; }
         yrow += 8 * M;
     }
-    FDS_D void emit_leaf(long long leaf, double s1, double s2) {
-        if (jp != nullptr && leaf >= 0 && leaf < nleaf)
-            *reinterpret_cast<double2*>(jp + leaf * (2LL * M)) = make_double2(s1, s2);
+    FDS_D void emit_node(long long node, double s1, double s2) {
+        if (jp != nullptr && node >= 0 && node < nnode)
+            *reinterpret_cast<double2*>(jp + node * (2LL * M)) = make_double2(s1, s2);
     }
+    FDS_D double ns_get(int l, int q) const { return nsm[(2 * l + q) * nthr]; }
+    FDS_D void ns_put(int l, int q, double v) { nsm[(2 * l + q) * nthr] = v; }
     FDS_D bool all(bool v) const { return __all_sync(0xffffffffu, v); }
 };
 
@@ -108,50 +150,45 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
-    double* sdata = reinterpret_cast<double*>(smem_raw + 128);
+    double* nsm = reinterpret_cast<double*>(smem_raw + 128);
+    const int levels = p.node_shift - kLeafShift;
+    double* sdata = nsm + (size_t)2 * levels * (blockDim.x - 32 * p.dedicated);
 
     const int tid = threadIdx.x;
-    const int ncw = (p.nconsumer + 31) >> 5;          // consumer warps
+    const int nwarps = (blockDim.x >> 5) - p.dedicated;   // consumer warps
     const int warp = tid >> 5, lane = tid & 31;
     const int stage_stride = p.R * p.run_stride;
 
     if (tid == 0) {
         for (int s = 0; s < p.nstages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], ncw);
+            mbar_init(&empty[s], nwarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // strips past the end of the plan (last CTA only) mirror the last strip: same loads,
-    // same arithmetic, same stores of the same values -- no thread ever takes its own path
     const long long last_strip = p.nstrips - 1;
-    const int nit = march_iterations(p.nblk);          // blocks b = -2 .. nblk
-    if (warp == ncw) {
-        // ------- producer warp: lane r issues the bulk copy of strip r (r, r+32, ...) ------- //
-        const uint32_t chunk_bytes = (uint32_t)(8 * p.M * sizeof(double));
-        int st = 0;
-        uint32_t par = 0;
-        for (int it = 0; it < nit; ++it) {
-            if (it >= p.nstages) mbar_wait(&empty[st], par ^ 1u);
-            if (lane == 0) mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)p.R);
-            __syncwarp();
-            double* dst = sdata + (size_t)st * stage_stride;
-            for (int r = lane; r < p.R; r += 32) {
-                long long strip = (long long)blockIdx.x * p.R + r;
-                strip = strip < last_strip ? strip : last_strip;
-                // input chunk of block b = it - 2: sites a + 8b + 4 .. a + 8b + 11 (inside the allocation
-                // by construction of the plan, l96_core.cuh)
-                const long long cs = p.a0 + strip * p.ls + 8LL * it - 12;
-                bulk_g2s(dst + r * p.run_stride, p.X + cs * p.M, chunk_bytes, &full[st]);
-            }
-            if (++st == p.nstages) { st = 0; par ^= 1u; }
+    StreamProducer prod;
+    const int pwarp = p.dedicated ? nwarps : 0;
+    if (warp == pwarp) {
+        prod.X = p.X; prod.sdata = sdata; prod.full = full; prod.empty = empty;
+        prod.a0 = p.a0; prod.ls = p.ls; prod.last_strip = last_strip;
+        prod.M = p.M; prod.R = p.R; prod.run_stride = p.run_stride; prod.stage_stride = stage_stride;
+        prod.nstages = p.nstages; prod.nit = march_iterations(p.nblk);   // blocks b = -2 .. nblk
+        prod.chunk_bytes = (uint32_t)(8 * p.M * sizeof(double));
+        prod.lane = lane; prod.it = 0; prod.st = 0; prod.par = 0;
+        if (p.dedicated) {
+            while (prod.it < prod.nit) prod.issue_next();
+            return;
         }
-        return;
+        for (int j = 0; j < p.nstages - 1; ++j) prod.issue_next();          // prologue: fill all but one stage
     }
+
     // -------------------- consumer threads: (run r, column k) ------------------ //
-    // idle lanes of the last consumer warp mirror the last thread
+    // idle lanes of the last warp mirror the last thread, strips past the end of the plan mirror
+    // the last strip: same loads, same arithmetic, same stores of the same values -- no
+    // thread ever takes a path of its own
     const int t = tid < p.nconsumer ? tid : p.nconsumer - 1;
     const int r = t / p.M, k = t - r * p.M;
     long long strip = (long long)blockIdx.x * p.R + r;
@@ -162,6 +199,7 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     g.n = p.n;
     g.nblk = p.nblk;
     g.stats = p.jpart != nullptr;
+    g.node_shift = p.node_shift;
 
     StreamIO io;
     io.sdata = sdata + r * p.run_stride + k;
@@ -172,8 +210,11 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     io.empty = empty;
     io.yrow = p.Y + (g.a - 8 * 2 - Rk4Pipe<MP>::kLag) * p.M + k;   // block b = -2
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
-    io.nleaf = p.nleaf;
+    io.nnode = p.nnode;
+    io.nsm = nsm + tid;
+    io.nthr = nwarps * 32;
     io.lane = lane;
+    io.prod = (!p.dedicated && warp == 0) ? &prod : nullptr;
     io.st = 0;
     io.par = 0;
     io.cur = io.sdata;
@@ -182,15 +223,23 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     l96_rk4_march<MP>(io, g, F, p.c);
 }
 
-// 16 warps per CTA (4 per scheduler, so each thread can hold up to 128 registers):
-// 15 consumer warps + the producer warp.  R strips x M columns <= 480 consumer threads.
-constexpr int kMaxConsumers = 480;
-int stream_runs_per_cta(int M) { return M <= kMaxConsumers ? kMaxConsumers / M : 0; }
+// 16 warps per CTA (4 per scheduler, so each thread can hold up to 128 registers), all of
+// them consumers: R strips x M columns <= 512 threads.
+static int producer_dedicated() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FDS_PRODUCER"); v = (e && e[0] == 'i') ? 0 : 1; }
+    return v;
+}
+int stream_runs_per_cta(int M) {
+    const int maxc = producer_dedicated() ? 480 : 512;
+    return M <= maxc ? maxc / M : 0;
+}
 
 cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls) {
     StreamParams p;
-    p.X = a.X; p.Y = a.Y; p.jpart = a.jpart; p.nleaf = a.nleaf;
+    p.X = a.X; p.Y = a.Y; p.jpart = a.jpart; p.nnode = plan.nnode;   // a.jpart: [nnode][M][2]
     p.n = a.n;
+    p.node_shift = plan.node_shift;
     p.M = a.M;
     p.R = stream_runs_per_cta(a.M);
     if (p.R < 1) return cudaErrorInvalidValue;            // M too large for this kernel
@@ -198,16 +247,20 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     int pad = (16 - (7 * a.M) % 16) % 16;
     if (pad & 1) pad += 1;
     p.run_stride = 8 * a.M + pad;
+    p.dedicated = producer_dedicated();
+    const int cthreads = ((p.nconsumer + 31) / 32) * 32;
+    const int block = cthreads + 32 * p.dedicated;
     const size_t stage_bytes = (size_t)p.R * p.run_stride * sizeof(double);
-    int nst = (int)std::min<size_t>(kMaxStages, (200 * 1024) / stage_bytes);
+    const size_t ns_bytes = (size_t)2 * (plan.node_shift - kLeafShift) * cthreads * sizeof(double);
+    const size_t budget = 226 * 1024 - 128 - ns_bytes;
+    int nst = (int)std::min<size_t>(kMaxStages, budget / stage_bytes);
     if (nst < 2) return cudaErrorInvalidValue;
     p.nstages = nst;
     p.a0 = plan.a0; p.ls = plan.ls; p.nstrips = plan.nstrips; p.nblk = plan.nblk;
     p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = (int)((plan.nstrips + p.R - 1) / p.R);
-    const int block = ((p.nconsumer + 31) / 32) * 32 + 32;
-    const size_t smem = 128 + stage_bytes * nst;
+    const size_t smem = 128 + ns_bytes + stage_bytes * nst;
     cudaError_t e;
     if (a.exact) {
         e = cudaFuncSetAttribute(l96_rk4_stream_kernel<ExactMath>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -295,6 +348,8 @@ __global__ void __launch_bounds__(1024) tree_level_kernel(const double* __restri
     extern __shared__ double sm[];                 // [Q][C]
     const int c = threadIdx.x % C, q = threadIdx.x / C;
     const long long g = blockIdx.x;
+    in += (size_t)blockIdx.y * n_in * C;             // batch element
+    out += (size_t)blockIdx.y * gridDim.x * C;
     if (q < Q) {
         const int per = kLG / Q;                   // power of two
         int L = 0;
@@ -318,6 +373,13 @@ __global__ void __launch_bounds__(1024) tree_level_kernel(const double* __restri
 
 cudaError_t launch_tree_reduce(const double* in, long long n_in, int C, double* out, double* scratch,
                                cudaStream_t st, LaunchStats* ls) {
+    return launch_tree_reduce_batched(in, n_in, C, 1, out, scratch, st, ls);
+}
+
+// batch of independent reductions: in[batch][n_in][C] -> out[batch][C]
+// scratch holds 2 * batch * ceil(n_in/256) * C doubles
+cudaError_t launch_tree_reduce_batched(const double* in, long long n_in, int C, long long batch, double* out,
+                                       double* scratch, cudaStream_t st, LaunchStats* ls) {
     int Q = 1;
     while (Q * 2 * C <= 1024 && Q * 2 <= kLG) Q *= 2;
     if (C > 1024) return cudaErrorInvalidValue;
@@ -325,10 +387,12 @@ cudaError_t launch_tree_reduce(const double* in, long long n_in, int C, double* 
     const double* src = in;
     long long n = n_in;
     int flip = 0;
+    if (batch < 1) return cudaSuccess;
     for (;;) {
         const long long n_out = (n + kLG - 1) / kLG;
-        double* dst = (n_out == 1) ? out : scratch + (size_t)flip * cap * C;
-        tree_level_kernel<<<(unsigned)n_out, Q * C, (size_t)Q * C * sizeof(double), st>>>(src, n, C, Q, dst);
+        double* dst = (n_out == 1) ? out : scratch + (size_t)flip * cap * C * batch;
+        dim3 grid((unsigned)n_out, (unsigned)batch);
+        tree_level_kernel<<<grid, Q * C, (size_t)Q * C * sizeof(double), st>>>(src, n, C, Q, dst);
         if (ls) ls->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

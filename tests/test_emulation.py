@@ -37,9 +37,9 @@ LL = ctypes.c_longlong
 
 
 def plan_of(emul, N, H, max_strips):
-    out = (LL * 6)()
+    out = (LL * 8)()
     emul.emul_plan(LL(N), LL(H), LL(max_strips), out)
-    return dict(zip(('a0', 'ls', 'nstrips', 'nblk', 'alo', 'ahi'), out))
+    return dict(zip(('a0', 'ls', 'nstrips', 'nblk', 'alo', 'ahi', 'node_shift', 'nnode'), out))
 
 
 def padded(U, alo, ahi, ghost_l, ghost_r):
@@ -54,19 +54,21 @@ def padded(U, alo, ahi, ghost_l, ghost_r):
 
 @pytest.mark.parametrize('N,M,H,max_strips,exact', [
     (200, 5, 3, 7, 1), (40, 18, 1, 4, 1), (37, 3, 2, 64, 1), (1024, 4, 4, 16, 1),
-    (4096, 2, 2, 37, 1), (333, 1, 3, 1, 1), (200, 5, 3, 7, 0), (4, 2, 3, 5, 1), (640, 3, 5, 3, 1)])
+    (4096, 2, 2, 37, 1), (333, 1, 3, 1, 1), (200, 5, 3, 7, 0), (4, 2, 3, 5, 1), (640, 3, 5, 3, 1), (5000, 2, 2, 2, 1), (3000, 1, 1, 1, 1), (70000, 1, 2, 5, 1)])
 def test_streaming_march_matches_oracle(emul, N, M, H, max_strips, exact):
     rng = np.random.RandomState(N + M)
     U = rng.rand(M, N) * 6 - 1
     F = 8.0 + np.r_[np.zeros(M - 1), 1e-4] if M > 1 else np.array([8.1])
     pl = plan_of(emul, N, H, max_strips)
     alo, ahi = pl['alo'], pl['ahi']
-    assert pl['nstrips'] <= max_strips and pl['ls'] % 64 == 0 and pl['a0'] % 64 == 0
+    g = 1 << pl['node_shift']
+    assert pl['nstrips'] <= max_strips and pl['ls'] % g == 0 and pl['a0'] % g == 0 and g >= 64
+    assert pl['nnode'] == (N + g - 1) // g
     assert alo <= -8 * H and ahi >= N + 4 * H and alo % 8 == 4 and ahi % 8 == 4
     assert pl['a0'] + pl['nstrips'] * pl['ls'] >= N + 4 * (H - 1)
     bufA = padded(U, alo, ahi, 8 * H, 4 * H)
     bufB = np.full_like(bufA, np.nan)
-    nleaf = (N + 63) // 64
+    nleaf = pl['nnode']
     Xo, Jo = plugins.run_l96_ensemble(plugins.l96_rk4_step, U, F, H)
     for j in range(H):
         jpart = np.full((nleaf, M, 2), np.nan)
