@@ -193,7 +193,7 @@ def run_ours(args):
     eng.segment(s, eps, S)
 
     def one_segment():
-        R, b, Gd, gd = eng.boundary(s, eps, from_ensemble=1, do_qr=1, build=1)
+        R, b, Gd, gd = eng.boundary(s, eps, from_ensemble=1, do_qr=1, build=1, keep_tangents=False)
         J0, G, g = sensitivities(eng.segment(s, eps, S), eps)
         return R, b, Gd, gd, J0, G, g
 

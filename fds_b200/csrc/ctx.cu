@@ -32,6 +32,8 @@ struct fds_ctx {
     double* small_block = nullptr;
     SmallBufs small{};
     double* c4 = nullptr;
+    double* A_host = nullptr;      // pinned copy of small.A (+ status): A travels to apply_fast as a kernel parameter
+    bool fast_boundary = false;    // register-blocked gram / apply kernels (boundary_fast.cu)
     double* jpart = nullptr;
     double* jscratch = nullptr;
     double* jsum = nullptr;
@@ -72,13 +74,33 @@ static std::string g_create_err;
 
 static int fail(fds_ctx* c, const std::string& msg) { c->err = msg; return 2; }
 
+// after small1 / small2: bring A (for the by-value kernel parameter) and the Cholesky status to the host
 static int check_small_status(fds_ctx* c, const char* what) {
     int st = 0;
     FDS_CK(c, cudaMemcpyAsync(&st, c->small.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (c->fast_boundary)
+        FDS_CK(c, cudaMemcpyAsync(c->A_host, c->small.A, (size_t)c->MO * c->MX * sizeof(double),
+                                  cudaMemcpyDeviceToHost, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     if (st != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(st) +
                                     " (tangent block numerically rank deficient)");
     return 0;
+}
+
+static cudaError_t do_gram(fds_ctx* c, int src, double inv_eps) {
+    if (c->fast_boundary)
+        return launch_gram_fast(src, c->Ecur(), c->T, c->d, c->m, inv_eps, c->n, c->gram_part, c->max_part,
+                                c->small.gram, c->num_sms, c->stream, &c->ls);
+    return launch_gram(src, c->Ecur(), c->T, c->d, c->m, inv_eps, c->n, c->gram_part, c->max_part, c->small.gram,
+                       c->num_sms, c->stream, &c->ls);
+}
+
+static cudaError_t do_apply(fds_ctx* c, int src, double inv_eps, double* Tout, double* E_out, double eps) {
+    if (c->fast_boundary)
+        return launch_apply_fast(src, c->Ecur(), c->T, c->d, c->A_host, c->m, inv_eps, c->n, Tout, E_out, c->P(0),
+                                 eps, c->num_sms, c->stream, &c->ls);
+    return launch_apply(src, c->Ecur(), c->T, c->d, c->small.A, c->m, inv_eps, c->n, Tout != nullptr ? Tout : c->T,
+                        E_out, c->P(0), eps, c->stream, &c->ls);
 }
 
 extern "C" {
@@ -141,9 +163,10 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         CK0(cudaMalloc(&c->Pbase[j], sites * sizeof(double)));
         CK0(cudaMemsetAsync(c->Pbase[j], 0, sites * sizeof(double), c->stream));
     }
-    CK0(cudaMalloc(&c->T, (size_t)c->n * c->MO * sizeof(double)));
+    // +2 doubles: the boundary kernels fetch tiles with 16-byte-granular bulk copies
+    CK0(cudaMalloc(&c->T, ((size_t)c->n * c->MO + 2) * sizeof(double)));
     CK0(cudaMemsetAsync(c->T, 0, (size_t)c->n * c->MO * sizeof(double), c->stream));
-    CK0(cudaMalloc(&c->d, (size_t)c->n * sizeof(double)));
+    CK0(cudaMalloc(&c->d, ((size_t)c->n + 2) * sizeof(double)));
     CK0(cudaMemsetAsync(c->d, 0, (size_t)c->n * sizeof(double), c->stream));
     c->max_part = 2 * c->num_sms;
     CK0(cudaMalloc(&c->gram_part, (size_t)c->max_part * c->MX * c->MX * sizeof(double)));
@@ -161,6 +184,8 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         c->small.gdil = p; p += c->MO;
         c->small.status = reinterpret_cast<int*>(p);
     }
+    c->fast_boundary = apply_fast_supported(c->m) && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS);
+    CK0(cudaMallocHost(&c->A_host, (size_t)c->MO * c->MX * sizeof(double)));
     CK0(cudaMalloc(&c->c4, 4 * sizeof(double)));
     {
         const double w[4] = {-11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0};
@@ -190,6 +215,7 @@ void fds_ctx_destroy(fds_ctx* c) {
     cudaFree(c->T); cudaFree(c->d); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
     cudaFree(c->jpart); cudaFree(c->jscratch); cudaFree(c->jsum); cudaFree(c->stage);
     cudaFree(c->jnode); cudaFree(c->jnode_scratch);
+    cudaFreeHost(c->A_host);
     for (auto& pe : c->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -537,36 +563,35 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
     }
     const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
     if (!from_ensemble) if (int r = materialize_tangents(c)) return r;
-    FDS_CK(c, launch_gram(src, c->Ecur(), c->T, c->d, c->m, from_ensemble ? 1.0 / eps : 0.0, c->n, c->gram_part,
-                          c->max_part, c->small.gram, c->num_sms, c->stream, &c->ls));
+    FDS_CK(c, do_gram(c, src, from_ensemble ? 1.0 / eps : 0.0));
     return 0;
 }
 
 int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
     FDS_CK(c, launch_small1(c->small, c->m, c->time_dilation ? 1 : 0, do_qr, c->stream, &c->ls));
-    if (do_qr) if (int r = check_small_status(c, "CholeskyQR pass 1")) return r;
+    if (do_qr || c->fast_boundary) if (int r = check_small_status(c, "CholeskyQR pass 1")) return r;
     const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
-    FDS_CK(c, launch_apply(src, c->Ecur(), c->T, c->d, c->small.A, c->m, from_ensemble ? 1.0 / eps : 0.0, c->n, c->T,
-                           nullptr, nullptr, 0.0, c->stream, &c->ls));
+    FDS_CK(c, do_apply(c, src, from_ensemble ? 1.0 / eps : 0.0, c->T, nullptr, 0.0));
     c->tangents_implicit = false;
-    if (do_qr)
-        FDS_CK(c, launch_gram(SRC_TANGENT, nullptr, c->T, c->d, c->m, 0.0, c->n, c->gram_part, c->max_part,
-                              c->small.gram, c->num_sms, c->stream, &c->ls));
+    if (do_qr) FDS_CK(c, do_gram(c, SRC_TANGENT, 0.0));
     return 0;
 }
 
 int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
+    const bool ens = (build & FDS_BUILD_ENSEMBLE) != 0;
+    // explicit tangents are written unless the caller only wants the next ensemble (hot loop)
+    const bool keepT = !ens || (build & FDS_BUILD_KEEP_TANGENTS) != 0 || !c->fast_boundary;
+    c->tangents_implicit = false;
     if (do_qr) {
         FDS_CK(c, launch_small2(c->small, c->m, c->stream, &c->ls));
         if (int r = check_small_status(c, "CholeskyQR pass 2")) return r;
-        FDS_CK(c, launch_apply(SRC_TANGENT, nullptr, c->T, c->d, c->small.A, c->m, 0.0, c->n, c->T,
-                               build ? c->Ecur() : nullptr, c->P(0), eps, c->stream, &c->ls));
-    } else if (build) {
+        FDS_CK(c, do_apply(c, SRC_TANGENT, 0.0, keepT ? c->T : nullptr, ens ? c->Ecur() : nullptr, eps));
+        if (!keepT) c->tangents_implicit = true;    // T holds the pass-1 intermediate; the ensemble is the record
+    } else if (ens) {
         FDS_CK(c, launch_make_ensemble(c->P(0), c->T, c->M, eps, c->Ecur(), c->n, c->stream, &c->ls));
     }
-    if (build) { c->ens_halo_valid = 0; c->eps_last = eps; }
+    if (ens) { c->ens_halo_valid = 0; c->eps_last = eps; }
     c->state_in_ensemble = false;
-    c->tangents_implicit = false;
     return 0;
 }
 

@@ -85,6 +85,17 @@ cudaError_t launch_small1(const SmallBufs&, int m, int use_d, int do_qr, cudaStr
 cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*);
 size_t small_smem_bytes(int m);
 
+// ---- boundary_fast.cu ---------------------------------------------------------- //
+// register-blocked versions of launch_gram / launch_apply; A_host is the (m+1) x (m+2) matrix on
+// the HOST (it travels as a by-value kernel parameter); Tout / E_out may be nullptr
+cudaError_t launch_gram_fast(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
+                             long long n, double* part, int max_part, double* out, int num_sms, cudaStream_t,
+                             LaunchStats*);
+bool apply_fast_supported(int m);
+cudaError_t launch_apply_fast(int src, const double* E, const double* Tin, const double* d, const double* A_host,
+                              int m, double inv_eps, long long n, double* Tout, double* E_out, const double* u,
+                              double eps, int num_sms, cudaStream_t, LaunchStats*);
+
 // ---- lss.cu ----------------------------------------------------------------- //
 // R[K][m][m], b[K][m] (device) -> alpha[K][m] (device); work: (2*m*m + 2*m) * K doubles
 cudaError_t launch_lss_solve(const double* R, const double* b, long long K, int m, double* alpha,

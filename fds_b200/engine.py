@@ -114,10 +114,12 @@ class Engine:
         return None if Js is None else Js / self.n_global
 
     # -- one boundary ----------------------------------------------------------- #
-    def boundary(self, s, eps, from_ensemble, do_qr, build):
+    def boundary(self, s, eps, from_ensemble, do_qr, build, keep_tangents=True):
         """Time dilation + projection (+ QR) at the current state; optionally builds the
-        next perturbed ensemble.  Returns (R, b, G_dil, g_dil)."""
+        next perturbed ensemble.  ``keep_tangents=False`` (the hot loop) skips storing the
+        tangents explicitly when the ensemble is built.  Returns (R, b, G_dil, g_dil)."""
         c = self.ctx
+        build = (_lib.FDS_BUILD_ENSEMBLE if build else 0) | (_lib.FDS_BUILD_KEEP_TANGENTS if keep_tangents else 0)
         c.boundary_begin(from_ensemble)
         if self.time_dilation:
             self._halo(_lib.FDS_BUF_PRIMAL, 3)

@@ -93,13 +93,15 @@ def _segment_loop(eng, parameter, lss, G_lss, g_lss, J_hist, G_dil, g_dil, num_s
     record_segment()
     for i in range(lss.K_segments() + 1, num_segments + 1):
         last = i == num_segments
-        R, b, Gd, gd = eng.boundary(parameter, epsilon, from_ensemble=1, do_qr=1, build=not last)
+        save = bool(checkpoint_path) and i % checkpoint_interval == 0
+        R, b, Gd, gd = eng.boundary(parameter, epsilon, from_ensemble=1, do_qr=1, build=not last,
+                                    keep_tangents=save)
         lss.append(R, b)
         G_dil.append(Gd), g_dil.append(gd)
         if verbose:
             print(lss_gradient(Checkpoint(None, None, None, lss, G_lss, g_lss, J_hist, G_dil, g_dil)))
             sys.stdout.flush()
-        if checkpoint_path and i % checkpoint_interval == 0:
+        if save:
             save_checkpoint(checkpoint_path, snapshot())
         if not last:
             record_segment()

@@ -39,6 +39,14 @@ enum {
     FDS_MATH_FAST  = 1     /* FMA contraction allowed (statistically equivalent)   */
 };
 
+/* `build` argument of fds_boundary_finish / fds_boundary */
+enum {
+    FDS_BUILD_ENSEMBLE      = 1, /* write the next perturbed ensemble u + eps*[W; w]                */
+    FDS_BUILD_KEEP_TANGENTS = 2  /* also store W, w explicitly (for fds_get_tangents right after);
+                                    without it they are recovered from the ensemble, (E_k - E_0)/eps,
+                                    to ~1e-9 relative -- enough to continue, not for a checkpoint   */
+};
+
 /* context flags */
 enum {
     FDS_FLAG_SIMPLE_KERNELS = 1  /* use the one-thread-per-element step kernel (cross-check path) */

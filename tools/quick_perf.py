@@ -28,10 +28,13 @@ def main():
         gbs = 16.0 * N * (m + 2) * steps / dt / 1e9
         print('N=2^%d m=%d %s: %d steps %.2f ms/step  %.3e upd/s  %.0f GB/s algorithmic  (%d launches)'
               % (logN, m, math, steps, dt / steps * 1e3, upd, gbs, eng.ctx.launches - l0))
-    t0 = time.perf_counter()
-    eng.boundary(0.0, eps, 1, 1, 1)
-    eng.ctx.sync()
-    dt = time.perf_counter() - t0
-    print('boundary (dilation+QR+ensemble): %.2f ms' % (dt * 1e3))
+    for keep in (True, False):
+        eng.segment(0.0, eps, 2)
+        eng.ctx.sync()
+        t0 = time.perf_counter()
+        eng.boundary(0.0, eps, 1, 1, 1, keep_tangents=keep)
+        eng.ctx.sync()
+        dt = time.perf_counter() - t0
+        print('boundary (dilation+QR+ensemble, keep_tangents=%s): %.2f ms' % (keep, dt * 1e3))
 
 main()
