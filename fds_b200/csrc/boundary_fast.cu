@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(288) gram_fast_kernel(const double* __restrict
     constexpr int NC = 256;
     const int W = SRC == SRC_ENSEMBLE ? MX : MX - 1;
     const int MO = MX - 1;
-    const int LD = NB * B + 1;                    // odd row stride of the work buffer
+    const int LD = NB * B + ((B & 1) ? 1 : 2);    // even B: rows and blocks 16-byte aligned -> 128-bit loads
     const int NP = NB * (NB + 1) / 2;             // block pairs of the upper triangle
     const int SLOTS = NC / NP;                    // sites in flight per iteration
     TileStage ts;
@@ -146,8 +146,17 @@ __global__ void __launch_bounds__(288) gram_fast_kernel(const double* __restrict
             for (int s = slot; s < S; s += SLOTS) {
                 const double* row = xs + s * LD;
                 double av[B], bv[B];
+                if ((B & 1) == 0) {
 #pragma unroll
-                for (int a = 0; a < B; ++a) { av[a] = row[bi * B + a]; bv[a] = row[bj * B + a]; }
+                    for (int a = 0; a < B; a += 2) {
+                        const double2 pa = *reinterpret_cast<const double2*>(row + bi * B + a);
+                        const double2 pb = *reinterpret_cast<const double2*>(row + bj * B + a);
+                        av[a] = pa.x; av[a + 1] = pa.y; bv[a] = pb.x; bv[a + 1] = pb.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int a = 0; a < B; ++a) { av[a] = row[bi * B + a]; bv[a] = row[bj * B + a]; }
+                }
 #pragma unroll
                 for (int a = 0; a < B; ++a)
 #pragma unroll
@@ -197,7 +206,7 @@ static cudaError_t gram_fast_launch(int src, const double* E, const double* T, c
                                     int num_sms, cudaStream_t st, LaunchStats* ls) {
     const int NB = (MX + B - 1) / B;
     const int NP = NB * (NB + 1) / 2;
-    const int LD = NB * B + 1;
+    const int LD = NB * B + ((B & 1) ? 1 : 2);
     const int SLOTS = 256 / NP;
     if (SLOTS < 1) return cudaErrorInvalidValue;
     const int W = src == SRC_ENSEMBLE ? MX : MX - 1;
@@ -235,20 +244,13 @@ static cudaError_t gram_fast_launch(int src, const double* E, const double* T, c
     return cudaGetLastError();
 }
 
-// block size: as many busy lanes as possible, then the largest block (fewest loads per FMA)
+// Block size of the register tile.  Measured on B200 at m = 32 (N = 2^24): B = 4 (72 registers,
+// several CTAs per SM, 128-bit shared loads) 19.2 ms per boundary, B = 5: 19.6, B = 6..8: 23 --
+// occupancy beats the lower load-per-FMA ratio of the larger tiles.  FDS_GRAM_B overrides.
 static int pick_gram_block(int MX) {
-    if (const char* e = getenv("FDS_GRAM_B")) { const int b = atoi(e); if (b >= 4 && b <= 7) return b; }
-    int best = 0;
-    double best_score = -1.0;
-    for (int B = 4; B <= 7; ++B) {
-        const int NB = (MX + B - 1) / B, NP = NB * (NB + 1) / 2;
-        if (NP > 256) continue;
-        const double lanes = (double)((256 / NP) * NP) / 256.0;
-        const double useful = (double)MX * (MX + 1) / 2.0 / ((double)NP * B * B);   // padding + diagonal blocks
-        const double score = lanes * useful * (B / (B + 3.0));                       // LSU pressure ~ 2B loads per B*B FMAs
-        if (score > best_score) { best_score = score; best = B; }
-    }
-    return best;
+    if (const char* e = getenv("FDS_GRAM_B")) { const int b = atoi(e); if (b >= 4 && b <= 8) return b; }
+    (void)MX;
+    return 4;
 }
 
 cudaError_t launch_gram_fast(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
@@ -260,6 +262,7 @@ cudaError_t launch_gram_fast(int src, const double* E, const double* T, const do
         case 5: return gram_fast_launch<5>(src, E, T, d, MX, inv_eps, n, part, max_part, out, num_sms, st, ls);
         case 6: return gram_fast_launch<6>(src, E, T, d, MX, inv_eps, n, part, max_part, out, num_sms, st, ls);
         case 7: return gram_fast_launch<7>(src, E, T, d, MX, inv_eps, n, part, max_part, out, num_sms, st, ls);
+        case 8: return gram_fast_launch<8>(src, E, T, d, MX, inv_eps, n, part, max_part, out, num_sms, st, ls);
     }
     return cudaErrorInvalidValue;
 }
