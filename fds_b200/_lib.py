@@ -15,6 +15,7 @@ c_int64_p = ctypes.POINTER(ctypes.c_int64)
 FDS_SYS_L96_RK4, FDS_SYS_L96_EULER = 0, 1
 FDS_MATH_EXACT, FDS_MATH_FAST = 0, 1
 FDS_FLAG_SIMPLE_KERNELS = 1
+FDS_FLAG_EXTERNAL_STREAM = 2
 FDS_BUILD_ENSEMBLE, FDS_BUILD_KEEP_TANGENTS = 1, 2
 FDS_BUF_ENSEMBLE, FDS_BUF_PRIMAL, FDS_BUF_GRAM, FDS_BUF_JSUM, FDS_BUF_TANGENT, FDS_BUF_DXDT = range(6)
 

@@ -136,7 +136,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
     } while (0)
     CK0(cudaSetDevice(cfg->device));
     CK0(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
-    if (cfg->stream) c->stream = (cudaStream_t)cfg->stream;
+    if (cfg->stream || (cfg->flags & FDS_FLAG_EXTERNAL_STREAM)) c->stream = (cudaStream_t)cfg->stream;
     else { CK0(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
 
     long long H = cfg->max_halo_steps > 0 ? cfg->max_halo_steps : std::min<long long>(128, std::max<long long>(1, c->n / 64));

@@ -32,7 +32,8 @@ class Context:
         cfg = _lib.FdsConfig(device=device, system=SYSTEMS[scheme], math=MATH[math], m=self.m,
                              n_local=self.n, n_global=self.n_global, site_offset=int(site_offset),
                              rank=self.rank, world=self.world, max_halo_steps=int(max_halo_steps),
-                             flags=_lib.FDS_FLAG_SIMPLE_KERNELS if simple_kernels else 0,
+                             flags=(_lib.FDS_FLAG_SIMPLE_KERNELS if simple_kernels else 0) |
+                                   (_lib.FDS_FLAG_EXTERNAL_STREAM if stream is not None else 0),
                              dt=float(dt), stream=stream)
         h = ctypes.c_void_p()
         rc = self.lib.fds_ctx_create(ctypes.byref(cfg), ctypes.byref(h))

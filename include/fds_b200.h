@@ -49,7 +49,9 @@ enum {
 
 /* context flags */
 enum {
-    FDS_FLAG_SIMPLE_KERNELS = 1  /* use the one-thread-per-element step kernel (cross-check path) */
+    FDS_FLAG_SIMPLE_KERNELS  = 1, /* use the one-thread-per-element step kernel (cross-check path) */
+    FDS_FLAG_EXTERNAL_STREAM = 2  /* launch on cfg.stream even if it is 0 (the legacy default stream);
+                                     without it a NULL stream means "create my own"                 */
 };
 
 /* device buffers a multi-GPU host may need to address (halo exchange, reductions) */
