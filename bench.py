@@ -237,18 +237,21 @@ def run_ours(args):
     if not args.no_e2e:
         from fds_b200.lsstan import LssTangent
         from fds_b200.checkpoint import Checkpoint
+        # host inputs in page-locked memory (get_* return pinned arrays; global arrays would be
+        # sliced per rank inside the API)
         V, v = eng.ctx.get_tangents()
         u = eng.ctx.get_state()
-        # pinned host buffers (global arrays are sliced per rank inside the API)
-        def pinned(a):
-            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
-            t.numpy()[...] = a
-            return t.numpy()
-        cp = Checkpoint(pinned(u), pinned(V), pinned(v), LssTangent(), [], [], [], [], [])
+        plug = _LocalShardPlugin(run, eng)
+
+        def call():
+            cp = Checkpoint(u, V, v, LssTangent(), [], [], [], [], [])
+            return fds_b200.continue_shadowing(plug, s, cp, args.steps, S, epsilon=eps, return_checkpoint=True)
+
+        out = call()          # untimed: first use allocates the pinned result buffers (recycled afterwards)
+        del out
         barrier()
         t0 = time.perf_counter()
-        out = fds_b200.continue_shadowing(_LocalShardPlugin(run, eng), s, cp, args.steps, S, epsilon=eps,
-                                          return_checkpoint=True)
+        out = call()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], device='cuda', dtype=torch.float64)

@@ -11,7 +11,7 @@ from . import checkpoint
 from . import timeseries
 from .fds import shadowing, continue_shadowing, lss_gradient, lss_gradient_series
 from .plugins import L96
-from ._lib import FdsError
+from ._lib import FdsError, pinned_empty
 
 __all__ = ['shadowing', 'continue_shadowing', 'lss_gradient', 'lss_gradient_series', 'L96',
-           'FdsError', 'checkpoint', 'timeseries', 'lsstan', 'segment', 'timedilation', 'core']
+           'FdsError', 'pinned_empty', 'checkpoint', 'timeseries', 'lsstan', 'segment', 'timedilation', 'core']

@@ -41,6 +41,8 @@ SIGNATURES = {
     'fds_get_state': (_I32, [_CTX, c_double_p]),
     'fds_set_tangents': (_I32, [_CTX, c_double_p, c_double_p]),
     'fds_get_tangents': (_I32, [_CTX, c_double_p, c_double_p]),
+    'fds_host_alloc': (ctypes.c_void_p, [ctypes.c_size_t]),
+    'fds_host_free': (None, [ctypes.c_void_p]),
     'fds_random_tangents': (_I32, [_CTX, ctypes.c_uint64]),
     'fds_set_dxdt_weights': (_I32, [_CTX, c_double_p]),
     'fds_set_time_dilation': (_I32, [_CTX, _I32]),
@@ -98,3 +100,67 @@ def dptr(a):
         return None
     assert a.dtype.name == 'float64' and a.flags['C_CONTIGUOUS']
     return a.ctypes.data_as(c_double_p)
+
+
+# --------------------------------------------------------------------------- #
+# Page-locked host arrays.  Large results (the (m, N) tangent block of a checkpoint)
+# are returned in pinned memory so the device -> host copy runs at PCIe rate;
+# blocks are recycled through a small pool because cudaHostAlloc itself is slow.
+# --------------------------------------------------------------------------- #
+PINNED_MIN_BYTES = 1 << 24      # smaller arrays are ordinary numpy allocations
+_POOL_MAX_FREE = 2              # free blocks kept per size
+_pool = {}
+
+
+class _PinnedBlock:
+    """Owner of one cudaHostAlloc block; exposes it through __array_interface__."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        self.ptr = None
+        free = _pool.get(self.nbytes)
+        self.ptr = free.pop() if free else load().fds_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise FdsError('fds_host_alloc(%d) failed' % self.nbytes)
+
+    def view(self, shape):
+        self.__array_interface__ = {'shape': tuple(int(x) for x in shape), 'typestr': '<f8',
+                                    'data': (int(self.ptr), False), 'version': 3}
+        import numpy as np
+        return np.asarray(self)
+
+    def __del__(self):
+        try:
+            if not self.ptr:
+                return
+            free = _pool.setdefault(self.nbytes, [])
+            if len(free) < _POOL_MAX_FREE:
+                free.append(self.ptr)
+            elif _lib is not None:
+                _lib.fds_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape):
+    """float64 numpy array in page-locked host memory (kept alive by the array's base)."""
+    import numpy as np
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    n = 1
+    for x in shape:
+        n *= int(x)
+    return _PinnedBlock(max(n, 1) * 8).view(shape)
+
+
+def host_empty(shape):
+    """Result buffer: pinned when large, plain numpy otherwise."""
+    import numpy as np
+    n = int(np.prod(shape)) * 8
+    return pinned_empty(shape) if n >= PINNED_MIN_BYTES else np.empty(shape)
+
+
+def pool_release():
+    """Free every pooled pinned block."""
+    for free in _pool.values():
+        while free:
+            load().fds_host_free(free.pop())

@@ -41,8 +41,12 @@ struct fds_ctx {
     double* jnode = nullptr;       // [jsum_cap][plan.nnode][M][2] node partials of the streaming kernel
     double* jnode_scratch = nullptr;
     long long nleaf = 0;
-    double* stage = nullptr;
+    // host <-> device staging of the tangent block: two buffers, a copy stream and events so
+    // that the PCIe transfer of chunk i+1 overlaps the transpose of chunk i
+    double* stage[2] = {nullptr, nullptr};
     long long stage_sites = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     // state machine
     bool state_in_ensemble = false;   // newest primal state is column 0 of the ensemble
     bool tangents_implicit = false;   // newest tangents are (E_k - E_0)/eps_last
@@ -213,13 +217,27 @@ void fds_ctx_destroy(fds_ctx* c) {
     for (int j = 0; j < 2; ++j) cudaFree(c->Ebase[j]);
     for (int j = 0; j < 4; ++j) cudaFree(c->Pbase[j]);
     cudaFree(c->T); cudaFree(c->d); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
-    cudaFree(c->jpart); cudaFree(c->jscratch); cudaFree(c->jsum); cudaFree(c->stage);
+    cudaFree(c->jpart); cudaFree(c->jscratch); cudaFree(c->jsum);
+    for (int j = 0; j < 2; ++j) {
+        cudaFree(c->stage[j]);
+        if (c->ev_copied[j]) cudaEventDestroy(c->ev_copied[j]);
+        if (c->ev_done[j]) cudaEventDestroy(c->ev_done[j]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->jnode); cudaFree(c->jnode_scratch);
     cudaFreeHost(c->A_host);
     for (auto& pe : c->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
+
+// pinned host memory for callers that want full-speed PCIe transfers (any host buffer works)
+void* fds_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void fds_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int fds_sync(fds_ctx* c) {
     FDS_CK(c, cudaStreamSynchronize(c->stream));
@@ -294,9 +312,14 @@ int fds_get_state(fds_ctx* c, double* u) {
 }
 
 static int ensure_stage(fds_ctx* c) {
-    if (c->stage) return 0;
-    c->stage_sites = std::min<long long>(c->n, 1LL << 20);
-    FDS_CK(c, cudaMalloc(&c->stage, (size_t)c->stage_sites * c->MO * sizeof(double)));
+    if (c->stage[0]) return 0;
+    c->stage_sites = std::min<long long>(c->n, 1LL << 18);
+    FDS_CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int j = 0; j < 2; ++j) {
+        FDS_CK(c, cudaMalloc(&c->stage[j], (size_t)c->stage_sites * c->MO * sizeof(double)));
+        FDS_CK(c, cudaEventCreateWithFlags(&c->ev_copied[j], cudaEventDisableTiming));
+        FDS_CK(c, cudaEventCreateWithFlags(&c->ev_done[j], cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -308,20 +331,30 @@ static int materialize_tangents(fds_ctx* c) {
     return 0;
 }
 
+// Host rows V[j][.] (j < m), v[.] -> device T[site][m+1], in chunks of stage_sites sites: the
+// copy stream uploads chunk i+1 while the context's stream transposes chunk i.
 int fds_set_tangents(fds_ctx* c, const double* V, const double* v) {
     if (int r = ensure_stage(c)) return r;
-    for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites) {
+    FDS_CK(c, cudaStreamSynchronize(c->stream));       // T and the stages are free
+    long long i = 0;
+    for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites, ++i) {
+        const int b = (int)(i & 1);
         const long long cnt = std::min(c->stage_sites, c->n - s0);
+        double* stg = c->stage[b];
+        if (i >= 2) FDS_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
         // stage[j][0..cnt) <- V[j][s0..s0+cnt), row m <- v
-        FDS_CK(c, cudaMemcpy2DAsync(c->stage, (size_t)c->stage_sites * sizeof(double), V + s0,
+        FDS_CK(c, cudaMemcpy2DAsync(stg, (size_t)c->stage_sites * sizeof(double), V + s0,
                                     (size_t)c->n * sizeof(double), (size_t)cnt * sizeof(double), c->m,
-                                    cudaMemcpyHostToDevice, c->stream));
-        if (v) FDS_CK(c, cudaMemcpyAsync(c->stage + (size_t)c->m * c->stage_sites, v + s0, (size_t)cnt * sizeof(double),
-                                         cudaMemcpyHostToDevice, c->stream));
-        else FDS_CK(c, cudaMemsetAsync(c->stage + (size_t)c->m * c->stage_sites, 0, (size_t)cnt * sizeof(double), c->stream));
-        FDS_CK(c, launch_transpose_back(c->stage, c->stage_sites, cnt, c->MO, c->T + (size_t)s0 * c->MO, c->stream, &c->ls));
-        FDS_CK(c, cudaStreamSynchronize(c->stream));
+                                    cudaMemcpyHostToDevice, c->copy_stream));
+        if (v) FDS_CK(c, cudaMemcpyAsync(stg + (size_t)c->m * c->stage_sites, v + s0, (size_t)cnt * sizeof(double),
+                                         cudaMemcpyHostToDevice, c->copy_stream));
+        else FDS_CK(c, cudaMemsetAsync(stg + (size_t)c->m * c->stage_sites, 0, (size_t)cnt * sizeof(double), c->copy_stream));
+        FDS_CK(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        FDS_CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+        FDS_CK(c, launch_transpose_back(stg, c->stage_sites, cnt, c->MO, c->T + (size_t)s0 * c->MO, c->stream, &c->ls));
+        FDS_CK(c, cudaEventRecord(c->ev_done[b], c->stream));
     }
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
     c->tangents_implicit = false;
     return 0;
 }
@@ -329,16 +362,24 @@ int fds_set_tangents(fds_ctx* c, const double* V, const double* v) {
 int fds_get_tangents(fds_ctx* c, double* V, double* v) {
     if (int r = materialize_tangents(c)) return r;
     if (int r = ensure_stage(c)) return r;
-    for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites) {
+    long long i = 0;
+    for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites, ++i) {
+        const int b = (int)(i & 1);
         const long long cnt = std::min(c->stage_sites, c->n - s0);
-        FDS_CK(c, launch_transpose(c->T + (size_t)s0 * c->MO, cnt, c->MO, c->stage, c->stage_sites, c->stream, &c->ls));
-        if (V) FDS_CK(c, cudaMemcpy2DAsync(V + s0, (size_t)c->n * sizeof(double), c->stage,
+        double* stg = c->stage[b];
+        if (i >= 2) FDS_CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));   // download of chunk i-2 done
+        FDS_CK(c, launch_transpose(c->T + (size_t)s0 * c->MO, cnt, c->MO, stg, c->stage_sites, c->stream, &c->ls));
+        FDS_CK(c, cudaEventRecord(c->ev_done[b], c->stream));
+        FDS_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        if (V) FDS_CK(c, cudaMemcpy2DAsync(V + s0, (size_t)c->n * sizeof(double), stg,
                                            (size_t)c->stage_sites * sizeof(double), (size_t)cnt * sizeof(double), c->m,
-                                           cudaMemcpyDeviceToHost, c->stream));
-        if (v) FDS_CK(c, cudaMemcpyAsync(v + s0, c->stage + (size_t)c->m * c->stage_sites, (size_t)cnt * sizeof(double),
-                                         cudaMemcpyDeviceToHost, c->stream));
-        FDS_CK(c, cudaStreamSynchronize(c->stream));
+                                           cudaMemcpyDeviceToHost, c->copy_stream));
+        if (v) FDS_CK(c, cudaMemcpyAsync(v + s0, stg + (size_t)c->m * c->stage_sites, (size_t)cnt * sizeof(double),
+                                         cudaMemcpyDeviceToHost, c->copy_stream));
+        FDS_CK(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
     }
+    FDS_CK(c, cudaStreamSynchronize(c->copy_stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 

@@ -85,7 +85,7 @@ class Context:
         self._ck(self.lib.fds_set_state(self.h, dptr(u)))
 
     def get_state(self):
-        u = np.empty(self.n)
+        u = _lib.host_empty((self.n,))
         self._ck(self.lib.fds_get_state(self.h, dptr(u)))
         return u
 
@@ -98,7 +98,7 @@ class Context:
         self._ck(self.lib.fds_set_tangents(self.h, dptr(V), dptr(v)))
 
     def get_tangents(self):
-        V, v = np.empty((self.m, self.n)), np.empty(self.n)
+        V, v = _lib.host_empty((self.m, self.n)), _lib.host_empty((self.n,))
         self._ck(self.lib.fds_get_tangents(self.h, dptr(V), dptr(v)))
         return V, v
 

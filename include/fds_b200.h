@@ -19,6 +19,7 @@
 #ifndef FDS_B200_H
 #define FDS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -90,6 +91,10 @@ int fds_set_state(fds_ctx*, const double* u_host);                 /* [n_local] 
 int fds_get_state(fds_ctx*, double* u_host);
 int fds_set_tangents(fds_ctx*, const double* V_host, const double* v_host); /* [m][n_local], [n_local] */
 int fds_get_tangents(fds_ctx*, double* V_host, double* v_host);
+/* page-locked host memory (cudaHostAlloc) for the buffers above: optional -- any host pointer is
+ * accepted -- but pinned buffers move at full PCIe rate and let uploads overlap the transposes  */
+void* fds_host_alloc(size_t bytes);                                  /* NULL on failure */
+void  fds_host_free(void* p);
 int fds_random_tangents(fds_ctx*, uint64_t seed);  /* uniform[0,1) V (pascal.random, fds/fds.py:23), v = 0 */
 
 /* FD stencil weights of the time-dilation derivative (fds/timedilation.py:16-19 gets them
