@@ -161,6 +161,24 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- #
+def djds_check(device):
+    """Third part of the BASELINE metric: dJ/ds of config 3 (Lorenz-96 N=40, m=16, 100 segments)
+    on the GPU next to the reference's value and its own error bar (committed fixture generated
+    from the reference by oracle/gen_golden.py); pass = ratio <= 1."""
+    import fds_b200
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'cfg3_l96rk4_N40_m16_K100.npz'))
+    np.random.seed(int(g['seed']))
+    run = fds_b200.L96(40, device=device, distributed=False)
+    J, G = fds_b200.shadowing(run, g['u0'], float(g['s']), int(g['m']), int(g['K']), int(g['steps']),
+                              int(g['runup']), epsilon=float(g['eps']))
+    run.close()
+    err = np.abs(G - g['G_ref'])
+    return {'config': 'Lorenz-96 N=40 F=8.1 RK4, m=16, 100 segments x 100 steps (BASELINE configs[2])',
+            'G': G.tolist(), 'G_ref': g['G_ref'].tolist(), 'sigma_ref': g['G_err'].tolist(),
+            'abs_err': err.tolist(), 'ratio': (err / g['G_err']).tolist(),
+            'pass': bool((err <= g['G_err']).all())}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -295,6 +313,7 @@ def run_ours(args):
                 'clocks': clocks, 'gpu_launches': int(launches.item())}
         if e2e is not None:
             line['e2e'] = e2e
+        line['djds'] = djds_check(local_rank)
         if not args.no_cpu and world == 1:
             line['cpu_baseline'] = cpu_baseline(args)
         print(json.dumps(line))

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libfds_b200.so')
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)
 
-FDS_SYS_L96_RK4, FDS_SYS_L96_EULER = 0, 1
+FDS_SYS_L96_RK4, FDS_SYS_L96_EULER, FDS_SYS_LORENZ63, FDS_SYS_VANDERPOL, FDS_SYS_CIRCULAR = range(5)
 FDS_MATH_EXACT, FDS_MATH_FAST = 0, 1
 FDS_FLAG_SIMPLE_KERNELS = 1
 FDS_FLAG_EXTERNAL_STREAM = 2

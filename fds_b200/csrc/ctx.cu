@@ -22,6 +22,7 @@ struct fds_ctx {
     long long alo = 0, ahi = 0;    // allocated site range of ensemble / primal arrays
     StripPlan plan{};              // fixed strip decomposition of the ensemble step kernel
     bool stream_ok = false;
+    bool toy = false;              // small ODE system (toy_ode.cu): no stencil, no halos, J recorded directly
     double* Ebase[2] = {nullptr, nullptr};
     int cur = 0;
     double* Pbase[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -115,7 +116,13 @@ const char* fds_last_error(const fds_ctx* c) { return c ? c->err.c_str() : g_cre
 
 int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
     *out = nullptr;
-    if (!cfg || cfg->m < 1 || cfg->n_local < 4 || cfg->world < 1) { g_create_err = "bad config"; return 2; }
+    if (!cfg || cfg->m < 1 || cfg->world < 1) { g_create_err = "bad config"; return 2; }
+    const int tdim = toy_dim(cfg->system);
+    if (tdim > 0 ? (cfg->n_local != tdim || cfg->world != 1) : cfg->n_local < 4) {
+        g_create_err = tdim > 0 ? "small ODE systems: n_local must equal the state dimension, world = 1"
+                                : "bad config: n_local < 4";
+        return 2;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -125,6 +132,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
     }
     fds_ctx* c = new fds_ctx();
     c->cfg = *cfg;
+    c->toy = tdim > 0;
     if (c->cfg.dt == 0.0) c->cfg.dt = 0.01;
     if (c->cfg.n_global == 0) c->cfg.n_global = cfg->n_local;
     c->m = cfg->m; c->M = cfg->m + 2; c->MO = cfg->m + 1; c->MX = cfg->m + 2;
@@ -390,9 +398,10 @@ int fds_random_tangents(fds_ctx* c, uint64_t seed) {
 }
 
 // ----------------------------------- halos ----------------------------------- //
-int64_t fds_halo_steps(const fds_ctx* c, int64_t steps) { return std::min<long long>(steps, c->H); }
+int64_t fds_halo_steps(const fds_ctx* c, int64_t steps) { return c->toy ? steps : std::min<long long>(steps, c->H); }
 
 int fds_halo_wrap_ensemble(fds_ctx* c, int64_t hs) {
+    if (c->toy) { c->ens_halo_valid = hs; return 0; }
     if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_ensemble: world > 1, exchange halos between ranks instead");
     if (hs < 1 || hs > c->H) return fail(c, "halo_steps out of range");
     FDS_CK(c, launch_halo_wrap(c->Ecur(), c->M, c->n, 8 * hs, 4 * hs, c->stream, &c->ls));
@@ -401,6 +410,7 @@ int fds_halo_wrap_ensemble(fds_ctx* c, int64_t hs) {
 }
 
 int fds_halo_wrap_primal(fds_ctx* c, int64_t hs) {
+    if (c->toy) { c->pri_halo_valid = hs; return 0; }
     if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_primal: world > 1, exchange halos between ranks instead");
     if (hs < 1 || hs > c->H) return fail(c, "halo_steps out of range");
     FDS_CK(c, launch_halo_wrap(c->P(0), 1, c->n, 8 * hs, 4 * hs, c->stream, &c->ls));
@@ -502,6 +512,11 @@ static int reduce_nodes(fds_ctx* c, long long step0, long long nsteps) {
 int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int record) {
     if (int r = sync_primal_from_ensemble(c)) return r;
     if (record) if (int r = ensure_jsum(c, step0 + nsteps)) return r;
+    if (c->toy) {
+        FDS_CK(c, launch_toy_advance(c->cfg.system, c->cfg.math == FDS_MATH_EXACT, c->P(0), c->P(0), 1, nsteps, s, s,
+                                     record ? c->jsum + (size_t)step0 * 2 : nullptr, c->stream, &c->ls));
+        return 0;
+    }
     const double F = s + 8.0;
     for (long long j = 0; j < nsteps; ++j) {
         if (c->pri_halo_valid < 1) return fail(c, "fds_primal_advance: primal halo exhausted; refresh it first");
@@ -526,7 +541,7 @@ int fds_run(fds_ctx* c, double s, int64_t steps, double* Jsum_host) {
     if (c->cfg.world != 1) return fail(c, "fds_run: world > 1, drive fds_primal_advance with halo exchanges");
     if (int r = sync_primal_from_ensemble(c)) return r;
     for (long long t = 0; t < steps;) {
-        const long long hs = std::min<long long>(c->H, steps - t);
+        const long long hs = fds_halo_steps(c, steps - t);
         if (int r = fds_halo_wrap_primal(c, hs)) return r;
         if (int r = fds_primal_advance(c, s, t, hs, Jsum_host != nullptr)) return r;
         t += hs;
@@ -539,6 +554,15 @@ int fds_run(fds_ctx* c, double s, int64_t steps, double* Jsum_host) {
 
 int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t nsteps) {
     if (int r = ensure_jsum(c, step0 + nsteps)) return r;
+    if (c->toy) {
+        // all nsteps in one launch, in place; column m+1 runs at parameter + epsilon (fds/segment.py:64)
+        FDS_CK(c, launch_toy_advance(c->cfg.system, c->cfg.math == FDS_MATH_EXACT, c->Ecur(), c->Ecur(), c->M, nsteps,
+                                     s, s + eps, c->jsum + (size_t)step0 * c->M * 2, c->stream, &c->ls));
+        c->state_in_ensemble = true;
+        c->tangents_implicit = true;
+        c->eps_last = eps;
+        return 0;
+    }
     const double F0 = s + 8.0, Flast = (s + eps) + 8.0;   // fds/segment.py:64: parameter + epsilon
     for (long long j = 0; j < nsteps; ++j) {
         if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
@@ -563,7 +587,7 @@ int fds_segment_jsums(fds_ctx* c, int64_t steps, double* out) {
 int fds_segment(fds_ctx* c, double s, double eps, int64_t steps, double* Jsum_host) {
     if (c->cfg.world != 1) return fail(c, "fds_segment: world > 1, drive fds_segment_advance with halo exchanges");
     for (long long t = 0; t < steps;) {
-        const long long hs = std::min<long long>(c->H, steps - t);
+        const long long hs = fds_halo_steps(c, steps - t);
         if (int r = fds_halo_wrap_ensemble(c, hs)) return r;
         if (int r = fds_segment_advance(c, s, eps, t, hs)) return r;
         t += hs;
@@ -584,7 +608,12 @@ int fds_boundary_begin(fds_ctx* c, int from_ensemble) {
 }
 
 int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
-    if (c->time_dilation) {
+    if (c->time_dilation && c->toy) {
+        for (int j = 1; j <= 3; ++j)
+            FDS_CK(c, launch_toy_advance(c->cfg.system, c->cfg.math == FDS_MATH_EXACT, c->P(j - 1), c->P(j), 1, 1, s, s,
+                                         nullptr, c->stream, &c->ls));
+        FDS_CK(c, launch_dxdt(c->P(0), c->P(1), c->P(2), c->P(3), c->c4, c->d, c->n, c->stream, &c->ls));
+    } else if (c->time_dilation) {
         if (c->pri_halo_valid < 3) return fail(c, "fds_boundary_dxdt: primal halo must be valid for 3 steps");
         const double F = s + 8.0;
         long long valid = 3;

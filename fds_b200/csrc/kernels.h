@@ -96,6 +96,13 @@ cudaError_t launch_apply_fast(int src, const double* E, const double* Tin, const
                               int m, double inv_eps, long long n, double* Tout, double* E_out, const double* u,
                               double eps, int num_sms, cudaStream_t, LaunchStats*);
 
+// ---- toy_ode.cu -------------------------------------------------------------- //
+// small ODE systems (Lorenz-63, Van der Pol, circular): state dimension, 0 for the L96 systems
+int toy_dim(int system);
+// X, Y: [dim][M] (may alias); all nsteps in one launch; jout: [nsteps][M][2] objective values or nullptr
+cudaError_t launch_toy_advance(int system, int exact, const double* X, double* Y, int M, long long nsteps,
+                               double s0, double s_last, double* jout, cudaStream_t st, LaunchStats* ls);
+
 // ---- lss.cu ----------------------------------------------------------------- //
 // R[K][m][m], b[K][m] (device) -> alpha[K][m] (device); work: (2*m*m + 2*m) * K doubles
 cudaError_t launch_lss_solve(const double* R, const double* b, long long K, int m, double* alpha,

@@ -13,7 +13,11 @@ import numpy as np
 from . import _lib
 from ._lib import FdsError, dptr
 
-SYSTEMS = {'rk4': _lib.FDS_SYS_L96_RK4, 'euler': _lib.FDS_SYS_L96_EULER}
+SYSTEMS = {'rk4': _lib.FDS_SYS_L96_RK4, 'euler': _lib.FDS_SYS_L96_EULER,
+           'lorenz63': _lib.FDS_SYS_LORENZ63, 'vanderpol': _lib.FDS_SYS_VANDERPOL,
+           'circular': _lib.FDS_SYS_CIRCULAR}
+# small ODE systems: (state dimension, n_qoi); their objective is recorded directly
+TOY_SYSTEMS = {'lorenz63': (3, 2), 'vanderpol': (2, 1), 'circular': (2, 1)}
 MATH = {'exact': _lib.FDS_MATH_EXACT, 'fast': _lib.FDS_MATH_FAST}
 
 

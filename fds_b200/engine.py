@@ -10,7 +10,7 @@ fds/segment.py:43-79).
 import numpy as np
 
 from . import _lib
-from .device import Context
+from .device import Context, TOY_SYSTEMS
 from .ring import Ring, shard_range
 
 
@@ -28,6 +28,12 @@ class Engine:
         self.n_global = int(n_global)
         self.m = int(m)
         self.M = self.m + 2
+        # Lorenz-96: the device returns SUMS over sites of [x, x^2] -> divide by N;
+        # small ODE systems: objective values as they are, n_qoi of the 2 slots used
+        self.j_div = 1.0 if scheme in TOY_SYSTEMS else float(self.n_global)
+        self.n_qoi = TOY_SYSTEMS[scheme][1] if scheme in TOY_SYSTEMS else 2
+        if scheme in TOY_SYSTEMS:
+            distributed = False
         self.ring = None
         self.torch = None
         if distributed is None:
@@ -111,7 +117,7 @@ class Engine:
             if want_J and steps > 0:
                 part = self._view(_lib.FDS_BUF_JSUM, 0, steps * 2).clone()
                 Js = self.ring.ordered_sum(part).reshape(steps, 2)
-        return None if Js is None else Js / self.n_global
+        return None if Js is None else Js[:, :self.n_qoi] / self.j_div
 
     # -- one boundary ----------------------------------------------------------- #
     def boundary(self, s, eps, from_ensemble, do_qr, build, keep_tangents=True):
@@ -146,7 +152,7 @@ class Engine:
         else:
             part = self._view(_lib.FDS_BUF_JSUM, 0, steps * self.M * 2).clone()
             Js = self.ring.ordered_sum(part).reshape(steps, self.M, 2)
-        return Js / self.n_global
+        return Js[:, :, :self.n_qoi] / self.j_div
 
     # -- state in / out (global host arrays) ------------------------------------ #
     def set_state(self, u):

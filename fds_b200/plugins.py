@@ -12,22 +12,14 @@ import numpy as np
 from .engine import Engine
 
 
-class L96:
-    """Lorenz-96 ring, ``dx_i/dt = (x_{i+1} - x_{i-2}) x_{i-1} - x_i + F``, ``F = s + 8``,
-    ``J = [mean x, mean x^2]`` -- the reference's own Lorenz-96 test solver
-    (tests/solvers/mock_fun3d/fun3d:39-57) with ``scheme='euler'``, and the classical
-    RK4 integrator of the north-star configuration with ``scheme='rk4'``.
-
-    math='exact': FMA-free, numpy operation order (bit-identical to oracle/plugins.py);
-    math='fast' : FMA contraction allowed.
-    """
+class _DevicePlugin:
+    """Common part of the device solver plugins: engines cached per subspace dimension, the
+    reference ``run`` call on host arrays, picklability (the reference's pool, fds/segment.py:37)."""
     n_qoi = 2
 
-    def __init__(self, N, scheme='rk4', dt=0.01, math='exact', device=None, group=None,
-                 max_halo_steps=0, simple_kernels=False, stream=None):
+    def _init(self, N, **kw):
         self.N = int(N)
-        self.kw = dict(scheme=scheme, math=math, dt=dt, device=device, group=group,
-                       max_halo_steps=max_halo_steps, simple_kernels=simple_kernels, stream=stream)
+        self.kw = kw
         self._engines = {}
 
     def engine(self, m):
@@ -41,13 +33,59 @@ class L96:
         eng.set_state(u0)
         J = eng.run(parameter, steps, want_J=True)
         if J is None:
-            J = np.empty((0, 2))
+            J = np.empty((0, self.n_qoi))
         return eng.get_state(), J
 
-    def __getstate__(self):          # picklable, as the reference's pool requires
+    def __getstate__(self):
         return {'N': self.N, 'kw': self.kw, '_engines': {}}
 
     def close(self):
         for e in self._engines.values():
             e.close()
         self._engines = {}
+
+
+class Lorenz63(_DevicePlugin):
+    """Lorenz-63, forward Euler dt = float32(0.001), parameters (10, s, 8/3),
+    ``J = [(z - 28)^2, 100]`` -- the reference's tests/solvers/lorenz/lorenz.f03:10-26 as
+    driven by tests/test_lorenz.py:18-31 (BASELINE config 1)."""
+    n_qoi = 2
+
+    def __init__(self, math='exact', device=None):
+        self._init(3, scheme='lorenz63', math=math, device=device)
+
+
+class VanDerPol(_DevicePlugin):
+    """Van der Pol oscillator, forward Euler dt = float32(0.01), ``J = x0^2`` -- the
+    reference's tests/solvers/vanderpol/vanderpol.f03:9-24 (BASELINE config 2)."""
+    n_qoi = 1
+
+    def __init__(self, math='exact', device=None):
+        self._init(2, scheme='vanderpol', math=math, device=device)
+
+
+class Circular(_DevicePlugin):
+    """Limit cycle of radius sqrt(s + 1), forward Euler dt = float32(0.001),
+    ``J = x0^2 + x1^2`` -- the reference's tests/solvers/circular/circular.f03:9-28."""
+    n_qoi = 1
+
+    def __init__(self, math='exact', device=None):
+        self._init(2, scheme='circular', math=math, device=device)
+
+
+class L96(_DevicePlugin):
+    """Lorenz-96 ring, ``dx_i/dt = (x_{i+1} - x_{i-2}) x_{i-1} - x_i + F``, ``F = s + 8``,
+    ``J = [mean x, mean x^2]`` -- the reference's own Lorenz-96 test solver
+    (tests/solvers/mock_fun3d/fun3d:39-57) with ``scheme='euler'``, and the classical
+    RK4 integrator of the north-star configuration with ``scheme='rk4'``.
+
+    math='exact': FMA-free, numpy operation order (bit-identical to oracle/plugins.py);
+    math='fast' : FMA contraction allowed.
+    """
+    n_qoi = 2
+
+    def __init__(self, N, scheme='rk4', dt=0.01, math='exact', device=None, group=None,
+                 max_halo_steps=0, simple_kernels=False, stream=None, distributed=None):
+        self._init(N, scheme=scheme, math=math, dt=dt, device=device, group=group,
+                   max_halo_steps=max_halo_steps, simple_kernels=simple_kernels, stream=stream,
+                   distributed=distributed)

@@ -33,5 +33,5 @@ def run_segment(run, u0, V, v, parameter, i_segment, steps, epsilon,
     V = np.asarray(V)
     eng = run.engine(V.shape[0])
     u1, V1, v1, Js = eng.ctx.run_segment_host(u0, V, v, parameter, epsilon, steps)
-    J0, G, g = sensitivities(Js / eng.n_global, epsilon)
+    J0, G, g = sensitivities(Js[:, :, :eng.n_qoi] / eng.j_div, epsilon)
     return u1, V1, v1, J0, G, g

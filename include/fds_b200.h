@@ -31,7 +31,13 @@ typedef struct fds_ctx fds_ctx;
 /* solver "systems" (the plugin on the far side of run(), fds/fds.py:184-200) */
 enum {
     FDS_SYS_L96_RK4   = 0, /* Lorenz-96, classical RK4, dt, F = s + 8            */
-    FDS_SYS_L96_EULER = 1  /* Lorenz-96, forward Euler: tests/solvers/mock_fun3d/fun3d:48-57 */
+    FDS_SYS_L96_EULER = 1, /* Lorenz-96, forward Euler: tests/solvers/mock_fun3d/fun3d:48-57 */
+    /* small ODE systems of the reference test-suite (world = 1, n_local = state dimension);
+     * their objective is recorded directly, not as sums over sites:                          */
+    FDS_SYS_LORENZ63  = 2, /* n = 3, J = [(z-28)^2, 100]: tests/solvers/lorenz/lorenz.f03:10-26,
+                              tests/test_lorenz.py:18-31                                     */
+    FDS_SYS_VANDERPOL = 3, /* n = 2, J = [x0^2, -]: tests/solvers/vanderpol/vanderpol.f03:9-24 */
+    FDS_SYS_CIRCULAR  = 4  /* n = 2, J = [x0^2+x1^2, -]: tests/solvers/circular/circular.f03:9-28 */
 };
 
 /* arithmetic modes */

@@ -1,0 +1,106 @@
+"""BASELINE configs 1-2 (Lorenz-63 m=2, Van der Pol m=1) and the reference's circular
+limit cycle through the device path: device solver plugins for the small ODE systems
+(fds_b200/csrc/toy_ode.cu) + the same boundary / LSS kernels as the Lorenz-96 path,
+against the reference's own outputs (tests/golden, oracle/gen_golden.py) and the
+reference test-suite's acceptance windows."""
+import numpy as np
+import pytest
+
+import fds_b200
+from oracle import plugins
+from conftest import golden
+
+gpu = pytest.mark.gpu
+
+
+def maxrel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@gpu
+@pytest.mark.parametrize('cls,oracle_run,u0,s,bitwise', [
+    (fds_b200.Lorenz63, plugins.run_lorenz63, [1.0, 2.0, 25.0], 28.0, True),
+    (fds_b200.Circular, plugins.run_circular, [1.0, 0.5], 1.0, True),
+    # the oracle's x0 ** 2 is libm pow(), not a correctly rounded product: close, not identical
+    (fds_b200.VanDerPol, plugins.run_vanderpol, [1.0, 1.0], 4.0, False)])
+def test_plugin_run_contract(cls, oracle_run, u0, s, bitwise):
+    """u1, J = run(u0, s, steps) on host arrays (reference fds/fds.py:184-200)."""
+    run = cls()
+    u0 = np.array(u0)
+    for steps in (1, 3, 500):
+        u1, J = run(u0, s, steps)
+        ru1, rJ = oracle_run(u0, s, steps)
+        assert J.shape == rJ.shape == (steps, run.n_qoi)
+        if bitwise:
+            assert np.array_equal(u1, ru1) and np.array_equal(J, rJ)
+        else:
+            assert maxrel(u1, ru1) < 1e-11 and maxrel(J, rJ) < 1e-11
+
+
+def run_fixture(cls, name, **kw):
+    g = golden(name)
+    np.random.seed(int(g['seed']))
+    cp = fds_b200.shadowing(cls(), g['u0'], float(g['s']), int(g['m']), int(g['K']), int(g['steps']),
+                            int(g['runup']), epsilon=float(g['eps']), return_checkpoint=True, **kw)
+    return g, cp
+
+
+@gpu
+def test_cfg1_lorenz63_m2_20_segments():
+    """BASELINE configs[0]: reference tests/test_lorenz.py:34-67."""
+    g, cp = run_fixture(fds_b200.Lorenz63, 'cfg1_lorenz63_m2_K20')
+    J = np.array(cp.J)
+    assert J.shape == (20, 1000, 2)
+    assert np.array_equal(J[0], g['J'][0])                 # first segment of the primal: same bits
+    Jm, G = J.mean((0, 1)), fds_b200.lss_gradient(cp)
+    # second objective is the constant 100: exact mean, zero sensitivity (test_lorenz.py:44-45)
+    assert abs(Jm[1] - 100) < 1e-12 and abs(G[1]) < 1e-12
+    # the reference's windows at rho = 28 (test_lorenz.py:42-43)
+    assert abs(Jm[0] - ((28 - 31) ** 2 + 85)) < 20 and abs(G[0] - 2 * (28 - 31)) < 2
+    # same seed, same tangents: chaos amplifies rounding by e^(0.9 * 20) over the run
+    assert maxrel(Jm, g['J_ref']) < 1e-6
+    assert abs(G[0] - g['G_ref'][0]) < 1e-3 * abs(g['G_ref'][0])
+    # Lyapunov exponents from R (test_lorenz.py:65-67)
+    L = cp.lss.lyapunov_exponents().mean(0) / (1000 * 0.001)
+    assert 0.5 < L[0] < 1.5 and -15 < L[1] < -5
+    Lr = np.log(np.abs(np.diagonal(g['Rs'], axis1=1, axis2=2))).mean(0) / (1000 * 0.001)
+    # the strongly contracting direction (-14.5) is resolved by finite differences at eps = 1e-6
+    # down to e^-14.5 of the perturbation: it carries the FD noise
+    assert abs(L[0] - Lr[0]) < 1e-5 and abs(L[1] - Lr[1]) < 1e-3 * abs(Lr[1])
+
+
+@gpu
+def test_cfg2_vanderpol_m1():
+    """BASELINE configs[1]: reference tests/test_vanderpol.py:33-36."""
+    g, cp = run_fixture(fds_b200.VanDerPol, 'cfg2_vanderpol_m1_K20')
+    J = np.array(cp.J)
+    assert J.shape == (int(g['K']), int(g['steps']), 1)
+    Jm, G = J.mean((0, 1)), fds_b200.lss_gradient(cp)
+    assert 1.5 < Jm[0] < 2.5 and 0.025 < G[0] < 0.035
+    assert maxrel(Jm, g['J_ref']) < 1e-9 and maxrel(G, g['G_ref']) < 1e-6
+    assert maxrel(J[:, -1], g['J_last']) < 1e-9
+
+
+@gpu
+def test_circular_analytic():
+    """reference tests/test_circular.py:33-42: J = s + 1, dJ/ds = 1."""
+    g, cp = run_fixture(fds_b200.Circular, 'circular_m1_K5')
+    J = np.array(cp.J)
+    assert np.array_equal(J[0], g['J'][0])
+    Jm, G = J.mean((0, 1)), fds_b200.lss_gradient(cp)
+    assert abs(Jm[0] - 2) < 1e-3 and abs(G[0] - 1) < 0.01
+    assert maxrel(Jm, g['J_ref']) < 1e-9 and maxrel(G, g['G_ref']) < 1e-6
+
+
+@gpu
+def test_toy_restart_equivalence():
+    """reference tests/test_restart.py:42-64 on its own solver (circular): 10 + 10 == 20."""
+    u0 = np.array([1.0, 0.5])
+    run = fds_b200.Circular()
+    np.random.seed(0)
+    cp = fds_b200.shadowing(run, u0, 1.0, 1, 10, 100, 0, return_checkpoint=True)
+    J2, G2 = fds_b200.continue_shadowing(run, 1.0, cp, 20, 100)
+    np.random.seed(0)
+    J1, G1 = fds_b200.shadowing(run, u0, 1.0, 1, 20, 100, 0)
+    assert np.array_equal(J1, J2) and np.allclose(G1, G2)
