@@ -72,10 +72,14 @@ struct StreamProducer {
     }
 };
 
+// MC = number of columns when known at compile time (every p*M offset becomes an immediate),
+// 0 = use the run-time value
+template <int MC>
 struct StreamIO {
     const double* sdata;     // this thread's (run, column) slot in stage 0
     int stage_stride;        // doubles per stage
     int M;
+    FDS_D int cols() const { return MC > 0 ? MC : M; }
     int nstages;
     uint64_t* full;
     uint64_t* empty;
@@ -95,25 +99,25 @@ struct StreamIO {
         mbar_wait(&full[st], par);
         cur = sdata + (size_t)st * stage_stride;
     }
-    FDS_D double load(int p) const { return cur[p * M]; }
-    FDS_D void store(int p, double v) { yrow[p * M] = v; }
+    FDS_D double load(int p) const { return cur[p * cols()]; }
+    FDS_D void store(int p, double v) { yrow[p * cols()] = v; }
     FDS_D void end_block(int) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
         if (prod != nullptr) prod->issue_next();
         if (++st == nstages) { st = 0; par ^= 1u; }
-        yrow += 8 * M;
+        yrow += 8 * cols();
     }
     FDS_D void emit_node(long long node, double s1, double s2) {
         if (jp != nullptr && node >= 0 && node < nnode)
-            *reinterpret_cast<double2*>(jp + node * (2LL * M)) = make_double2(s1, s2);
+            *reinterpret_cast<double2*>(jp + node * (2LL * cols())) = make_double2(s1, s2);
     }
     FDS_D double ns_get(int l, int q) const { return nsm[(2 * l + q) * nthr]; }
     FDS_D void ns_put(int l, int q, double v) { nsm[(2 * l + q) * nthr] = v; }
     FDS_D bool all(bool v) const { return __all_sync(0xffffffffu, v); }
 };
 
-template <class MP>
+template <class MP, int MC, bool STATS>
 __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -169,7 +173,7 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     g.stats = p.jpart != nullptr;
     g.node_shift = p.node_shift;
 
-    StreamIO io;
+    StreamIO<MC> io;
     io.sdata = sdata + r * p.run_stride + k;
     io.stage_stride = stage_stride;
     io.M = p.M;
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     io.cur = io.sdata;
 
     const double F = (k == p.M - 1) ? p.Flast : p.F0;
-    l96_rk4_march<MP>(io, g, F, p.c);
+    l96_rk4_march_t<MP, STATS>(io, g, F, p.c);
 }
 
 // 16 warps per CTA (4 per scheduler, so each thread can hold up to 128 registers), all of
@@ -229,16 +233,25 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = (int)((plan.nstrips + p.R - 1) / p.R);
     const size_t smem = 128 + ns_bytes + stage_bytes * nst;
-    cudaError_t e;
-    if (a.exact) {
-        e = cudaFuncSetAttribute(l96_rk4_stream_kernel<ExactMath>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        l96_rk4_stream_kernel<ExactMath><<<grid, block, smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(l96_rk4_stream_kernel<FastMath>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        l96_rk4_stream_kernel<FastMath><<<grid, block, smem, st>>>(p);
-    }
+    cudaError_t e = cudaSuccess;
+#define FDS_STREAM_LAUNCH(MP, MC, ST)                                                                          \
+    do {                                                                                                       \
+        e = cudaFuncSetAttribute(l96_rk4_stream_kernel<MP, MC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                                   \
+        if (e != cudaSuccess) return e;                                                                        \
+        l96_rk4_stream_kernel<MP, MC, ST><<<grid, block, smem, st>>>(p);                                       \
+    } while (0)
+#define FDS_STREAM_MC(MP, ST)                                      \
+    do {                                                           \
+        if (a.M == 34) FDS_STREAM_LAUNCH(MP, 34, ST);              \
+        else if (a.M == 18) FDS_STREAM_LAUNCH(MP, 18, ST);         \
+        else FDS_STREAM_LAUNCH(MP, 0, ST);                         \
+    } while (0)
+    const bool stats = p.jpart != nullptr;
+    if (a.exact) { if (stats) FDS_STREAM_MC(ExactMath, true); else FDS_STREAM_MC(ExactMath, false); }
+    else         { if (stats) FDS_STREAM_MC(FastMath, true);  else FDS_STREAM_MC(FastMath, false); }
+#undef FDS_STREAM_MC
+#undef FDS_STREAM_LAUNCH
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
