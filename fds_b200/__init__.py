@@ -9,9 +9,9 @@ from . import timedilation
 from . import segment
 from . import checkpoint
 from . import timeseries
-from .fds import shadowing, continue_shadowing, lss_gradient, lss_gradient_series
+from .fds import shadowing, continue_shadowing, lss_gradient, lss_gradient_series, shadowing_batch
 from .plugins import L96, Lorenz63, VanDerPol, Circular
 from ._lib import FdsError, pinned_empty
 
-__all__ = ['shadowing', 'continue_shadowing', 'lss_gradient', 'lss_gradient_series', 'L96', 'Lorenz63', 'VanDerPol', 'Circular',
+__all__ = ['shadowing', 'continue_shadowing', 'lss_gradient', 'lss_gradient_series', 'shadowing_batch', 'L96', 'Lorenz63', 'VanDerPol', 'Circular',
            'FdsError', 'pinned_empty', 'checkpoint', 'timeseries', 'lsstan', 'segment', 'timedilation', 'core']

@@ -26,7 +26,7 @@ class FdsConfig(ctypes.Structure):
                 ('m', ctypes.c_int32), ('n_local', ctypes.c_int64), ('n_global', ctypes.c_int64),
                 ('site_offset', ctypes.c_int64), ('rank', ctypes.c_int32), ('world', ctypes.c_int32),
                 ('max_halo_steps', ctypes.c_int32), ('flags', ctypes.c_int32), ('dt', ctypes.c_double),
-                ('stream', ctypes.c_void_p)]
+                ('stream', ctypes.c_void_p), ('batch', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol the header declares
@@ -64,6 +64,9 @@ SIGNATURES = {
     'fds_segment': (_I32, [_CTX, _D, _D, _I64, c_double_p]),
     'fds_run_segment_host': (_I32, [_CTX, c_double_p, c_double_p, c_double_p, _D, _D, _I64, c_double_p]),
     'fds_lss_solve': (_I32, [_I32, c_double_p, c_double_p, _I64, _I32, c_double_p]),
+    'fds_lss_solve_batch': (_I32, [_I32, c_double_p, c_double_p, _I64, _I32, _I64, c_double_p]),
+    'fds_set_batch_params': (_I32, [_CTX, c_double_p]),
+    'fds_batch_count': (_I32, [_CTX]),
     'fds_buffer_ptr': (ctypes.c_void_p, [_CTX, _I32]),
     'fds_kernel_launches': (_I64, [_CTX]),
     'fds_sync': (_I32, [_CTX]),

@@ -169,9 +169,15 @@ constexpr int kGramTile = 32;   // sites staged per iteration
 template <int SRC>
 __global__ void __launch_bounds__(1024) gram_kernel(const double* __restrict__ E, const double* __restrict__ T,
                                                     const double* __restrict__ d, int m, double inv_eps, long long n,
-                                                    int MXP, int nb, int GS, int NG, double* __restrict__ part) {
+                                                    int MXP, int nb, int GS, int NG, double* __restrict__ part,
+                                                    BatchDesc bd) {
     extern __shared__ __align__(16) double sm[];      // Xs[kGramTile][MXP], then reduction scratch
     const int MX = m + 2, M = m + 2, MO = m + 1;
+    {   // problem blockIdx.y of a batch
+        const size_t off = (size_t)blockIdx.y * bd.slot;
+        E += off * M; T += off * MO; d += off;
+        part += (size_t)blockIdx.y * bd.part_stride;
+    }
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int grp = tid / GS, lane = tid % GS;
     const int npair = nb * (nb + 1) / 2;
@@ -249,9 +255,12 @@ __global__ void __launch_bounds__(1024) gram_kernel(const double* __restrict__ E
     }
 }
 
-__global__ void sum_partials_kernel(const double* __restrict__ part, int nparts, int len, double* __restrict__ out) {
+__global__ void sum_partials_kernel(const double* __restrict__ part, int nparts, int len, double* __restrict__ out,
+                                    BatchDesc bd) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= len) return;
+    part += (size_t)blockIdx.y * bd.part_stride;
+    out += (size_t)blockIdx.y * bd.small_stride;
     double s = 0.0;
     for (int p = 0; p < nparts; ++p) s += part[(size_t)p * len + e];
     out[e] = s;
@@ -259,7 +268,9 @@ __global__ void sum_partials_kernel(const double* __restrict__ part, int nparts,
 
 cudaError_t launch_gram(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
                         long long n, double* part, int max_part, double* out, int num_sms, cudaStream_t st,
-                        LaunchStats* ls) {
+                        LaunchStats* ls, const BatchDesc* batch) {
+    BatchDesc bd;
+    if (batch) bd = *batch;
     const int MX = m + 2;
     const int MXP = (MX + 3) / 4 * 4;
     const int nb = MXP / 4;
@@ -271,22 +282,23 @@ cudaError_t launch_gram(int src, const double* E, const double* T, const double*
     const long long ntiles = (n + kGramTile - 1) / kGramTile;
     int grid = (int)std::min<long long>(ntiles, std::min(max_part, 2 * num_sms));
     if (grid < 1) grid = 1;
+    const dim3 grid2((unsigned)grid, (unsigned)bd.count);
     const size_t smem = sizeof(double) * std::max((size_t)kGramTile * MXP, (size_t)NG * npair * 16);
     cudaError_t e;
     if (src == SRC_ENSEMBLE) {
         e = cudaFuncSetAttribute(gram_kernel<SRC_ENSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gram_kernel<SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, T, d, m, inv_eps, n, MXP, nb, GS, NG, part);
+        gram_kernel<SRC_ENSEMBLE><<<grid2, block, smem, st>>>(E, T, d, m, inv_eps, n, MXP, nb, GS, NG, part, bd);
     } else {
         e = cudaFuncSetAttribute(gram_kernel<SRC_TANGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gram_kernel<SRC_TANGENT><<<grid, block, smem, st>>>(E, T, d, m, inv_eps, n, MXP, nb, GS, NG, part);
+        gram_kernel<SRC_TANGENT><<<grid2, block, smem, st>>>(E, T, d, m, inv_eps, n, MXP, nb, GS, NG, part, bd);
     }
     if (ls) ls->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int len = MX * MX;
-    sum_partials_kernel<<<(len + 255) / 256, 256, 0, st>>>(part, grid, len, out);
+    sum_partials_kernel<<<dim3((len + 255) / 256, bd.count), 256, 0, st>>>(part, grid, len, out, bd);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
@@ -300,9 +312,16 @@ template <int SRC>
 __global__ void __launch_bounds__(512) apply_kernel(const double* __restrict__ E, const double* Tin,
                                                     const double* __restrict__ d, const double* __restrict__ A, int m,
                                                     double inv_eps, long long n, double* Tout, double* E_out,
-                                                    const double* __restrict__ u, double eps, int MOP) {
+                                                    const double* __restrict__ u, double eps, int MOP, BatchDesc bd) {
     extern __shared__ __align__(16) double sm[];
     const int MX = m + 2, M = m + 2, MO = m + 1;
+    {   // problem blockIdx.y of a batch
+        const size_t off = (size_t)blockIdx.y * bd.slot;
+        E += off * M; Tin += off * MO; Tout += off * MO;
+        if (d != nullptr) d += off;
+        if (E_out != nullptr) { E_out += off * M; u += off; }
+        A += (size_t)blockIdx.y * bd.small_stride;
+    }
     double* At = sm;                         // [MX][MOP]
     double* Xt = sm + (size_t)MX * MOP;      // [MX][kApplyTile]
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -370,24 +389,26 @@ __global__ void __launch_bounds__(512) apply_kernel(const double* __restrict__ E
 
 cudaError_t launch_apply(int src, const double* E, const double* Tin, const double* d, const double* A, int m,
                          double inv_eps, long long n, double* Tout, double* E_out, const double* u, double eps,
-                         cudaStream_t st, LaunchStats* ls) {
+                         cudaStream_t st, LaunchStats* ls, const BatchDesc* batch) {
+    BatchDesc bd;
+    if (batch) bd = *batch;
     const int MX = m + 2, MO = m + 1;
     const int MOP = (MO + 3) / 4 * 4;
     const int nob = MOP / 4, nsb = kApplyTile / 4;
     int block = (nob * nsb + 31) / 32 * 32;
     if (block > 512) return cudaErrorInvalidValue;
     const long long ntiles = (n + kApplyTile - 1) / kApplyTile;
-    const int grid = (int)std::min<long long>(ntiles, 148 * 8);
+    const dim3 grid((unsigned)std::min<long long>(ntiles, bd.count > 1 ? 8 : 148 * 8), (unsigned)bd.count);
     const size_t smem = sizeof(double) * ((size_t)MX * MOP + (size_t)MX * kApplyTile);
     cudaError_t e;
     if (src == SRC_ENSEMBLE) {
         e = cudaFuncSetAttribute(apply_kernel<SRC_ENSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        apply_kernel<SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, Tin, d, A, m, inv_eps, n, Tout, E_out, u, eps, MOP);
+        apply_kernel<SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, Tin, d, A, m, inv_eps, n, Tout, E_out, u, eps, MOP, bd);
     } else {
         e = cudaFuncSetAttribute(apply_kernel<SRC_TANGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        apply_kernel<SRC_TANGENT><<<grid, block, smem, st>>>(E, Tin, d, A, m, inv_eps, n, Tout, E_out, u, eps, MOP);
+        apply_kernel<SRC_TANGENT><<<grid, block, smem, st>>>(E, Tin, d, A, m, inv_eps, n, Tout, E_out, u, eps, MOP, bd);
     }
     if (ls) ls->launches++;
     return cudaGetLastError();
@@ -436,8 +457,17 @@ size_t small_smem_bytes(int m) {
     return sizeof(double) * ((size_t)MX * MX + 2 * (size_t)m * m + 2 * MX) + 16;
 }
 
+// SmallBufs of problem p of a batch
+FDS_D SmallBufs small_of(SmallBufs B, long long stride, int p) {
+    const size_t o = (size_t)p * stride;
+    B.gram += o; B.A += o; B.L1 += o; B.R += o; B.b += o; B.gdil += o;
+    B.status = reinterpret_cast<int*>(reinterpret_cast<double*>(B.status) + o);
+    return B;
+}
+
 // pass 1: G_dil/g_dil, projection, (optionally) first Cholesky factor; builds A1
-__global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use_d, int do_qr) {
+__global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use_d, int do_qr, long long bstride) {
+    B = small_of(B, bstride, blockIdx.x);
     extern __shared__ __align__(16) double sm[];
     const int MX = m + 2, MO = m + 1, D = m + 1;
     double* G = sm;                      // MX*MX
@@ -497,7 +527,8 @@ __global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use
 }
 
 // pass 2: second Cholesky factor on the Gram of [Q1; p_w], b, R = (L1 L2)^T; builds A2
-__global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m) {
+__global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long long bstride) {
+    B = small_of(B, bstride, blockIdx.x);
     extern __shared__ __align__(16) double sm[];
     const int MX = m + 2, MO = m + 1, D = m + 1;
     double* G = sm;                      // MX*MX
@@ -546,19 +577,20 @@ __global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m) {
     if (tid == 0) *B.status = fail;
 }
 
-cudaError_t launch_small1(const SmallBufs& B, int m, int use_d, int do_qr, cudaStream_t st, LaunchStats* ls) {
+cudaError_t launch_small1(const SmallBufs& B, int m, int use_d, int do_qr, cudaStream_t st, LaunchStats* ls,
+                          const BatchDesc* batch) {
     const size_t smem = small_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(small1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    small1_kernel<<<1, 256, smem, st>>>(B, m, use_d, do_qr);
+    small1_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, do_qr, batch ? batch->small_stride : 0);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
-cudaError_t launch_small2(const SmallBufs& B, int m, cudaStream_t st, LaunchStats* ls) {
+cudaError_t launch_small2(const SmallBufs& B, int m, cudaStream_t st, LaunchStats* ls, const BatchDesc* batch) {
     const size_t smem = small_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(small2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    small2_kernel<<<1, 256, smem, st>>>(B, m);
+    small2_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, batch ? batch->small_stride : 0);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }

@@ -23,6 +23,19 @@ struct fds_ctx {
     StripPlan plan{};              // fixed strip decomposition of the ensemble step kernel
     bool stream_ok = false;
     bool toy = false;              // small ODE system (toy_ode.cu): no stencil, no halos, J recorded directly
+    // batch of nb independent problems stacked along the site axis (cfg.batch > 1): problem p owns the
+    // stacked sites [gl0 + p*slot, gl0 + p*slot + n); the gaps in between hold its ghost cells
+    int nb = 1;
+    long long slot = 0, gl0 = 0;
+    long long nall = 0;            // stacked sites (= n without a batch)
+    int spp = 1, runs_per_cta = 0; // streaming-kernel shape of the batch
+    BatchDesc bd{};
+    std::vector<double> ds;        // parameter offset of every problem
+    std::vector<double2> Fhost;
+    double2* Fpp = nullptr;        // device (F0, Flast) per problem
+    double* T_alloc = nullptr;     // stacked site 0 of the tangent array (T = site 0 of problem 0)
+    double* d_alloc = nullptr;
+    long long small_stride = 0;
     double* Ebase[2] = {nullptr, nullptr};
     int cur = 0;
     double* Pbase[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -61,9 +74,13 @@ struct fds_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
 
-    double* E(int which) const { return Ebase[which] + (-alo) * M; }
+    // *_all: stacked site 0; the others: site 0 of problem 0 (the same thing without a batch)
+    double* E_all(int which) const { return Ebase[which] + (-alo) * M; }
+    double* E(int which) const { return E_all(which) + gl0 * M; }
     double* Ecur() const { return E(cur); }
-    double* P(int j) const { return Pbase[j] + (-alo); }
+    double* P_all(int j) const { return Pbase[j] + (-alo); }
+    double* P(int j) const { return P_all(j) + gl0; }
+    const BatchDesc* batch() const { return nb > 1 ? &bd : nullptr; }
 };
 
 static std::string g_create_err;
@@ -82,6 +99,16 @@ static int fail(fds_ctx* c, const std::string& msg) { c->err = msg; return 2; }
 // after small1 / small2: bring A (for the by-value kernel parameter) and the Cholesky status to the host
 static int check_small_status(fds_ctx* c, const char* what) {
     int st = 0;
+    if (c->nb > 1) {
+        std::vector<int> all(c->nb, 0);
+        FDS_CK(c, cudaMemcpy2DAsync(all.data(), sizeof(int), c->small.status, (size_t)c->small_stride * sizeof(double),
+                                    sizeof(int), c->nb, cudaMemcpyDeviceToHost, c->stream));
+        FDS_CK(c, cudaStreamSynchronize(c->stream));
+        for (int p = 0; p < c->nb; ++p)
+            if (all[p] != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(all[p]) +
+                                            " of problem " + std::to_string(p) + " (tangent block numerically rank deficient)");
+        return 0;
+    }
     FDS_CK(c, cudaMemcpyAsync(&st, c->small.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (c->fast_boundary)
         FDS_CK(c, cudaMemcpyAsync(c->A_host, c->small.A, (size_t)c->MO * c->MX * sizeof(double),
@@ -97,7 +124,7 @@ static cudaError_t do_gram(fds_ctx* c, int src, double inv_eps) {
         return launch_gram_fast(src, c->Ecur(), c->T, c->d, c->m, inv_eps, c->n, c->gram_part, c->max_part,
                                 c->small.gram, c->num_sms, c->stream, &c->ls);
     return launch_gram(src, c->Ecur(), c->T, c->d, c->m, inv_eps, c->n, c->gram_part, c->max_part, c->small.gram,
-                       c->num_sms, c->stream, &c->ls);
+                       c->num_sms, c->stream, &c->ls, c->batch());
 }
 
 static cudaError_t do_apply(fds_ctx* c, int src, double inv_eps, double* Tout, double* E_out, double eps) {
@@ -105,7 +132,7 @@ static cudaError_t do_apply(fds_ctx* c, int src, double inv_eps, double* Tout, d
         return launch_apply_fast(src, c->Ecur(), c->T, c->d, c->A_host, c->m, inv_eps, c->n, Tout, E_out, c->P(0),
                                  eps, c->num_sms, c->stream, &c->ls);
     return launch_apply(src, c->Ecur(), c->T, c->d, c->small.A, c->m, inv_eps, c->n, Tout != nullptr ? Tout : c->T,
-                        E_out, c->P(0), eps, c->stream, &c->ls);
+                        E_out, c->P(0), eps, c->stream, &c->ls, c->batch());
 }
 
 extern "C" {
@@ -159,7 +186,41 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         return 2;
     }
     c->H = H;
-    {
+    c->nb = cfg->batch > 1 ? cfg->batch : 1;
+    c->nall = c->n;
+    if (c->nb > 1) {
+        // Batch: problems stacked along the site axis.  Between two problems lies a gap that holds the
+        // right ghost cells of the first (4H sites) and the left ghost cells of the second (8H), so the
+        // streaming kernel sweeps the whole stack as ONE array; a batched wrap refreshes the gaps.
+        const int R2 = 256 / c->M;                         // strips per CTA with two CTAs per SM
+        if (cfg->system != FDS_SYS_L96_RK4 || cfg->world != 1 || c->n % 64 != 0 || R2 < 1 ||
+            (cfg->flags & FDS_FLAG_SIMPLE_KERNELS)) {
+            g_create_err = "batch: needs the Lorenz-96 RK4 system, world = 1, n_local a multiple of 64, m <= 126";
+            fds_ctx_destroy(c);
+            return 2;
+        }
+        H = cfg->max_halo_steps > 0 ? cfg->max_halo_steps : 16;
+        H = std::max<long long>(8, (H + 7) / 8 * 8);       // 8H a multiple of the 64-site leaf
+        if (8 * H > c->n) H = std::max<long long>(8, c->n / 64 * 8);
+        c->H = H;
+        c->gl0 = 8 * H;
+        const long long slots_per_wave = (long long)2 * c->num_sms * R2;      // strips resident at once
+        c->spp = (int)std::max<long long>(1, std::min<long long>(8, (slots_per_wave + c->nb / 2) / c->nb));
+        while (c->spp > 1 && (c->n + 12 * H) / c->spp < 256) --c->spp;        // keep strips long
+        const long long unit = 64LL * c->spp;
+        c->slot = (c->n + 12 * H + unit - 1) / unit * unit;
+        c->nall = c->slot * c->nb;
+        const long long nstrips = (long long)c->nb * c->spp;
+        const long long waves = (nstrips + slots_per_wave - 1) / slots_per_wave;
+        c->runs_per_cta = (int)std::min<long long>(R2, (nstrips + waves * 2 * c->num_sms - 1) / (waves * 2 * c->num_sms));
+        c->stream_ok = true;
+        StripPlan& pl = c->plan;
+        pl.a0 = 0; pl.ls = c->slot / c->spp; pl.nstrips = nstrips; pl.nblk = (int)(pl.ls / 8);
+        pl.alo = -12; pl.ahi = c->nall + 12; pl.node_shift = kLeafShift; pl.nnode = c->nall / kLeafSites;
+        c->alo = pl.alo; c->ahi = pl.ahi;
+        c->ds.assign(c->nb, 0.0);
+        c->Fhost.assign(c->nb, make_double2(8.0, 8.0));
+    } else {
         const int R = stream_runs_per_cta(c->M);
         c->stream_ok = R >= 1 && cfg->system == FDS_SYS_L96_RK4 && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS);
         c->plan = make_strip_plan(c->n, H, (long long)c->num_sms * (R >= 1 ? R : 1));
@@ -176,17 +237,21 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         CK0(cudaMemsetAsync(c->Pbase[j], 0, sites * sizeof(double), c->stream));
     }
     // +2 doubles: the boundary kernels fetch tiles with 16-byte-granular bulk copies
-    CK0(cudaMalloc(&c->T, ((size_t)c->n * c->MO + 2) * sizeof(double)));
-    CK0(cudaMemsetAsync(c->T, 0, (size_t)c->n * c->MO * sizeof(double), c->stream));
-    CK0(cudaMalloc(&c->d, ((size_t)c->n + 2) * sizeof(double)));
-    CK0(cudaMemsetAsync(c->d, 0, (size_t)c->n * sizeof(double), c->stream));
-    c->max_part = 2 * c->num_sms;
-    CK0(cudaMalloc(&c->gram_part, (size_t)c->max_part * c->MX * c->MX * sizeof(double)));
-    {   // small matrices in one block
+    CK0(cudaMalloc(&c->T_alloc, ((size_t)c->nall * c->MO + 2) * sizeof(double)));
+    CK0(cudaMemsetAsync(c->T_alloc, 0, (size_t)c->nall * c->MO * sizeof(double), c->stream));
+    CK0(cudaMalloc(&c->d_alloc, ((size_t)c->nall + 2) * sizeof(double)));
+    CK0(cudaMemsetAsync(c->d_alloc, 0, (size_t)c->nall * sizeof(double), c->stream));
+    c->T = c->T_alloc + c->gl0 * c->MO;
+    c->d = c->d_alloc + c->gl0;
+    c->max_part = c->nb > 1 ? 4 : 2 * c->num_sms;
+    CK0(cudaMalloc(&c->gram_part, (size_t)c->nb * c->max_part * c->MX * c->MX * sizeof(double)));
+    if (c->nb > 1) CK0(cudaMalloc(&c->Fpp, (size_t)c->nb * sizeof(double2)));
+    {   // small matrices in one block (per problem)
         const size_t mm = (size_t)c->m * c->m;
-        const size_t tot = (size_t)c->MX * c->MX + (size_t)c->MO * c->MX + 2 * mm + c->m + c->MO + 4;
-        CK0(cudaMalloc(&c->small_block, tot * sizeof(double)));
-        CK0(cudaMemsetAsync(c->small_block, 0, tot * sizeof(double), c->stream));
+        const size_t tot = ((size_t)c->MX * c->MX + (size_t)c->MO * c->MX + 2 * mm + c->m + c->MO + 4 + 1) & ~(size_t)1;
+        c->small_stride = (long long)tot;
+        CK0(cudaMalloc(&c->small_block, tot * c->nb * sizeof(double)));
+        CK0(cudaMemsetAsync(c->small_block, 0, tot * c->nb * sizeof(double), c->stream));
         double* p = c->small_block;
         c->small.gram = p; p += (size_t)c->MX * c->MX;
         c->small.A = p;    p += (size_t)c->MO * c->MX;
@@ -196,7 +261,9 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         c->small.gdil = p; p += c->MO;
         c->small.status = reinterpret_cast<int*>(p);
     }
-    c->fast_boundary = apply_fast_supported(c->m) && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS);
+    c->bd.count = c->nb; c->bd.slot = c->slot; c->bd.small_stride = c->small_stride;
+    c->bd.part_stride = (long long)c->max_part * c->MX * c->MX;
+    c->fast_boundary = apply_fast_supported(c->m) && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS) && c->nb == 1;
     CK0(cudaMallocHost(&c->A_host, (size_t)c->MO * c->MX * sizeof(double)));
     CK0(cudaMalloc(&c->c4, 4 * sizeof(double)));
     {
@@ -204,7 +271,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         CK0(cudaMemcpyAsync(c->c4, w, sizeof(w), cudaMemcpyHostToDevice, c->stream));
         CK0(cudaStreamSynchronize(c->stream));
     }
-    c->nleaf = (c->n + 63) / 64;
+    c->nleaf = (c->nall + 63) / 64;
     CK0(cudaMalloc(&c->jpart, (size_t)c->nleaf * c->M * 2 * sizeof(double)));
     CK0(cudaMalloc(&c->jscratch, (size_t)2 * ((c->nleaf + 255) / 256) * c->M * 2 * sizeof(double)));
     if (small_smem_bytes(c->m) > 220 * 1024 || lss_smem_bytes(c->m) > 220 * 1024) {
@@ -224,7 +291,7 @@ void fds_ctx_destroy(fds_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int j = 0; j < 2; ++j) cudaFree(c->Ebase[j]);
     for (int j = 0; j < 4; ++j) cudaFree(c->Pbase[j]);
-    cudaFree(c->T); cudaFree(c->d); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
+    cudaFree(c->T_alloc); cudaFree(c->d_alloc); cudaFree(c->Fpp); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
     cudaFree(c->jpart); cudaFree(c->jscratch); cudaFree(c->jsum);
     for (int j = 0; j < 2; ++j) {
         cudaFree(c->stage[j]);
@@ -297,7 +364,7 @@ int fds_set_time_dilation(fds_ctx* c, int enabled) { c->time_dilation = enabled 
 // ------------------------------- state in / out ------------------------------ //
 static int sync_primal_from_ensemble(fds_ctx* c) {
     if (c->state_in_ensemble) {
-        FDS_CK(c, launch_extract_col0(c->Ecur(), c->M, c->P(0), c->n, c->stream, &c->ls));
+        FDS_CK(c, launch_extract_col0(c->E_all(c->cur), c->M, c->P_all(0), c->nall, c->stream, &c->ls));
         c->state_in_ensemble = false;
         c->pri_halo_valid = 0;
     }
@@ -305,7 +372,10 @@ static int sync_primal_from_ensemble(fds_ctx* c) {
 }
 
 int fds_set_state(fds_ctx* c, const double* u) {
-    FDS_CK(c, cudaMemcpyAsync(c->P(0), u, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // batch: u is [nb][n]; rows land `slot` sites apart
+    FDS_CK(c, cudaMemcpy2DAsync(c->P(0), (size_t)(c->nb > 1 ? c->slot : c->n) * sizeof(double), u,
+                                (size_t)c->n * sizeof(double), (size_t)c->n * sizeof(double), c->nb,
+                                cudaMemcpyHostToDevice, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     c->state_in_ensemble = false;
     c->pri_halo_valid = 0;
@@ -314,7 +384,9 @@ int fds_set_state(fds_ctx* c, const double* u) {
 
 int fds_get_state(fds_ctx* c, double* u) {
     if (int r = sync_primal_from_ensemble(c)) return r;
-    FDS_CK(c, cudaMemcpyAsync(u, c->P(0), (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaMemcpy2DAsync(u, (size_t)c->n * sizeof(double), c->P(0),
+                                (size_t)(c->nb > 1 ? c->slot : c->n) * sizeof(double), (size_t)c->n * sizeof(double),
+                                c->nb, cudaMemcpyDeviceToHost, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -333,7 +405,7 @@ static int ensure_stage(fds_ctx* c) {
 
 static int materialize_tangents(fds_ctx* c) {
     if (c->tangents_implicit) {
-        FDS_CK(c, launch_diff_tangents(c->Ecur(), c->M, c->eps_last, c->T, c->n, c->stream, &c->ls));
+        FDS_CK(c, launch_diff_tangents(c->E_all(c->cur), c->M, c->eps_last, c->T_alloc, c->nall, c->stream, &c->ls));
         c->tangents_implicit = false;
     }
     return 0;
@@ -341,10 +413,15 @@ static int materialize_tangents(fds_ctx* c) {
 
 // Host rows V[j][.] (j < m), v[.] -> device T[site][m+1], in chunks of stage_sites sites: the
 // copy stream uploads chunk i+1 while the context's stream transposes chunk i.
-int fds_set_tangents(fds_ctx* c, const double* V, const double* v) {
+// batch: V is [nb][m][n], v is [nb][n]
+int fds_set_tangents(fds_ctx* c, const double* Vall, const double* vall) {
     if (int r = ensure_stage(c)) return r;
     FDS_CK(c, cudaStreamSynchronize(c->stream));       // T and the stages are free
     long long i = 0;
+    for (int pb = 0; pb < c->nb; ++pb) {
+    const double* V = Vall + (size_t)pb * c->m * c->n;
+    const double* v = vall ? vall + (size_t)pb * c->n : nullptr;
+    double* Tp = c->T + (size_t)pb * c->slot * c->MO;
     for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites, ++i) {
         const int b = (int)(i & 1);
         const long long cnt = std::min(c->stage_sites, c->n - s0);
@@ -359,24 +436,29 @@ int fds_set_tangents(fds_ctx* c, const double* V, const double* v) {
         else FDS_CK(c, cudaMemsetAsync(stg + (size_t)c->m * c->stage_sites, 0, (size_t)cnt * sizeof(double), c->copy_stream));
         FDS_CK(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
         FDS_CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-        FDS_CK(c, launch_transpose_back(stg, c->stage_sites, cnt, c->MO, c->T + (size_t)s0 * c->MO, c->stream, &c->ls));
+        FDS_CK(c, launch_transpose_back(stg, c->stage_sites, cnt, c->MO, Tp + (size_t)s0 * c->MO, c->stream, &c->ls));
         FDS_CK(c, cudaEventRecord(c->ev_done[b], c->stream));
+    }
     }
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     c->tangents_implicit = false;
     return 0;
 }
 
-int fds_get_tangents(fds_ctx* c, double* V, double* v) {
+int fds_get_tangents(fds_ctx* c, double* Vall, double* vall) {
     if (int r = materialize_tangents(c)) return r;
     if (int r = ensure_stage(c)) return r;
     long long i = 0;
+    for (int pb = 0; pb < c->nb; ++pb) {
+    double* V = Vall ? Vall + (size_t)pb * c->m * c->n : nullptr;
+    double* v = vall ? vall + (size_t)pb * c->n : nullptr;
+    const double* Tp = c->T + (size_t)pb * c->slot * c->MO;
     for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites, ++i) {
         const int b = (int)(i & 1);
         const long long cnt = std::min(c->stage_sites, c->n - s0);
         double* stg = c->stage[b];
         if (i >= 2) FDS_CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));   // download of chunk i-2 done
-        FDS_CK(c, launch_transpose(c->T + (size_t)s0 * c->MO, cnt, c->MO, stg, c->stage_sites, c->stream, &c->ls));
+        FDS_CK(c, launch_transpose(Tp + (size_t)s0 * c->MO, cnt, c->MO, stg, c->stage_sites, c->stream, &c->ls));
         FDS_CK(c, cudaEventRecord(c->ev_done[b], c->stream));
         FDS_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
         if (V) FDS_CK(c, cudaMemcpy2DAsync(V + s0, (size_t)c->n * sizeof(double), stg,
@@ -386,13 +468,15 @@ int fds_get_tangents(fds_ctx* c, double* V, double* v) {
                                          cudaMemcpyDeviceToHost, c->copy_stream));
         FDS_CK(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
     }
+    }
     FDS_CK(c, cudaStreamSynchronize(c->copy_stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 int fds_random_tangents(fds_ctx* c, uint64_t seed) {
-    FDS_CK(c, launch_fill_random(c->T, c->n, c->MO, c->m, c->cfg.site_offset, c->cfg.n_global, seed, c->stream, &c->ls));
+    if (c->nb > 1) FDS_CK(c, launch_fill_random(c->T_alloc, c->nall, c->MO, c->m, 0, c->nall, seed, c->stream, &c->ls));
+    else FDS_CK(c, launch_fill_random(c->T, c->n, c->MO, c->m, c->cfg.site_offset, c->cfg.n_global, seed, c->stream, &c->ls));
     c->tangents_implicit = false;
     return 0;
 }
@@ -404,6 +488,8 @@ int fds_halo_wrap_ensemble(fds_ctx* c, int64_t hs) {
     if (c->toy) { c->ens_halo_valid = hs; return 0; }
     if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_ensemble: world > 1, exchange halos between ranks instead");
     if (hs < 1 || hs > c->H) return fail(c, "halo_steps out of range");
+    if (c->nb > 1) FDS_CK(c, launch_halo_wrap_batch(c->Ecur(), c->M, c->n, 8 * hs, 4 * hs, c->nb, c->slot, c->stream, &c->ls));
+    else
     FDS_CK(c, launch_halo_wrap(c->Ecur(), c->M, c->n, 8 * hs, 4 * hs, c->stream, &c->ls));
     c->ens_halo_valid = hs;
     return 0;
@@ -413,6 +499,8 @@ int fds_halo_wrap_primal(fds_ctx* c, int64_t hs) {
     if (c->toy) { c->pri_halo_valid = hs; return 0; }
     if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_primal: world > 1, exchange halos between ranks instead");
     if (hs < 1 || hs > c->H) return fail(c, "halo_steps out of range");
+    if (c->nb > 1) FDS_CK(c, launch_halo_wrap_batch(c->P(0), 1, c->n, 8 * hs, 4 * hs, c->nb, c->slot, c->stream, &c->ls));
+    else
     FDS_CK(c, launch_halo_wrap(c->P(0), 1, c->n, 8 * hs, 4 * hs, c->stream, &c->ls));
     c->pri_halo_valid = hs;
     return 0;
@@ -443,16 +531,20 @@ static int ensure_jsum(fds_ctx* c, long long steps) {
     if (steps <= c->jsum_cap) return 0;
     double* nj = nullptr;
     const long long cap = std::max<long long>(steps, 2 * c->jsum_cap);
-    FDS_CK(c, cudaMalloc(&nj, (size_t)cap * c->M * 2 * sizeof(double)));
-    FDS_CK(c, cudaMemsetAsync(nj, 0, (size_t)cap * c->M * 2 * sizeof(double), c->stream));
+    const size_t per_step = (size_t)c->nb * c->M * 2;          // [step][problem][column][2]
+    FDS_CK(c, cudaMalloc(&nj, cap * per_step * sizeof(double)));
+    FDS_CK(c, cudaMemsetAsync(nj, 0, cap * per_step * sizeof(double), c->stream));
     if (c->jsum) {
-        FDS_CK(c, cudaMemcpyAsync(nj, c->jsum, (size_t)c->jsum_cap * c->M * 2 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        FDS_CK(c, cudaMemcpyAsync(nj, c->jsum, (size_t)c->jsum_cap * per_step * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         FDS_CK(c, cudaStreamSynchronize(c->stream));
         cudaFree(c->jsum);
     }
     c->jsum = nj;
     c->jsum_cap = cap;
-    if (c->stream_ok) {
+    if (c->stream_ok && c->nb > 1) {
+        // batch: leaf partials of one halo chunk (<= H steps) at a time, reduced per problem right after it
+        if (!c->jnode) FDS_CK(c, cudaMalloc(&c->jnode, (size_t)c->H * c->plan.nnode * c->M * 2 * sizeof(double)));
+    } else if (c->stream_ok) {
         cudaFree(c->jnode); cudaFree(c->jnode_scratch);
         c->jnode = c->jnode_scratch = nullptr;
         const size_t row = (size_t)c->plan.nnode * c->M * 2;
@@ -467,17 +559,18 @@ static int ensure_jsum(fds_ctx* c, long long steps) {
 // (streaming kernel: node partials into jnode[jstep], reduced later in one batch by
 // reduce_nodes(); simple kernels: reduced right away into jsum[jstep])
 static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, double Flast, long long valid,
-                    long long jstep) {
+                    long long jstep, long long jslot) {
     double* jsum_slot = c->jsum + (size_t)jstep * M_ * 2;
     StepArgs a;
-    a.X = X; a.Y = Y; a.M = M_; a.n = c->n;
+    a.X = X; a.Y = Y; a.M = M_; a.n = c->nall;
+    if (c->nb > 1) { a.Fpp = c->Fpp; a.spp = c->spp; a.slot = c->slot; a.runs_per_cta = c->runs_per_cta; a.ctas_per_sm = 2; }
     a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
     a.F0 = F0; a.Flast = Flast; a.dt = c->cfg.dt; a.exact = c->cfg.math == FDS_MATH_EXACT;
     a.jpart = jsum_slot ? c->jpart : nullptr;
     a.nleaf = c->nleaf;
     const bool euler = c->cfg.system == FDS_SYS_L96_EULER;
     if (c->stream_ok && M_ == c->M) {
-        a.jpart = c->jnode + (size_t)jstep * c->plan.nnode * c->M * 2;
+        a.jpart = c->jnode + (size_t)jslot * c->plan.nnode * c->M * 2;
         cudaEvent_t e1 = nullptr;
         if (c->profiling) {
             if (c->prof_used == c->prof_events.size()) {
@@ -503,11 +596,47 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
 // node partials of steps [step0, step0 + nsteps) -> jsum, one batched canonical-tree reduction
 static int reduce_nodes(fds_ctx* c, long long step0, long long nsteps) {
     if (!c->stream_ok || nsteps < 1) return 0;
+    if (c->nb > 1) {
+        FDS_CK(c, launch_batch_jreduce(c->jnode, c->plan.nnode, c->gl0 / kLeafSites, c->slot / kLeafSites,
+                                       c->n / kLeafSites, 2 * c->M, c->nb, nsteps,
+                                       c->jsum + (size_t)step0 * c->nb * c->M * 2, c->stream, &c->ls));
+        return 0;
+    }
     const size_t row = (size_t)c->plan.nnode * c->M * 2;
     FDS_CK(c, launch_tree_reduce_batched(c->jnode + (size_t)step0 * row, c->plan.nnode, 2 * c->M, nsteps,
                                          c->jsum + (size_t)step0 * c->M * 2, c->jnode_scratch, c->stream, &c->ls));
     return 0;
 }
+
+// arguments of one single-column step P(from) -> P(to) with `valid` halo steps left; a batch is
+// swept as one stacked array (the gaps hold the ghost cells)
+static void primal_step_args(fds_ctx* c, StepArgs& a, int from, int to, long long valid, double s) {
+    const double F = s + 8.0;
+    a.X = c->P_all(from); a.Y = c->P_all(to); a.M = 1; a.n = c->nall;
+    if (c->nb > 1) { a.lo = 0; a.hi = c->nall; a.Fpp = c->Fpp; a.slot = c->slot; }
+    else { a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1); }
+    a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
+    a.exact = c->cfg.math == FDS_MATH_EXACT; a.jpart = nullptr; a.nleaf = c->nleaf;
+}
+
+// batch: (F0, Flast) of every problem for parameter s + ds[p] (and s + ds[p] + eps for the last column)
+static int upload_forcing(fds_ctx* c, double s, double eps) {
+    if (c->nb <= 1) return 0;
+    for (int p = 0; p < c->nb; ++p) {
+        const double sp = s + c->ds[p];
+        c->Fhost[p] = make_double2(sp + 8.0, (sp + eps) + 8.0);
+    }
+    // pageable source: the copy is staged before the call returns, so Fhost may be rewritten afterwards
+    FDS_CK(c, cudaMemcpyAsync(c->Fpp, c->Fhost.data(), (size_t)c->nb * sizeof(double2), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int fds_set_batch_params(fds_ctx* c, const double* ds) {
+    for (int p = 0; p < c->nb; ++p) c->ds[p] = ds ? ds[p] : 0.0;
+    return 0;
+}
+
+int fds_batch_count(const fds_ctx* c) { return c->nb; }
 
 int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int record) {
     if (int r = sync_primal_from_ensemble(c)) return r;
@@ -517,15 +646,13 @@ int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int 
                                      record ? c->jsum + (size_t)step0 * 2 : nullptr, c->stream, &c->ls));
         return 0;
     }
-    const double F = s + 8.0;
+    if (c->nb > 1 && record) return fail(c, "fds_primal_advance: objective recording is not available for a batch");
+    if (int r = upload_forcing(c, s, 0.0)) return r;
     for (long long j = 0; j < nsteps; ++j) {
         if (c->pri_halo_valid < 1) return fail(c, "fds_primal_advance: primal halo exhausted; refresh it first");
         // primal stepping uses the one-thread-per-element kernel (single column)
         StepArgs a;
-        a.X = c->P(0); a.Y = c->P(1); a.M = 1; a.n = c->n;
-        a.lo = -8 * (c->pri_halo_valid - 1); a.hi = c->n + 4 * (c->pri_halo_valid - 1);
-        a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
-        a.exact = c->cfg.math == FDS_MATH_EXACT; a.jpart = nullptr; a.nleaf = c->nleaf;
+        primal_step_args(c, a, 0, 1, c->pri_halo_valid, s);
         FDS_CK(c, launch_l96_simple(a, c->cfg.system == FDS_SYS_L96_EULER, c->stream, &c->ls));
         if (record) {
             FDS_CK(c, launch_stats_leaf(c->P(1), 1, c->n, c->jpart, c->nleaf, c->stream, &c->ls));
@@ -564,9 +691,12 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
         return 0;
     }
     const double F0 = s + 8.0, Flast = (s + eps) + 8.0;   // fds/segment.py:64: parameter + epsilon
+    if (c->nb > 1 && nsteps > c->H) return fail(c, "fds_segment_advance: a batch advances at most halo_steps per call");
+    if (int r = upload_forcing(c, s, eps)) return r;
     for (long long j = 0; j < nsteps; ++j) {
         if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
-        if (int r = one_step(c, c->Ecur(), c->E(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, step0 + j)) return r;
+        if (int r = one_step(c, c->E_all(c->cur), c->E_all(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, step0 + j,
+                             c->nb > 1 ? j : step0 + j)) return r;
         c->cur ^= 1;
         c->ens_halo_valid--;
     }
@@ -579,7 +709,7 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
 
 int fds_segment_jsums(fds_ctx* c, int64_t steps, double* out) {
     if (steps > c->jsum_cap) return fail(c, "fds_segment_jsums: more steps than were run");
-    FDS_CK(c, cudaMemcpyAsync(out, c->jsum, (size_t)steps * c->M * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaMemcpyAsync(out, c->jsum, (size_t)steps * c->nb * c->M * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -615,21 +745,18 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
         FDS_CK(c, launch_dxdt(c->P(0), c->P(1), c->P(2), c->P(3), c->c4, c->d, c->n, c->stream, &c->ls));
     } else if (c->time_dilation) {
         if (c->pri_halo_valid < 3) return fail(c, "fds_boundary_dxdt: primal halo must be valid for 3 steps");
-        const double F = s + 8.0;
+        if (int r = upload_forcing(c, s, 0.0)) return r;
         long long valid = 3;
         for (int j = 1; j <= 3; ++j) {
             StepArgs a;
-            a.X = c->P(j - 1); a.Y = c->P(j); a.M = 1; a.n = c->n;
-            a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
-            a.F0 = F; a.Flast = F; a.dt = c->cfg.dt;
-            a.exact = c->cfg.math == FDS_MATH_EXACT; a.jpart = nullptr; a.nleaf = c->nleaf;
+            primal_step_args(c, a, j - 1, j, valid, s);
             FDS_CK(c, launch_l96_simple(a, c->cfg.system == FDS_SYS_L96_EULER, c->stream, &c->ls));
             --valid;
         }
         c->pri_halo_valid = 0;
-        FDS_CK(c, launch_dxdt(c->P(0), c->P(1), c->P(2), c->P(3), c->c4, c->d, c->n, c->stream, &c->ls));
+        FDS_CK(c, launch_dxdt(c->P_all(0), c->P_all(1), c->P_all(2), c->P_all(3), c->c4, c->d_alloc, c->nall, c->stream, &c->ls));
     } else {
-        FDS_CK(c, cudaMemsetAsync(c->d, 0, (size_t)c->n * sizeof(double), c->stream));
+        FDS_CK(c, cudaMemsetAsync(c->d_alloc, 0, (size_t)c->nall * sizeof(double), c->stream));
     }
     const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
     if (!from_ensemble) if (int r = materialize_tangents(c)) return r;
@@ -638,7 +765,7 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
 }
 
 int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
-    FDS_CK(c, launch_small1(c->small, c->m, c->time_dilation ? 1 : 0, do_qr, c->stream, &c->ls));
+    FDS_CK(c, launch_small1(c->small, c->m, c->time_dilation ? 1 : 0, do_qr, c->stream, &c->ls, c->batch()));
     if (do_qr || c->fast_boundary) if (int r = check_small_status(c, "CholeskyQR pass 1")) return r;
     const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
     FDS_CK(c, do_apply(c, src, from_ensemble ? 1.0 / eps : 0.0, c->T, nullptr, 0.0));
@@ -653,12 +780,12 @@ int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
     const bool keepT = !ens || (build & FDS_BUILD_KEEP_TANGENTS) != 0 || !c->fast_boundary;
     c->tangents_implicit = false;
     if (do_qr) {
-        FDS_CK(c, launch_small2(c->small, c->m, c->stream, &c->ls));
+        FDS_CK(c, launch_small2(c->small, c->m, c->stream, &c->ls, c->batch()));
         if (int r = check_small_status(c, "CholeskyQR pass 2")) return r;
         FDS_CK(c, do_apply(c, SRC_TANGENT, 0.0, keepT ? c->T : nullptr, ens ? c->Ecur() : nullptr, eps));
         if (!keepT) c->tangents_implicit = true;    // T holds the pass-1 intermediate; the ensemble is the record
     } else if (ens) {
-        FDS_CK(c, launch_make_ensemble(c->P(0), c->T, c->M, eps, c->Ecur(), c->n, c->stream, &c->ls));
+        FDS_CK(c, launch_make_ensemble(c->P_all(0), c->T_alloc, c->M, eps, c->E_all(c->cur), c->nall, c->stream, &c->ls));
     }
     if (ens) { c->ens_halo_valid = 0; c->eps_last = eps; }
     c->state_in_ensemble = false;
@@ -666,10 +793,16 @@ int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
 }
 
 int fds_boundary_results(fds_ctx* c, double* R, double* b, double* G_dil, double* g_dil) {
-    if (R) FDS_CK(c, cudaMemcpyAsync(R, c->small.R, (size_t)c->m * c->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (b) FDS_CK(c, cudaMemcpyAsync(b, c->small.b, (size_t)c->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (G_dil) FDS_CK(c, cudaMemcpyAsync(G_dil, c->small.gdil, (size_t)c->m * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (g_dil) FDS_CK(c, cudaMemcpyAsync(g_dil, c->small.gdil + c->m, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    // batch: one row per problem -- R[nb][m][m], b[nb][m], G_dil[nb][m], g_dil[nb]
+    const size_t pitch = (size_t)c->small_stride * sizeof(double);
+    auto fetch = [&](double* dst, const double* src, size_t count) {
+        return cudaMemcpy2DAsync(dst, count * sizeof(double), src, pitch, count * sizeof(double), c->nb,
+                                 cudaMemcpyDeviceToHost, c->stream);
+    };
+    if (R) FDS_CK(c, fetch(R, c->small.R, (size_t)c->m * c->m));
+    if (b) FDS_CK(c, fetch(b, c->small.b, c->m));
+    if (G_dil) FDS_CK(c, fetch(G_dil, c->small.gdil, c->m));
+    if (g_dil) FDS_CK(c, fetch(g_dil, c->small.gdil + c->m, 1));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -691,7 +824,7 @@ int fds_run_segment_host(fds_ctx* c, double* u, double* V, double* v, double s, 
     if (c->cfg.world != 1) return fail(c, "fds_run_segment_host: world == 1 only");
     if (int r = fds_set_state(c, u)) return r;
     if (int r = fds_set_tangents(c, V, v)) return r;
-    FDS_CK(c, launch_make_ensemble(c->P(0), c->T, c->M, eps, c->Ecur(), c->n, c->stream, &c->ls));
+    FDS_CK(c, launch_make_ensemble(c->P_all(0), c->T_alloc, c->M, eps, c->E_all(c->cur), c->nall, c->stream, &c->ls));
     c->eps_last = eps;
     if (int r = fds_segment(c, s, eps, steps, Jsum_host)) return r;
     if (int r = fds_get_state(c, u)) return r;
@@ -700,7 +833,11 @@ int fds_run_segment_host(fds_ctx* c, double* u, double* V, double* v, double s, 
 
 // ---------------------------------- LSS solve -------------------------------- //
 int fds_lss_solve(int device, const double* R, const double* b, int64_t K, int m, double* alpha) {
-    if (K < 1 || m < 1 || lss_smem_bytes(m) > 220 * 1024) { g_create_err = "fds_lss_solve: bad K or m"; return 2; }
+    return fds_lss_solve_batch(device, R, b, K, m, 1, alpha);
+}
+
+int fds_lss_solve_batch(int device, const double* R, const double* b, int64_t K, int m, int64_t nbatch, double* alpha) {
+    if (K < 1 || m < 1 || nbatch < 1 || lss_smem_bytes(m) > 220 * 1024) { g_create_err = "fds_lss_solve: bad K, m or batch"; return 2; }
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) { g_create_err = std::string("fds_lss_solve: ") + cudaGetErrorString(e) + " -- no CPU fallback"; return 3; }
     const size_t mm = (size_t)m * m;
@@ -712,17 +849,23 @@ int fds_lss_solve(int device, const double* R, const double* b, int64_t K, int m
         cudaError_t e__ = (call);                                                          \
         if (e__ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__); rc = 1; goto done; } \
     } while (0)
-    CKL(cudaMalloc(&dR, K * mm * sizeof(double)));
-    CKL(cudaMalloc(&db, (size_t)K * m * sizeof(double)));
-    CKL(cudaMalloc(&da, (size_t)K * m * sizeof(double)));
-    CKL(cudaMalloc(&dw, ((size_t)2 * K * mm + (size_t)2 * K * m) * sizeof(double)));
-    CKL(cudaMalloc(&dst, sizeof(int)));
-    CKL(cudaMemcpy(dR, R, K * mm * sizeof(double), cudaMemcpyHostToDevice));
-    CKL(cudaMemcpy(db, b, (size_t)K * m * sizeof(double), cudaMemcpyHostToDevice));
-    CKL(launch_lss_solve(dR, db, K, m, da, dw, dst, nullptr, nullptr));
-    CKL(cudaMemcpy(alpha, da, (size_t)K * m * sizeof(double), cudaMemcpyDeviceToHost));
-    CKL(cudaMemcpy(&st, dst, sizeof(int), cudaMemcpyDeviceToHost));
-    if (st != 0) { g_create_err = "fds_lss_solve: Schur complement not positive definite at row " + std::to_string(st); rc = 4; }
+    {
+    const size_t nbz = (size_t)nbatch;
+    std::vector<int> sts(nbz, 0);
+    CKL(cudaMalloc(&dR, nbz * K * mm * sizeof(double)));
+    CKL(cudaMalloc(&db, nbz * K * m * sizeof(double)));
+    CKL(cudaMalloc(&da, nbz * K * m * sizeof(double)));
+    CKL(cudaMalloc(&dw, nbz * ((size_t)2 * K * mm + (size_t)2 * K * m) * sizeof(double)));
+    CKL(cudaMalloc(&dst, nbz * sizeof(int)));
+    CKL(cudaMemcpy(dR, R, nbz * K * mm * sizeof(double), cudaMemcpyHostToDevice));
+    CKL(cudaMemcpy(db, b, nbz * K * m * sizeof(double), cudaMemcpyHostToDevice));
+    CKL(launch_lss_solve(dR, db, K, m, da, dw, dst, nullptr, nullptr, (int)nbatch));
+    CKL(cudaMemcpy(alpha, da, nbz * K * m * sizeof(double), cudaMemcpyDeviceToHost));
+    CKL(cudaMemcpy(sts.data(), dst, nbz * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t p = 0; p < nbz; ++p)
+        if (sts[p] != 0) { st = sts[p]; g_create_err = "fds_lss_solve: Schur complement not positive definite at row " +
+                                                      std::to_string(st) + " (problem " + std::to_string(p) + ")"; rc = 4; break; }
+    }
 done:
     cudaFree(dR); cudaFree(db); cudaFree(da); cudaFree(dw); cudaFree(dst);
     return rc;

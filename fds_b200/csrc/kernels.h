@@ -22,6 +22,17 @@ struct StepArgs {
     double* jpart;         // simple kernels: [nleaf][M][2] 64-site partial sums; streaming kernel:
                            // [plan.nnode][M][2] node partial sums; or nullptr
     long long nleaf;
+    // batch of independent problems stacked along the site axis, `slot` sites apart (0 = no batch):
+    // forcing pair (F0, Flast) of problem p in Fpp[p]; the streaming kernel cuts every slot into
+    // `spp` strips, the simple kernel maps site i to problem i / slot
+    const double2* Fpp = nullptr;
+    int spp = 0;
+    long long slot = 0;
+    // streaming kernel launch shape (0 = default: as many strips per CTA as fit 480 threads, one
+    // CTA per SM with a dedicated producer warp).  ctas_per_sm = 2: <= 256 threads and half the
+    // shared memory per CTA, warp 0 produces in between its blocks
+    int runs_per_cta = 0;
+    int ctas_per_sm = 1;
 };
 
 // streaming TMA-fed kernel (RK4 only); `plan` = make_strip_plan(n, H, num_sms * stream_runs_per_cta(M)),
@@ -42,6 +53,14 @@ cudaError_t launch_tree_reduce_batched(const double* in, long long n_in, int C, 
 // periodic ghosts: A[g][:] = A[g mod n][:] for g in [-gl,0) U [n, n+gr)
 cudaError_t launch_halo_wrap(double* A, int M, long long n, long long gl, long long gr,
                              cudaStream_t st, LaunchStats* ls);
+// the same for `batch` problems whose site 0 is `slot` sites apart (A points at site 0 of problem 0)
+cudaError_t launch_halo_wrap_batch(double* A, int M, long long n, long long gl, long long gr, int batch,
+                                   long long slot, cudaStream_t st, LaunchStats* ls);
+// objective sums of a batch: leaves[step][nleaf_total][C] (64-site partials of the stacked array) ->
+// out[step][p][C], canonical tree over the n/64 leaves of problem p (first leaf: leaf0 + p*slot_leaves)
+cudaError_t launch_batch_jreduce(const double* leaves, long long nleaf_total, long long leaf0, long long slot_leaves,
+                                 long long leaves_pp, int C, int batch, long long steps, double* out,
+                                 cudaStream_t st, LaunchStats* ls);
 
 // ---- boundary.cu ------------------------------------------------------------ //
 cudaError_t launch_extract_col0(const double* E, int M, double* P, long long n, cudaStream_t, LaunchStats*);
@@ -61,16 +80,25 @@ cudaError_t launch_fill_random(double* T, long long n, int MO, int m, long long 
                                long long n_global, uint64_t seed, cudaStream_t, LaunchStats*);
 
 enum { SRC_ENSEMBLE = 0, SRC_TANGENT = 1 };
+
+// Batch of independent problems for the boundary kernels: problem p = blockIdx.y works on arrays
+// offset by p * slot sites; its small matrices live p * small_stride doubles further on.
+struct BatchDesc {
+    int count = 1;
+    long long slot = 0;          // sites between consecutive problems
+    long long small_stride = 0;  // doubles between consecutive SmallBufs blocks
+    long long part_stride = 0;   // doubles between consecutive Gram partial blocks
+};
 // Gram of X_i = [t_0..t_m, d_i]  (MX = m+2), t from the ensemble ((E_k - E_0) * inv_eps) or from T.
 // part: [grid][MX*MX] scratch; out: MX*MX (deterministic fixed-order sum of the partials)
 cudaError_t launch_gram(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
                         long long n, double* part, int max_part, double* out, int num_sms,
-                        cudaStream_t, LaunchStats*);
+                        cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr);
 // out_i = A . X_i  (A: (m+1) x (m+2) row-major on device); writes T (may alias the source T) and,
 // if E_out != nullptr, the next ensemble E_out[i] = [u_i, u_i + eps*out_i]
 cudaError_t launch_apply(int src, const double* E, const double* Tin, const double* d, const double* A,
                          int m, double inv_eps, long long n, double* Tout, double* E_out, const double* u,
-                         double eps, cudaStream_t, LaunchStats*);
+                         double eps, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr);
 
 struct SmallBufs {          // all device pointers
     double* gram;           // (m+2)^2
@@ -81,8 +109,9 @@ struct SmallBufs {          // all device pointers
     double* gdil;           // m+1  (G_dil[0..m-1], g_dil)
     int* status;            // 0 ok, >0 Cholesky pivot failure (1-based column)
 };
-cudaError_t launch_small1(const SmallBufs&, int m, int use_d, int do_qr, cudaStream_t, LaunchStats*);
-cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*);
+cudaError_t launch_small1(const SmallBufs&, int m, int use_d, int do_qr, cudaStream_t, LaunchStats*,
+                          const BatchDesc* batch = nullptr);
+cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr);
 size_t small_smem_bytes(int m);
 
 // ---- boundary_fast.cu ---------------------------------------------------------- //
@@ -105,8 +134,9 @@ cudaError_t launch_toy_advance(int system, int exact, const double* X, double* Y
 
 // ---- lss.cu ----------------------------------------------------------------- //
 // R[K][m][m], b[K][m] (device) -> alpha[K][m] (device); work: (2*m*m + 2*m) * K doubles
+// batch > 1: R[batch][K][m][m], b / alpha [batch][K][m], work and status per problem (one CTA each)
 cudaError_t launch_lss_solve(const double* R, const double* b, long long K, int m, double* alpha,
-                             double* work, int* status, cudaStream_t, LaunchStats*);
+                             double* work, int* status, cudaStream_t, LaunchStats*, int batch = 1);
 size_t lss_smem_bytes(int m);
 
 }  // namespace fds

@@ -32,6 +32,8 @@ struct StreamParams {
     int M, R, run_stride, nstages, nconsumer;  // nconsumer = R*M
     int dedicated;                             // 1: the last warp only produces; 0: warp 0 produces in between its blocks
     double F0, Flast;
+    const double2* Fpp;                        // per-problem (F0, Flast) of a batch, or nullptr
+    int spp;                                   // strips per problem (batch)
     Rk4Coef c;
 };
 
@@ -191,7 +193,11 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     io.par = 0;
     io.cur = io.sdata;
 
-    const double F = (k == p.M - 1) ? p.Flast : p.F0;
+    double F = (k == p.M - 1) ? p.Flast : p.F0;
+    if (p.Fpp != nullptr) {
+        const double2 f = p.Fpp[strip / p.spp];
+        F = (k == p.M - 1) ? f.y : f.x;
+    }
     l96_rk4_march_t<MP, STATS>(io, g, F, p.c);
 }
 
@@ -215,21 +221,32 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.M = a.M;
     p.R = stream_runs_per_cta(a.M);
     if (p.R < 1) return cudaErrorInvalidValue;            // M too large for this kernel
+    p.dedicated = producer_dedicated();
+    size_t smem_budget = 226 * 1024;
+    if (a.runs_per_cta > 0) {
+        if (a.runs_per_cta > p.R) return cudaErrorInvalidValue;
+        p.R = a.runs_per_cta;
+        if (a.ctas_per_sm >= 2) {
+            if (p.R * a.M > 256) return cudaErrorInvalidValue;
+            p.dedicated = 0;
+            smem_budget = 112 * 1024;
+        }
+    }
     p.nconsumer = p.R * a.M;
     int pad = (16 - (7 * a.M) % 16) % 16;
     if (pad & 1) pad += 1;
     p.run_stride = 8 * a.M + pad;
-    p.dedicated = producer_dedicated();
     const int cthreads = ((p.nconsumer + 31) / 32) * 32;
     const int block = cthreads + 32 * p.dedicated;
     const size_t stage_bytes = (size_t)p.R * p.run_stride * sizeof(double);
     const size_t ns_bytes = (size_t)2 * (plan.node_shift - kLeafShift) * cthreads * sizeof(double);
-    const size_t budget = 226 * 1024 - 128 - ns_bytes;
+    const size_t budget = smem_budget - 128 - ns_bytes;
     int nst = (int)std::min<size_t>(kMaxStages, budget / stage_bytes);
     if (nst < 2) return cudaErrorInvalidValue;
     p.nstages = nst;
     p.a0 = plan.a0; p.ls = plan.ls; p.nstrips = plan.nstrips; p.nblk = plan.nblk;
     p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
+    p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = (int)((plan.nstrips + p.R - 1) / p.R);
     const size_t smem = 128 + ns_bytes + stage_bytes * nst;
@@ -260,12 +277,17 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
 template <class MP, int EULER>
 __global__ void __launch_bounds__(256) l96_simple_kernel(const double* __restrict__ X, double* __restrict__ Y,
                                                          int M, long long lo, long long count, double F0,
-                                                         double Flast, Rk4Coef c) {
+                                                         double Flast, Rk4Coef c, const double2* __restrict__ Fpp,
+                                                         long long slot) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= count) return;
     const long long i = lo + idx / M;
     const int k = (int)(idx % M);
-    const double F = (k == M - 1) ? Flast : F0;
+    double F = (k == M - 1) ? Flast : F0;
+    if (Fpp != nullptr) {                      // batch: site i belongs to problem i / slot (lo >= 0)
+        const double2 f = Fpp[i / slot];
+        F = (M > 1 && k == M - 1) ? f.y : f.x;
+    }
     if (EULER) {
         double x[4];
 #pragma unroll
@@ -287,7 +309,7 @@ cudaError_t launch_l96_simple(const StepArgs& a, int euler, cudaStream_t st, Lau
     Rk4Coef c{0.5 * a.dt, a.dt, a.dt / 6.0};
     const double Fl = a.M > 1 ? a.Flast : a.F0;
 #define FDS_LAUNCH_SIMPLE(MP, E) \
-    l96_simple_kernel<MP, E><<<(unsigned)grid, block, 0, st>>>(a.X, a.Y, a.M, a.lo, count, a.F0, Fl, c)
+    l96_simple_kernel<MP, E><<<(unsigned)grid, block, 0, st>>>(a.X, a.Y, a.M, a.lo, count, a.F0, Fl, c, a.Fpp, a.slot)
     if (a.exact) { if (euler) FDS_LAUNCH_SIMPLE(ExactMath, 1); else FDS_LAUNCH_SIMPLE(ExactMath, 0); }
     else         { if (euler) FDS_LAUNCH_SIMPLE(FastMath, 1);  else FDS_LAUNCH_SIMPLE(FastMath, 0); }
 #undef FDS_LAUNCH_SIMPLE
@@ -402,6 +424,60 @@ cudaError_t launch_halo_wrap(double* A, int M, long long n, long long gl, long l
     const long long total = (gl + gr) * M;
     if (total <= 0) return cudaSuccess;
     halo_wrap_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(A, M, n, gl, gr);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) halo_wrap_batch_kernel(double* __restrict__ A, int M, long long n,
+                                                              long long gl, long long gr, long long slot) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (gl + gr) * M;
+    if (idx >= total) return;
+    A += (size_t)blockIdx.y * slot * M;
+    const long long s = idx / M;
+    const int k = (int)(idx % M);
+    const long long g = s < gl ? s - gl : n + (s - gl);
+    long long src = g % n;
+    if (src < 0) src += n;
+    A[g * M + k] = A[src * M + k];
+}
+
+cudaError_t launch_halo_wrap_batch(double* A, int M, long long n, long long gl, long long gr, int batch,
+                                   long long slot, cudaStream_t st, LaunchStats* ls) {
+    const long long total = (gl + gr) * M;
+    if (total <= 0 || batch < 1) return cudaSuccess;
+    dim3 grid((unsigned)((total + 255) / 256), (unsigned)batch);
+    halo_wrap_batch_kernel<<<grid, 256, 0, st>>>(A, M, n, gl, gr, slot);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// one thread per (step, problem, column-sum): canonical tree over the problem's leaves
+__global__ void __launch_bounds__(128) batch_jreduce_kernel(const double* __restrict__ leaves, long long nleaf_total,
+                                                            long long leaf0, long long slot_leaves, long long leaves_pp,
+                                                            int C, int batch, long long steps, double* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= steps * batch * C) return;
+    const int c = (int)(idx % C);
+    const long long sp = idx / C;
+    const int p = (int)(sp % batch);
+    const long long step = sp / batch;
+    const double* in = leaves + ((size_t)step * nleaf_total + leaf0 + (size_t)p * slot_leaves) * C + c;
+    int L = 0;
+    while ((1LL << L) < leaves_pp) ++L;
+    TreeAcc<24> acc;
+    acc.reset();
+    for (long long j = 0; j < (1LL << L); ++j) acc.push(j < leaves_pp ? in[(size_t)j * C] : 0.0);
+    out[idx] = acc.result(L);
+}
+
+cudaError_t launch_batch_jreduce(const double* leaves, long long nleaf_total, long long leaf0, long long slot_leaves,
+                                 long long leaves_pp, int C, int batch, long long steps, double* out,
+                                 cudaStream_t st, LaunchStats* ls) {
+    const long long total = steps * batch * C;
+    if (total <= 0) return cudaSuccess;
+    batch_jreduce_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(leaves, nleaf_total, leaf0, slot_leaves,
+                                                                          leaves_pp, C, batch, steps, out);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }

@@ -31,6 +31,12 @@ __global__ void __launch_bounds__(512) lss_solve_kernel(const double* __restrict
     __shared__ int fail;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const size_t mm = (size_t)m * m;
+    {   // problem blockIdx.x of a batch
+        const size_t p = blockIdx.x;
+        R += p * K * mm; b += p * K * m; alpha += p * K * m;
+        work += p * ((size_t)2 * K * mm + (size_t)2 * K * m);
+        status += p;
+    }
     double* Cst = work;                       // [K][m][m]
     double* Est = work + (size_t)K * mm;      // [K][m][m]
     double* yst = Est + (size_t)K * mm;       // [K][m]
@@ -149,11 +155,11 @@ __global__ void __launch_bounds__(512) lss_solve_kernel(const double* __restrict
 }
 
 cudaError_t launch_lss_solve(const double* R, const double* b, long long K, int m, double* alpha, double* work,
-                             int* status, cudaStream_t st, LaunchStats* ls) {
+                             int* status, cudaStream_t st, LaunchStats* ls, int batch) {
     const size_t smem = lss_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(lss_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    lss_solve_kernel<<<1, 512, smem, st>>>(R, b, K, m, alpha, work, status);
+    lss_solve_kernel<<<batch > 0 ? batch : 1, 512, smem, st>>>(R, b, K, m, alpha, work, status);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }

@@ -26,8 +26,11 @@ class Context:
 
     def __init__(self, n_local, m, scheme='rk4', math='exact', dt=0.01, device=0,
                  n_global=None, site_offset=0, rank=0, world=1, max_halo_steps=0,
-                 simple_kernels=False, stream=None):
+                 simple_kernels=False, stream=None, batch=1):
         self.lib = _lib.load()
+        self.batch = int(batch)
+        # leading problem axis of every host array of a batched context
+        self.lead = (self.batch,) if self.batch > 1 else ()
         self.n = int(n_local)
         self.m = int(m)
         self.M = self.m + 2
@@ -38,7 +41,7 @@ class Context:
                              rank=self.rank, world=self.world, max_halo_steps=int(max_halo_steps),
                              flags=(_lib.FDS_FLAG_SIMPLE_KERNELS if simple_kernels else 0) |
                                    (_lib.FDS_FLAG_EXTERNAL_STREAM if stream is not None else 0),
-                             dt=float(dt), stream=stream)
+                             dt=float(dt), stream=stream, batch=self.batch if self.batch > 1 else 0)
         h = ctypes.c_void_p()
         rc = self.lib.fds_ctx_create(ctypes.byref(cfg), ctypes.byref(h))
         if rc != 0:
@@ -85,24 +88,24 @@ class Context:
     # -- state --------------------------------------------------------------- #
     def set_state(self, u):
         u = np.ascontiguousarray(u, dtype=np.float64)
-        assert u.shape == (self.n,)
+        assert u.shape == self.lead + (self.n,)
         self._ck(self.lib.fds_set_state(self.h, dptr(u)))
 
     def get_state(self):
-        u = _lib.host_empty((self.n,))
+        u = _lib.host_empty(self.lead + (self.n,))
         self._ck(self.lib.fds_get_state(self.h, dptr(u)))
         return u
 
     def set_tangents(self, V, v=None):
         V = np.ascontiguousarray(V, dtype=np.float64)
-        assert V.shape == (self.m, self.n)
+        assert V.shape == self.lead + (self.m, self.n)
         if v is not None:
             v = np.ascontiguousarray(v, dtype=np.float64)
-            assert v.shape == (self.n,)
+            assert v.shape == self.lead + (self.n,)
         self._ck(self.lib.fds_set_tangents(self.h, dptr(V), dptr(v)))
 
     def get_tangents(self):
-        V, v = _lib.host_empty((self.m, self.n)), _lib.host_empty((self.n,))
+        V, v = _lib.host_empty(self.lead + (self.m, self.n)), _lib.host_empty(self.lead + (self.n,))
         self._ck(self.lib.fds_get_tangents(self.h, dptr(V), dptr(v)))
         return V, v
 
@@ -116,6 +119,12 @@ class Context:
 
     def set_time_dilation(self, enabled):
         self._ck(self.lib.fds_set_time_dilation(self.h, int(bool(enabled))))
+
+    def set_batch_params(self, ds):
+        """Problem p of a batched context runs at parameter s + ds[p]."""
+        ds = np.ascontiguousarray(ds, dtype=np.float64)
+        assert ds.shape == (self.batch,)
+        self._ck(self.lib.fds_set_batch_params(self.h, dptr(ds)))
 
     # -- solver plugin ------------------------------------------------------- #
     def run(self, s, steps, want_J=True):
@@ -159,18 +168,18 @@ class Context:
         self._ck(self.lib.fds_boundary_finish(self.h, int(do_qr), float(eps), int(build)))
 
     def boundary_results(self, do_qr):
-        m = self.m
-        R = np.empty((m, m)) if do_qr else None
-        b = np.empty(m) if do_qr else None
-        Gd, gd = np.empty(m), np.empty(1)
+        m, L = self.m, self.lead
+        R = np.empty(L + (m, m)) if do_qr else None
+        b = np.empty(L + (m,)) if do_qr else None
+        Gd, gd = np.empty(L + (m,)), np.empty(L + (1,))
         self._ck(self.lib.fds_boundary_results(self.h, dptr(R), dptr(b), dptr(Gd), dptr(gd)))
-        return R, b, Gd, float(gd[0])
+        return R, b, Gd, (gd[:, 0] if L else float(gd[0]))
 
     def segment_advance(self, s, eps, step0, nsteps):
         self._ck(self.lib.fds_segment_advance(self.h, float(s), float(eps), int(step0), int(nsteps)))
 
     def segment_jsums(self, steps):
-        J = np.empty((int(steps), self.M, 2))
+        J = np.empty((int(steps),) + self.lead + (self.M, 2))
         self._ck(self.lib.fds_segment_jsums(self.h, int(steps), dptr(J)))
         return J
 
@@ -196,21 +205,23 @@ class Context:
         u = np.array(u, dtype=np.float64, order='C')
         V = np.array(V, dtype=np.float64, order='C')
         v = np.array(v, dtype=np.float64, order='C')
-        J = np.empty((int(steps), self.M, 2))
+        J = np.empty((int(steps),) + self.lead + (self.M, 2))
         self._ck(self.lib.fds_run_segment_host(self.h, dptr(u), dptr(V), dptr(v), float(s), float(eps),
                                                int(steps), dptr(J)))
         return u, V, v, J
 
 
 def lss_solve(R, b, device=0):
-    """LssTangent.solve on the device (reference fds/lsstan.py:36-50)."""
+    """LssTangent.solve on the device (reference fds/lsstan.py:36-50).  R (K, m, m), b (K, m)
+    -> alpha (K, m); with a leading batch axis on both, one CTA per problem."""
     lib = _lib.load()
     R = np.ascontiguousarray(R, dtype=np.float64)
     b = np.ascontiguousarray(b, dtype=np.float64)
-    K, m = b.shape
-    assert R.shape == (K, m, m)
-    alpha = np.empty((K, m))
-    rc = lib.fds_lss_solve(int(device), dptr(R), dptr(b), K, m, dptr(alpha))
+    K, m = b.shape[-2:]
+    assert R.shape == b.shape[:-1] + (m, m) and b.ndim in (2, 3)
+    alpha = np.empty(b.shape)
+    nbatch = b.shape[0] if b.ndim == 3 else 1
+    rc = lib.fds_lss_solve_batch(int(device), dptr(R), dptr(b), K, m, nbatch, dptr(alpha))
     if rc != 0:
         raise FdsError(lib.fds_last_error(None).decode())
     return alpha

@@ -24,8 +24,11 @@ class _DevView:
 
 class Engine:
     def __init__(self, n_global, m, scheme='rk4', math='exact', dt=0.01, device=None,
-                 group=None, distributed=None, max_halo_steps=0, simple_kernels=False, stream=None):
+                 group=None, distributed=None, max_halo_steps=0, simple_kernels=False, stream=None, batch=1):
         self.n_global = int(n_global)
+        self.batch = int(batch)
+        if self.batch > 1:
+            distributed = False        # a batch lives on one GPU; ranks take disjoint slices of the sweep
         self.m = int(m)
         self.M = self.m + 2
         # Lorenz-96: the device returns SUMS over sites of [x, x^2] -> divide by N;
@@ -58,7 +61,8 @@ class Engine:
         self.lo, self.hi = shard_range(self.n_global, rank, world)
         self.ctx = Context(self.hi - self.lo, m, scheme=scheme, math=math, dt=dt, device=self.device,
                            n_global=self.n_global, site_offset=self.lo, rank=rank, world=world,
-                           max_halo_steps=max_halo_steps, simple_kernels=simple_kernels, stream=stream)
+                           max_halo_steps=max_halo_steps, simple_kernels=simple_kernels, stream=stream,
+                           batch=self.batch)
         self.time_dilation = True
 
     # -- sharding of host arrays --------------------------------------------- #
@@ -117,7 +121,7 @@ class Engine:
             if want_J and steps > 0:
                 part = self._view(_lib.FDS_BUF_JSUM, 0, steps * 2).clone()
                 Js = self.ring.ordered_sum(part).reshape(steps, 2)
-        return None if Js is None else Js[:, :self.n_qoi] / self.j_div
+        return None if Js is None else Js[..., :self.n_qoi] / self.j_div
 
     # -- one boundary ----------------------------------------------------------- #
     def boundary(self, s, eps, from_ensemble, do_qr, build, keep_tangents=True):
@@ -152,7 +156,7 @@ class Engine:
         else:
             part = self._view(_lib.FDS_BUF_JSUM, 0, steps * self.M * 2).clone()
             Js = self.ring.ordered_sum(part).reshape(steps, self.M, 2)
-        return Js[:, :, :self.n_qoi] / self.j_div
+        return Js[..., :self.n_qoi] / self.j_div
 
     # -- state in / out (global host arrays) ------------------------------------ #
     def set_state(self, u):
@@ -174,7 +178,7 @@ class Engine:
         numpy (small N; honours np.random.seed like the reference); otherwise a
         counter-based device generator keyed on the global (row, site) index."""
         if host_rng is not None:
-            W = host_rng.rand(self.m, self.n_global)
+            W = host_rng.rand(*(self.ctx.lead + (self.m, self.n_global)))
             self.ctx.set_tangents(self.local(W), None)
         else:
             self.ctx.random_tangents(seed)

@@ -143,3 +143,80 @@ def shadowing(run, u0, parameter, subspace_dimension, num_segments, steps_per_se
     return _segment_loop(eng, parameter, LssTangent(device_ordinal=eng.device), [], [], [], [], [],
                          num_segments, steps_per_segment, epsilon, checkpoint_path,
                          checkpoint_interval, return_checkpoint, verbose)
+
+
+# --------------------------------------------------------------------------- #
+# Batched parameter sweep (BASELINE configs[4]): B independent shadowing problems of the
+# same system in ONE device context.  The reference can only loop over them
+# (tests/test_lorenz.py:35-41, apps/lorenz_demo.py:86-89); the result of problem p equals
+# shadowing(run, u0[p], parameters[p], ...) on its own.
+# --------------------------------------------------------------------------- #
+def lss_gradient_batch(Rs, bs, G_lss, g_lss, J, G_dil, g_dil, device=0):
+    """Vectorised lss_gradient (reference fds/fds.py:29-51) over a leading problem axis.
+    Rs (B,K,m,m), bs (B,K,m), G_lss (B,K,m,q), g_lss (B,K,q), J (B,K,steps,q), G_dil (B,K,m),
+    g_dil (B,K) -> dJ/ds (B,q)."""
+    from . import device as dev
+    alpha = dev.lss_solve(Rs, bs, device)                                    # (B,K,m)
+    grad_lss = (alpha[..., np.newaxis] * G_lss).sum(2) + g_lss                 # (B,K,q)
+    dJ = trapez_mean(J.mean(1), 1)[:, np.newaxis] - J[:, :, -1]                # (B,K,q)
+    dil = ((alpha * G_dil).sum(2) + g_dil) / J.shape[2]                        # (B,K)
+    grad_dil = dil[..., np.newaxis] * dJ
+    K = grad_lss.shape[1]
+    return grad_lss.sum(1) / K + grad_dil.sum(1) / K
+
+
+def shadowing_batch(run, u0, parameters, subspace_dimension, num_segments, steps_per_segment,
+                    runup_steps, epsilon=1E-6, run_ddt=None, tangent_seed=None, return_histories=False):
+    """``shadowing`` for a sweep of parameters: problem p starts from ``u0[p]`` (or the shared
+    ``u0`` if it is one-dimensional) and runs at ``parameters[p]``.
+    Returns (J (B, n_qoi), dJ/ds (B, n_qoi)); with ``return_histories`` also the dict of the
+    per-segment histories (Rs, bs, G_lss, g_lss, J, G_dil, g_dil, each with a leading B axis)."""
+    parameters = np.ascontiguousarray(parameters, dtype=np.float64).ravel()
+    B, m = parameters.size, int(subspace_dimension)
+    if run_ddt is not None and run_ddt != 0:
+        raise NotImplementedError('run_ddt: only None (finite-difference time dilation) or 0 (off)')
+    if B < 2:
+        raise ValueError('shadowing_batch needs at least two problems; use shadowing() for one')
+    be = getattr(run, 'batch_engine', None)
+    if be is None:
+        raise TypeError('shadowing_batch needs a device plugin (e.g. fds_b200.L96)')
+    eng = be(m, B)
+    N = eng.n_global
+    u0 = np.asarray(u0, dtype=np.float64)
+    if u0.ndim == 1:
+        u0 = np.broadcast_to(u0, (B, N))
+    eng.set_time_dilation(run_ddt is None)
+    eng.ctx.set_dxdt_weights(stencil_weights(3))
+    eng.ctx.set_batch_params(parameters)          # problem p runs at 0.0 + parameters[p]
+    eng.set_state(np.ascontiguousarray(u0))
+    s = 0.0
+    if runup_steps > 0:
+        eng.run(s, runup_steps, want_J=False)
+    if tangent_seed is None and B * m * N <= HOST_RNG_MAX_ELEMS:
+        eng.orthonormal_random_tangents(host_rng=np.random)
+    else:
+        seed = np.random.randint(2 ** 31 - 1) if tangent_seed is None else tangent_seed
+        eng.orthonormal_random_tangents(seed=seed)
+
+    Rs, bs, G_lss, g_lss, J_hist, G_dil, g_dil = [], [], [], [], [], [], []
+
+    def record_segment():
+        J = eng.segment(s, epsilon, steps_per_segment)          # (steps, B, m+2, q)
+        J0 = np.ascontiguousarray(J[:, :, 0])
+        G = np.stack([trapez_mean(J[:, :, 1 + j] - J0, 0) / epsilon for j in range(m)], axis=1)   # (B,m,q)
+        g = trapez_mean(J[:, :, m + 1] - J0, 0) / epsilon                                        # (B,q)
+        J_hist.append(np.moveaxis(J0, 0, 1)), G_lss.append(G), g_lss.append(g)
+
+    eng.boundary(s, epsilon, from_ensemble=0, do_qr=0, build=1)
+    record_segment()
+    for i in range(1, num_segments + 1):
+        last = i == num_segments
+        R, b, Gd, gd = eng.boundary(s, epsilon, from_ensemble=1, do_qr=1, build=not last, keep_tangents=False)
+        Rs.append(R), bs.append(b), G_dil.append(Gd), g_dil.append(gd)
+        if not last:
+            record_segment()
+    H = dict(Rs=np.stack(Rs, 1), bs=np.stack(bs, 1), G_lss=np.stack(G_lss, 1), g_lss=np.stack(g_lss, 1),
+             J=np.stack(J_hist, 1), G_dil=np.stack(G_dil, 1), g_dil=np.stack(g_dil, 1))
+    G = lss_gradient_batch(H['Rs'], H['bs'], H['G_lss'], H['g_lss'], H['J'], H['G_dil'], H['g_dil'], eng.device)
+    Jm = H['J'].mean((1, 2))
+    return (Jm, G, H) if return_histories else (Jm, G)

@@ -28,6 +28,15 @@ class _DevicePlugin:
             self._engines[m] = Engine(self.N, m, **self.kw)
         return self._engines[m]
 
+    def batch_engine(self, m, batch):
+        """Engine holding ``batch`` independent problems of this system (parameter sweep)."""
+        key = (m, int(batch))
+        if key not in self._engines:
+            kw = dict(self.kw)
+            kw.pop('group', None), kw.pop('distributed', None)
+            self._engines[key] = Engine(self.N, m, batch=int(batch), **kw)
+        return self._engines[key]
+
     def __call__(self, u0, parameter, steps, run_id=None, interprocess=None):
         eng = self.engine(1)
         eng.set_state(u0)

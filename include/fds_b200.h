@@ -84,6 +84,10 @@ typedef struct fds_config {
     int32_t flags;         /* FDS_FLAG_*                                           */
     double  dt;            /* time step (0 = 0.01)                                 */
     void*   stream;        /* cudaStream_t to launch on (NULL = own stream)        */
+    int32_t batch;         /* > 1: that many INDEPENDENT problems of n_local sites
+                              each in one context (parameter sweep; world = 1,
+                              Lorenz-96 RK4, n_local a multiple of 64)            */
+    int32_t reserved;
 } fds_config;
 
 /* ---- life cycle ------------------------------------------------------------- */
@@ -167,6 +171,17 @@ int fds_segment(fds_ctx*, double s, double eps, int64_t steps, double* Jsum_host
  * u, V, v in -> advanced u, V, v out, Jsum[steps][m+2][2]; H2D and D2H inside     */
 int fds_run_segment_host(fds_ctx*, double* u, double* V, double* v, double s, double eps,
                          int64_t steps, double* Jsum_host);
+
+/* ---- batched parameter sweep (BASELINE configs[4]) -----------------------------
+ * A context created with cfg.batch = B holds B independent problems; the reference can only
+ * loop over them (tests/test_lorenz.py:35-41, apps/lorenz_demo.py:86-89).  Every call above acts
+ * on all problems at once; host arrays gain a leading problem axis -- u[B][n], V[B][m][n],
+ * v[B][n], R[B][m][m], b[B][m], G_dil[B][m], g_dil[B], Jsum[steps][B][m+2][2] -- and problem p
+ * runs at parameter s + ds[p].  fds_segment_advance takes at most fds_halo_steps() per call.   */
+int fds_set_batch_params(fds_ctx*, const double* ds);   /* ds[B] (NULL = all zero) */
+int fds_batch_count(const fds_ctx*);
+int fds_lss_solve_batch(int device, const double* R, const double* b, int64_t K, int m, int64_t nbatch,
+                        double* alpha);                  /* R[B][K][m][m], b / alpha [B][K][m] */
 
 /* ---- LssTangent.solve (fds/lsstan.py:36-50): min |a|^2 s.t. a_{i+1}=R_i a_i+b_i */
 /* R[K][m][m], b[K][m] -> alpha[K][m]; single-CTA block-tridiagonal Cholesky       */
