@@ -54,6 +54,7 @@ def parse():
     ap.add_argument('--cpu-seg-steps', type=int, default=10)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-sweep', action='store_true', help='skip the batched-sweep side measurement')
     return ap.parse_args()
 
 
@@ -177,6 +178,36 @@ def djds_check(device):
             'G': G.tolist(), 'G_ref': g['G_ref'].tolist(), 'sigma_ref': g['G_err'].tolist(),
             'abs_err': err.tolist(), 'ratio': (err / g['G_err']).tolist(),
             'pass': bool((err <= g['G_err']).all())}
+
+
+def sweep_check(device, B=4096, N=4096, m=16, K=2, steps=100):
+    """BASELINE configs[4] measured beside the headline: B independent Lorenz-96 problems (F swept
+    over [6, 10]) in one batched context; whole segments (boundary + 100 steps), device resident."""
+    import fds_b200
+    eps = 1e-4
+    run = fds_b200.L96(N, device=device, distributed=False)
+    eng = run.batch_engine(m, B)
+    eng.ctx.set_batch_params(np.linspace(-2.0, 2.0, B))
+    eng.set_state(np.random.RandomState(0).rand(B, N))
+    eng.run(0.0, 200, want_J=False)
+    eng.orthonormal_random_tangents(seed=1)
+    eng.boundary(0.0, eps, 0, 0, 1)
+    eng.segment(0.0, eps, steps)
+
+    def seg():
+        R = eng.boundary(0.0, eps, 1, 1, 1, keep_tangents=False)[0]
+        return R, eng.segment(0.0, eps, steps)
+    seg()
+    eng.ctx.sync()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        R, J = seg()
+    eng.ctx.sync()
+    dt = time.perf_counter() - t0
+    ok = bool(np.isfinite(J).all() and np.isfinite(R).all())
+    run.close()
+    return {'config': '%d independent Lorenz-96 N=%d problems, m=%d, one batched context on one GPU' % (B, N, m),
+            'value': B * N * (m + 1) * steps * K / dt, 'unit': UNIT, 'segments': K, 'seconds': dt, 'finite': ok}
 
 
 def run_ours(args):
@@ -314,6 +345,8 @@ def run_ours(args):
         if e2e is not None:
             line['e2e'] = e2e
         line['djds'] = djds_check(local_rank)
+        if world == 1 and not args.no_sweep:
+            line['sweep_cfg5'] = sweep_check(local_rank)
         if not args.no_cpu and world == 1:
             line['cpu_baseline'] = cpu_baseline(args)
         print(json.dumps(line))
