@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SOURCES = ['l96_step.cu', 'boundary.cu', 'boundary_fast.cu', 'lss.cu', 'toy_ode.cu', 'ctx.cu']
+SOURCES = ['l96_step.cu', 'boundary.cu', 'boundary_fast.cu', 'boundary_mma.cu', 'lss.cu', 'toy_ode.cu', 'ctx.cu']
 OUT = os.path.join(HERE, 'libfds_b200.so')
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']

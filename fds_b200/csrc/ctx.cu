@@ -120,6 +120,9 @@ static int check_small_status(fds_ctx* c, const char* what) {
 }
 
 static cudaError_t do_gram(fds_ctx* c, int src, double inv_eps) {
+    if (c->fast_boundary && gram_mma_supported(c->m))
+        return launch_gram_mma(src, c->Ecur(), c->T, c->d, c->m, inv_eps, c->n, c->gram_part, c->max_part,
+                               c->small.gram, c->num_sms, c->stream, &c->ls);
     if (c->fast_boundary)
         return launch_gram_fast(src, c->Ecur(), c->T, c->d, c->m, inv_eps, c->n, c->gram_part, c->max_part,
                                 c->small.gram, c->num_sms, c->stream, &c->ls);

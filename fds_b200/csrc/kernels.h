@@ -125,6 +125,13 @@ cudaError_t launch_apply_fast(int src, const double* E, const double* Tin, const
                               int m, double inv_eps, long long n, double* Tout, double* E_out, const double* u,
                               double eps, int num_sms, cudaStream_t, LaunchStats*);
 
+// ---- boundary_mma.cu ----------------------------------------------------------- //
+// Gram on the FP64 tensor cores (mma.sync m8n8k4); same contract as launch_gram_fast
+bool gram_mma_supported(int m);
+cudaError_t launch_gram_mma(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
+                            long long n, double* part, int max_part, double* out, int num_sms, cudaStream_t,
+                            LaunchStats*);
+
 // ---- toy_ode.cu -------------------------------------------------------------- //
 // small ODE systems (Lorenz-63, Van der Pol, circular): state dimension, 0 for the L96 systems
 int toy_dim(int system);
