@@ -1,6 +1,6 @@
 """Turn gpurun_out ncu artefacts into the committed summaries under profiles/ (development aid).
 
-    python tools/summarize_profiles.py <round-tag> <launches.csv> <prof.ncu-rep>
+    python tools/summarize_profiles.py <round-tag> <launches.csv> <name>=<prof.ncu-rep> [...]
 """
 import collections
 import csv
@@ -8,7 +8,7 @@ import json
 import subprocess
 import sys
 
-tag, launches, rep = sys.argv[1], sys.argv[2], sys.argv[3]
+tag, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
 
 # ---- launch list: per-kernel totals and shares -------------------------------
 lines = [l for l in open(launches) if not l.startswith('==')]
@@ -25,44 +25,58 @@ for row in csv.DictReader(lines):
     a[1] += v
 tot = sum(v[1] for v in agg.values())
 with open('profiles/%s_launches_summary.txt' % tag, 'w') as f:
-    f.write('# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e\n')
-    f.write('# launches after the set-up phase (-s 420); times are cold-cache and serialised: compare SHARES\n')
+    f.write('# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-sweep\n')
+    f.write('# launches of the timed region (set-up skipped with -s); times are cold-cache and serialised: compare SHARES\n')
     f.write('%-58s %7s %12s %10s %7s\n' % ('kernel', 'n', 'total_ms', 'avg_ms', 'share'))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write('%-58s %7d %12.3f %10.4f %6.1f%%\n' % (k[:58], v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
     f.write('%-58s %7d %12.3f\n' % ('TOTAL', sum(v[0] for v in agg.values()), tot))
 
-# ---- full capture of the step kernel -----------------------------------------
-raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-rows = list(csv.reader(raw.splitlines()))
-hdr, units, data = rows[0], rows[1], rows[2:]
-want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
-        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram__cycles_active.avg.pct_of_peak_sustained_elapsed',
-        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'launch__grid_size',
-        'launch__block_size', 'sm__cycles_elapsed.avg.per_second', 'sm__inst_executed.sum',
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'launch__shared_mem_per_block_dynamic', 'sm__cycles_elapsed.avg.per_second',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
         'lts__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
-        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio']
-ix = {h: i for i, h in enumerate(hdr)}
-kname = data[0][ix['Kernel Name']] if 'Kernel Name' in ix else 'l96_rk4_stream_kernel'
-with open('profiles/%s_step_kernel_ncu.txt' % tag, 'w') as f:
-    f.write('# ncu --set full --clock-control none --import-source on -k regex:l96_rk4_stream : bench.py, N=2^24, m=32\n')
-    f.write('# kernel: %s ; one column per captured launch\n' % kname)
-    for w in want:
-        if w in ix:
-            f.write('%-92s %-14s %s\n' % (w, units[ix[w]], ' | '.join(r[ix[w]] for r in data)))
-rd = [float(r[ix['dram__bytes_read.sum']]) for r in data]
-wr = [float(r[ix['dram__bytes_write.sum']]) for r in data]
-scale = {'Gbyte': 1e9, 'Mbyte': 1e6, 'byte': 1.0, 'Kbyte': 1e3, 'Tbyte': 1e12}
-su = scale[units[ix['dram__bytes_read.sum']]]
-wu = scale[units[ix['dram__bytes_write.sum']]]
-traffic = sum(a * su + b * wu for a, b in zip(rd, wr)) / len(rd)
-json.dump({'kernel': 'l96_rk4_stream_kernel', 'dram_bytes_per_launch': traffic,
-           'source': 'profiles/%s_step_kernel_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)' % tag,
-           'workload': 'N=2^24 sites, m=32 (34 trajectories)'}, open('profiles/step_kernel_traffic.json', 'w'), indent=1)
-print('traffic per launch: %.3f GB' % (traffic / 1e9))
+        'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio']
+
+traffic = {}
+for spec in reps:
+    name, rep = spec.split('=')
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    ki = hdr.index('Kernel Name')
+    with open('profiles/%s_%s_ncu.txt' % (tag, name), 'w') as f:
+        f.write('# ncu --set full --clock-control none --import-source on : bench.py, N=2^24, m=32; one column per captured launch\n')
+        f.write('# kernels: %s\n' % ' | '.join(r[ki] for r in data))
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                f.write('%-92s %-14s %s\n' % (w, units[i], ' | '.join(r[i] for r in data)))
+    def val(r, w):
+        i = hdr.index(w)
+        x = float(r[i].replace(',', ''))
+        return x * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12}[units[i]]
+    for r in data:
+        k = r[ki].split('(')[0].replace('void ', '').replace('fds::', '')
+        traffic.setdefault(k, []).append(val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum'))
+out = {k: {'dram_bytes_per_launch': sum(v) / len(v)} for k, v in traffic.items()}
+if out:
+    step = [k for k in out if 'l96_rk4_stream' in k]
+    doc = {'kernel': 'l96_rk4_stream_kernel',
+           'dram_bytes_per_launch': out[step[0]]['dram_bytes_per_launch'] if step else None,
+           'source': 'profiles/%s_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)' % tag,
+           'workload': 'N=2^24 sites, m=32 (34 trajectories)', 'all_kernels': out}
+    json.dump(doc, open('profiles/step_kernel_traffic.json', 'w'), indent=1)
+print('ok', list(out))
