@@ -105,7 +105,7 @@ def run_reference(args):
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args):
@@ -349,7 +349,7 @@ def run_ours(args):
             line['sweep_cfg5'] = sweep_check(local_rank)
         if not args.no_cpu and world == 1:
             line['cpu_baseline'] = cpu_baseline(args)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -388,7 +388,18 @@ class _LocalEngine:
         self.e.ctx.set_tangents(V, v)
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints at the C level
+    (e.g. NCCL's version banner) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == '__main__':
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == 'reference':
         run_reference(a)
