@@ -46,6 +46,8 @@ SIGNATURES = {
     'fds_random_tangents': (_I32, [_CTX, ctypes.c_uint64]),
     'fds_set_dxdt_weights': (_I32, [_CTX, c_double_p]),
     'fds_set_time_dilation': (_I32, [_CTX, _I32]),
+    'fds_set_qr_passes': (_I32, [_CTX, _I32]),
+    'fds_last_condition': (_D, [_CTX]),
     'fds_run': (_I32, [_CTX, _D, _I64, c_double_p]),
     'fds_primal_advance': (_I32, [_CTX, _D, _I64, _I64, _I32]),
     'fds_halo_mark_valid': (_I32, [_CTX, _I32, _I64]),

@@ -577,6 +577,120 @@ __global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long lo
     if (tid == 0) *B.status = fail;
 }
 
+// Single-pass CholeskyQR with its own certificate: everything the boundary needs -- G_dil, g_dil,
+// the projection, Q = L^-1 P, R = L^T, b = Q p_w, w <- p_w - b^T Q -- from ONE extended Gram, as the
+// constant matrix A.  The loss of orthogonality of one Cholesky pass is ~ cond_2(P)^2 u = cond_2(G) u
+// with G = P P^T the projected Gram; for the symmetric G, |G|_2 <= |G|_inf, so
+// sqrt(|G|_inf |G^-1|_inf) >= cond_2(P).  The kernel reports that bound next to the status so that
+// the host can fall back to the two-pass CholeskyQR2 (small1 / small2) whenever it is not negligible.
+__global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, int use_d, long long bstride) {
+    B = small_of(B, bstride, blockIdx.x);
+    extern __shared__ __align__(16) double sm[];
+    const int MX = m + 2, MO = m + 1, D = m + 1;
+    double* G = sm;                      // MX*MX
+    double* Gp = G + MX * MX;            // m*m   projected Gram -> L
+    double* Li = Gp + m * m;             // m*m
+    double* c = Li + m * m;              // MX    projection coefficients
+    double* bb = c + MX;                 // m     b, then b^T L^-1
+    __shared__ int fail;
+    __shared__ double nrm[2];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) { fail = 0; nrm[0] = 0.0; nrm[1] = 0.0; }
+    for (int e = tid; e < MX * MX; e += nthr) G[e] = B.gram[e];
+    __syncthreads();
+    const double dd = G[D * MX + D];
+    for (int k = tid; k < MO; k += nthr) {
+        const double ck = use_d ? G[k * MX + D] / dd : 0.0;
+        c[k] = ck;
+        B.gdil[k] = ck;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * m; e += nthr) {
+        const int j = e / m, l = e % m;
+        Gp[e] = use_d ? G[j * MX + l] - c[j] * G[l * MX + D] : G[j * MX + l];
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += nthr) {            // row sums of |G| (before it is factored in place)
+        double r = 0.0;
+        for (int l = 0; l < m; ++l) r += fabs(Gp[j * m + l]);
+        bb[j] = r;
+    }
+    __syncthreads();
+    if (tid == 0) { double a = 0.0; for (int j = 0; j < m; ++j) a = fmax(a, bb[j]); nrm[0] = a; }
+    __syncthreads();
+    cta_cholesky(Gp, m, m, &fail);
+    cta_tri_inverse(Gp, m, m, Li);
+    for (int a = tid; a < m; a += nthr) {            // row sums of |G^-1| = |L^-T L^-1|
+        double r = 0.0;
+        for (int b = 0; b < m; ++b) {
+            double e = 0.0;
+            for (int k = a > b ? a : b; k < m; ++k) e += Li[k * m + a] * Li[k * m + b];
+            r += fabs(e);
+        }
+        bb[a] = r;
+    }
+    __syncthreads();
+    if (tid == 0) { double a = 0.0; for (int j = 0; j < m; ++j) a = fmax(a, bb[j]); nrm[1] = a; }
+    __syncthreads();
+    // b = L^-1 <P_j, p_w>,  <P_j, p_w> = G[j][m] - c_j G[m][D]
+    for (int j = tid; j < m; j += nthr) {
+        double s = 0.0;
+        for (int l = 0; l <= j; ++l) s += Li[j * m + l] * (use_d ? G[l * MX + m] - c[l] * G[m * MX + D] : G[l * MX + m]);
+        B.b[j] = s;
+        bb[j] = s;
+    }
+    for (int e = tid; e < m * m; e += nthr) {        // R = L^T (upper triangular); L1 kept for completeness
+        const int a = e / m, b = e % m;
+        B.R[e] = b >= a ? Gp[b * m + a] : 0.0;
+        B.L1[e] = b <= a ? Gp[e] : 0.0;
+    }
+    __syncthreads();
+    // q_l = (b^T L^-1)_l
+    for (int e = tid; e < MO * MX; e += nthr) {
+        const int o = e / MX, l = e % MX;
+        double v = 0.0;
+        if (o < m) {
+            if (l < m) v = l <= o ? Li[o * m + l] : 0.0;
+            else if (l == D) {                        // -(L^-1 c)_o
+                double s = 0.0;
+                for (int k = 0; k <= o; ++k) s += Li[o * m + k] * c[k];
+                v = -s;
+            }
+        } else {
+            if (l < m) {                              // -(b^T L^-1)_l
+                double s = 0.0;
+                for (int j = l; j < m; ++j) s += bb[j] * Li[j * m + l];
+                v = -s;
+            } else if (l == m) v = 1.0;
+            else {                                    // d column: -c_m + sum_l (b^T L^-1)_l c_l
+                double t = 0.0;
+                for (int ll = 0; ll < m; ++ll) {
+                    double s = 0.0;
+                    for (int j = ll; j < m; ++j) s += bb[j] * Li[j * m + ll];
+                    t += s * c[ll];
+                }
+                v = -c[m] + t;
+            }
+        }
+        B.A[e] = v;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        *B.status = fail;
+        reinterpret_cast<double*>(B.status)[1] = sqrt(nrm[0] * nrm[1]);
+    }
+}
+
+cudaError_t launch_small_single(const SmallBufs& B, int m, int use_d, cudaStream_t st, LaunchStats* ls,
+                                const BatchDesc* batch) {
+    const size_t smem = small_smem_bytes(m);
+    cudaError_t e = cudaFuncSetAttribute(small_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    small_single_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, batch ? batch->small_stride : 0);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_small1(const SmallBufs& B, int m, int use_d, int do_qr, cudaStream_t st, LaunchStats* ls,
                           const BatchDesc* batch) {
     const size_t smem = small_smem_bytes(m);

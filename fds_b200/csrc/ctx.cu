@@ -65,6 +65,12 @@ struct fds_ctx {
     bool state_in_ensemble = false;   // newest primal state is column 0 of the ensemble
     bool tangents_implicit = false;   // newest tangents are (E_k - E_0)/eps_last
     bool time_dilation = true;
+    // CholeskyQR: 0 = one pass when the first factor certifies cond^2 u negligible, else two; 2 = always two
+    int qr_mode = 0;
+    bool qr_single = false;           // a certified single-pass factor is waiting for fds_boundary_finish
+    int pend_src = 0;
+    double pend_inv_eps = 0.0;
+    double cond_last = 0.0;           // upper bound of cond_2 from the last single-pass attempt
     double eps_last = 0.0;
     long long ens_halo_valid = 0, pri_halo_valid = 0;
     LaunchStats ls;
@@ -109,11 +115,14 @@ static int check_small_status(fds_ctx* c, const char* what) {
                                             " of problem " + std::to_string(p) + " (tangent block numerically rank deficient)");
         return 0;
     }
-    FDS_CK(c, cudaMemcpyAsync(&st, c->small.status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    struct { int st; int pad; double cond; } sc = {0, 0, 0.0};
+    FDS_CK(c, cudaMemcpyAsync(&sc, c->small.status, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
     if (c->fast_boundary)
         FDS_CK(c, cudaMemcpyAsync(c->A_host, c->small.A, (size_t)c->MO * c->MX * sizeof(double),
                                   cudaMemcpyDeviceToHost, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
+    st = sc.st;
+    c->cond_last = sc.cond;
     if (st != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(st) +
                                     " (tangent block numerically rank deficient)");
     return 0;
@@ -363,6 +372,14 @@ int fds_set_dxdt_weights(fds_ctx* c, const double w[4]) {
 }
 
 int fds_set_time_dilation(fds_ctx* c, int enabled) { c->time_dilation = enabled != 0; return 0; }
+
+int fds_set_qr_passes(fds_ctx* c, int passes) {
+    if (passes != 0 && passes != 2) return fail(c, "fds_set_qr_passes: 0 (adaptive) or 2 (always CholeskyQR2)");
+    c->qr_mode = passes;
+    return 0;
+}
+
+double fds_last_condition(const fds_ctx* c) { return c->cond_last; }
 
 // ------------------------------- state in / out ------------------------------ //
 static int sync_primal_from_ensemble(fds_ctx* c) {
@@ -768,6 +785,21 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
 }
 
 int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
+    c->qr_single = false;
+    if (do_qr && c->fast_boundary && c->qr_mode == 0) {
+        // one Cholesky pass loses orthogonality like cond^2 u: take it when that is below 2e-13
+        FDS_CK(c, launch_small_single(c->small, c->m, c->time_dilation ? 1 : 0, c->stream, &c->ls));
+        const std::string keep = c->err;
+        const int r = check_small_status(c, "CholeskyQR");
+        if (r == 0 && c->cond_last * c->cond_last * 2.3e-16 < 2e-13) {
+            c->qr_single = true;
+            c->pend_src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
+            c->pend_inv_eps = from_ensemble ? 1.0 / eps : 0.0;
+            return 0;
+        }
+        if (r == 1) return r;             // CUDA error
+        c->err = keep;                    // ill conditioned or rank deficient: CholeskyQR2 decides
+    }
     FDS_CK(c, launch_small1(c->small, c->m, c->time_dilation ? 1 : 0, do_qr, c->stream, &c->ls, c->batch()));
     if (do_qr || c->fast_boundary) if (int r = check_small_status(c, "CholeskyQR pass 1")) return r;
     const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
@@ -782,7 +814,11 @@ int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
     // explicit tangents are written unless the caller only wants the next ensemble (hot loop)
     const bool keepT = !ens || (build & FDS_BUILD_KEEP_TANGENTS) != 0 || !c->fast_boundary;
     c->tangents_implicit = false;
-    if (do_qr) {
+    if (do_qr && c->qr_single) {
+        c->qr_single = false;
+        FDS_CK(c, do_apply(c, c->pend_src, c->pend_inv_eps, keepT ? c->T : nullptr, ens ? c->Ecur() : nullptr, eps));
+        if (!keepT) c->tangents_implicit = true;    // the new ensemble is the record of the tangents
+    } else if (do_qr) {
         FDS_CK(c, launch_small2(c->small, c->m, c->stream, &c->ls, c->batch()));
         if (int r = check_small_status(c, "CholeskyQR pass 2")) return r;
         FDS_CK(c, do_apply(c, SRC_TANGENT, 0.0, keepT ? c->T : nullptr, ens ? c->Ecur() : nullptr, eps));

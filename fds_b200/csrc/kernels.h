@@ -112,6 +112,9 @@ struct SmallBufs {          // all device pointers
 cudaError_t launch_small1(const SmallBufs&, int m, int use_d, int do_qr, cudaStream_t, LaunchStats*,
                           const BatchDesc* batch = nullptr);
 cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr);
+// single-pass CholeskyQR from one Gram; writes sqrt(|G|_inf |G^-1|_inf) >= cond_2 to ((double*)status)[1]
+cudaError_t launch_small_single(const SmallBufs&, int m, int use_d, cudaStream_t, LaunchStats*,
+                                const BatchDesc* batch = nullptr);
 size_t small_smem_bytes(int m);
 
 // ---- boundary_fast.cu ---------------------------------------------------------- //

@@ -120,6 +120,14 @@ class Context:
     def set_time_dilation(self, enabled):
         self._ck(self.lib.fds_set_time_dilation(self.h, int(bool(enabled))))
 
+    def set_qr_passes(self, passes):
+        """0: adaptive (one CholeskyQR pass when certified well conditioned), 2: always CholeskyQR2."""
+        self._ck(self.lib.fds_set_qr_passes(self.h, int(passes)))
+
+    @property
+    def last_condition(self):
+        return float(self.lib.fds_last_condition(self.h))
+
     def set_batch_params(self, ds):
         """Problem p of a batched context runs at parameter s + ds[p]."""
         ds = np.ascontiguousarray(ds, dtype=np.float64)

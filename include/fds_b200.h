@@ -113,6 +113,14 @@ int fds_set_dxdt_weights(fds_ctx*, const double c[4]);
 /* run_ddt=0 of the reference (fds/timedilation.py:59-61): no time dilation at boundaries   */
 int fds_set_time_dilation(fds_ctx*, int enabled);
 
+/* thin QR of the tangent block (LssTangent.checkpoint, fds/lsstan.py:20-34): CholeskyQR from the
+ * extended Gram.  passes = 0 (default): ONE pass when the first factor certifies that the loss of
+ * orthogonality cond^2 u is below 2e-13 (the usual case: one segment of growth leaves the block
+ * well conditioned), otherwise CholeskyQR2; passes = 2: always CholeskyQR2.
+ * fds_last_condition: the bound sqrt(|G|_inf |G^-1|_inf) >= cond_2 of the last single-pass attempt. */
+int    fds_set_qr_passes(fds_ctx*, int passes);
+double fds_last_condition(const fds_ctx*);
+
 /* ---- the solver plugin itself: u1, J = run(u0, s, steps), fds/fds.py:184-200 -- */
 /* single trajectory on the context's primal array (world == 1; halos wrapped inside);
  * Jsum_host is [steps][2] = [sum x, sum x^2] (divide by n_global for J) or NULL      */

@@ -238,3 +238,52 @@ def test_lss_solve_on_reference_history():
     sgn = np.sign(np.diagonal(g['Rs'], axis1=1, axis2=2))
     alpha = fds_b200.device.lss_solve(g['Rs'], g['bs'])
     assert maxrel(alpha, g['alpha_ref']) < 1e-9      # kappa of the 100-block Schur complement
+
+
+# --------------------------------------------------------------------------- #
+# adaptive CholeskyQR: one certified pass vs CholeskyQR2
+# --------------------------------------------------------------------------- #
+@gpu
+@pytest.mark.parametrize('name', ['seg_l96rk4_N40_m16', 'seg_l96rk4_N2048_m32'])
+def test_single_pass_qr_agrees_with_choleskyqr2(name):
+    g = golden(name)
+    N, m = g['u0'].shape[0], g['V'].shape[0]
+    out = {}
+    for passes in (0, 2):
+        eng = fds_b200.L96(N).engine(m)
+        eng.ctx.set_qr_passes(passes)
+        eng.ctx.set_dxdt_weights(fds_b200.timedilation.stencil_weights(3))
+        eng.set_state(g['u1'])
+        eng.set_tangents(g['V1'], g['v1'])
+        launches = eng.ctx.launches
+        R, b, Gd, gd = eng.boundary(float(g['s']), float(g['eps']), from_ensemble=0, do_qr=1, build=0)
+        out[passes] = (R, b, Gd, gd) + eng.get_tangents() + (eng.ctx.launches - launches, eng.ctx.last_condition)
+        eng.close()
+    one, two = out[0], out[2]
+    assert one[7] >= 1.0
+    if name == 'seg_l96rk4_N2048_m32':
+        assert one[7] < 29.5 and one[6] < two[6]           # certified: fewer kernels than two passes
+    for a, b in zip(one[:6], two[:6]):
+        assert maxrel(a, b) < 1e-12
+    Q = one[4]
+    assert np.abs(Q @ Q.T - np.eye(m)).max() < 1e-13
+    _check_boundary(g, *one[:6])
+
+
+@gpu
+def test_ill_conditioned_block_falls_back_to_two_passes():
+    """Nearly parallel tangents (cond ~ 1e3): cond^2 u is not negligible, the single pass is refused
+    and CholeskyQR2 still orthonormalises to rounding."""
+    N, m = 512, 8
+    eng = fds_b200.L96(N).engine(m)
+    eng.set_state(np.random.RandomState(0).rand(N))
+    rng = np.random.RandomState(1)
+    W = rng.rand(N) + 2e-3 * rng.rand(m, N)
+    eng.set_tangents(W, np.zeros(N))
+    eng.set_time_dilation(False)
+    R, b, _, _ = eng.boundary(0.0, 1e-4, from_ensemble=0, do_qr=1, build=0)
+    assert eng.ctx.last_condition > 30
+    Q, _ = eng.get_tangents()
+    assert np.abs(Q @ Q.T - np.eye(m)).max() < 1e-13
+    assert maxrel(R.T @ Q, W) < 1e-12
+    eng.close()
