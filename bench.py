@@ -196,7 +196,7 @@ def sweep_check(device, B=4096, N=4096, m=16, K=2, steps=100):
 
     def seg():
         R = eng.boundary(0.0, eps, 1, 1, 1, keep_tangents=False)[0]
-        return R, eng.segment(0.0, eps, steps)
+        return R, eng.segment_sens(0.0, eps, steps)[1]
     seg()
     eng.ctx.sync()
     t0 = time.perf_counter()

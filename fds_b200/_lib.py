@@ -69,6 +69,7 @@ SIGNATURES = {
     'fds_lss_solve_batch': (_I32, [_I32, c_double_p, c_double_p, _I64, _I32, _I64, c_double_p]),
     'fds_set_batch_params': (_I32, [_CTX, c_double_p]),
     'fds_batch_count': (_I32, [_CTX]),
+    'fds_segment_sensitivities': (_I32, [_CTX, _I64, _D, c_double_p, c_double_p]),
     'fds_buffer_ptr': (ctypes.c_void_p, [_CTX, _I32]),
     'fds_kernel_launches': (_I64, [_CTX]),
     'fds_sync': (_I32, [_CTX]),

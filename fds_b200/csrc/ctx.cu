@@ -28,11 +28,13 @@ struct fds_ctx {
     int nb = 1;
     long long slot = 0, gl0 = 0;
     long long nall = 0;            // stacked sites (= n without a batch)
-    int spp = 1, runs_per_cta = 0; // streaming-kernel shape of the batch
+    int spp = 1, runs_per_cta = 0, ctas_per_sm = 2; // streaming-kernel shape of the batch
     BatchDesc bd{};
     std::vector<double> ds;        // parameter offset of every problem
     std::vector<double2> Fhost;
     double2* Fpp = nullptr;        // device (F0, Flast) per problem
+    double* sens = nullptr;        // device staging of fds_segment_sensitivities
+    size_t sens_cap = 0;
     double* T_alloc = nullptr;     // stacked site 0 of the tangent array (T = site 0 of problem 0)
     double* d_alloc = nullptr;
     long long small_stride = 0;
@@ -204,7 +206,9 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         // Batch: problems stacked along the site axis.  Between two problems lies a gap that holds the
         // right ghost cells of the first (4H sites) and the left ghost cells of the second (8H), so the
         // streaming kernel sweeps the whole stack as ONE array; a batched wrap refreshes the gaps.
-        const int R2 = 256 / c->M;                         // strips per CTA with two CTAs per SM
+        if (const char* e = getenv("FDS_BATCH_CTAS_PER_SM")) c->ctas_per_sm = atoi(e) == 1 ? 1 : 2;
+        // strips per CTA: two CTAs of <= 256 threads per SM, or one of <= 480 with a producer warp
+        const int R2 = c->ctas_per_sm == 2 ? 256 / c->M : stream_runs_per_cta(c->M);
         if (cfg->system != FDS_SYS_L96_RK4 || cfg->world != 1 || c->n % 64 != 0 || R2 < 1 ||
             (cfg->flags & FDS_FLAG_SIMPLE_KERNELS)) {
             g_create_err = "batch: needs the Lorenz-96 RK4 system, world = 1, n_local a multiple of 64, m <= 126";
@@ -216,7 +220,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         if (8 * H > c->n) H = std::max<long long>(8, c->n / 64 * 8);
         c->H = H;
         c->gl0 = 8 * H;
-        const long long slots_per_wave = (long long)2 * c->num_sms * R2;      // strips resident at once
+        const long long slots_per_wave = (long long)c->ctas_per_sm * c->num_sms * R2;   // strips resident at once
         c->spp = (int)std::max<long long>(1, std::min<long long>(8, (slots_per_wave + c->nb / 2) / c->nb));
         while (c->spp > 1 && (c->n + 12 * H) / c->spp < 256) --c->spp;        // keep strips long
         const long long unit = 64LL * c->spp;
@@ -224,7 +228,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         c->nall = c->slot * c->nb;
         const long long nstrips = (long long)c->nb * c->spp;
         const long long waves = (nstrips + slots_per_wave - 1) / slots_per_wave;
-        c->runs_per_cta = (int)std::min<long long>(R2, (nstrips + waves * 2 * c->num_sms - 1) / (waves * 2 * c->num_sms));
+        c->runs_per_cta = (int)std::min<long long>(R2, (nstrips + waves * c->ctas_per_sm * c->num_sms - 1) / (waves * c->ctas_per_sm * c->num_sms));
         c->stream_ok = true;
         StripPlan& pl = c->plan;
         pl.a0 = 0; pl.ls = c->slot / c->spp; pl.nstrips = nstrips; pl.nblk = (int)(pl.ls / 8);
@@ -303,7 +307,7 @@ void fds_ctx_destroy(fds_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int j = 0; j < 2; ++j) cudaFree(c->Ebase[j]);
     for (int j = 0; j < 4; ++j) cudaFree(c->Pbase[j]);
-    cudaFree(c->T_alloc); cudaFree(c->d_alloc); cudaFree(c->Fpp); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
+    cudaFree(c->T_alloc); cudaFree(c->d_alloc); cudaFree(c->Fpp); cudaFree(c->sens); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
     cudaFree(c->jpart); cudaFree(c->jscratch); cudaFree(c->jsum);
     for (int j = 0; j < 2; ++j) {
         cudaFree(c->stage[j]);
@@ -583,7 +587,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
     double* jsum_slot = c->jsum + (size_t)jstep * M_ * 2;
     StepArgs a;
     a.X = X; a.Y = Y; a.M = M_; a.n = c->nall;
-    if (c->nb > 1) { a.Fpp = c->Fpp; a.spp = c->spp; a.slot = c->slot; a.runs_per_cta = c->runs_per_cta; a.ctas_per_sm = 2; }
+    if (c->nb > 1) { a.Fpp = c->Fpp; a.spp = c->spp; a.slot = c->slot; a.runs_per_cta = c->runs_per_cta; a.ctas_per_sm = c->ctas_per_sm; }
     a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
     a.F0 = F0; a.Flast = Flast; a.dt = c->cfg.dt; a.exact = c->cfg.math == FDS_MATH_EXACT;
     a.jpart = jsum_slot ? c->jpart : nullptr;
@@ -657,6 +661,23 @@ int fds_set_batch_params(fds_ctx* c, const double* ds) {
 }
 
 int fds_batch_count(const fds_ctx* c) { return c->nb; }
+
+int fds_segment_sensitivities(fds_ctx* c, int64_t steps, double eps, double* J0_host, double* G_host) {
+    if (steps > c->jsum_cap || steps < 2) return fail(c, "fds_segment_sensitivities: needs 2 <= steps <= steps run");
+    const size_t nj = (size_t)c->nb * steps * 2, ng = (size_t)c->nb * c->MO * 2;
+    if (c->sens_cap < nj + ng) {
+        cudaFree(c->sens);
+        c->sens = nullptr;
+        FDS_CK(c, cudaMalloc(&c->sens, (nj + ng) * sizeof(double)));
+        c->sens_cap = nj + ng;
+    }
+    FDS_CK(c, launch_batch_sens(c->jsum, c->nb, c->M, steps, (double)c->cfg.n_global, eps, c->sens, c->sens + nj,
+                                c->stream, &c->ls));
+    FDS_CK(c, cudaMemcpyAsync(J0_host, c->sens, nj * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaMemcpyAsync(G_host, c->sens + nj, ng * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
 
 int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int record) {
     if (int r = sync_primal_from_ensemble(c)) return r;

@@ -62,6 +62,10 @@ cudaError_t launch_batch_jreduce(const double* leaves, long long nleaf_total, lo
                                  long long leaves_pp, int C, int batch, long long steps, double* out,
                                  cudaStream_t st, LaunchStats* ls);
 
+// batch: J0[p][steps][2] (means) and G[p][m+1][2] (trapezoid-mean FD sensitivities / eps) from jsum[steps][nb][M][2]
+cudaError_t launch_batch_sens(const double* jsum, int nb, int M, long long steps, double n_sites, double eps,
+                              double* J0, double* G, cudaStream_t st, LaunchStats* ls);
+
 // ---- boundary.cu ------------------------------------------------------------ //
 cudaError_t launch_extract_col0(const double* E, int M, double* P, long long n, cudaStream_t, LaunchStats*);
 cudaError_t launch_dxdt(const double* P0, const double* P1, const double* P2, const double* P3,

@@ -482,4 +482,46 @@ cudaError_t launch_batch_jreduce(const double* leaves, long long nleaf_total, lo
     return cudaGetLastError();
 }
 
+// Batch: finite-difference sensitivities of the objective on the device, so that only KBs per
+// problem leave the GPU.  jsum[steps][nb][M][2] (sums over sites) ->
+//   J0[p][t][q]  = jsum[t][p][0][q] / n                                    (primal objective history)
+//   G[p][j][q]   = trapez_mean_t(J[t][p][1+j][q] - J0[p][t][q]) / eps,  j = 0..m (row m: inhomogeneous)
+// with the reference's trapez_mean (fds/segment.py:9-12): (sum_t d_t + sum_{t<n-1} d_t + (2 d_0 - d_1)) / (2n),
+// sums accumulated in step order like numpy's reduction over the leading axis.
+__global__ void __launch_bounds__(128) batch_sens_kernel(const double* __restrict__ jsum, int nb, int M,
+                                                         long long steps, double n_sites, double eps,
+                                                         double* __restrict__ J0, double* __restrict__ G) {
+    const int p = blockIdx.x;
+    const int MO = M - 1;
+    for (int e = threadIdx.x; e < MO * 2; e += blockDim.x) {
+        const int j = e >> 1, q = e & 1;
+        double sum_all = 0.0, sum_head = 0.0, d0 = 0.0, d1 = 0.0;
+        for (long long t = 0; t < steps; ++t) {
+            const double* row = jsum + (((size_t)t * nb + p) * M) * 2;
+            const double j0 = row[q] / n_sites;
+            const double d = __dsub_rn(row[(1 + j) * 2 + q] / n_sites, j0);
+            if (t == 0) d0 = d;
+            if (t == 1) d1 = d;
+            sum_all = t == 0 ? d : __dadd_rn(sum_all, d);
+            if (t < steps - 1) sum_head = t == 0 ? d : __dadd_rn(sum_head, d);
+        }
+        const double ghost = __dsub_rn(__dmul_rn(2.0, d0), d1);
+        const double tm = __dadd_rn(__dadd_rn(sum_all, sum_head), ghost) / (double)(2 * steps);
+        G[((size_t)p * MO + j) * 2 + q] = tm / eps;
+    }
+    for (long long e = threadIdx.x; e < steps * 2; e += blockDim.x) {
+        const long long t = e >> 1;
+        const int q = (int)(e & 1);
+        J0[((size_t)p * steps + t) * 2 + q] = jsum[(((size_t)t * nb + p) * M) * 2 + q] / n_sites;
+    }
+}
+
+cudaError_t launch_batch_sens(const double* jsum, int nb, int M, long long steps, double n_sites, double eps,
+                              double* J0, double* G, cudaStream_t st, LaunchStats* ls) {
+    if (steps < 2) return cudaErrorInvalidValue;
+    batch_sens_kernel<<<nb, 128, 0, st>>>(jsum, nb, M, steps, n_sites, eps, J0, G);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
 }  // namespace fds

@@ -191,6 +191,13 @@ class Context:
         self._ck(self.lib.fds_segment_jsums(self.h, int(steps), dptr(J)))
         return J
 
+    def segment_sensitivities(self, steps, eps):
+        """(J0 lead+(steps, 2), G lead+(m, 2), g lead+(2,)) of the last segment, reduced on the device."""
+        J0 = np.empty(self.lead + (int(steps), 2))
+        G = np.empty(self.lead + (self.m + 1, 2))
+        self._ck(self.lib.fds_segment_sensitivities(self.h, int(steps), float(eps), dptr(J0), dptr(G)))
+        return J0, G[..., :self.m, :], G[..., self.m, :]
+
     # -- world == 1 conveniences --------------------------------------------- #
     def boundary(self, s, eps, from_ensemble, do_qr, build, halo_steps=0):
         """One segment boundary; returns (R, b, G_dil, g_dil) (R, b None unless do_qr)."""

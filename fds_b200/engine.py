@@ -158,6 +158,19 @@ class Engine:
             Js = self.ring.ordered_sum(part).reshape(steps, self.M, 2)
         return Js[..., :self.n_qoi] / self.j_div
 
+    def segment_sens(self, s, eps, steps):
+        """Advance one segment and return (J0, G, g) reduced on the device (single rank / batch):
+        the (steps, m+2, n_qoi) objective block never crosses PCIe."""
+        assert self.ring is None
+        steps = int(steps)
+        t = 0
+        while t < steps:
+            hs = self.ctx.halo_steps(steps - t)
+            self._halo(_lib.FDS_BUF_ENSEMBLE, hs)
+            self.ctx.segment_advance(s, eps, t, hs)
+            t += hs
+        return self.ctx.segment_sensitivities(steps, eps)
+
     # -- state in / out (global host arrays) ------------------------------------ #
     def set_state(self, u):
         self.ctx.set_state(self.local(u))

@@ -201,11 +201,8 @@ def shadowing_batch(run, u0, parameters, subspace_dimension, num_segments, steps
     Rs, bs, G_lss, g_lss, J_hist, G_dil, g_dil = [], [], [], [], [], [], []
 
     def record_segment():
-        J = eng.segment(s, epsilon, steps_per_segment)          # (steps, B, m+2, q)
-        J0 = np.ascontiguousarray(J[:, :, 0])
-        G = np.stack([trapez_mean(J[:, :, 1 + j] - J0, 0) / epsilon for j in range(m)], axis=1)   # (B,m,q)
-        g = trapez_mean(J[:, :, m + 1] - J0, 0) / epsilon                                        # (B,q)
-        J_hist.append(np.moveaxis(J0, 0, 1)), G_lss.append(G), g_lss.append(g)
+        J0, G, g = eng.segment_sens(s, epsilon, steps_per_segment)      # (B,steps,q), (B,m,q), (B,q)
+        J_hist.append(J0), G_lss.append(G.copy()), g_lss.append(g.copy())
 
     eng.boundary(s, epsilon, from_ensemble=0, do_qr=0, build=1)
     record_segment()

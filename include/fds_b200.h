@@ -187,6 +187,11 @@ int fds_run_segment_host(fds_ctx*, double* u, double* V, double* v, double s, do
  * v[B][n], R[B][m][m], b[B][m], G_dil[B][m], g_dil[B], Jsum[steps][B][m+2][2] -- and problem p
  * runs at parameter s + ds[p].  fds_segment_advance takes at most fds_halo_steps() per call.   */
 int fds_set_batch_params(fds_ctx*, const double* ds);   /* ds[B] (NULL = all zero) */
+/* what run_segment returns besides the state (fds/segment.py:75,79), reduced on the device so that
+ * only KBs per problem cross PCIe: J0[B][steps][2] = objective history of the primal (means over
+ * sites), G[B][m+1][2] = trapez_mean(J_j - J_0) / eps, rows 0..m-1 homogeneous, row m inhomogeneous.
+ * Works for B = 1 too.                                                                          */
+int fds_segment_sensitivities(fds_ctx*, int64_t steps, double eps, double* J0_host, double* G_host);
 int fds_batch_count(const fds_ctx*);
 int fds_lss_solve_batch(int device, const double* R, const double* b, int64_t K, int m, int64_t nbatch,
                         double* alpha);                  /* R[B][K][m][m], b / alpha [B][K][m] */

@@ -23,8 +23,8 @@ def main():
 
     def seg():
         R, b, Gd, gd = eng.boundary(0.0, eps, 1, 1, 1, keep_tangents=False)
-        J = eng.segment(0.0, eps, steps)
-        return R, J
+        J, G, g = eng.segment_sens(0.0, eps, steps)
+        return R, G
     seg()
     eng.ctx.sync()
     l0 = eng.ctx.launches
