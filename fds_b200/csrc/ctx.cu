@@ -209,9 +209,10 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         if (const char* e = getenv("FDS_BATCH_CTAS_PER_SM")) c->ctas_per_sm = atoi(e) == 1 ? 1 : 2;
         // strips per CTA: two CTAs of <= 256 threads per SM, or one of <= 480 with a producer warp
         const int R2 = c->ctas_per_sm == 2 ? 256 / c->M : stream_runs_per_cta(c->M);
-        if (cfg->system != FDS_SYS_L96_RK4 || cfg->world != 1 || c->n % 64 != 0 || R2 < 1 ||
+        if ((cfg->system != FDS_SYS_L96_RK4 && cfg->system != FDS_SYS_L96_EULER) || cfg->world != 1 ||
+            c->n % 64 != 0 || R2 < 1 ||
             (cfg->flags & FDS_FLAG_SIMPLE_KERNELS)) {
-            g_create_err = "batch: needs the Lorenz-96 RK4 system, world = 1, n_local a multiple of 64, m <= 126";
+            g_create_err = "batch: needs a Lorenz-96 system, world = 1, n_local a multiple of 64, m <= 126";
             fds_ctx_destroy(c);
             return 2;
         }
@@ -238,7 +239,8 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         c->Fhost.assign(c->nb, make_double2(8.0, 8.0));
     } else {
         const int R = stream_runs_per_cta(c->M);
-        c->stream_ok = R >= 1 && cfg->system == FDS_SYS_L96_RK4 && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS);
+        c->stream_ok = R >= 1 && (cfg->system == FDS_SYS_L96_RK4 || cfg->system == FDS_SYS_L96_EULER) &&
+                       !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS);
         c->plan = make_strip_plan(c->n, H, (long long)c->num_sms * (R >= 1 ? R : 1));
         c->alo = c->plan.alo;
         c->ahi = c->plan.ahi;
@@ -607,7 +609,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
             e1 = c->prof_events[c->prof_used].second;
             c->prof_used++;
         }
-        FDS_CK(c, launch_l96_rk4_stream(a, c->plan, c->stream, &c->ls));
+        FDS_CK(c, launch_l96_rk4_stream(a, c->plan, c->stream, &c->ls, euler ? 1 : 0));
         if (e1) FDS_CK(c, cudaEventRecord(e1, c->stream));
     } else {
         FDS_CK(c, launch_l96_simple(a, euler ? 1 : 0, c->stream, &c->ls));

@@ -65,6 +65,22 @@ int emul_l96_rk4_step(const double* X, double* Y, int M, long long n, long long 
     return 0;
 }
 
+// the same with the forward-Euler pipe
+int emul_l96_euler_step(const double* X, double* Y, int M, long long n, long long H,
+                        const double* F /*[M]*/, double dt, int exact, long long max_strips, double* jpart) {
+    StripPlan plan = make_strip_plan(n, H, max_strips);
+    Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+    for (long long s = 0; s < plan.nstrips; ++s) {
+        for (int k = 0; k < M; ++k) {
+            HostIO io{X, Y, jpart, plan.nnode, plan.a0 + s * plan.ls, M, k};
+            MarchGeom g{io.a, n, plan.nblk, jpart != nullptr, plan.node_shift};
+            if (exact) l96_euler_march<ExactMath>(io, g, F[k], c);
+            else       l96_euler_march<FastMath>(io, g, F[k], c);
+        }
+    }
+    return 0;
+}
+
 // simple-kernel math: one site from its 13-point cone
 int emul_l96_rk4_point(const double* X, double* Y, int M, long long lo, long long hi,
                        const double* F, double dt, int exact) {

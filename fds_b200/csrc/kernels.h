@@ -38,7 +38,9 @@ struct StepArgs {
 // streaming TMA-fed kernel (RK4 only); `plan` = make_strip_plan(n, H, num_sms * stream_runs_per_cta(M)),
 // X and Y allocated for sites [plan.alo, plan.ahi)
 int stream_runs_per_cta(int M);
-cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls);
+// euler = 1: forward Euler with the reference's operation order instead of RK4
+cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls,
+                                  int euler = 0);
 // one thread per element, global loads (RK4 or Euler); no objective sums
 cudaError_t launch_l96_simple(const StepArgs& a, int euler, cudaStream_t st, LaunchStats* ls);
 // 64-site leaf partials of an array: jpart[leaf][M][2]

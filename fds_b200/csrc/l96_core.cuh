@@ -94,6 +94,33 @@ struct Rk4Pipe {
     }
 };
 
+// Forward Euler (the reference's own Lorenz-96 solver, tests/solvers/mock_fun3d/fun3d:48-57)
+// behind the same interface: push x[i+4], get x'[i-3], so that strip plan, halo widths, IO
+// policy and objective tree of the streaming kernel are shared with RK4.  x'[i-3] needs
+// x[i-5 .. i-2]: the ring holds x[i-3 .. i+4], the two older values ride in two registers.
+template <class MP>
+struct EulerPipe {
+    double X[8], xm4, xm5;
+    static constexpr int kLag = 3;
+
+    FDS_HD void reset() {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) X[j] = 0.0;
+        xm4 = 0.0; xm5 = 0.0;
+    }
+
+    template <int P>
+    FDS_HD double push(double xn, double F, const Rk4Coef& c) {
+#define FDS_SLOT(o) ((P + (o) + 16) & 7)
+        xm5 = xm4;
+        xm4 = X[FDS_SLOT(4)];              // the slot about to be overwritten holds x[i-4]
+        X[FDS_SLOT(4)] = xn;
+        const double k = l96_rhs_fun3d<MP>(xm5, xm4, X[FDS_SLOT(-3)], X[FDS_SLOT(-2)], F);
+        return MP::muladd(c.h, k, X[FDS_SLOT(-3)]);
+#undef FDS_SLOT
+    }
+};
+
 // One RK4 step at a single site from its 13-point dependency cone
 // x[0..12] = x_{i-8} .. x_{i+4}  (straightforward form; used by the simple kernel).
 template <class MP>

@@ -33,12 +33,12 @@ struct MarchGeom {
 
 // One site of one block.  FAST: the whole block lies inside the store range and the
 // objective range, so no per-site checks are needed.
-template <class MP, int P, bool FAST, bool STATS, class IO>
-FDS_HD void march_site(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, double& b1, double& b2,
+template <class MP, class PIPE, int P, bool FAST, bool STATS, class IO>
+FDS_HD void march_site(IO& io, PIPE& pipe, Tree8& t1, Tree8& t2, double& b1, double& b2,
                        long long j0, long long slo, long long shi, long long jlo, long long jhi,
                        double F, const Rk4Coef& c) {
     constexpr bool stats = STATS;
-    constexpr int Q = (P + 8 - Rk4Pipe<MP>::kLag) & 7;   // output site mod 8
+    constexpr int Q = (P + 8 - PIPE::kLag) & 7;   // output site mod 8
     const double xo = pipe.template push<P>(io.load(P), F, c);
     if (FAST) {
         io.store(P, xo);
@@ -59,16 +59,16 @@ FDS_HD void march_site(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, double& 
     }
 }
 
-template <class MP, bool FAST, bool STATS, class IO>
-FDS_HD void march_block(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, LeafStack& l1, LeafStack& l2,
+template <class MP, class PIPE, bool FAST, bool STATS, class IO>
+FDS_HD void march_block(IO& io, PIPE& pipe, Tree8& t1, Tree8& t2, LeafStack& l1, LeafStack& l2,
                         NodeCounter& ns, const MarchGeom& g, int b, long long slo, long long shi, long long jlo, long long jhi,
                         double F, const Rk4Coef& c) {
-    const long long j0 = g.a + 8LL * b - Rk4Pipe<MP>::kLag;
+    const long long j0 = g.a + 8LL * b - PIPE::kLag;
     constexpr bool stats = STATS;
     double b1 = 0.0, b2 = 0.0;
-    march_site<MP, 0, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
-    march_site<MP, 1, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
-    march_site<MP, 2, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
+    march_site<MP, PIPE, 0, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
+    march_site<MP, PIPE, 1, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
+    march_site<MP, PIPE, 2, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
     // sites a+8(b-1) .. a+8b-1 are complete here: 8-block (b-1) of the strip
     if (stats && b >= 1) {
         double s1, s2;
@@ -81,11 +81,11 @@ FDS_HD void march_block(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, LeafSta
             if (ns.push(io, s1, s2, g.node_shift - kLeafShift)) io.emit_node(leaf >> (g.node_shift - kLeafShift), s1, s2);
         }
     }
-    march_site<MP, 3, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
-    march_site<MP, 4, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
-    march_site<MP, 5, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
-    march_site<MP, 6, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
-    march_site<MP, 7, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
+    march_site<MP, PIPE, 3, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
+    march_site<MP, PIPE, 4, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
+    march_site<MP, PIPE, 5, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
+    march_site<MP, PIPE, 6, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
+    march_site<MP, PIPE, 7, FAST, STATS>(io, pipe, t1, t2, b1, b2, j0, slo, shi, jlo, jhi, F, c);
 }
 
 // number of blocks a strip of nblk 8-blocks runs through: two warm-up blocks fill the
@@ -93,9 +93,9 @@ FDS_HD void march_block(IO& io, Rk4Pipe<MP>& pipe, Tree8& t1, Tree8& t2, LeafSta
 FDS_HD int march_iterations(int nblk) { return nblk + 3; }
 
 // STATS (compile time) = accumulate the objective partials; g.stats is ignored here
-template <class MP, bool STATS, class IO>
-FDS_HD void l96_rk4_march_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
-    Rk4Pipe<MP> pipe;
+template <class MP, bool STATS, class PIPE, class IO>
+FDS_HD void l96_march_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
+    PIPE pipe;
     pipe.reset();
     Tree8 t1, t2;
     LeafStack l1, l2;
@@ -113,22 +113,33 @@ FDS_HD void l96_rk4_march_t(IO& io, const MarchGeom& g, double F, const Rk4Coef&
     const long long ncl = (g.n + kLeafSites - 1) & ~(long long)(kLeafSites - 1);
 #pragma unroll 1
     for (int b = -2; b <= g.nblk; ++b) {
-        const long long j0 = g.a + 8LL * b - Rk4Pipe<MP>::kLag;
+        const long long j0 = g.a + 8LL * b - PIPE::kLag;
         io.begin_block(b);
         // unchecked path: all 8 outputs belong to this strip and none lies in the partial leaf
         const bool fast = j0 >= slo && j0 + 8 <= shi && (j0 + 8 <= nfl || j0 >= ncl);
         if (io.all(fast))
-            march_block<MP, true, STATS>(io, pipe, t1, t2, l1, l2, ns, g, b, slo, shi, jlo, jhi, F, c);
+            march_block<MP, PIPE, true, STATS>(io, pipe, t1, t2, l1, l2, ns, g, b, slo, shi, jlo, jhi, F, c);
         else
-            march_block<MP, false, STATS>(io, pipe, t1, t2, l1, l2, ns, g, b, slo, shi, jlo, jhi, F, c);
+            march_block<MP, PIPE, false, STATS>(io, pipe, t1, t2, l1, l2, ns, g, b, slo, shi, jlo, jhi, F, c);
         io.end_block(b);
     }
 }
 
+template <class MP, bool STATS, class IO>
+FDS_HD void l96_rk4_march_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
+    l96_march_t<MP, STATS, Rk4Pipe<MP>>(io, g, F, c);
+}
+
 template <class MP, class IO>
 FDS_HD void l96_rk4_march(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
-    if (g.stats) l96_rk4_march_t<MP, true>(io, g, F, c);
-    else l96_rk4_march_t<MP, false>(io, g, F, c);
+    if (g.stats) l96_march_t<MP, true, Rk4Pipe<MP>>(io, g, F, c);
+    else l96_march_t<MP, false, Rk4Pipe<MP>>(io, g, F, c);
+}
+
+template <class MP, class IO>
+FDS_HD void l96_euler_march(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
+    if (g.stats) l96_march_t<MP, true, EulerPipe<MP>>(io, g, F, c);
+    else l96_march_t<MP, false, EulerPipe<MP>>(io, g, F, c);
 }
 
 }  // namespace fds

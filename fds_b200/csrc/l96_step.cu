@@ -119,7 +119,7 @@ struct StreamIO {
     FDS_D bool all(bool v) const { return __all_sync(0xffffffffu, v); }
 };
 
-template <class MP, int MC, bool STATS>
+template <class MP, int MC, bool STATS, bool EULER>
 __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     io.nstages = p.nstages;
     io.full = full;
     io.empty = empty;
-    io.yrow = p.Y + (g.a - 8 * 2 - Rk4Pipe<MP>::kLag) * p.M + k;   // block b = -2
+    io.yrow = p.Y + (g.a - 8 * 2 - 3) * p.M + k;   // both pipes lag 3 sites   // block b = -2
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
     io.nnode = p.nnode;
     io.nsm = nsm + tid;
@@ -198,7 +198,8 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
         const double2 f = p.Fpp[strip / p.spp];
         F = (k == p.M - 1) ? f.y : f.x;
     }
-    l96_rk4_march_t<MP, STATS>(io, g, F, p.c);
+    if (EULER) l96_march_t<MP, STATS, EulerPipe<MP>>(io, g, F, p.c);
+    else l96_march_t<MP, STATS, Rk4Pipe<MP>>(io, g, F, p.c);
 }
 
 // 16 warps per CTA (4 per scheduler, so each thread can hold up to 128 registers), all of
@@ -213,7 +214,8 @@ int stream_runs_per_cta(int M) {
     return M <= maxc ? maxc / M : 0;
 }
 
-cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls) {
+cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls,
+                                  int euler) {
     StreamParams p;
     p.X = a.X; p.Y = a.Y; p.jpart = a.jpart; p.nnode = plan.nnode;   // a.jpart: [nnode][M][2]
     p.n = a.n;
@@ -251,13 +253,15 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     const int grid = (int)((plan.nstrips + p.R - 1) / p.R);
     const size_t smem = 128 + ns_bytes + stage_bytes * nst;
     cudaError_t e = cudaSuccess;
-#define FDS_STREAM_LAUNCH(MP, MC, ST)                                                                          \
-    do {                                                                                                       \
-        e = cudaFuncSetAttribute(l96_rk4_stream_kernel<MP, MC, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 (int)smem);                                                                   \
-        if (e != cudaSuccess) return e;                                                                        \
-        l96_rk4_stream_kernel<MP, MC, ST><<<grid, block, smem, st>>>(p);                                       \
+#define FDS_STREAM_LAUNCH2(MP, MC, ST, EU)                                                                         \
+    do {                                                                                                           \
+        e = cudaFuncSetAttribute(l96_rk4_stream_kernel<MP, MC, ST, EU>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                                       \
+        if (e != cudaSuccess) return e;                                                                            \
+        l96_rk4_stream_kernel<MP, MC, ST, EU><<<grid, block, smem, st>>>(p);                                       \
     } while (0)
+#define FDS_STREAM_LAUNCH(MP, MC, ST) \
+    do { if (euler) FDS_STREAM_LAUNCH2(MP, MC, ST, true); else FDS_STREAM_LAUNCH2(MP, MC, ST, false); } while (0)
 #define FDS_STREAM_MC(MP, ST)                                      \
     do {                                                           \
         if (a.M == 34) FDS_STREAM_LAUNCH(MP, 34, ST);              \
@@ -269,6 +273,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     else         { if (stats) FDS_STREAM_MC(FastMath, true);  else FDS_STREAM_MC(FastMath, false); }
 #undef FDS_STREAM_MC
 #undef FDS_STREAM_LAUNCH
+#undef FDS_STREAM_LAUNCH2
     if (ls) ls->launches++;
     return cudaGetLastError();
 }

@@ -55,7 +55,10 @@ def padded(U, alo, ahi, ghost_l, ghost_r):
 @pytest.mark.parametrize('N,M,H,max_strips,exact', [
     (200, 5, 3, 7, 1), (40, 18, 1, 4, 1), (37, 3, 2, 64, 1), (1024, 4, 4, 16, 1),
     (4096, 2, 2, 37, 1), (333, 1, 3, 1, 1), (200, 5, 3, 7, 0), (4, 2, 3, 5, 1), (640, 3, 5, 3, 1), (5000, 2, 2, 2, 1), (3000, 1, 1, 1, 1), (70000, 1, 2, 5, 1)])
-def test_streaming_march_matches_oracle(emul, N, M, H, max_strips, exact):
+@pytest.mark.parametrize('scheme', ['rk4', 'euler'])
+def test_streaming_march_matches_oracle(emul, N, M, H, max_strips, exact, scheme):
+    step_fn = emul.emul_l96_rk4_step if scheme == 'rk4' else emul.emul_l96_euler_step
+    oracle_step = plugins.l96_rk4_step if scheme == 'rk4' else plugins.l96_euler_step
     rng = np.random.RandomState(N + M)
     U = rng.rand(M, N) * 6 - 1
     F = 8.0 + np.r_[np.zeros(M - 1), 1e-4] if M > 1 else np.array([8.1])
@@ -69,11 +72,11 @@ def test_streaming_march_matches_oracle(emul, N, M, H, max_strips, exact):
     bufA = padded(U, alo, ahi, 8 * H, 4 * H)
     bufB = np.full_like(bufA, np.nan)
     nleaf = pl['nnode']
-    Xo, Jo = plugins.run_l96_ensemble(plugins.l96_rk4_step, U, F, H)
+    Xo, Jo = plugins.run_l96_ensemble(oracle_step, U, F, H)
     for j in range(H):
         jpart = np.full((nleaf, M, 2), np.nan)
         with np.errstate(all='ignore'):
-            emul.emul_l96_rk4_step(ptr(bufA, -alo * M), ptr(bufB, -alo * M), M, LL(N), LL(H), ptr(F),
+            step_fn(ptr(bufA, -alo * M), ptr(bufB, -alo * M), M, LL(N), LL(H), ptr(F),
                                    ctypes.c_double(0.01), exact, LL(max_strips), ptr(jpart))
         assert not np.isnan(jpart).any()
         # still-valid range after step j+1: [-8(H-1-j), N + 4(H-1-j))
@@ -90,7 +93,7 @@ def test_streaming_march_matches_oracle(emul, N, M, H, max_strips, exact):
     if exact:
         assert np.array_equal(got, Xo)
     else:
-        assert np.abs(got - Xo).max() < 1e-13 and not np.array_equal(got, Xo)
+        assert np.abs(got - Xo).max() < 1e-13 and (scheme == 'euler' or not np.array_equal(got, Xo))
 
 
 def test_point_forms_match_oracle(emul):

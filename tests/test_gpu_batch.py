@@ -96,5 +96,22 @@ def test_lss_solve_batch_equals_single_solves():
 def test_batch_rejects_what_it_cannot_do():
     with pytest.raises(fds_b200.FdsError, match='batch'):
         Context(100, 4, batch=3)               # n not a multiple of 64
-    with pytest.raises(fds_b200.FdsError, match='batch'):
-        Context(128, 4, batch=3, scheme='euler')
+    with pytest.raises(fds_b200.FdsError):
+        Context(3, 2, batch=3, scheme='lorenz63')
+
+
+@gpu
+def test_batched_euler_segment_bitwise():
+    """The reference's own Lorenz-96 solver (forward Euler, tests/solvers/mock_fun3d/fun3d:48-57) in a batch."""
+    B, N, m, steps, eps = 3, 128, 5, 21, 1e-4
+    rng = np.random.RandomState(3)
+    params = np.array([0.0, 0.1, -0.2])
+    U = np.stack([plugins.run_l96_euler(rng.rand(N), s, 30)[0] for s in params])
+    V, v = rng.randn(B, m, N) / np.sqrt(N), rng.randn(B, N) / np.sqrt(N)
+    bc = Context(N, m, batch=B, scheme='euler', max_halo_steps=8)
+    bc.set_batch_params(params)
+    Ub, Vb, vb, Jb = bc.run_segment_host(U, V, v, 0.0, eps, steps)
+    for p in range(B):
+        ru, rV, rv, rJ0, rG, rg = port.run_segment(plugins.run_l96_euler, U[p], V[p], v[p], params[p], steps, eps)
+        assert np.array_equal(Ub[p], ru) and np.array_equal(Vb[p], rV) and np.array_equal(vb[p], rv)
+        assert np.array_equal(Jb[:, p, 0] / N, rJ0)
