@@ -185,12 +185,14 @@ class Engine:
         V, v = self.ctx.get_tangents()
         return self.gather_sites(V), self.gather_sites(v)
 
-    def orthonormal_random_tangents(self, seed=None, host_rng=None):
+    def orthonormal_random_tangents(self, seed=None, host_rng=None, block=None):
         """V = Q of the thin QR of a uniform [0,1) (m, N) block, v = 0
         (reference fds/fds.py:21-27).  ``host_rng`` draws the block on the host with
         numpy (small N; honours np.random.seed like the reference); otherwise a
         counter-based device generator keyed on the global (row, site) index."""
-        if host_rng is not None:
+        if block is not None:
+            self.ctx.set_tangents(self.local(block), None)
+        elif host_rng is not None:
             W = host_rng.rand(*(self.ctx.lead + (self.m, self.n_global)))
             self.ctx.set_tangents(self.local(W), None)
         else:

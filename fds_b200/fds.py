@@ -165,12 +165,51 @@ def lss_gradient_batch(Rs, bs, G_lss, g_lss, J, G_dil, g_dil, device=0):
     return grad_lss.sum(1) / K + grad_dil.sum(1) / K
 
 
+def _dist_world(group):
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(group), dist.get_world_size(group)
+    except ImportError:
+        pass
+    return None, 0, 1
+
+
 def shadowing_batch(run, u0, parameters, subspace_dimension, num_segments, steps_per_segment,
-                    runup_steps, epsilon=1E-6, run_ddt=None, tangent_seed=None, return_histories=False):
+                    runup_steps, epsilon=1E-6, run_ddt=None, tangent_seed=None, return_histories=False,
+                    tangents=None, group=None):
     """``shadowing`` for a sweep of parameters: problem p starts from ``u0[p]`` (or the shared
     ``u0`` if it is one-dimensional) and runs at ``parameters[p]``.
     Returns (J (B, n_qoi), dJ/ds (B, n_qoi)); with ``return_histories`` also the dict of the
-    per-segment histories (Rs, bs, G_lss, g_lss, J, G_dil, g_dil, each with a leading B axis)."""
+    per-segment histories (Rs, bs, G_lss, g_lss, J, G_dil, g_dil, each with a leading B axis).
+    ``tangents`` (B, m, N): initial tangent blocks to orthonormalise instead of random ones.
+    Under torch.distributed (one process per GPU) the sweep is split into contiguous slices, one
+    per rank -- the problems are independent, so there is no data-path collective -- and every
+    rank returns the gathered result."""
+    dist, rank, world = _dist_world(group)
+    if world > 1:
+        from .ring import shard_range
+        parameters = np.ascontiguousarray(parameters, dtype=np.float64).ravel()
+        lo, hi = shard_range(parameters.size, rank, world)
+        if hi - lo < 2:
+            raise ValueError('shadowing_batch: fewer than two problems per rank')
+        u0 = np.asarray(u0, dtype=np.float64)
+        out = _shadowing_batch_local(run, u0 if u0.ndim == 1 else u0[lo:hi], parameters[lo:hi], subspace_dimension,
+                                     num_segments, steps_per_segment, runup_steps, epsilon, run_ddt,
+                                     None if tangent_seed is None else tangent_seed + rank, return_histories,
+                                     None if tangents is None else np.asarray(tangents)[lo:hi])
+        parts = [None] * world
+        dist.all_gather_object(parts, out, group=group)
+        res = [np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])]
+        if return_histories:
+            res.append({k: np.concatenate([p[2][k] for p in parts]) for k in parts[0][2]})
+        return tuple(res)
+    return _shadowing_batch_local(run, u0, parameters, subspace_dimension, num_segments, steps_per_segment,
+                                  runup_steps, epsilon, run_ddt, tangent_seed, return_histories, tangents)
+
+
+def _shadowing_batch_local(run, u0, parameters, subspace_dimension, num_segments, steps_per_segment,
+                           runup_steps, epsilon, run_ddt, tangent_seed, return_histories, tangents):
     parameters = np.ascontiguousarray(parameters, dtype=np.float64).ravel()
     B, m = parameters.size, int(subspace_dimension)
     if run_ddt is not None and run_ddt != 0:
@@ -192,7 +231,9 @@ def shadowing_batch(run, u0, parameters, subspace_dimension, num_segments, steps
     s = 0.0
     if runup_steps > 0:
         eng.run(s, runup_steps, want_J=False)
-    if tangent_seed is None and B * m * N <= HOST_RNG_MAX_ELEMS:
+    if tangents is not None:
+        eng.orthonormal_random_tangents(block=np.ascontiguousarray(tangents, dtype=np.float64))
+    elif tangent_seed is None and B * m * N <= HOST_RNG_MAX_ELEMS:
         eng.orthonormal_random_tangents(host_rng=np.random)
     else:
         seed = np.random.randint(2 ** 31 - 1) if tangent_seed is None else tangent_seed

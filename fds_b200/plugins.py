@@ -12,6 +12,18 @@ import numpy as np
 from .engine import Engine
 
 
+def _current_device():
+    """The rank's GPU when running under torch.distributed (one process per GPU), else 0."""
+    try:
+        import torch
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except ImportError:
+        pass
+    return 0
+
+
 class _DevicePlugin:
     """Common part of the device solver plugins: engines cached per subspace dimension, the
     reference ``run`` call on host arrays, picklability (the reference's pool, fds/segment.py:37)."""
@@ -34,6 +46,8 @@ class _DevicePlugin:
         if key not in self._engines:
             kw = dict(self.kw)
             kw.pop('group', None), kw.pop('distributed', None)
+            if kw.get('device') is None:
+                kw['device'] = _current_device()
             self._engines[key] = Engine(self.N, m, batch=int(batch), **kw)
         return self._engines[key]
 

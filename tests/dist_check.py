@@ -62,6 +62,21 @@ def main():
         print('segment-0 objective bit-identical: %s; final primal bit-identical: %s; R0 rel err %.1e; dJ/ds rel err %.1e'
               % (jj, uu, rr, gg))
         ok &= jj and uu and rr < 1e-10 and gg < 1e-6
+    # --- batched sweep split over the ranks (replicas only) vs the same sweep on one GPU
+    B, Nb, mb = 3 * world, 128, 4
+    params = np.linspace(-0.4, 0.5, B)
+    rng = np.random.RandomState(9)
+    Ub, Wb = rng.rand(B, Nb), rng.rand(B, mb, Nb)
+    runb = fds_b200.L96(Nb, device=local)
+    Jd, Gd, Hd = fds_b200.shadowing_batch(runb, Ub, params, mb, 3, 20, 40, epsilon=eps, tangents=Wb,
+                                          return_histories=True)
+    if rank == 0:
+        from fds_b200 import fds as core
+        Js, Gs, Hs = core._shadowing_batch_local(fds_b200.L96(Nb, device=local), Ub, params, mb, 3, 20, 40, eps,
+                                                 None, None, True, Wb)
+        bb = bool(np.array_equal(Jd, Js) and np.array_equal(Hd['Rs'], Hs['Rs']) and np.array_equal(Gd, Gs))
+        print('batched sweep over %d ranks bit-identical to one GPU: %s' % (world, bb))
+        ok &= bb and Jd.shape == (B, 2)
         print('DIST_CHECK_OK' if ok else 'DIST_CHECK_FAILED')
     dist.barrier()
     dist.destroy_process_group()
