@@ -10,8 +10,8 @@ from . import segment
 from . import checkpoint
 from . import timeseries
 from .fds import shadowing, continue_shadowing, lss_gradient, lss_gradient_series, shadowing_batch
-from .plugins import L96, Lorenz63, VanDerPol, Circular
+from .plugins import L96, Lorenz63, VanDerPol, Circular, HostSolver
 from ._lib import FdsError, pinned_empty
 
-__all__ = ['shadowing', 'continue_shadowing', 'lss_gradient', 'lss_gradient_series', 'shadowing_batch', 'L96', 'Lorenz63', 'VanDerPol', 'Circular',
+__all__ = ['shadowing', 'continue_shadowing', 'lss_gradient', 'lss_gradient_series', 'shadowing_batch', 'L96', 'Lorenz63', 'VanDerPol', 'Circular', 'HostSolver',
            'FdsError', 'pinned_empty', 'checkpoint', 'timeseries', 'lsstan', 'segment', 'timedilation', 'core']

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, 'libfds_b200.so')
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)
 
-FDS_SYS_L96_RK4, FDS_SYS_L96_EULER, FDS_SYS_LORENZ63, FDS_SYS_VANDERPOL, FDS_SYS_CIRCULAR = range(5)
+FDS_SYS_L96_RK4, FDS_SYS_L96_EULER, FDS_SYS_LORENZ63, FDS_SYS_VANDERPOL, FDS_SYS_CIRCULAR, FDS_SYS_HOST = range(6)
 FDS_MATH_EXACT, FDS_MATH_FAST = 0, 1
 FDS_FLAG_SIMPLE_KERNELS = 1
 FDS_FLAG_EXTERNAL_STREAM = 2
@@ -44,6 +44,9 @@ SIGNATURES = {
     'fds_host_alloc': (ctypes.c_void_p, [ctypes.c_size_t]),
     'fds_host_free': (None, [ctypes.c_void_p]),
     'fds_random_tangents': (_I32, [_CTX, ctypes.c_uint64]),
+    'fds_get_ensemble': (_I32, [_CTX, c_double_p]),
+    'fds_set_ensemble': (_I32, [_CTX, c_double_p, _D]),
+    'fds_set_primal_history': (_I32, [_CTX, _I32, c_double_p]),
     'fds_set_dxdt_weights': (_I32, [_CTX, c_double_p]),
     'fds_set_time_dilation': (_I32, [_CTX, _I32]),
     'fds_set_qr_passes': (_I32, [_CTX, _I32]),

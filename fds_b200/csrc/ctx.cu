@@ -22,7 +22,8 @@ struct fds_ctx {
     long long alo = 0, ahi = 0;    // allocated site range of ensemble / primal arrays
     StripPlan plan{};              // fixed strip decomposition of the ensemble step kernel
     bool stream_ok = false;
-    bool toy = false;              // small ODE system (toy_ode.cu): no stencil, no halos, J recorded directly
+    bool toy = false;              // small ODE system (toy_ode.cu) or host solver: no stencil, no halos
+    bool host_sys = false;         // FDS_SYS_HOST: the solver runs on the host, only the algebra lives here
     // batch of nb independent problems stacked along the site axis (cfg.batch > 1): problem p owns the
     // stacked sites [gl0 + p*slot, gl0 + p*slot + n); the gaps in between hold its ghost cells
     int nb = 1;
@@ -158,8 +159,13 @@ const char* fds_last_error(const fds_ctx* c) { return c ? c->err.c_str() : g_cre
 int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
     *out = nullptr;
     if (!cfg || cfg->m < 1 || cfg->world < 1) { g_create_err = "bad config"; return 2; }
-    const int tdim = toy_dim(cfg->system);
-    if (tdim > 0 ? (cfg->n_local != tdim || cfg->world != 1) : cfg->n_local < 4) {
+    const bool host_sys = cfg->system == FDS_SYS_HOST;
+    const int tdim = host_sys ? 1 : toy_dim(cfg->system);
+    if (host_sys && (cfg->n_local < 1 || cfg->world != 1 || cfg->batch > 1)) {
+        g_create_err = "host-solver system: n_local >= 1, world = 1, no batch";
+        return 2;
+    }
+    if (!host_sys && (tdim > 0 ? (cfg->n_local != tdim || cfg->world != 1) : cfg->n_local < 4)) {
         g_create_err = tdim > 0 ? "small ODE systems: n_local must equal the state dimension, world = 1"
                                 : "bad config: n_local < 4";
         return 2;
@@ -174,6 +180,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
     fds_ctx* c = new fds_ctx();
     c->cfg = *cfg;
     c->toy = tdim > 0;
+    c->host_sys = host_sys;
     if (c->cfg.dt == 0.0) c->cfg.dt = 0.01;
     if (c->cfg.n_global == 0) c->cfg.n_global = cfg->n_local;
     c->m = cfg->m; c->M = cfg->m + 2; c->MO = cfg->m + 1; c->MX = cfg->m + 2;
@@ -422,7 +429,7 @@ static int ensure_stage(fds_ctx* c) {
     c->stage_sites = std::min<long long>(c->n, 1LL << 18);
     FDS_CK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int j = 0; j < 2; ++j) {
-        FDS_CK(c, cudaMalloc(&c->stage[j], (size_t)c->stage_sites * c->MO * sizeof(double)));
+        FDS_CK(c, cudaMalloc(&c->stage[j], (size_t)c->stage_sites * c->M * sizeof(double)));
         FDS_CK(c, cudaEventCreateWithFlags(&c->ev_copied[j], cudaEventDisableTiming));
         FDS_CK(c, cudaEventCreateWithFlags(&c->ev_done[j], cudaEventDisableTiming));
     }
@@ -496,6 +503,64 @@ int fds_get_tangents(fds_ctx* c, double* Vall, double* vall) {
     }
     }
     FDS_CK(c, cudaStreamSynchronize(c->copy_stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- host-solver mode: the ensemble itself crosses the boundary --------------------------- //
+// E_host[M][n] (row k = trajectory k) <-> device [n][M], same staged transposes as the tangents
+int fds_get_ensemble(fds_ctx* c, double* Eh) {
+    if (c->nb > 1) return fail(c, "fds_get_ensemble: not available for a batch");
+    if (int r = ensure_stage(c)) return r;
+    long long i = 0;
+    for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites, ++i) {
+        const int b = (int)(i & 1);
+        const long long cnt = std::min(c->stage_sites, c->n - s0);
+        double* stg = c->stage[b];
+        if (i >= 2) FDS_CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+        FDS_CK(c, launch_transpose(c->Ecur() + (size_t)s0 * c->M, cnt, c->M, stg, c->stage_sites, c->stream, &c->ls));
+        FDS_CK(c, cudaEventRecord(c->ev_done[b], c->stream));
+        FDS_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        FDS_CK(c, cudaMemcpy2DAsync(Eh + s0, (size_t)c->n * sizeof(double), stg, (size_t)c->stage_sites * sizeof(double),
+                                    (size_t)cnt * sizeof(double), c->M, cudaMemcpyDeviceToHost, c->copy_stream));
+        FDS_CK(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+    }
+    FDS_CK(c, cudaStreamSynchronize(c->copy_stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// the advanced ensemble comes back: column 0 is the new primal state, the tangents are implicit
+// in it, (E_k - E_0) / eps, exactly as after fds_segment_advance
+int fds_set_ensemble(fds_ctx* c, const double* Eh, double eps) {
+    if (c->nb > 1) return fail(c, "fds_set_ensemble: not available for a batch");
+    if (int r = ensure_stage(c)) return r;
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    long long i = 0;
+    for (long long s0 = 0; s0 < c->n; s0 += c->stage_sites, ++i) {
+        const int b = (int)(i & 1);
+        const long long cnt = std::min(c->stage_sites, c->n - s0);
+        double* stg = c->stage[b];
+        if (i >= 2) FDS_CK(c, cudaStreamWaitEvent(c->copy_stream, c->ev_done[b], 0));
+        FDS_CK(c, cudaMemcpy2DAsync(stg, (size_t)c->stage_sites * sizeof(double), Eh + s0, (size_t)c->n * sizeof(double),
+                                    (size_t)cnt * sizeof(double), c->M, cudaMemcpyHostToDevice, c->copy_stream));
+        FDS_CK(c, cudaEventRecord(c->ev_copied[b], c->copy_stream));
+        FDS_CK(c, cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
+        FDS_CK(c, launch_transpose_back(stg, c->stage_sites, cnt, c->M, c->Ecur() + (size_t)s0 * c->M, c->stream, &c->ls));
+        FDS_CK(c, cudaEventRecord(c->ev_done[b], c->stream));
+    }
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    c->state_in_ensemble = true;
+    c->tangents_implicit = true;
+    c->eps_last = eps;
+    c->ens_halo_valid = 0;
+    return 0;
+}
+
+// time dilation of the host-solver mode: the states after 1, 2, 3 steps (fds/timedilation.py:63-82)
+int fds_set_primal_history(fds_ctx* c, int j, const double* u_host) {
+    if (j < 1 || j > 3) return fail(c, "fds_set_primal_history: j must be 1, 2 or 3");
+    FDS_CK(c, cudaMemcpyAsync(c->P(j), u_host, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -684,6 +749,7 @@ int fds_segment_sensitivities(fds_ctx* c, int64_t steps, double eps, double* J0_
 int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int record) {
     if (int r = sync_primal_from_ensemble(c)) return r;
     if (record) if (int r = ensure_jsum(c, step0 + nsteps)) return r;
+    if (c->host_sys) return fail(c, "host-solver system: the solver runs on the host (fds_set_state / fds_set_ensemble)");
     if (c->toy) {
         FDS_CK(c, launch_toy_advance(c->cfg.system, c->cfg.math == FDS_MATH_EXACT, c->P(0), c->P(0), 1, nsteps, s, s,
                                      record ? c->jsum + (size_t)step0 * 2 : nullptr, c->stream, &c->ls));
@@ -723,6 +789,7 @@ int fds_run(fds_ctx* c, double s, int64_t steps, double* Jsum_host) {
 }
 
 int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t nsteps) {
+    if (c->host_sys) return fail(c, "host-solver system: advance the ensemble on the host (fds_get_ensemble / fds_set_ensemble)");
     if (int r = ensure_jsum(c, step0 + nsteps)) return r;
     if (c->toy) {
         // all nsteps in one launch, in place; column m+1 runs at parameter + epsilon (fds/segment.py:64)
@@ -781,7 +848,10 @@ int fds_boundary_begin(fds_ctx* c, int from_ensemble) {
 }
 
 int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
-    if (c->time_dilation && c->toy) {
+    if (c->time_dilation && c->host_sys) {
+        // u1, u2, u3 were put into P(1..3) by fds_set_primal_history
+        FDS_CK(c, launch_dxdt(c->P(0), c->P(1), c->P(2), c->P(3), c->c4, c->d, c->n, c->stream, &c->ls));
+    } else if (c->time_dilation && c->toy) {
         for (int j = 1; j <= 3; ++j)
             FDS_CK(c, launch_toy_advance(c->cfg.system, c->cfg.math == FDS_MATH_EXACT, c->P(j - 1), c->P(j), 1, 1, s, s,
                                          nullptr, c->stream, &c->ls));

@@ -15,7 +15,7 @@ from ._lib import FdsError, dptr
 
 SYSTEMS = {'rk4': _lib.FDS_SYS_L96_RK4, 'euler': _lib.FDS_SYS_L96_EULER,
            'lorenz63': _lib.FDS_SYS_LORENZ63, 'vanderpol': _lib.FDS_SYS_VANDERPOL,
-           'circular': _lib.FDS_SYS_CIRCULAR}
+           'circular': _lib.FDS_SYS_CIRCULAR, 'host': _lib.FDS_SYS_HOST}
 # small ODE systems: (state dimension, n_qoi); their objective is recorded directly
 TOY_SYSTEMS = {'lorenz63': (3, 2), 'vanderpol': (2, 1), 'circular': (2, 1)}
 MATH = {'exact': _lib.FDS_MATH_EXACT, 'fast': _lib.FDS_MATH_FAST}
@@ -108,6 +108,23 @@ class Context:
         V, v = _lib.host_empty(self.lead + (self.m, self.n)), _lib.host_empty(self.lead + (self.n,))
         self._ck(self.lib.fds_get_tangents(self.h, dptr(V), dptr(v)))
         return V, v
+
+    # -- host-solver mode ------------------------------------------------------ #
+    def get_ensemble(self):
+        """(m+2, n): row 0 the primal, rows 1..m homogeneous, row m+1 inhomogeneous perturbed states."""
+        E = _lib.host_empty((self.M, self.n))
+        self._ck(self.lib.fds_get_ensemble(self.h, dptr(E)))
+        return E
+
+    def set_ensemble(self, E, eps):
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        assert E.shape == (self.M, self.n)
+        self._ck(self.lib.fds_set_ensemble(self.h, dptr(E), float(eps)))
+
+    def set_primal_history(self, j, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.shape == (self.n,)
+        self._ck(self.lib.fds_set_primal_history(self.h, int(j), dptr(u)))
 
     def random_tangents(self, seed):
         self._ck(self.lib.fds_random_tangents(self.h, ctypes.c_uint64(int(seed) & (2 ** 64 - 1))))

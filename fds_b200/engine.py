@@ -100,6 +100,9 @@ class Engine:
             self.ring.allreduce_sum(self._view(_lib.FDS_BUF_GRAM, 0, (self.m + 2) ** 2))
 
     # -- the solver plugin on the primal --------------------------------------- #
+    def set_dxdt_weights(self, w):
+        self.ctx.set_dxdt_weights(w)
+
     def set_time_dilation(self, enabled):
         self.time_dilation = bool(enabled)
         self.ctx.set_time_dilation(enabled)
@@ -212,3 +215,112 @@ class Engine:
 
     def close(self):
         self.ctx.close()
+
+
+class HostSolverEngine(Engine):
+    """Engine for a solver that lives on the host (reference SURVEY 8f-4): the user's own
+    ``run(u0, parameter, steps[, run_id][, interprocess])`` advances the m+2 trajectories, everything
+    else of the segment loop -- time-dilation algebra, projection, Gram, CholeskyQR, ``R``, ``b``,
+    ``G_dil``, the next perturbed ensemble, the LSS solve -- runs on the device.  Per segment the
+    ensemble crosses PCIe once in each direction, as it would cross the reference's process pool.
+    The run_id strings are the reference's (fds/segment.py:38-49, fds/fds.py:109,131)."""
+
+    def __init__(self, run, m, math='exact', device=None, simultaneous_runs=1):
+        self.user_run = run
+        self.m, self.M = int(m), int(m) + 2
+        self.kw = dict(math=math, device=0 if device is None else int(device))
+        self.device = self.kw['device']
+        self.simultaneous_runs = max(1, int(simultaneous_runs or 1))
+        self.ctx = None
+        self.ring = None
+        self.batch = 1
+        self.time_dilation = True
+        self.j_div, self.n_qoi = 1.0, None
+        self.i_segment = 0
+        self._weights = None
+
+    # -- the reference's RunWrapper (fds/fds.py:53-90): 3-, 4- or 5-argument plugins -------------- #
+    def _call(self, u0, parameter, steps, run_id):
+        run, last = self.user_run, None
+        for kw in (dict(run_id=run_id, interprocess=None), dict(run_id=run_id), dict(interprocess=None), {}):
+            try:
+                u1, J = run(np.array(u0), parameter, steps, **kw)
+                return np.asarray(u1, dtype=np.float64), np.array(J, dtype=np.float64).reshape([steps, -1])
+            except TypeError as e:
+                last = e
+        raise last
+
+    def _map(self, jobs):
+        if self.simultaneous_runs == 1 or len(jobs) == 1:
+            return [self._call(*j) for j in jobs]
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(self.simultaneous_runs) as pool:
+            return list(pool.map(lambda j: self._call(*j), jobs))
+
+    def _ensure(self, n):
+        if self.ctx is None:
+            self.n_global = int(n)
+            self.lo, self.hi = 0, self.n_global
+            self.ctx = Context(self.n_global, self.m, scheme='host', **self.kw)
+            self.ctx.set_time_dilation(self.time_dilation)
+            if self._weights is not None:
+                self.ctx.set_dxdt_weights(self._weights)
+        elif int(n) != self.n_global:
+            raise ValueError('state dimension changed from %d to %d' % (self.n_global, n))
+
+    def set_dxdt_weights(self, w):
+        self._weights = np.asarray(w, dtype=np.float64)
+        if self.ctx is not None:
+            self.ctx.set_dxdt_weights(self._weights)
+
+    def set_time_dilation(self, enabled):
+        self.time_dilation = bool(enabled)
+        if self.ctx is not None:
+            self.ctx.set_time_dilation(enabled)
+
+    def set_state(self, u):
+        u = np.asarray(u, dtype=np.float64).ravel()
+        self._ensure(u.size)
+        self.ctx.set_state(u)
+
+    def run(self, s, steps, want_J=True):
+        u1, J = self._call(self.ctx.get_state(), s, int(steps), 'run_up')
+        self.ctx.set_state(u1)
+        return J if want_J else None
+
+    def boundary(self, s, eps, from_ensemble, do_qr, build, keep_tangents=True):
+        c = self.ctx
+        flags = (_lib.FDS_BUILD_ENSEMBLE if build else 0) | (_lib.FDS_BUILD_KEEP_TANGENTS if keep_tangents else 0)
+        c.boundary_begin(from_ensemble)
+        if self.time_dilation:
+            u0 = c.get_state()
+            rid = 'time_dilation_{0:02d}'.format(self.i_segment)
+            res = self._map([(u0, s, k, rid + '_{0}steps'.format(k)) for k in (1, 2, 3)])
+            for k, (uk, _) in zip((1, 2, 3), res):
+                c.set_primal_history(k, uk)
+        c.boundary_dxdt(s, from_ensemble, eps)
+        c.boundary_factor(do_qr, from_ensemble, eps)
+        c.boundary_finish(do_qr, eps, flags)
+        return c.boundary_results(do_qr)
+
+    def segment(self, s, eps, steps):
+        """The m+2 solver runs of fds/segment.py:56-64 on the host; returns J (steps, m+2, n_qoi)."""
+        c, m, i = self.ctx, self.m, self.i_segment
+        E = c.get_ensemble()
+        ids = ['segment{0:02d}_baseline'.format(i)] + \
+              ['segment{0:02d}_init_perturb{1:03d}'.format(i, j) for j in range(m)] + \
+              ['segment{0:02d}_param_perturb{1:03d}'.format(i, m)]
+        jobs = [(E[k], s + eps if k == m + 1 else s, int(steps), ids[k]) for k in range(m + 2)]
+        res = self._map(jobs)
+        for k, (uk, _) in enumerate(res):
+            E[k] = uk
+        c.set_ensemble(E, eps)
+        self.i_segment += 1
+        J = np.stack([r[1] for r in res], axis=1)
+        self.n_qoi = J.shape[2]
+        return J
+
+    def orthonormal_random_tangents(self, seed=None, host_rng=None, block=None):
+        if block is None and host_rng is None and seed is None:
+            host_rng = np.random
+        return Engine.orthonormal_random_tangents(self, seed=seed, host_rng=host_rng, block=block)

@@ -2,11 +2,13 @@
 ``lss_gradient`` -- same signatures, argument meaning and return values as the
 reference ``fds/fds.py`` (:29-51, :92-176, :178-220).
 
-``run`` must be a device plugin (``fds_b200.L96``).  The whole segment loop --
-ensemble time stepping, finite-difference tangents, time dilation, projection,
+``run`` must be a device plugin (``fds_b200.L96``, ``Lorenz63``, ...).  The whole segment loop
+-- ensemble time stepping, finite-difference tangents, time dilation, projection,
 QR, next perturbed ensemble -- runs in CUDA kernels on device-resident state;
 per segment only KBs (R, b, G_dil, g_dil, the objective sums) come back to the
-host.  There is no CPU fallback: an arbitrary Python ``run`` raises TypeError.
+host.  There is no CPU fallback: an arbitrary Python ``run`` raises TypeError.  A solver
+that cannot move to the GPU is wrapped explicitly, ``fds_b200.HostSolver(run)``: it advances
+the trajectories on the host, the algebra of the loop still runs on the device.
 """
 import sys
 from copy import deepcopy
@@ -28,7 +30,8 @@ def _engine_of(run, m):
     eng = getattr(run, 'engine', None)
     if eng is None:
         raise TypeError('fds_b200.shadowing needs a device plugin (e.g. fds_b200.L96); '
-                        'arbitrary Python solvers are not supported -- there is no CPU path')
+                        'arbitrary Python solvers are not run on the CPU behind your back -- wrap a '
+                        'host solver explicitly with fds_b200.HostSolver(run)')
     return eng(m)
 
 
@@ -70,9 +73,11 @@ def continue_shadowing(run, parameter, checkpoint, num_segments, steps_per_segme
     V = np.asarray(V)
     eng = _engine_of(run, V.shape[0])
     eng.set_time_dilation(run_ddt is None)
-    eng.ctx.set_dxdt_weights(stencil_weights(3))
+    eng.set_dxdt_weights(stencil_weights(3))
     eng.set_state(u0)
     eng.set_tangents(V, v)
+    if hasattr(eng, 'i_segment'):
+        eng.i_segment = lss.K_segments()       # run_id numbering of a host solver continues
     return _segment_loop(eng, parameter, lss, G_lss, g_lss, J_hist, G_dil, g_dil, num_segments,
                          steps_per_segment, epsilon, checkpoint_path, checkpoint_interval,
                          return_checkpoint, verbose)
@@ -130,7 +135,7 @@ def shadowing(run, u0, parameter, subspace_dimension, num_segments, steps_per_se
         raise NotImplementedError('run_ddt: only None (finite-difference time dilation) or 0 (off)')
     eng = _engine_of(run, m)
     eng.set_time_dilation(run_ddt is None)
-    eng.ctx.set_dxdt_weights(stencil_weights(3))
+    eng.set_dxdt_weights(stencil_weights(3))
     eng.set_state(u0)
     if runup_steps > 0:
         eng.run(parameter, runup_steps, want_J=False)
@@ -225,7 +230,7 @@ def _shadowing_batch_local(run, u0, parameters, subspace_dimension, num_segments
     if u0.ndim == 1:
         u0 = np.broadcast_to(u0, (B, N))
     eng.set_time_dilation(run_ddt is None)
-    eng.ctx.set_dxdt_weights(stencil_weights(3))
+    eng.set_dxdt_weights(stencil_weights(3))
     eng.ctx.set_batch_params(parameters)          # problem p runs at 0.0 + parameters[p]
     eng.set_state(np.ascontiguousarray(u0))
     s = 0.0

@@ -9,7 +9,7 @@ and the whole segment loop stays on the GPU.
 """
 import numpy as np
 
-from .engine import Engine
+from .engine import Engine, HostSolverEngine
 
 
 def _current_device():
@@ -65,6 +65,33 @@ class _DevicePlugin:
     def close(self):
         for e in self._engines.values():
             e.close()
+        self._engines = {}
+
+
+class HostSolver:
+    """Opt-in wrapper for a solver that cannot move to the GPU: ``HostSolver(run)`` hands the user's
+    ``run(u0, parameter, steps[, run_id][, interprocess]) -> (u1, J)`` (reference fds/fds.py:184-200) to
+    ``shadowing`` / ``continue_shadowing``; the trajectories are advanced by that solver on the host, the
+    algebra of the segment loop runs on the device (``HostSolverEngine``).  A bare Python callable is
+    still rejected: nothing in this package runs the hot path on the CPU behind the user's back."""
+
+    def __init__(self, run, math='exact', device=None, simultaneous_runs=1):
+        self.user_run = run
+        self.kw = dict(math=math, device=device, simultaneous_runs=simultaneous_runs)
+        self._engines = {}
+
+    def engine(self, m):
+        if m not in self._engines:
+            self._engines[m] = HostSolverEngine(self.user_run, m, **self.kw)
+        return self._engines[m]
+
+    def __call__(self, u0, parameter, steps, run_id=None, interprocess=None):
+        return self.user_run(u0, parameter, steps)
+
+    def close(self):
+        for e in self._engines.values():
+            if e.ctx is not None:
+                e.close()
         self._engines = {}
 
 

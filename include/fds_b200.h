@@ -37,7 +37,10 @@ enum {
     FDS_SYS_LORENZ63  = 2, /* n = 3, J = [(z-28)^2, 100]: tests/solvers/lorenz/lorenz.f03:10-26,
                               tests/test_lorenz.py:18-31                                     */
     FDS_SYS_VANDERPOL = 3, /* n = 2, J = [x0^2, -]: tests/solvers/vanderpol/vanderpol.f03:9-24 */
-    FDS_SYS_CIRCULAR  = 4  /* n = 2, J = [x0^2+x1^2, -]: tests/solvers/circular/circular.f03:9-28 */
+    FDS_SYS_CIRCULAR  = 4, /* n = 2, J = [x0^2+x1^2, -]: tests/solvers/circular/circular.f03:9-28 */
+    /* no built-in solver: the caller's own run(u, s, steps) advances the trajectories on the host
+     * (any n_local, any objective) and only the algebra of the segment loop runs here              */
+    FDS_SYS_HOST      = 5
 };
 
 /* arithmetic modes */
@@ -179,6 +182,17 @@ int fds_segment(fds_ctx*, double s, double eps, int64_t steps, double* Jsum_host
  * u, V, v in -> advanced u, V, v out, Jsum[steps][m+2][2]; H2D and D2H inside     */
 int fds_run_segment_host(fds_ctx*, double* u, double* V, double* v, double s, double eps,
                          int64_t steps, double* Jsum_host);
+
+/* ---- host-solver mode (cfg.system = FDS_SYS_HOST) -------------------------------------------
+ * For solvers that cannot move to the GPU (the reference's CFD applications, apps/): the perturbed
+ * initial conditions u0 + eps*[V; v] come out as E_host[m+2][n] (row 0 = u0, rows 1..m homogeneous,
+ * row m+1 inhomogeneous -- the inputs of the m+2 run() calls of fds/segment.py:56-64), the advanced
+ * states go back in, and time dilation takes the states after 1, 2, 3 steps
+ * (fds/timedilation.py:63-82).  Everything else (Gram, CholeskyQR, projection, R, b, G_dil) is
+ * fds_boundary_* as usual.  fds_run / fds_segment_advance fail for this system.                 */
+int fds_get_ensemble(fds_ctx*, double* E_host);                    /* [m+2][n] */
+int fds_set_ensemble(fds_ctx*, const double* E_host, double eps);  /* [m+2][n] */
+int fds_set_primal_history(fds_ctx*, int j, const double* u_host); /* j = 1, 2, 3 */
 
 /* ---- batched parameter sweep (BASELINE configs[4]) -----------------------------
  * A context created with cfg.batch = B holds B independent problems; the reference can only

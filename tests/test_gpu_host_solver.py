@@ -1,0 +1,85 @@
+"""Host-solver mode: the reference's plugins -- plain Python run(u0, s, steps) callables --
+through fds_b200.shadowing with the algebra on the device, against the reference's own outputs.
+This is the other half of the cross-check matrix of SURVEY 8b (our driver running THEIR plugin)."""
+import numpy as np
+import pytest
+
+import fds_b200
+from fds_b200 import checkpoint as ckpt
+from oracle import plugins, shadowing_port as port
+from conftest import golden
+
+gpu = pytest.mark.gpu
+
+
+def maxrel(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@gpu
+@pytest.mark.parametrize('name,run,tol', [
+    ('cfg1_lorenz63_m2_K20', plugins.run_lorenz63, 1e-3),
+    ('circular_m1_K5', plugins.run_circular, 1e-6),
+    ('fun3d_l96euler_N40_m16_K20', plugins.run_l96_euler, None)])
+def test_reference_plugins_through_the_device_algebra(name, run, tol):
+    g = golden(name)
+    np.random.seed(int(g['seed']))
+    cp = fds_b200.shadowing(fds_b200.HostSolver(run), g['u0'], float(g['s']), int(g['m']), int(g['K']),
+                            int(g['steps']), int(g['runup']), epsilon=float(g['eps']), return_checkpoint=True)
+    J = np.array(cp.J)
+    assert np.array_equal(J[0], g['J'][0])                 # the solver is theirs: identical primal
+    G = fds_b200.lss_gradient(cp)
+    if tol is not None:
+        assert maxrel(J.mean((0, 1)), g['J_ref']) < 1e-6
+        assert abs(G[0] - g['G_ref'][0]) < tol * abs(g['G_ref'][0])
+    else:                                                  # chaotic, 20 segments: the reference's windows
+        Jm = J.mean((0, 1))
+        assert 1 < Jm[0] < 4 and 10 < Jm[1] < 40 and -0.1 < G[0] < 0.5 and 1 < G[1] < 8
+        assert (np.abs(G - g['G_ref']) <= 3 * g['G_err']).all()
+
+
+@gpu
+def test_host_solver_equals_device_plugin():
+    """Same system advanced by the numpy plugin on the host and by the CUDA plugin: the two engines
+    differ only in who integrates -- and both integrators are bit-identical."""
+    N, m, K, steps, eps, s = 64, 5, 3, 20, 1e-4, 0.1
+    u0 = plugins.run_l96_rk4(np.random.RandomState(0).rand(N), s, 300)[0]
+    np.random.seed(3)
+    a = fds_b200.shadowing(fds_b200.HostSolver(plugins.run_l96_rk4), u0, s, m, K, steps, 10, epsilon=eps,
+                           return_checkpoint=True)
+    np.random.seed(3)
+    b = fds_b200.shadowing(fds_b200.L96(N), u0, s, m, K, steps, 10, epsilon=eps, return_checkpoint=True)
+    assert np.array_equal(np.array(a.J), np.array(b.J))
+    assert np.array_equal(a.u0, b.u0) and maxrel(a.V, b.V) < 1e-9
+    assert maxrel(np.array(a.lss.Rs), np.array(b.lss.Rs)) < 1e-9
+    assert maxrel(fds_b200.lss_gradient(a), fds_b200.lss_gradient(b)) < 1e-7
+
+
+@gpu
+def test_host_solver_restart_and_plugin_signatures(tmp_path):
+    """reference tests/test_restart.py:42-64 with a 4-argument plugin (run_id) and a thread pool."""
+    seen = []
+
+    def run(u0, s, steps, run_id=None):
+        seen.append(run_id)
+        return plugins.run_circular(u0, s, steps)
+
+    hs = fds_b200.HostSolver(run, simultaneous_runs=3)
+    u0 = np.array([1.0, 0.5])
+    np.random.seed(0)
+    fds_b200.shadowing(hs, u0, 1.0, 1, 10, 100, 0, checkpoint_path=str(tmp_path))
+    cp = ckpt.load_last_checkpoint(str(tmp_path), 1)
+    assert cp.lss.K_segments() == 10
+    J2, G2 = fds_b200.continue_shadowing(hs, 1.0, cp, 20, 100)
+    np.random.seed(0)
+    J1, G1 = fds_b200.shadowing(fds_b200.HostSolver(run), u0, 1.0, 1, 20, 100, 0)
+    assert np.array_equal(J1, J2) and np.allclose(G1, G2)
+    assert 'segment00_baseline' in seen and 'segment10_param_perturb001' in seen
+    assert any(r and r.startswith('time_dilation_') and r.endswith('_3steps') for r in seen)
+
+
+@gpu
+def test_bare_callable_is_still_rejected():
+    with pytest.raises(TypeError, match='HostSolver'):
+        fds_b200.shadowing(plugins.run_l96_rk4, np.zeros(40), 0.0, 2, 2, 10, 0)
