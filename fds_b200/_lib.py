@@ -78,6 +78,7 @@ SIGNATURES = {
     'fds_sync': (_I32, [_CTX]),
     'fds_profile_enable': (_I32, [_CTX, _I32]),
     'fds_profile_read': (_I32, [_CTX, c_double_p, c_int64_p]),
+    'fds_profile_steps': (_I64, [_CTX]),
 }
 
 _lib = None

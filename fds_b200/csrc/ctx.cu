@@ -22,6 +22,8 @@ struct fds_ctx {
     long long alo = 0, ahi = 0;    // allocated site range of ensemble / primal arrays
     StripPlan plan{};              // fixed strip decomposition of the ensemble step kernel
     bool stream_ok = false;
+    bool fuse2 = false;            // two RK4 steps per pass of the streaming kernel (l96_march2.cuh)
+    long long prof_steps = 0;      // time steps covered by the profiled launches
     bool toy = false;              // small ODE system (toy_ode.cu) or host solver: no stencil, no halos
     bool host_sys = false;         // FDS_SYS_HOST: the solver runs on the host, only the algebra lives here
     // batch of nb independent problems stacked along the site axis (cfg.batch > 1): problem p owns the
@@ -240,14 +242,22 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         c->stream_ok = true;
         StripPlan& pl = c->plan;
         pl.a0 = 0; pl.ls = c->slot / c->spp; pl.nstrips = nstrips; pl.nblk = (int)(pl.ls / 8);
-        pl.alo = -12; pl.ahi = c->nall + 12; pl.node_shift = kLeafShift; pl.nnode = c->nall / kLeafSites;
+        pl.alo = -20; pl.ahi = c->nall + 20; pl.node_shift = kLeafShift; pl.nnode = c->nall / kLeafSites;
         c->alo = pl.alo; c->ahi = pl.ahi;
         c->ds.assign(c->nb, 0.0);
         c->Fhost.assign(c->nb, make_double2(8.0, 8.0));
     } else {
-        const int R = stream_runs_per_cta(c->M);
+        int R = stream_runs_per_cta(c->M);
         c->stream_ok = R >= 1 && (cfg->system == FDS_SYS_L96_RK4 || cfg->system == FDS_SYS_L96_EULER) &&
                        !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS);
+        // temporal blocking: two RK4 steps per pass halve the HBM traffic per step; the kernel then holds
+        // twice the pipeline state per thread, so a CTA carries 256 / M strips instead of 480 / M
+        {
+            const char* e = getenv("FDS_FUSE2");
+            const bool want = e ? e[0] != '0' : true;
+            c->fuse2 = want && c->stream_ok && cfg->system == FDS_SYS_L96_RK4 && two_step_runs_per_cta(c->M) >= 1 && H >= 2;
+            if (c->fuse2) { R = two_step_runs_per_cta(c->M); c->runs_per_cta = R; }
+        }
         c->plan = make_strip_plan(c->n, H, (long long)c->num_sms * (R >= 1 ? R : 1));
         c->alo = c->plan.alo;
         c->ahi = c->plan.ahi;
@@ -346,9 +356,12 @@ int fds_sync(fds_ctx* c) {
 
 int64_t fds_kernel_launches(const fds_ctx* c) { return c->ls.launches; }
 
+int64_t fds_profile_steps(const fds_ctx* c) { return c->prof_steps; }
+
 int fds_profile_enable(fds_ctx* c, int enabled) {
     c->profiling = enabled != 0;
     c->prof_used = 0;
+    c->prof_steps = 0;
     return 0;
 }
 
@@ -650,11 +663,12 @@ static int ensure_jsum(fds_ctx* c, long long steps) {
 // (streaming kernel: node partials into jnode[jstep], reduced later in one batch by
 // reduce_nodes(); simple kernels: reduced right away into jsum[jstep])
 static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, double Flast, long long valid,
-                    long long jstep, long long jslot) {
+                    long long jstep, long long jslot, bool two = false) {
     double* jsum_slot = c->jsum + (size_t)jstep * M_ * 2;
     StepArgs a;
     a.X = X; a.Y = Y; a.M = M_; a.n = c->nall;
     if (c->nb > 1) { a.Fpp = c->Fpp; a.spp = c->spp; a.slot = c->slot; a.runs_per_cta = c->runs_per_cta; a.ctas_per_sm = c->ctas_per_sm; }
+    else if (c->fuse2) a.runs_per_cta = c->runs_per_cta;
     a.lo = -8 * (valid - 1); a.hi = c->n + 4 * (valid - 1);
     a.F0 = F0; a.Flast = Flast; a.dt = c->cfg.dt; a.exact = c->cfg.math == FDS_MATH_EXACT;
     a.jpart = jsum_slot ? c->jpart : nullptr;
@@ -662,6 +676,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
     const bool euler = c->cfg.system == FDS_SYS_L96_EULER;
     if (c->stream_ok && M_ == c->M) {
         a.jpart = c->jnode + (size_t)jslot * c->plan.nnode * c->M * 2;
+        if (two) { a.two_steps = 1; a.jpart2 = a.jpart + (size_t)c->plan.nnode * c->M * 2; }
         cudaEvent_t e1 = nullptr;
         if (c->profiling) {
             if (c->prof_used == c->prof_events.size()) {
@@ -673,6 +688,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
             FDS_CK(c, cudaEventRecord(c->prof_events[c->prof_used].first, c->stream));
             e1 = c->prof_events[c->prof_used].second;
             c->prof_used++;
+            c->prof_steps += two ? 2 : 1;
         }
         FDS_CK(c, launch_l96_rk4_stream(a, c->plan, c->stream, &c->ls, euler ? 1 : 0));
         if (e1) FDS_CK(c, cudaEventRecord(e1, c->stream));
@@ -803,12 +819,14 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
     const double F0 = s + 8.0, Flast = (s + eps) + 8.0;   // fds/segment.py:64: parameter + epsilon
     if (c->nb > 1 && nsteps > c->H) return fail(c, "fds_segment_advance: a batch advances at most halo_steps per call");
     if (int r = upload_forcing(c, s, eps)) return r;
-    for (long long j = 0; j < nsteps; ++j) {
+    for (long long j = 0; j < nsteps;) {
         if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
+        const bool two = c->fuse2 && c->nb == 1 && nsteps - j >= 2 && c->ens_halo_valid >= 2;
         if (int r = one_step(c, c->E_all(c->cur), c->E_all(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, step0 + j,
-                             c->nb > 1 ? j : step0 + j)) return r;
+                             c->nb > 1 ? j : step0 + j, two)) return r;
         c->cur ^= 1;
-        c->ens_halo_valid--;
+        c->ens_halo_valid -= two ? 2 : 1;
+        j += two ? 2 : 1;
     }
     if (int r = reduce_nodes(c, step0, nsteps)) return r;
     c->state_in_ensemble = true;

@@ -5,6 +5,7 @@
 // policy (plain arrays instead of a TMA-fed shared-memory ring) differs.
 #include <vector>
 #include "l96_march.cuh"
+#include "l96_march2.cuh"
 
 using namespace fds;
 
@@ -36,6 +37,33 @@ struct HostIO {
     double ns_get(int l, int q) const { return ns[l][q]; }
     void ns_put(int l, int q, double v) { ns[l][q] = v; }
 };
+// two steps per pass: output cursor at site a + 8b - 10, two sets of objective partials
+struct HostIO2 {
+    const double* X;
+    double* Y;
+    double* jpart[2];  // [nnode][M][2] of step 1 and step 2
+    long long nleaf;
+    long long a;
+    int M, k;
+    long long cs = 0, j0 = 0;
+    void begin_block(int b) {
+        cs = a + 8LL * b + 4;
+        j0 = a + 8LL * b - 10;
+    }
+    void end_block(int) {}
+    double load(int p) const { return X[(cs + p) * M + k]; }
+    void store(int p, double v) { Y[(j0 + p) * M + k] = v; }
+    void emit_node2(int step, long long node, double s1, double s2) {
+        if (node >= 0 && node < nleaf) {
+            jpart[step][(node * M + k) * 2 + 0] = s1;
+            jpart[step][(node * M + k) * 2 + 1] = s2;
+        }
+    }
+    bool all(bool v) const { return v; }
+    double ns[2][kMaxNodeLevels + 1][2];
+    double ns_get2(int st, int l, int q) const { return ns[st][l][q]; }
+    void ns_put2(int st, int l, int q, double v) { ns[st][l][q] = v; }
+};
 }  // namespace
 
 extern "C" {
@@ -60,6 +88,23 @@ int emul_l96_rk4_step(const double* X, double* Y, int M, long long n, long long 
             MarchGeom g{io.a, n, plan.nblk, jpart != nullptr, plan.node_shift};
             if (exact) l96_rk4_march<ExactMath>(io, g, F[k], c);
             else       l96_rk4_march<FastMath>(io, g, F[k], c);
+        }
+    }
+    return 0;
+}
+
+// TWO steps in one pass (l96_march2.cuh); jpart1 / jpart2: objective partials of step 1 and step 2
+int emul_l96_rk4_step2(const double* X, double* Y, int M, long long n, long long H,
+                       const double* F /*[M]*/, double dt, int exact, long long max_strips, double* jpart1,
+                       double* jpart2) {
+    StripPlan plan = make_strip_plan(n, H, max_strips);
+    Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+    for (long long s = 0; s < plan.nstrips; ++s) {
+        for (int k = 0; k < M; ++k) {
+            HostIO2 io{X, Y, {jpart1, jpart2}, plan.nnode, plan.a0 + s * plan.ls, M, k};
+            MarchGeom g{io.a, n, plan.nblk, jpart1 != nullptr, plan.node_shift};
+            if (exact) l96_rk4_march2<ExactMath>(io, g, F[k], c);
+            else       l96_rk4_march2<FastMath>(io, g, F[k], c);
         }
     }
     return 0;

@@ -33,11 +33,16 @@ struct StepArgs {
     // shared memory per CTA, warp 0 produces in between its blocks
     int runs_per_cta = 0;
     int ctas_per_sm = 1;
+    // two RK4 steps in one pass (l96_march2.cuh): Y receives the state after TWO steps, jpart the node
+    // partials of the first and jpart2 those of the second step; needs runs_per_cta * M <= 256 threads and the in-between producer
+    int two_steps = 0;
+    double* jpart2 = nullptr;
 };
 
 // streaming TMA-fed kernel (RK4 only); `plan` = make_strip_plan(n, H, num_sms * stream_runs_per_cta(M)),
 // X and Y allocated for sites [plan.alo, plan.ahi)
 int stream_runs_per_cta(int M);
+int two_step_runs_per_cta(int M);      // strips per CTA of the two-steps-per-pass kernel (256 threads)
 // euler = 1: forward Euler with the reference's operation order instead of RK4
 cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls,
                                   int euler = 0);

@@ -242,7 +242,8 @@ struct NodeCounter {
 // step computes the whole span (cells outside the still-valid halo receive values
 // that are never used), so the kernel needs no range checks, and the arrays are
 // allocated for sites [alo, ahi) = [a0 - 12, a0 + nstrips*ls + 12): exactly the
-// input chunks the strips read (both bounds == 4 mod 8).
+// input chunks the strips read (both bounds == 4 mod 8); the two-steps-per-pass kernel
+// (l96_march2.cuh) starts one block earlier and drains one block later, hence 20 instead of 12.
 // --------------------------------------------------------------------------- //
 struct StripPlan {
     long long a0;       // first strip starts here (multiple of the node size)
@@ -287,8 +288,8 @@ inline StripPlan make_strip_plan(long long n, long long H, long long max_strips)
         break;
     }
     p.nblk = (int)(p.ls / 8);
-    p.alo = p.a0 - 12;
-    p.ahi = p.a0 + p.nstrips * p.ls + 12;
+    p.alo = p.a0 - 20;
+    p.ahi = p.a0 + p.nstrips * p.ls + 20;
     p.nnode = (n + (1LL << p.node_shift) - 1) >> p.node_shift;
     return p;
 }

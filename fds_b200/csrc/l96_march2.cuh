@@ -1,0 +1,151 @@
+// Two RK4 steps per pass: the per-thread body of the temporally blocked streaming kernel.
+//
+// A second Rk4Pipe is chained behind the first: the step-1 value that leaves pipe 1 (site i-7 for a
+// push of site i) is pushed straight into pipe 2, whose output is the step-2 value at site i-14.  The
+// intermediate state never touches shared or global memory, so a site is read once and written once
+// per TWO time steps: 8 B of HBM traffic per trajectory-site-step instead of 16.  Both steps'
+// objective sums are accumulated on the way (the intermediate state's from pipe 1's output) in the
+// same specified tree, so the result is bit-identical to two single-step passes.
+//
+// Block b of a strip that starts at site a consumes the 8 input sites a + 8b + 4 .. a + 8b + 11,
+// produces the step-1 values of sites a + 8b - 3 .. a + 8b + 4 (never stored) and the step-2 values
+// of sites a + 8b - 10 .. a + 8b - 3.  Blocks run from b = -3 (warm-up: x'' is exact from site a - 4
+// on) to b = nblk + 1 (drain of the 14-site lag).
+//
+// IO policy: as in l96_march.cuh, with the output cursor at site a + 8b - 10 and the per-step
+// variants   emit_node2(step, node, s1, s2),   ns_get2(step, level, which),   ns_put2(step, level, which, v).
+#pragma once
+#include "l96_march.cuh"
+
+namespace fds {
+
+constexpr int kFuse2First = -3;                              // first block index
+FDS_HD int march2_iterations(int nblk) { return nblk + 5; }  // b = -3 .. nblk + 1
+
+template <class IO>
+struct NsStep {            // NodeCounter storage view of one of the two steps
+    IO& io;
+    int step;
+    FDS_HD double ns_get(int l, int q) const { return io.ns_get2(step, l, q); }
+    FDS_HD void ns_put(int l, int q, double v) { io.ns_put2(step, l, q, v); }
+};
+
+struct StepStats {         // objective accumulators of one step
+    Tree8 t1, t2;
+    LeafStack l1, l2;
+    NodeCounter ns;
+    double b1, b2;
+    FDS_HD void reset() {
+        t1.t1 = t1.t2 = t1.t4 = 0.0; t2 = t1;
+        l1.s0 = l1.s1 = l1.s2 = 0.0; l2 = l1;
+        ns.reset();
+        b1 = b2 = 0.0;
+    }
+};
+
+// 8-block k of the strip (sites a + 8k .. a + 8k + 7) of step `step` is complete: fold it into the leaf
+template <class IO>
+FDS_HD void march2_leaf(IO& io, StepStats& s, const MarchGeom& g, int step, int k) {
+    double s1, s2;
+    const bool d1 = s.l1.push(s.b1, k & 7, s1);
+    const bool d2 = s.l2.push(s.b2, k & 7, s2);
+    if (d1 && d2) {
+        const long long leaf = (g.a + 8LL * k) >> kLeafShift;
+        if (leaf < 0 || leaf * kLeafSites >= g.n) { s1 = 0.0; s2 = 0.0; }
+        NsStep<IO> view{io, step};
+        if (s.ns.push(view, s1, s2, g.node_shift - kLeafShift))
+            io.emit_node2(step, leaf >> (g.node_shift - kLeafShift), s1, s2);
+    }
+}
+
+template <class MP, int P, bool FAST, bool STATS, class IO>
+FDS_HD void march2_site(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, StepStats& sa, StepStats& sb, long long j1,
+                        long long j2, long long slo, long long shi, long long jlo, long long jhi, double F,
+                        const Rk4Coef& c) {
+    constexpr int P2 = (P + 1) & 7;      // pipe 2 sees site i - 7 as its push site: (i - 7) - 4 = i - 11 = P + 1 (mod 8)
+    constexpr int Q1 = (P + 5) & 7;      // step-1 output site mod 8
+    constexpr int Q2 = (P + 6) & 7;      // step-2 output site mod 8
+    const double x1 = p1.template push<P>(io.load(P), F, c);
+    const double x2 = p2.template push<P2>(x1, F, c);
+    if (FAST) {
+        io.store(P, x2);
+        if (STATS) {
+            const double r1 = sa.t1.template push<Q1>(x1);
+            const double r2 = sa.t2.template push<Q1>(MP::mul(x1, x1));
+            if (Q1 == 7) { sa.b1 = r1; sa.b2 = r2; }
+            const double q1 = sb.t1.template push<Q2>(x2);
+            const double q2 = sb.t2.template push<Q2>(MP::mul(x2, x2));
+            if (Q2 == 7) { sb.b1 = q1; sb.b2 = q2; }
+        }
+    } else {
+        const long long s1 = j1 + P, s2 = j2 + P;
+        if (s2 >= slo && s2 < shi) io.store(P, x2);
+        if (STATS) {
+            const double v1 = (s1 >= jlo && s1 < jhi) ? x1 : 0.0;
+            const double r1 = sa.t1.template push<Q1>(v1);
+            const double r2 = sa.t2.template push<Q1>(MP::mul(v1, v1));
+            if (Q1 == 7) { sa.b1 = r1; sa.b2 = r2; }
+            const double v2 = (s2 >= jlo && s2 < jhi) ? x2 : 0.0;
+            const double q1 = sb.t1.template push<Q2>(v2);
+            const double q2 = sb.t2.template push<Q2>(MP::mul(v2, v2));
+            if (Q2 == 7) { sb.b1 = q1; sb.b2 = q2; }
+        }
+    }
+}
+
+template <class MP, bool FAST, bool STATS, class IO>
+FDS_HD void march2_block(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, StepStats& sa, StepStats& sb, const MarchGeom& g,
+                         int b, long long slo, long long shi, long long jlo, long long jhi, double F,
+                         const Rk4Coef& c) {
+    const long long j1 = g.a + 8LL * b - 3, j2 = g.a + 8LL * b - 10;
+#define FDS_M2(P) march2_site<MP, P, FAST, STATS>(io, p1, p2, sa, sb, j1, j2, slo, shi, jlo, jhi, F, c)
+    FDS_M2(0);
+    FDS_M2(1);
+    // step 2: sites a + 8(b-2) .. a + 8(b-2) + 7 are complete (Q2 == 7 at P == 1)
+    if (STATS && b >= 2 && b - 2 < g.nblk) march2_leaf(io, sb, g, 1, b - 2);
+    FDS_M2(2);
+    // step 1: sites a + 8(b-1) .. a + 8(b-1) + 7 are complete (Q1 == 7 at P == 2)
+    if (STATS && b >= 1 && b - 1 < g.nblk) march2_leaf(io, sa, g, 0, b - 1);
+    FDS_M2(3);
+    FDS_M2(4);
+    FDS_M2(5);
+    FDS_M2(6);
+    FDS_M2(7);
+#undef FDS_M2
+}
+
+template <class MP, bool STATS, class IO>
+FDS_HD void l96_rk4_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
+    Rk4Pipe<MP> p1, p2;
+    p1.reset();
+    p2.reset();
+    StepStats sa, sb;
+    sa.reset();
+    sb.reset();
+    const long long slo = g.a, shi = g.a + 8LL * g.nblk;
+    const long long jlo = slo > 0 ? slo : 0;
+    const long long jhi = g.n < shi ? g.n : shi;
+    const long long nfl = g.n & ~(long long)(kLeafSites - 1);
+    const long long ncl = (g.n + kLeafSites - 1) & ~(long long)(kLeafSites - 1);
+#pragma unroll 1
+    for (int b = kFuse2First; b <= g.nblk + 1; ++b) {
+        const long long j1 = g.a + 8LL * b - 3, j2 = g.a + 8LL * b - 10;
+        io.begin_block(b);
+        // unchecked path: the 8 step-2 outputs are stored by this strip and neither they nor the 8
+        // step-1 values lie in the partial leaf (leaves wholly outside [0, n) are zeroed as a whole)
+        const bool fast = j2 >= slo && j2 + 8 <= shi && (j1 + 8 <= nfl || j2 >= ncl);
+        if (io.all(fast))
+            march2_block<MP, true, STATS>(io, p1, p2, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
+        else
+            march2_block<MP, false, STATS>(io, p1, p2, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
+        io.end_block(b);
+    }
+}
+
+template <class MP, class IO>
+FDS_HD void l96_rk4_march2(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
+    if (g.stats) l96_rk4_march2_t<MP, true>(io, g, F, c);
+    else l96_rk4_march2_t<MP, false>(io, g, F, c);
+}
+
+}  // namespace fds

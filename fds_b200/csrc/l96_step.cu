@@ -17,6 +17,7 @@
 #include <algorithm>
 #include "kernels.h"
 #include "l96_march.cuh"
+#include "l96_march2.cuh"
 
 namespace fds {
 
@@ -32,6 +33,8 @@ struct StreamParams {
     int M, R, run_stride, nstages, nconsumer;  // nconsumer = R*M
     int dedicated;                             // 1: the last warp only produces; 0: warp 0 produces in between its blocks
     double F0, Flast;
+    double* jpart2;                            // two steps per pass: node partials of the second step
+    int fuse2;                                 // 1: two steps per pass (l96_march2.cuh)
     const double2* Fpp;                        // per-problem (F0, Flast) of a batch, or nullptr
     int spp;                                   // strips per problem (batch)
     Rk4Coef c;
@@ -53,6 +56,7 @@ struct StreamProducer {
     int lane;
     int it, st;
     uint32_t par;
+    int first_off;       // first input site of block 0 relative to the strip start: -12, or -20 for two steps per pass
 
     FDS_D void issue_next() {
         if (it >= nit) return;
@@ -66,7 +70,7 @@ struct StreamProducer {
             strip = strip < last_strip ? strip : last_strip;
             // input chunk of block b = it - 2: sites a + 8b + 4 .. a + 8b + 11 (inside the allocation
             // by construction of the plan, l96_core.cuh)
-            const long long cs = a0 + strip * ls + 8LL * it - 12;
+            const long long cs = a0 + strip * ls + 8LL * it + first_off;
             bulk_g2s(dst + r * run_stride, X + cs * M, chunk_bytes, &full[st]);
         }
         ++it;
@@ -87,6 +91,8 @@ struct StreamIO {
     uint64_t* empty;
     double* yrow;            // output cursor: site a + 8b - 3 of this thread's column
     double* jp;              // node 0, already offset by column (or nullptr)
+    double* jp2;             // the same for the second step of a two-step pass
+    int levels;              // node levels above the leaf (stride of the second step's counter storage)
     long long nnode;
     double* nsm;             // node-counter storage of this thread: nsm[(2*level + which) * nthr]
     int nthr;
@@ -116,17 +122,26 @@ struct StreamIO {
     }
     FDS_D double ns_get(int l, int q) const { return nsm[(2 * l + q) * nthr]; }
     FDS_D void ns_put(int l, int q, double v) { nsm[(2 * l + q) * nthr] = v; }
+    // two steps per pass: step 1 uses the first `levels` slots, step 2 the next
+    FDS_D void emit_node2(int step, long long node, double s1, double s2) {
+        double* j = step ? jp2 : jp;
+        if (j != nullptr && node >= 0 && node < nnode)
+            *reinterpret_cast<double2*>(j + node * (2LL * cols())) = make_double2(s1, s2);
+    }
+    FDS_D double ns_get2(int step, int l, int q) const { return nsm[(2 * (step * levels + l) + q) * nthr]; }
+    FDS_D void ns_put2(int step, int l, int q, double v) { nsm[(2 * (step * levels + l) + q) * nthr] = v; }
     FDS_D bool all(bool v) const { return __all_sync(0xffffffffu, v); }
 };
 
-template <class MP, int MC, bool STATS, bool EULER>
-__global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamParams p) {
+// MODE 0: RK4, 1: forward Euler, 2: RK4, two steps per pass (<= 256 threads = 2 warps per scheduler: twice the pipeline state in up to 255 registers)
+template <class MP, int MC, bool STATS, int MODE>
+__global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kernel(const StreamParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
     double* nsm = reinterpret_cast<double*>(smem_raw + 128);
     const int levels = p.node_shift - kLeafShift;
-    double* sdata = nsm + (size_t)2 * levels * (blockDim.x - 32 * p.dedicated);
+    double* sdata = nsm + (size_t)(MODE == 2 ? 4 : 2) * levels * (blockDim.x - 32 * p.dedicated);
 
     const int tid = threadIdx.x;
     const int nwarps = (blockDim.x >> 5) - p.dedicated;   // consumer warps
@@ -149,7 +164,9 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
         prod.X = p.X; prod.sdata = sdata; prod.full = full; prod.empty = empty;
         prod.a0 = p.a0; prod.ls = p.ls; prod.last_strip = last_strip;
         prod.M = p.M; prod.R = p.R; prod.run_stride = p.run_stride; prod.stage_stride = stage_stride;
-        prod.nstages = p.nstages; prod.nit = march_iterations(p.nblk);   // blocks b = -2 .. nblk
+        prod.nstages = p.nstages;
+        prod.nit = MODE == 2 ? march2_iterations(p.nblk) : march_iterations(p.nblk);   // blocks b = -2 .. nblk (-3 .. nblk + 1)
+        prod.first_off = MODE == 2 ? -20 : -12;
         prod.chunk_bytes = (uint32_t)(8 * p.M * sizeof(double));
         prod.lane = lane; prod.it = 0; prod.st = 0; prod.par = 0;
         if (p.dedicated) {
@@ -182,8 +199,11 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
     io.nstages = p.nstages;
     io.full = full;
     io.empty = empty;
-    io.yrow = p.Y + (g.a - 8 * 2 - 3) * p.M + k;   // both pipes lag 3 sites   // block b = -2
+    // output cursor of the first block: site a - 16 - 3 (b = -2), or a - 24 - 10 (b = -3, two steps per pass)
+    io.yrow = p.Y + (MODE == 2 ? g.a - 8 * 3 - 10 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
+    io.jp2 = p.jpart2 != nullptr ? p.jpart2 + 2 * k : nullptr;
+    io.levels = levels;
     io.nnode = p.nnode;
     io.nsm = nsm + tid;
     io.nthr = nwarps * 32;
@@ -198,7 +218,8 @@ __global__ void __launch_bounds__(512, 1) l96_rk4_stream_kernel(const StreamPara
         const double2 f = p.Fpp[strip / p.spp];
         F = (k == p.M - 1) ? f.y : f.x;
     }
-    if (EULER) l96_march_t<MP, STATS, EulerPipe<MP>>(io, g, F, p.c);
+    if (MODE == 1) l96_march_t<MP, STATS, EulerPipe<MP>>(io, g, F, p.c);
+    else if (MODE == 2) l96_rk4_march2_t<MP, STATS>(io, g, F, p.c);
     else l96_march_t<MP, STATS, Rk4Pipe<MP>>(io, g, F, p.c);
 }
 
@@ -209,6 +230,7 @@ static int producer_dedicated() {
     if (v < 0) { const char* e = getenv("FDS_PRODUCER"); v = (e && e[0] == 'i') ? 0 : 1; }
     return v;
 }
+int two_step_runs_per_cta(int M) { return M <= 256 ? 256 / M : 0; }
 int stream_runs_per_cta(int M) {
     const int maxc = producer_dedicated() ? 480 : 512;
     return M <= maxc ? maxc / M : 0;
@@ -216,6 +238,8 @@ int stream_runs_per_cta(int M) {
 
 cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls,
                                   int euler) {
+    const int fuse2 = a.jpart2 != nullptr || a.two_steps;
+    if (fuse2 && euler) return cudaErrorInvalidValue;
     StreamParams p;
     p.X = a.X; p.Y = a.Y; p.jpart = a.jpart; p.nnode = plan.nnode;   // a.jpart: [nnode][M][2]
     p.n = a.n;
@@ -234,6 +258,10 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
             smem_budget = 112 * 1024;
         }
     }
+    if (fuse2) {
+        if (p.R * a.M > 256) return cudaErrorInvalidValue;   // set runs_per_cta = two_step_runs_per_cta(M)
+        p.dedicated = 0;                                      // all 8 warps compute; warp 0 also issues the copies
+    }
     p.nconsumer = p.R * a.M;
     int pad = (16 - (7 * a.M) % 16) % 16;
     if (pad & 1) pad += 1;
@@ -241,7 +269,8 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     const int cthreads = ((p.nconsumer + 31) / 32) * 32;
     const int block = cthreads + 32 * p.dedicated;
     const size_t stage_bytes = (size_t)p.R * p.run_stride * sizeof(double);
-    const size_t ns_bytes = (size_t)2 * (plan.node_shift - kLeafShift) * cthreads * sizeof(double);
+    if (fuse2 && block > 256) return cudaErrorInvalidValue;
+    const size_t ns_bytes = (size_t)(fuse2 ? 4 : 2) * (plan.node_shift - kLeafShift) * cthreads * sizeof(double);
     const size_t budget = smem_budget - 128 - ns_bytes;
     int nst = (int)std::min<size_t>(kMaxStages, budget / stage_bytes);
     if (nst < 2) return cudaErrorInvalidValue;
@@ -249,6 +278,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.a0 = plan.a0; p.ls = plan.ls; p.nstrips = plan.nstrips; p.nblk = plan.nblk;
     p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
     p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
+    p.jpart2 = a.jpart2; p.fuse2 = fuse2;
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = (int)((plan.nstrips + p.R - 1) / p.R);
     const size_t smem = 128 + ns_bytes + stage_bytes * nst;
@@ -261,7 +291,8 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
         l96_rk4_stream_kernel<MP, MC, ST, EU><<<grid, block, smem, st>>>(p);                                       \
     } while (0)
 #define FDS_STREAM_LAUNCH(MP, MC, ST) \
-    do { if (euler) FDS_STREAM_LAUNCH2(MP, MC, ST, true); else FDS_STREAM_LAUNCH2(MP, MC, ST, false); } while (0)
+    do { if (euler) FDS_STREAM_LAUNCH2(MP, MC, ST, 1); else if (fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 2); \
+         else FDS_STREAM_LAUNCH2(MP, MC, ST, 0); } while (0)
 #define FDS_STREAM_MC(MP, ST)                                      \
     do {                                                           \
         if (a.M == 34) FDS_STREAM_LAUNCH(MP, 34, ST);              \

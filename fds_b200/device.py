@@ -76,6 +76,11 @@ class Context:
         """Time every launch of the ensemble step kernel with CUDA events on the context's stream."""
         self._ck(self.lib.fds_profile_enable(self.h, int(bool(enabled))))
 
+    @property
+    def profile_steps(self):
+        """Time steps covered by the profiled launches (2 per launch with temporal blocking)."""
+        return int(self.lib.fds_profile_steps(self.h))
+
     def profile_read(self):
         """(summed device milliseconds, launches) of the step kernel since profile_enable()."""
         ms, cnt = ctypes.c_double(), ctypes.c_int64()

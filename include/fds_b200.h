@@ -222,6 +222,7 @@ int     fds_sync(fds_ctx*);
  * enable, run, then read the summed duration and the number of launches since enabling   */
 int     fds_profile_enable(fds_ctx*, int enabled);
 int     fds_profile_read(fds_ctx*, double* total_ms, int64_t* launches);
+int64_t fds_profile_steps(const fds_ctx*);   /* time steps those launches covered (2 per launch with temporal blocking) */
 
 #ifdef __cplusplus
 }
