@@ -42,39 +42,52 @@ struct StreamParams {
 
 constexpr int kMaxStages = 8;
 
-// The TMA producer role, carried by warp 0 in between its own blocks: after releasing block
-// `it`, it refills the stage released one block earlier (by then every warp has let go of it)
-// with block it + nstages - 1.  Lane r issues the bulk copy of strip r (r, r+32, ...).
+// The TMA producer role.  Dedicated mode: one extra warp does nothing else.  Shared mode (all warps
+// compute): the consumer warps take turns -- at the end of consumer block c, warp (c mod nwarps)
+// fetches block c + nstages - 2 into the stage that block c - 2 occupied (every warp has let go of it
+// unless it lags two blocks behind), so no warp is systematically slower than the others.
+// Lane r issues the bulk copy of strip r: one contiguous 8 * M * 8-byte chunk per strip and block.
 struct StreamProducer {
-    const double* X;
-    double* sdata;
-    uint64_t* full;
-    uint64_t* empty;
-    long long a0, ls, last_strip;
-    int M, R, run_stride, stage_stride, nstages, nit;
-    uint32_t chunk_bytes;
-    int lane;
-    int it, st;
+    const StreamParams* P;   // kernel parameters (constant bank)
+    const double* src;       // this lane's strip, first input site of block 0 (lane < R)
+    double* dst0;            // this lane's slot in stage 0
+    uint64_t* full;          // empty = full + kMaxStages
+    int lane, nit;
+    int it, st;              // next block to fetch and its stage
     uint32_t par;
-    int first_off;       // first input site of block 0 relative to the strip start: -12, or -20 for two steps per pass
 
-    FDS_D void issue_next() {
-        if (it >= nit) return;
-        if (it >= nstages) mbar_wait(&empty[st], par ^ 1u);
+    FDS_D void init(const StreamParams* P_, double* sdata, uint64_t* full_, int lane_, int first_off, int nit_) {
+        P = P_; full = full_; lane = lane_; nit = nit_;
+        const int R = P->R;
+        // strips past the end of the plan (last CTA only) mirror the last strip
+        long long strip = (long long)blockIdx.x * R + (lane < R ? lane : 0);
+        strip = strip < P->nstrips - 1 ? strip : P->nstrips - 1;
+        src = P->X + (P->a0 + strip * P->ls + first_off) * P->M;
+        dst0 = sdata + (lane < R ? lane : 0) * P->run_stride;
+        it = 0; st = 0; par = 0;
+    }
+    FDS_D bool done() const { return it >= nit; }
+    // fetch block `it` (8 input sites of every strip) into stage `st`
+    FDS_D void issue() {
+        uint64_t* empty = full + kMaxStages;
+        const int R = P->R, M = P->M, stage_stride = R * P->run_stride;
+        const uint32_t chunk_bytes = (uint32_t)(8 * M * sizeof(double));
+        if (it >= P->nstages) mbar_wait(&empty[st], par ^ 1u);
         if (lane == 0) mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)R);
         __syncwarp();
-        double* dst = sdata + (size_t)st * stage_stride;
-        for (int r = lane; r < R; r += 32) {
-            // strips past the end of the plan (last CTA only) mirror the last strip
+        if (lane < R) bulk_g2s(dst0 + (size_t)st * stage_stride, src + (long long)it * (8 * M), chunk_bytes, &full[st]);
+        for (int r = lane + 32; r < R; r += 32) {            // more than 32 strips per CTA (tiny M)
             long long strip = (long long)blockIdx.x * R + r;
-            strip = strip < last_strip ? strip : last_strip;
-            // input chunk of block b = it - 2: sites a + 8b + 4 .. a + 8b + 11 (inside the allocation
-            // by construction of the plan, l96_core.cuh)
-            const long long cs = a0 + strip * ls + 8LL * it + first_off;
-            bulk_g2s(dst + r * run_stride, X + cs * M, chunk_bytes, &full[st]);
+            strip = strip < P->nstrips - 1 ? strip : P->nstrips - 1;
+            const long long off = (strip - ((long long)blockIdx.x * R + lane < P->nstrips - 1
+                                                ? (long long)blockIdx.x * R + lane : P->nstrips - 1)) * P->ls;
+            bulk_g2s(dst0 + (size_t)st * stage_stride + (r - lane) * P->run_stride,
+                     src + (off + 8LL * it) * M, chunk_bytes, &full[st]);
         }
+    }
+    FDS_D void advance() {
         ++it;
-        if (++st == nstages) { st = 0; par ^= 1u; }
+        if (++st == P->nstages) { st = 0; par ^= 1u; }
     }
 };
 
@@ -97,7 +110,8 @@ struct StreamIO {
     double* nsm;             // node-counter storage of this thread: nsm[(2*level + which) * nthr]
     int nthr;
     int lane;
-    StreamProducer* prod;    // non-null in warp 0
+    StreamProducer* prod;    // shared-producer mode: every consumer warp carries the producer state
+    int warp, nwarps, turn;  // whose turn it is to fetch
     // ring position
     int st;
     uint32_t par;
@@ -112,7 +126,13 @@ struct StreamIO {
     FDS_D void end_block(int) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
-        if (prod != nullptr) prod->issue_next();
+        if (prod != nullptr) {
+            if (!prod->done()) {
+                if (turn == warp) prod->issue();
+                prod->advance();
+            }
+            if (++turn == nwarps) turn = 0;
+        }
         if (++st == nstages) { st = 0; par ^= 1u; }
         yrow += 8 * cols();
     }
@@ -135,7 +155,7 @@ struct StreamIO {
 
 // MODE 0: RK4, 1: forward Euler, 2: RK4, two steps per pass (<= 256 threads = 2 warps per scheduler: twice the pipeline state in up to 255 registers)
 template <class MP, int MC, bool STATS, int MODE>
-__global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kernel(const StreamParams p) {
+__global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kernel(const __grid_constant__ StreamParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
@@ -159,21 +179,19 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
 
     const long long last_strip = p.nstrips - 1;
     StreamProducer prod;
-    const int pwarp = p.dedicated ? nwarps : 0;
-    if (warp == pwarp) {
-        prod.X = p.X; prod.sdata = sdata; prod.full = full; prod.empty = empty;
-        prod.a0 = p.a0; prod.ls = p.ls; prod.last_strip = last_strip;
-        prod.M = p.M; prod.R = p.R; prod.run_stride = p.run_stride; prod.stage_stride = stage_stride;
-        prod.nstages = p.nstages;
-        prod.nit = MODE == 2 ? march2_iterations(p.nblk) : march_iterations(p.nblk);   // blocks b = -2 .. nblk (-3 .. nblk + 1)
-        prod.first_off = MODE == 2 ? -20 : -12;
-        prod.chunk_bytes = (uint32_t)(8 * p.M * sizeof(double));
-        prod.lane = lane; prod.it = 0; prod.st = 0; prod.par = 0;
-        if (p.dedicated) {
-            while (prod.it < prod.nit) prod.issue_next();
+    prod.init(&p, sdata, full, lane, MODE == 2 ? -20 : -12,
+              MODE == 2 ? march2_iterations(p.nblk) : march_iterations(p.nblk));   // blocks b = -2 .. nblk (-3 .. nblk + 1)
+    if (p.dedicated) {
+        if (warp == nwarps) {
+            while (!prod.done()) { prod.issue(); prod.advance(); }
             return;
         }
-        for (int j = 0; j < p.nstages - 1; ++j) prod.issue_next();          // prologue: fill all but one stage
+    } else {
+        // prologue: warp 0 fills all but two stages; every warp tracks the producer position
+        for (int j = 0; j < p.nstages - 2 && !prod.done(); ++j) {
+            if (warp == 0) prod.issue();
+            prod.advance();
+        }
     }
 
     // -------------------- consumer threads: (run r, column k) ------------------ //
@@ -208,7 +226,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.nsm = nsm + tid;
     io.nthr = nwarps * 32;
     io.lane = lane;
-    io.prod = (!p.dedicated && warp == 0) ? &prod : nullptr;
+    io.prod = p.dedicated ? nullptr : &prod;
+    io.warp = warp; io.nwarps = nwarps; io.turn = 0;
     io.st = 0;
     io.par = 0;
     io.cur = io.sdata;
