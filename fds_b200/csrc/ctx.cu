@@ -216,8 +216,13 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         // right ghost cells of the first (4H sites) and the left ghost cells of the second (8H), so the
         // streaming kernel sweeps the whole stack as ONE array; a batched wrap refreshes the gaps.
         if (const char* e = getenv("FDS_BATCH_CTAS_PER_SM")) c->ctas_per_sm = atoi(e) == 1 ? 1 : 2;
+        {   // two RK4 steps per pass (one 256-thread CTA per SM), as for a single problem
+            const char* e = getenv("FDS_FUSE2");
+            c->fuse2 = (e ? e[0] != '0' : true) && cfg->system == FDS_SYS_L96_RK4 && two_step_runs_per_cta(c->M) >= 1;
+            if (c->fuse2) c->ctas_per_sm = 1;
+        }
         // strips per CTA: two CTAs of <= 256 threads per SM, or one of <= 480 with a producer warp
-        const int R2 = c->ctas_per_sm == 2 ? 256 / c->M : stream_runs_per_cta(c->M);
+        const int R2 = c->fuse2 ? two_step_runs_per_cta(c->M) : (c->ctas_per_sm == 2 ? 256 / c->M : stream_runs_per_cta(c->M));
         if ((cfg->system != FDS_SYS_L96_RK4 && cfg->system != FDS_SYS_L96_EULER) || cfg->world != 1 ||
             c->n % 64 != 0 || R2 < 1 ||
             (cfg->flags & FDS_FLAG_SIMPLE_KERNELS)) {
@@ -821,7 +826,7 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
     if (int r = upload_forcing(c, s, eps)) return r;
     for (long long j = 0; j < nsteps;) {
         if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
-        const bool two = c->fuse2 && c->nb == 1 && nsteps - j >= 2 && c->ens_halo_valid >= 2;
+        const bool two = c->fuse2 && nsteps - j >= 2 && c->ens_halo_valid >= 2;
         if (int r = one_step(c, c->E_all(c->cur), c->E_all(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, step0 + j,
                              c->nb > 1 ? j : step0 + j, two)) return r;
         c->cur ^= 1;
