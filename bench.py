@@ -341,7 +341,11 @@ def run_ours(args):
                              'algorithmic_bytes_per_launch': alg_bytes, 'time_steps_per_launch': steps_per_launch,
                              'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s',
                              'frac_of_nominal_8TBs': achieved / 8000.0,
-                             'step_kernel_share_of_time': kms * (S / steps_per_launch) * args.steps / total_ms},
+                             'step_kernel_share_of_time': kms * (S / steps_per_launch) * args.steps / total_ms,
+                             'note': ('temporal blocking: one launch advances %g time steps, so DRAM traffic per launch '
+                                      '(`traffic`) is 1/%g of the algorithmic bytes and `frac` can exceed 1; the kernel is '
+                                      'then bound by the FP64 pipe (profiles/)' % (steps_per_launch, steps_per_launch))
+                                     if steps_per_launch > 1 else 'one time step per launch'},
                 'clocks': clocks, 'gpu_launches': int(launches.item())}
         if e2e is not None:
             line['e2e'] = e2e
