@@ -37,7 +37,7 @@ struct HostIO {
     double ns_get(int l, int q) const { return ns[l][q]; }
     void ns_put(int l, int q, double v) { ns[l][q] = v; }
 };
-// two steps per pass: output cursor at site a + 8b - 10, two sets of objective partials
+// two steps per pass: output cursor at site a + 8b - 11, two sets of objective partials
 struct HostIO2 {
     const double* X;
     double* Y;
@@ -48,7 +48,7 @@ struct HostIO2 {
     long long cs = 0, j0 = 0;
     void begin_block(int b) {
         cs = a + 8LL * b + 4;
-        j0 = a + 8LL * b - 10;
+        j0 = a + 8LL * b - 11;
     }
     void end_block(int) {}
     double load(int p) const { return X[(cs + p) * M + k]; }

@@ -1,7 +1,8 @@
 // Two RK4 steps per pass: the per-thread body of the temporally blocked streaming kernel.
 //
 // A second Rk4Pipe is chained behind the first: the step-1 value that leaves pipe 1 (site i-7 for a
-// push of site i) is pushed straight into pipe 2, whose output is the step-2 value at site i-14.  The
+// push of site i) is pushed into pipe 2 ONE PUSH LATER (so that the eight stage computations of a push
+// -- four per pipe -- are all independent), whose output is the step-2 value at site i-15.  The
 // intermediate state never touches shared or global memory, so a site is read once and written once
 // per TWO time steps: 8 B of HBM traffic per trajectory-site-step instead of 16.  Both steps'
 // objective sums are accumulated on the way (the intermediate state's from pipe 1's output) in the
@@ -9,10 +10,10 @@
 //
 // Block b of a strip that starts at site a consumes the 8 input sites a + 8b + 4 .. a + 8b + 11,
 // produces the step-1 values of sites a + 8b - 3 .. a + 8b + 4 (never stored) and the step-2 values
-// of sites a + 8b - 10 .. a + 8b - 3.  Blocks run from b = -3 (warm-up: x'' is exact from site a - 4
-// on) to b = nblk + 1 (drain of the 14-site lag).
+// of sites a + 8b - 11 .. a + 8b - 4.  Blocks run from b = -3 (warm-up: x'' is exact from site a - 4
+// on) to b = nblk + 1 (drain of the 15-site lag).
 //
-// IO policy: as in l96_march.cuh, with the output cursor at site a + 8b - 10 and the per-step
+// IO policy: as in l96_march.cuh, with the output cursor at site a + 8b - 11 and the per-step
 // variants   emit_node2(step, node, s1, s2),   ns_get2(step, level, which),   ns_put2(step, level, which, v).
 #pragma once
 #include "l96_march.cuh"
@@ -59,14 +60,16 @@ FDS_HD void march2_leaf(IO& io, StepStats& s, const MarchGeom& g, int step, int 
 }
 
 template <class MP, int P, bool FAST, bool STATS, class IO>
-FDS_HD void march2_site(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, StepStats& sa, StepStats& sb, long long j1,
-                        long long j2, long long slo, long long shi, long long jlo, long long jhi, double F,
-                        const Rk4Coef& c) {
-    constexpr int P2 = (P + 1) & 7;      // pipe 2 sees site i - 7 as its push site: (i - 7) - 4 = i - 11 = P + 1 (mod 8)
-    constexpr int Q1 = (P + 5) & 7;      // step-1 output site mod 8
-    constexpr int Q2 = (P + 6) & 7;      // step-2 output site mod 8
+FDS_HD void march2_site(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_prev, StepStats& sa, StepStats& sb,
+                        long long j1, long long j2, long long slo, long long shi, long long jlo, long long jhi,
+                        double F, const Rk4Coef& c) {
+    // pipe 2 is fed the step-1 value of the PREVIOUS push (site i - 8 for pipe 1's index i = P mod 8):
+    // (i - 8) = i2 + 4  =>  i2 = P (mod 8)
+    constexpr int Q1 = (P + 5) & 7;      // step-1 output site i - 3, mod 8
+    constexpr int Q2 = (P + 5) & 7;      // step-2 output site i - 11, mod 8
+    const double x2 = p2.template push<P>(x1_prev, F, c);
     const double x1 = p1.template push<P>(io.load(P), F, c);
-    const double x2 = p2.template push<P2>(x1, F, c);
+    x1_prev = x1;
     if (FAST) {
         io.store(P, x2);
         if (STATS) {
@@ -94,16 +97,16 @@ FDS_HD void march2_site(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, StepStats& sa,
 }
 
 template <class MP, bool FAST, bool STATS, class IO>
-FDS_HD void march2_block(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, StepStats& sa, StepStats& sb, const MarchGeom& g,
-                         int b, long long slo, long long shi, long long jlo, long long jhi, double F,
-                         const Rk4Coef& c) {
-    const long long j1 = g.a + 8LL * b - 3, j2 = g.a + 8LL * b - 10;
-#define FDS_M2(P) march2_site<MP, P, FAST, STATS>(io, p1, p2, sa, sb, j1, j2, slo, shi, jlo, jhi, F, c)
+FDS_HD void march2_block(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_prev, StepStats& sa, StepStats& sb,
+                         const MarchGeom& g, int b, long long slo, long long shi, long long jlo, long long jhi,
+                         double F, const Rk4Coef& c) {
+    const long long j1 = g.a + 8LL * b - 3, j2 = g.a + 8LL * b - 11;
+#define FDS_M2(P) march2_site<MP, P, FAST, STATS>(io, p1, p2, x1_prev, sa, sb, j1, j2, slo, shi, jlo, jhi, F, c)
     FDS_M2(0);
     FDS_M2(1);
-    // step 2: sites a + 8(b-2) .. a + 8(b-2) + 7 are complete (Q2 == 7 at P == 1)
-    if (STATS && b >= 2 && b - 2 < g.nblk) march2_leaf(io, sb, g, 1, b - 2);
     FDS_M2(2);
+    // step 2: sites a + 8(b-2) .. a + 8(b-2) + 7 are complete (Q2 == 7 at P == 2)
+    if (STATS && b >= 2 && b - 2 < g.nblk) march2_leaf(io, sb, g, 1, b - 2);
     // step 1: sites a + 8(b-1) .. a + 8(b-1) + 7 are complete (Q1 == 7 at P == 2)
     if (STATS && b >= 1 && b - 1 < g.nblk) march2_leaf(io, sa, g, 0, b - 1);
     FDS_M2(3);
@@ -122,6 +125,7 @@ FDS_HD void l96_rk4_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef
     StepStats sa, sb;
     sa.reset();
     sb.reset();
+    double x1_prev = 0.0;
     const long long slo = g.a, shi = g.a + 8LL * g.nblk;
     const long long jlo = slo > 0 ? slo : 0;
     const long long jhi = g.n < shi ? g.n : shi;
@@ -129,15 +133,15 @@ FDS_HD void l96_rk4_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef
     const long long ncl = (g.n + kLeafSites - 1) & ~(long long)(kLeafSites - 1);
 #pragma unroll 1
     for (int b = kFuse2First; b <= g.nblk + 1; ++b) {
-        const long long j1 = g.a + 8LL * b - 3, j2 = g.a + 8LL * b - 10;
+        const long long j1 = g.a + 8LL * b - 3, j2 = g.a + 8LL * b - 11;
         io.begin_block(b);
         // unchecked path: the 8 step-2 outputs are stored by this strip and neither they nor the 8
         // step-1 values lie in the partial leaf (leaves wholly outside [0, n) are zeroed as a whole)
         const bool fast = j2 >= slo && j2 + 8 <= shi && (j1 + 8 <= nfl || j2 >= ncl);
         if (io.all(fast))
-            march2_block<MP, true, STATS>(io, p1, p2, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
+            march2_block<MP, true, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
         else
-            march2_block<MP, false, STATS>(io, p1, p2, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
+            march2_block<MP, false, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
         io.end_block(b);
     }
 }

@@ -217,8 +217,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.nstages = p.nstages;
     io.full = full;
     io.empty = empty;
-    // output cursor of the first block: site a - 16 - 3 (b = -2), or a - 24 - 10 (b = -3, two steps per pass)
-    io.yrow = p.Y + (MODE == 2 ? g.a - 8 * 3 - 10 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
+    // output cursor of the first block: site a - 16 - 3 (b = -2), or a - 24 - 11 (b = -3, two steps per pass)
+    io.yrow = p.Y + (MODE == 2 ? g.a - 8 * 3 - 11 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
     io.jp2 = p.jpart2 != nullptr ? p.jpart2 + 2 * k : nullptr;
     io.levels = levels;
