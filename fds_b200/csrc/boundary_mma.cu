@@ -188,4 +188,172 @@ cudaError_t launch_gram_mma(int src, const double* E, const double* T, const dou
     return cudaErrorInvalidValue;
 }
 
+// ------------------------------------------------------------------------------------------------ //
+//   apply_mma   out_i = A X_i for every site, A the constant (m+1) x (m+2) matrix of the boundary
+//               (projection, L^-1, b^T L^-1 ...; lower triangular in its first m+1 columns plus the d
+//               column).  As a GEMM: Out[sites x outputs] = X[sites x MX] A^T; a warp takes 8 sites per
+//               group, the A operand fragments come straight from the TMA-staged raw rows (FD tangents
+//               formed in registers), and the B fragments -- A^T, the same for every site -- are loaded
+//               ONCE into registers (only the blocks the triangular structure leaves non-zero).  The
+//               result goes through a shared-memory tile so that the explicit tangents and / or the next
+//               perturbed ensemble u + eps * out leave as coalesced rows.  ~110 registers, two CTAs per
+//               SM: one CTA's stores overlap the other's loads and tensor-core work.
+// ------------------------------------------------------------------------------------------------ //
+constexpr int kApplyMmaWarps = 7;       // consumer warps: 7 + 1 producer = 256 threads, two CTAs per SM at 128 registers
+constexpr int kApplyMmaSites = 112;     // sites per tile: 14 groups of 8, two per consumer warp
+
+template <int MX>
+struct ApplyMmaShape {
+    static constexpr int MO = MX - 1, D = MX - 1;
+    static constexpr int NJ = (MO + 7) / 8;      // output tiles of 8
+    static constexpr int KS = (MX + 3) / 4;      // k-steps of 4 columns of X
+    static constexpr int KD = D / 4;             // the k-step that holds the d column
+    // k-step kk contributes to output tile j?  (columns l <= 8j + 7, or the d column)
+    static __host__ __device__ constexpr bool used(int j, int kk) { return kk <= 2 * j + 1 || kk == KD; }
+};
+
+template <int MX, int SRC>
+__global__ void __launch_bounds__(32 * (kApplyMmaWarps + 1), 2) apply_mma_kernel(
+    const double* __restrict__ E, const double* Tin, const double* __restrict__ d, const double* __restrict__ A,
+    double inv_eps, long long n, double* Tout, double* E_out, const double* __restrict__ u, double eps, int nst) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using SH = ApplyMmaShape<MX>;
+    constexpr int MO = SH::MO, M = MX, D = SH::D, NJ = SH::NJ, KS = SH::KS, S = kApplyMmaSites, NC = 32 * kApplyMmaWarps;
+    constexpr int W = SRC == SRC_ENSEMBLE ? MX : MX - 1;
+    constexpr int LD = (8 * NJ + 2) | 1;                      // odd row stride of the output tile (>= MO + 1)
+    TileStage ts;
+    ts.full = reinterpret_cast<uint64_t*>(smem_raw);
+    ts.empty = ts.full + kBndMaxStages;
+    double* os = reinterpret_cast<double*>(smem_raw + 128);   // [S][LD] output rows (+ u in column 8 NJ)
+    ts.raw = os + (((size_t)S * LD + 15) & ~(size_t)15);
+    ts.stage_doubles = (S * W + 2 * S + 15) & ~15;
+    ts.nst = nst;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < ts.nst; ++s) { mbar_init(&ts.full[s], 1); mbar_init(&ts.empty[s], kApplyMmaWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const long long ntiles = (n + S - 1) / S;
+    if (warp == kApplyMmaWarps) { tile_producer<SRC>(ts, E, Tin, d, E_out != nullptr ? u : nullptr, MX, n, S, ntiles); return; }
+
+    const int g = lane >> 2, t = lane & 3;
+    // B fragments: b[j][kk] = A[o = 8j + g][l = 4kk + t]   (col-major 4 x 8 operand), zero outside A
+    double bf[NJ][KS];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j)
+#pragma unroll
+        for (int kk = 0; kk < KS; ++kk) {
+            const int o = 8 * j + g, l = 4 * kk + t;
+            bf[j][kk] = (SH::used(j, kk) && o < MO && l < MX) ? A[o * MX + l] : 0.0;
+        }
+
+    int st = 0;
+    uint32_t par = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long s0 = tile * S;
+        const int cnt = (int)((n - s0) < S ? (n - s0) : S);
+        mbar_wait(&ts.full[st], par);
+        const double* raw = ts.raw + (size_t)st * ts.stage_doubles;
+#pragma unroll 1
+        for (int grp = warp; grp < S / 8; grp += kApplyMmaWarps) {
+            const int site = 8 * grp + g;
+            const double* row = raw + (size_t)site * W;
+            const double e0 = SRC == SRC_ENSEMBLE ? row[0] : 0.0;
+            double xa[KS];                                     // A operand: X[site g][4kk + t]
+#pragma unroll
+            for (int kk = 0; kk < KS; ++kk) {
+                const int l = 4 * kk + t;
+                double v = 0.0;
+                if (l < MO) v = SRC == SRC_ENSEMBLE ? (row[l + 1] - e0) * inv_eps : row[l];
+                else if (l == D) v = d != nullptr ? raw[(size_t)S * W + site] : 0.0;
+                xa[kk] = v;
+            }
+            double acc[NJ][2];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                acc[j][0] = 0.0; acc[j][1] = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < KS; ++kk)
+                    if (SH::used(j, kk)) dmma_8x8x4(acc[j][0], acc[j][1], xa[kk], bf[j][kk]);
+            }
+            // C fragment: row = site g, columns 8j + 2t + {0, 1}
+            double* orow = os + site * LD + 2 * t;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) { orow[8 * j] = acc[j][0]; orow[8 * j + 1] = acc[j][1]; }
+            if (E_out != nullptr && t == 0) os[site * LD + 8 * NJ] = raw[(size_t)S * W + S + site];   // u_i
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ts.empty[st]);              // the raw stage may be refilled
+        if (++st == ts.nst) { st = 0; par ^= 1u; }
+        named_barrier(1, NC);
+        // coalesced stores: explicit tangents and / or the next perturbed ensemble
+        // the rows of a tile are one contiguous block of the output arrays: flat, fully coalesced
+        if (Tout != nullptr) {
+            double* dst = Tout + s0 * MO;
+            for (int e = tid; e < cnt * MO; e += NC) {
+                const int s = e / MO, o = e - s * MO;
+                dst[e] = os[s * LD + o];
+            }
+        }
+        if (E_out != nullptr) {
+            double* dst = E_out + s0 * M;
+            for (int e = tid; e < cnt * M; e += NC) {
+                const int s = e / M, k = e - s * M;
+                const double ui = os[s * LD + 8 * NJ];
+                dst[e] = k == 0 ? ui : __dadd_rn(ui, __dmul_rn(os[s * LD + k - 1], eps));
+            }
+        }
+        named_barrier(1, NC);
+    }
+}
+
+template <int MX>
+static cudaError_t apply_mma_launch(int src, const double* E, const double* Tin, const double* d, const double* A,
+                                    double inv_eps, long long n, double* Tout, double* E_out, const double* u,
+                                    double eps, int num_sms, cudaStream_t st, LaunchStats* ls) {
+    using SH = ApplyMmaShape<MX>;
+    constexpr int S = kApplyMmaSites, LD = (8 * SH::NJ + 2) | 1;
+    const int W = src == SRC_ENSEMBLE ? MX : MX - 1;
+    const size_t stage_doubles = ((size_t)S * W + 2 * S + 15) & ~(size_t)15;
+    const size_t fixed = 128 + sizeof(double) * (((size_t)S * LD + 15) & ~(size_t)15);
+    const int nst = (int)std::min<size_t>(kBndMaxStages, (112 * 1024 - fixed) / (stage_doubles * sizeof(double)));
+    if (nst < 2) return cudaErrorInvalidValue;
+    const size_t smem = fixed + sizeof(double) * nst * stage_doubles;
+    const long long ntiles = (n + S - 1) / S;
+    const int grid = (int)std::min<long long>(ntiles, 2LL * num_sms);
+    const int block = 32 * (kApplyMmaWarps + 1);
+    cudaError_t e;
+    if (src == SRC_ENSEMBLE) {
+        e = cudaFuncSetAttribute(apply_mma_kernel<MX, SRC_ENSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        apply_mma_kernel<MX, SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, nst);
+    } else {
+        e = cudaFuncSetAttribute(apply_mma_kernel<MX, SRC_TANGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        apply_mma_kernel<MX, SRC_TANGENT><<<grid, block, smem, st>>>(E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, nst);
+    }
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+bool apply_mma_supported(int m) {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("FDS_APPLY_MMA"); on = (e && e[0] == '0') ? 0 : 1; }
+    if (!on) return false;
+    switch (m + 2) { case 18: case 34: return true; }
+    return false;
+}
+
+// A: the (m+1) x (m+2) matrix in DEVICE memory
+cudaError_t launch_apply_mma(int src, const double* E, const double* Tin, const double* d, const double* A, int m,
+                             double inv_eps, long long n, double* Tout, double* E_out, const double* u, double eps,
+                             int num_sms, cudaStream_t st, LaunchStats* ls) {
+    switch (m + 2) {
+        case 18: return apply_mma_launch<18>(src, E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, num_sms, st, ls);
+        case 34: return apply_mma_launch<34>(src, E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, num_sms, st, ls);
+    }
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace fds

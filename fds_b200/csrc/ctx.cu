@@ -145,6 +145,9 @@ static cudaError_t do_gram(fds_ctx* c, int src, double inv_eps) {
 }
 
 static cudaError_t do_apply(fds_ctx* c, int src, double inv_eps, double* Tout, double* E_out, double eps) {
+    if (c->fast_boundary && apply_mma_supported(c->m))
+        return launch_apply_mma(src, c->Ecur(), c->T, c->d, c->small.A, c->m, inv_eps, c->n, Tout, E_out, c->P(0),
+                                eps, c->num_sms, c->stream, &c->ls);
     if (c->fast_boundary)
         return launch_apply_fast(src, c->Ecur(), c->T, c->d, c->A_host, c->m, inv_eps, c->n, Tout, E_out, c->P(0),
                                  eps, c->num_sms, c->stream, &c->ls);
