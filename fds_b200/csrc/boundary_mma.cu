@@ -35,11 +35,17 @@ constexpr int kMmaSites = 128;        // sites per tile (32 groups of 4)
 template <int NBK, int SRC>
 __global__ void __launch_bounds__(32 * (kMmaWarps + 1), 1) gram_mma_kernel(
     const double* __restrict__ E, const double* __restrict__ T, const double* __restrict__ d, int MX, double inv_eps,
-    long long n, int nst, double* __restrict__ part) {
+    long long n, int nst, double* __restrict__ part, BatchDesc bd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int NP = NBK * (NBK + 1) / 2, S = kMmaSites, NC = 32 * kMmaWarps;
     const int W = SRC == SRC_ENSEMBLE ? MX : MX - 1;
     const int MO = MX - 1;
+    {   // problem blockIdx.y of a batch
+        const size_t off = (size_t)blockIdx.y * bd.slot;
+        if (SRC == SRC_ENSEMBLE) E += off * MX; else T += off * MO;
+        if (d != nullptr) d += off;
+        part += (size_t)blockIdx.y * bd.part_stride;
+    }
     TileStage ts;
     ts.full = reinterpret_cast<uint64_t*>(smem_raw);
     ts.empty = ts.full + kBndMaxStages;
@@ -126,9 +132,11 @@ __global__ void __launch_bounds__(32 * (kMmaWarps + 1), 1) gram_mma_kernel(
 }
 
 __global__ void sum_partials_mma_kernel(const double* __restrict__ part, int nparts, int len,
-                                        double* __restrict__ out) {
+                                        double* __restrict__ out, BatchDesc bd) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= len) return;
+    part += (size_t)blockIdx.y * bd.part_stride;
+    out += (size_t)blockIdx.y * bd.small_stride;
     double s = 0.0;
     for (int p = 0; p < nparts; ++p) s += part[(size_t)p * len + e];
     out[e] = s;
@@ -137,7 +145,7 @@ __global__ void sum_partials_mma_kernel(const double* __restrict__ part, int npa
 template <int NBK>
 static cudaError_t gram_mma_launch(int src, const double* E, const double* T, const double* d, int MX,
                                    double inv_eps, long long n, double* part, int max_part, double* out,
-                                   int num_sms, cudaStream_t st, LaunchStats* ls) {
+                                   int num_sms, cudaStream_t st, LaunchStats* ls, const BatchDesc& bd) {
     constexpr int NP = NBK * (NBK + 1) / 2, S = kMmaSites;
     const int W = src == SRC_ENSEMBLE ? MX : MX - 1;
     const size_t stage_doubles = ((size_t)S * W + S + 15) & ~(size_t)15;
@@ -146,24 +154,25 @@ static cudaError_t gram_mma_launch(int src, const double* E, const double* T, co
     if (nst < 2) return cudaErrorInvalidValue;
     const size_t smem = 128 + sizeof(double) * std::max(scratch, (size_t)nst * stage_doubles);
     const long long ntiles = (n + S - 1) / S;
-    int grid = (int)std::min<long long>(ntiles, std::min(max_part, num_sms));
-    if (grid < 1) grid = 1;
+    int gx = (int)std::min<long long>(ntiles, std::min(max_part, num_sms));
+    if (gx < 1) gx = 1;
+    const dim3 grid((unsigned)gx, (unsigned)bd.count);
     const int block = 32 * (kMmaWarps + 1);
     cudaError_t e;
     if (src == SRC_ENSEMBLE) {
         e = cudaFuncSetAttribute(gram_mma_kernel<NBK, SRC_ENSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gram_mma_kernel<NBK, SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, T, d, MX, inv_eps, n, nst, part);
+        gram_mma_kernel<NBK, SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, T, d, MX, inv_eps, n, nst, part, bd);
     } else {
         e = cudaFuncSetAttribute(gram_mma_kernel<NBK, SRC_TANGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        gram_mma_kernel<NBK, SRC_TANGENT><<<grid, block, smem, st>>>(E, T, d, MX, inv_eps, n, nst, part);
+        gram_mma_kernel<NBK, SRC_TANGENT><<<grid, block, smem, st>>>(E, T, d, MX, inv_eps, n, nst, part, bd);
     }
     if (ls) ls->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     const int len = MX * MX;
-    sum_partials_mma_kernel<<<(len + 255) / 256, 256, 0, st>>>(part, grid, len, out);
+    sum_partials_mma_kernel<<<dim3((len + 255) / 256, bd.count), 256, 0, st>>>(part, gx, len, out, bd);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
@@ -176,10 +185,12 @@ bool gram_mma_supported(int m) {
 
 cudaError_t launch_gram_mma(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
                             long long n, double* part, int max_part, double* out, int num_sms, cudaStream_t st,
-                            LaunchStats* ls) {
+                            LaunchStats* ls, const BatchDesc* batch) {
     const int MX = m + 2;
+    BatchDesc bd;
+    if (batch) bd = *batch;
 #define FDS_GRAM_MMA_CASE(K) \
-    case K: return gram_mma_launch<K>(src, E, T, d, MX, inv_eps, n, part, max_part, out, num_sms, st, ls)
+    case K: return gram_mma_launch<K>(src, E, T, d, MX, inv_eps, n, part, max_part, out, num_sms, st, ls, bd)
     switch ((MX + 7) / 8) {
         FDS_GRAM_MMA_CASE(1); FDS_GRAM_MMA_CASE(2); FDS_GRAM_MMA_CASE(3); FDS_GRAM_MMA_CASE(4);
         FDS_GRAM_MMA_CASE(5); FDS_GRAM_MMA_CASE(6); FDS_GRAM_MMA_CASE(7);
@@ -215,9 +226,18 @@ struct ApplyMmaShape {
 template <int MX, int SRC>
 __global__ void __launch_bounds__(32 * (kApplyMmaWarps + 1), 2) apply_mma_kernel(
     const double* __restrict__ E, const double* Tin, const double* __restrict__ d, const double* __restrict__ A,
-    double inv_eps, long long n, double* Tout, double* E_out, const double* __restrict__ u, double eps, int nst) {
+    double inv_eps, long long n, double* Tout, double* E_out, const double* __restrict__ u, double eps, int nst,
+    BatchDesc bd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using SH = ApplyMmaShape<MX>;
+    {   // problem blockIdx.y of a batch
+        const size_t off = (size_t)blockIdx.y * bd.slot;
+        E += off * MX; Tin += off * (MX - 1);
+        if (Tout != nullptr) Tout += off * (MX - 1);
+        if (d != nullptr) d += off;
+        if (E_out != nullptr) { E_out += off * MX; u += off; }
+        A += (size_t)blockIdx.y * bd.small_stride;
+    }
     constexpr int MO = SH::MO, M = MX, D = SH::D, NJ = SH::NJ, KS = SH::KS, S = kApplyMmaSites, NC = 32 * kApplyMmaWarps;
     constexpr int W = SRC == SRC_ENSEMBLE ? MX : MX - 1;
     constexpr int LD = (8 * NJ + 2) | 1;                      // odd row stride of the output tile (>= MO + 1)
@@ -311,7 +331,7 @@ __global__ void __launch_bounds__(32 * (kApplyMmaWarps + 1), 2) apply_mma_kernel
 template <int MX>
 static cudaError_t apply_mma_launch(int src, const double* E, const double* Tin, const double* d, const double* A,
                                     double inv_eps, long long n, double* Tout, double* E_out, const double* u,
-                                    double eps, int num_sms, cudaStream_t st, LaunchStats* ls) {
+                                    double eps, int num_sms, cudaStream_t st, LaunchStats* ls, const BatchDesc& bd) {
     using SH = ApplyMmaShape<MX>;
     constexpr int S = kApplyMmaSites, LD = (8 * SH::NJ + 2) | 1;
     const int W = src == SRC_ENSEMBLE ? MX : MX - 1;
@@ -321,17 +341,17 @@ static cudaError_t apply_mma_launch(int src, const double* E, const double* Tin,
     if (nst < 2) return cudaErrorInvalidValue;
     const size_t smem = fixed + sizeof(double) * nst * stage_doubles;
     const long long ntiles = (n + S - 1) / S;
-    const int grid = (int)std::min<long long>(ntiles, 2LL * num_sms);
+    const dim3 grid((unsigned)std::min<long long>(ntiles, bd.count > 1 ? 4LL : 2LL * num_sms), (unsigned)bd.count);
     const int block = 32 * (kApplyMmaWarps + 1);
     cudaError_t e;
     if (src == SRC_ENSEMBLE) {
         e = cudaFuncSetAttribute(apply_mma_kernel<MX, SRC_ENSEMBLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        apply_mma_kernel<MX, SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, nst);
+        apply_mma_kernel<MX, SRC_ENSEMBLE><<<grid, block, smem, st>>>(E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, nst, bd);
     } else {
         e = cudaFuncSetAttribute(apply_mma_kernel<MX, SRC_TANGENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        apply_mma_kernel<MX, SRC_TANGENT><<<grid, block, smem, st>>>(E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, nst);
+        apply_mma_kernel<MX, SRC_TANGENT><<<grid, block, smem, st>>>(E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, nst, bd);
     }
     if (ls) ls->launches++;
     return cudaGetLastError();
@@ -348,10 +368,12 @@ bool apply_mma_supported(int m) {
 // A: the (m+1) x (m+2) matrix in DEVICE memory
 cudaError_t launch_apply_mma(int src, const double* E, const double* Tin, const double* d, const double* A, int m,
                              double inv_eps, long long n, double* Tout, double* E_out, const double* u, double eps,
-                             int num_sms, cudaStream_t st, LaunchStats* ls) {
+                             int num_sms, cudaStream_t st, LaunchStats* ls, const BatchDesc* batch) {
+    BatchDesc bd;
+    if (batch) bd = *batch;
     switch (m + 2) {
-        case 18: return apply_mma_launch<18>(src, E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, num_sms, st, ls);
-        case 34: return apply_mma_launch<34>(src, E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, num_sms, st, ls);
+        case 18: return apply_mma_launch<18>(src, E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, num_sms, st, ls, bd);
+        case 34: return apply_mma_launch<34>(src, E, Tin, d, A, inv_eps, n, Tout, E_out, u, eps, num_sms, st, ls, bd);
     }
     return cudaErrorInvalidValue;
 }

@@ -53,6 +53,7 @@ struct fds_ctx {
     double* c4 = nullptr;
     double* A_host = nullptr;      // pinned copy of small.A (+ status): A travels to apply_fast as a kernel parameter
     bool fast_boundary = false;    // register-blocked gram / apply kernels (boundary_fast.cu)
+    bool mma_boundary = false;     // tensor-core gram / apply kernels (boundary_mma.cu): single problem or batch
     double* jpart = nullptr;
     double* jscratch = nullptr;
     double* jsum = nullptr;
@@ -111,13 +112,17 @@ static int fail(fds_ctx* c, const std::string& msg) { c->err = msg; return 2; }
 static int check_small_status(fds_ctx* c, const char* what) {
     int st = 0;
     if (c->nb > 1) {
-        std::vector<int> all(c->nb, 0);
-        FDS_CK(c, cudaMemcpy2DAsync(all.data(), sizeof(int), c->small.status, (size_t)c->small_stride * sizeof(double),
-                                    sizeof(int), c->nb, cudaMemcpyDeviceToHost, c->stream));
+        struct SC { int st; int pad; double cond; };
+        std::vector<SC> all(c->nb, SC{0, 0, 0.0});
+        FDS_CK(c, cudaMemcpy2DAsync(all.data(), sizeof(SC), c->small.status, (size_t)c->small_stride * sizeof(double),
+                                    sizeof(SC), c->nb, cudaMemcpyDeviceToHost, c->stream));
         FDS_CK(c, cudaStreamSynchronize(c->stream));
-        for (int p = 0; p < c->nb; ++p)
-            if (all[p] != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(all[p]) +
-                                            " of problem " + std::to_string(p) + " (tangent block numerically rank deficient)");
+        c->cond_last = 0.0;
+        for (int p = 0; p < c->nb; ++p) {
+            if (all[p].st != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(all[p].st) +
+                                               " of problem " + std::to_string(p) + " (tangent block numerically rank deficient)");
+            c->cond_last = std::max(c->cond_last, all[p].cond);      // the worst problem decides
+        }
         return 0;
     }
     struct { int st; int pad; double cond; } sc = {0, 0, 0.0};
@@ -134,9 +139,9 @@ static int check_small_status(fds_ctx* c, const char* what) {
 }
 
 static cudaError_t do_gram(fds_ctx* c, int src, double inv_eps) {
-    if (c->fast_boundary && gram_mma_supported(c->m))
+    if (c->mma_boundary || (c->fast_boundary && gram_mma_supported(c->m)))
         return launch_gram_mma(src, c->Ecur(), c->T, c->d, c->m, inv_eps, c->n, c->gram_part, c->max_part,
-                               c->small.gram, c->num_sms, c->stream, &c->ls);
+                               c->small.gram, c->num_sms, c->stream, &c->ls, c->batch());
     if (c->fast_boundary)
         return launch_gram_fast(src, c->Ecur(), c->T, c->d, c->m, inv_eps, c->n, c->gram_part, c->max_part,
                                 c->small.gram, c->num_sms, c->stream, &c->ls);
@@ -145,9 +150,9 @@ static cudaError_t do_gram(fds_ctx* c, int src, double inv_eps) {
 }
 
 static cudaError_t do_apply(fds_ctx* c, int src, double inv_eps, double* Tout, double* E_out, double eps) {
-    if (c->fast_boundary && apply_mma_supported(c->m))
+    if (c->mma_boundary)
         return launch_apply_mma(src, c->Ecur(), c->T, c->d, c->small.A, c->m, inv_eps, c->n, Tout, E_out, c->P(0),
-                                eps, c->num_sms, c->stream, &c->ls);
+                                eps, c->num_sms, c->stream, &c->ls, c->batch());
     if (c->fast_boundary)
         return launch_apply_fast(src, c->Ecur(), c->T, c->d, c->A_host, c->m, inv_eps, c->n, Tout, E_out, c->P(0),
                                  eps, c->num_sms, c->stream, &c->ls);
@@ -307,6 +312,8 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
     c->bd.count = c->nb; c->bd.slot = c->slot; c->bd.small_stride = c->small_stride;
     c->bd.part_stride = (long long)c->max_part * c->MX * c->MX;
     c->fast_boundary = apply_fast_supported(c->m) && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS) && c->nb == 1;
+    c->mma_boundary = gram_mma_supported(c->m) && apply_mma_supported(c->m) && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS) &&
+                      !c->toy;
     CK0(cudaMallocHost(&c->A_host, (size_t)c->MO * c->MX * sizeof(double)));
     CK0(cudaMalloc(&c->c4, 4 * sizeof(double)));
     {
@@ -905,9 +912,9 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
 
 int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
     c->qr_single = false;
-    if (do_qr && c->fast_boundary && c->qr_mode == 0) {
+    if (do_qr && (c->fast_boundary || c->mma_boundary) && c->qr_mode == 0) {
         // one Cholesky pass loses orthogonality like cond^2 u: take it when that is below 2e-13
-        FDS_CK(c, launch_small_single(c->small, c->m, c->time_dilation ? 1 : 0, c->stream, &c->ls));
+        FDS_CK(c, launch_small_single(c->small, c->m, c->time_dilation ? 1 : 0, c->stream, &c->ls, c->batch()));
         const std::string keep = c->err;
         const int r = check_small_status(c, "CholeskyQR");
         if (r == 0 && c->cond_last * c->cond_last * 2.3e-16 < 2e-13) {
@@ -931,7 +938,7 @@ int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
 int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
     const bool ens = (build & FDS_BUILD_ENSEMBLE) != 0;
     // explicit tangents are written unless the caller only wants the next ensemble (hot loop)
-    const bool keepT = !ens || (build & FDS_BUILD_KEEP_TANGENTS) != 0 || !c->fast_boundary;
+    const bool keepT = !ens || (build & FDS_BUILD_KEEP_TANGENTS) != 0 || !(c->fast_boundary || c->mma_boundary);
     c->tangents_implicit = false;
     if (do_qr && c->qr_single) {
         c->qr_single = false;

@@ -144,13 +144,13 @@ cudaError_t launch_apply_fast(int src, const double* E, const double* Tin, const
 bool gram_mma_supported(int m);
 cudaError_t launch_gram_mma(int src, const double* E, const double* T, const double* d, int m, double inv_eps,
                             long long n, double* part, int max_part, double* out, int num_sms, cudaStream_t,
-                            LaunchStats*);
+                            LaunchStats*, const BatchDesc* batch = nullptr);
 
 // out_i = A X_i on the FP64 tensor cores; A in DEVICE memory; same contract as launch_apply_fast otherwise
 bool apply_mma_supported(int m);
 cudaError_t launch_apply_mma(int src, const double* E, const double* Tin, const double* d, const double* A, int m,
                              double inv_eps, long long n, double* Tout, double* E_out, const double* u, double eps,
-                             int num_sms, cudaStream_t, LaunchStats*);
+                             int num_sms, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr);
 
 // ---- toy_ode.cu -------------------------------------------------------------- //
 // small ODE systems (Lorenz-63, Van der Pol, circular): state dimension, 0 for the L96 systems
