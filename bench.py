@@ -283,7 +283,7 @@ def run_ours(args):
     assert np.isfinite(hist[-1][4]).all()
 
     # ---- end to end through the public API on host buffers ----------------- #
-    e2e = None
+    e2e = per_seg = None
     if not args.no_e2e:
         from fds_b200.lsstan import LssTangent
         from fds_b200.checkpoint import Checkpoint
@@ -309,6 +309,24 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         assert out.lss.K_segments() == args.steps and np.isfinite(out.V).all()
+        # strictest reading: the reference's run_segment(u0, V, v) -> (u0, V, v, J0, G, g) on host arrays, i.e.
+        # the whole ensemble state crosses PCIe in both directions EVERY segment (single GPU only)
+        bytes_in_1 = M * n_local * 8
+        if world == 1:
+            from fds_b200.segment import run_segment
+            run_segment(run, u, V, v, s, 0, S, eps)
+            barrier()
+            t1 = time.perf_counter()
+            res = None
+            for _ in range(2):
+                res = None                 # hand the pinned result buffers back to the pool before the next call
+                res = run_segment(run, u, V, v, s, 0, S, eps)
+            barrier()
+            dt1 = (time.perf_counter() - t1) / 2
+            assert np.isfinite(res[1]).all()
+            per_seg = {'value': N * (m + 1) * S / dt1, 'unit': UNIT, 'seconds_per_segment': dt1,
+                       'h2d_bytes_per_step': float(bytes_in_1), 'd2h_bytes_per_step': float(bytes_in_1 + S * M * 16),
+                       'call': 'segment.run_segment(run, u0, V, v, s, 0, %d, eps) on pinned host arrays, one call per segment' % S}
         bytes_in = (M * n_local * 8) * world
         small = args.steps * (m * m + m + m + 1 + S * M * 2) * 8
         e2e = {'value': N * (m + 1) * S * args.steps / dt, 'unit': UNIT,
@@ -349,6 +367,8 @@ def run_ours(args):
                 'clocks': clocks, 'gpu_launches': int(launches.item())}
         if e2e is not None:
             line['e2e'] = e2e
+            if per_seg is not None:
+                line['e2e_run_segment'] = per_seg
         line['djds'] = djds_check(local_rank)
         if world == 1 and not args.no_sweep:
             line['sweep_cfg5'] = sweep_check(local_rank)

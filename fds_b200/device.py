@@ -233,19 +233,20 @@ class Context:
 
     def segment(self, s, eps, steps, want_J=True):
         """Advance all m+2 trajectories ``steps`` steps; objective SUMS [steps][m+2][2]."""
-        J = np.empty((int(steps), self.M, 2)) if want_J else None
+        J = np.empty((int(steps),) + self.lead + (self.M, 2)) if want_J else None
         self._ck(self.lib.fds_segment(self.h, float(s), float(eps), int(steps), dptr(J)))
         return J
 
     def run_segment_host(self, u, V, v, s, eps, steps):
-        """Host-buffer form of the reference's run_segment (fds/segment.py:14-82)."""
-        u = np.array(u, dtype=np.float64, order='C')
-        V = np.array(V, dtype=np.float64, order='C')
-        v = np.array(v, dtype=np.float64, order='C')
-        J = np.empty((int(steps),) + self.lead + (self.M, 2))
-        self._ck(self.lib.fds_run_segment_host(self.h, dptr(u), dptr(V), dptr(v), float(s), float(eps),
-                                               int(steps), dptr(J)))
-        return u, V, v, J
+        """Host-buffer form of the reference's run_segment (fds/segment.py:14-82): u, V, v are read
+        where they lie (at PCIe rate if page-locked), the advanced u, V, v come back in pinned arrays.
+        (The C entry point fds_run_segment_host does the same in place on caller-owned buffers.)"""
+        self.set_state(u)
+        self.set_tangents(V, v)
+        self.boundary_finish(0, eps, _lib.FDS_BUILD_ENSEMBLE | _lib.FDS_BUILD_KEEP_TANGENTS)   # u + eps [V; v]
+        J = self.segment(s, eps, steps)
+        V1, v1 = self.get_tangents()
+        return self.get_state(), V1, v1, J
 
 
 def lss_solve(R, b, device=0):
