@@ -271,7 +271,10 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
             c->fuse2 = want && c->stream_ok && cfg->system == FDS_SYS_L96_RK4 && two_step_runs_per_cta(c->M) >= 1 && H >= 2;
             if (c->fuse2) { R = two_step_runs_per_cta(c->M); c->runs_per_cta = R; }
         }
-        c->plan = make_strip_plan(c->n, H, (long long)c->num_sms * (R >= 1 ? R : 1));
+        long long max_strips = (long long)c->num_sms * (R >= 1 ? R : 1);
+        // the two-step kernel packs (strip, column) pairs over all 256 lanes of a CTA (l96_step.cu)
+        if (c->fuse2 && c->M >= 9) max_strips = (long long)c->num_sms * 256 / c->M;
+        c->plan = make_strip_plan(c->n, H, max_strips);
         c->alo = c->plan.alo;
         c->ahi = c->plan.ahi;
     }

@@ -31,6 +31,8 @@ struct StreamParams {
     long long n;
     int nblk, node_shift;
     int M, R, run_stride, nstages, nconsumer;  // nconsumer = R*M
+    int pack;                                  // 1: (strip, column) pairs are packed over ALL consumer lanes of the grid: a strip may
+                                               // straddle two CTAs, which both stage its input; R = stage slots per CTA
     int dedicated;                             // 1: the last warp only produces; 0: warp 0 produces in between its blocks
     double F0, Flast;
     double* jpart2;                            // two steps per pass: node partials of the second step
@@ -52,15 +54,24 @@ struct StreamProducer {
     const double* src;       // this lane's strip, first input site of block 0 (lane < R)
     double* dst0;            // this lane's slot in stage 0
     uint64_t* full;          // empty = full + kMaxStages
-    int lane, nit;
+    int lane, nit, rcta;     // rcta: strips this CTA stages
     int it, st;              // next block to fetch and its stage
     uint32_t par;
 
     FDS_D void init(const StreamParams* P_, double* sdata, uint64_t* full_, int lane_, int first_off, int nit_) {
         P = P_; full = full_; lane = lane_; nit = nit_;
         const int R = P->R;
+        rcta = R;
         // strips past the end of the plan (last CTA only) mirror the last strip
         long long strip = (long long)blockIdx.x * R + (lane < R ? lane : 0);
+        if (P->pack) {
+            const long long g0 = (long long)blockIdx.x * P->nconsumer;           // first (strip, column) pair of this CTA
+            const long long sf = g0 / P->M;
+            long long sl = (g0 + P->nconsumer - 1) / P->M;
+            sl = sl < P->nstrips - 1 ? sl : P->nstrips - 1;
+            rcta = sl >= sf ? (int)(sl - sf + 1) : 1;
+            strip = sf + (lane < rcta ? lane : 0);
+        }
         strip = strip < P->nstrips - 1 ? strip : P->nstrips - 1;
         src = P->X + (P->a0 + strip * P->ls + first_off) * P->M;
         dst0 = sdata + (lane < R ? lane : 0) * P->run_stride;
@@ -73,10 +84,10 @@ struct StreamProducer {
         const int R = P->R, M = P->M, stage_stride = R * P->run_stride;
         const uint32_t chunk_bytes = (uint32_t)(8 * M * sizeof(double));
         if (it >= P->nstages) mbar_wait(&empty[st], par ^ 1u);
-        if (lane == 0) mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)R);
+        if (lane == 0) mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)rcta);
         __syncwarp();
-        if (lane < R) bulk_g2s(dst0 + (size_t)st * stage_stride, src + (long long)it * (8 * M), chunk_bytes, &full[st]);
-        for (int r = lane + 32; r < R; r += 32) {            // more than 32 strips per CTA (tiny M)
+        if (lane < rcta) bulk_g2s(dst0 + (size_t)st * stage_stride, src + (long long)it * (8 * M), chunk_bytes, &full[st]);
+        for (int r = lane + 32; r < rcta; r += 32) {         // more than 32 strips per CTA (tiny M; never packed)
             long long strip = (long long)blockIdx.x * R + r;
             strip = strip < P->nstrips - 1 ? strip : P->nstrips - 1;
             const long long off = (strip - ((long long)blockIdx.x * R + lane < P->nstrips - 1
@@ -199,8 +210,17 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     // the last strip: same loads, same arithmetic, same stores of the same values -- no
     // thread ever takes a path of its own
     const int t = tid < p.nconsumer ? tid : p.nconsumer - 1;
-    const int r = t / p.M, k = t - r * p.M;
+    int r = t / p.M, k = t - r * p.M;
     long long strip = (long long)blockIdx.x * p.R + r;
+    if (p.pack) {
+        // every lane of the grid carries its own (strip, column) pair; pairs past the end mirror the last one
+        long long gidx = (long long)blockIdx.x * p.nconsumer + t;
+        const long long total = p.nstrips * p.M;
+        gidx = gidx < total ? gidx : total - 1;
+        strip = gidx / p.M;
+        k = (int)(gidx - strip * p.M);
+        r = (int)(strip - ((long long)blockIdx.x * p.nconsumer) / p.M);
+    }
     strip = strip < last_strip ? strip : last_strip;
 
     MarchGeom g;
@@ -277,11 +297,19 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
             smem_budget = 112 * 1024;
         }
     }
+    p.pack = 0;
     if (fuse2) {
         if (p.R * a.M > 256) return cudaErrorInvalidValue;   // set runs_per_cta = two_step_runs_per_cta(M)
-        p.dedicated = 0;                                      // all 8 warps compute; warp 0 also issues the copies
+        p.dedicated = 0;                                      // all 8 warps compute and take turns issuing the copies
     }
     p.nconsumer = p.R * a.M;
+    if (fuse2 && a.M >= 9 && a.M <= 256) {
+        // 256 / M strips leave lanes idle (238 of 256 at M = 34): pack the (strip, column) pairs over all 256
+        // lanes of every CTA instead; a CTA then touches up to 256 / M + 2 strips and stages all of them
+        p.pack = 1;
+        p.nconsumer = 256;
+        p.R = (256 + a.M - 1) / a.M + 1;
+    }
     int pad = (16 - (7 * a.M) % 16) % 16;
     if (pad & 1) pad += 1;
     p.run_stride = 8 * a.M + pad;
@@ -299,7 +327,8 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
     p.jpart2 = a.jpart2; p.fuse2 = fuse2;
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
-    const int grid = (int)((plan.nstrips + p.R - 1) / p.R);
+    const int grid = p.pack ? (int)((plan.nstrips * a.M + p.nconsumer - 1) / p.nconsumer)
+                            : (int)((plan.nstrips + p.R - 1) / p.R);
     const size_t smem = 128 + ns_bytes + stage_bytes * nst;
     cudaError_t e = cudaSuccess;
 #define FDS_STREAM_LAUNCH2(MP, MC, ST, EU)                                                                         \
