@@ -181,15 +181,22 @@ struct Tree8 {
 
 struct LeafStack {
     double s0, s1, s2;
-    // b = index of the 8-block inside its 64-site leaf; true when the leaf is complete
+    // b = index of the 8-block inside its 64-site leaf; true when the leaf is complete.
+    // Branch-free binary counter: the three sums are always formed and selected by the bits of b
+    // (a sum whose operands are not both due is simply not used), so the hot loop has no
+    // data-independent-but-unpredictable control flow and no register shuffling at merge points.
     FDS_HD bool push(double p, int b, double& leaf) {
-        if ((b & 1) == 0) { s0 = p; return false; }
-        p = s0 + p;
-        if ((b & 2) == 0) { s1 = p; return false; }
-        p = s1 + p;
-        if ((b & 4) == 0) { s2 = p; return false; }
-        leaf = s2 + p;
-        return true;
+        const bool b0 = (b & 1) != 0, b1 = (b & 2) != 0, b2 = (b & 4) != 0;
+        const double t0 = s0 + p;
+        const double p1 = b0 ? t0 : p;          // value carried into level 1 (meaningful when b0)
+        s0 = b0 ? s0 : p;
+        const double t1 = s1 + p1;
+        const double p2 = b1 ? t1 : p1;         // carried into level 2 (meaningful when b0 && b1)
+        s1 = (b0 && !b1) ? p1 : s1;
+        const double t2 = s2 + p2;
+        s2 = (b0 && b1 && !b2) ? p2 : s2;
+        leaf = t2;
+        return b0 && b1 && b2;
     }
 };
 
