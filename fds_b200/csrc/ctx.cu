@@ -58,7 +58,7 @@ struct fds_ctx {
     double* jscratch = nullptr;
     double* jsum = nullptr;
     long long jsum_cap = 0;        // steps
-    double* jnode = nullptr;       // [jsum_cap][plan.nnode][M][2] node partials of the streaming kernel
+    double* jnode = nullptr;       // [H][plan.nnode][M][2] node partials of one halo chunk of the streaming kernel
     double* jnode_scratch = nullptr;
     long long nleaf = 0;
     // host <-> device staging of the tangent block: two buffers, a copy stream and events so
@@ -663,16 +663,14 @@ static int ensure_jsum(fds_ctx* c, long long steps) {
     }
     c->jsum = nj;
     c->jsum_cap = cap;
-    if (c->stream_ok && c->nb > 1) {
-        // batch: leaf partials of one halo chunk (<= H steps) at a time, reduced per problem right after it
-        if (!c->jnode) FDS_CK(c, cudaMalloc(&c->jnode, (size_t)c->H * c->plan.nnode * c->M * 2 * sizeof(double)));
-    } else if (c->stream_ok) {
-        cudaFree(c->jnode); cudaFree(c->jnode_scratch);
-        c->jnode = c->jnode_scratch = nullptr;
+    if (c->stream_ok && !c->jnode) {
+        // node partials of one halo chunk (<= H steps) at a time, reduced right after it: the buffer does
+        // not grow with the number of steps of a segment
         const size_t row = (size_t)c->plan.nnode * c->M * 2;
-        FDS_CK(c, cudaMalloc(&c->jnode, (size_t)cap * row * sizeof(double)));
-        FDS_CK(c, cudaMalloc(&c->jnode_scratch,
-                             (size_t)2 * cap * ((c->plan.nnode + 255) / 256) * c->M * 2 * sizeof(double)));
+        FDS_CK(c, cudaMalloc(&c->jnode, (size_t)c->H * row * sizeof(double)));
+        if (c->nb == 1)
+            FDS_CK(c, cudaMalloc(&c->jnode_scratch,
+                                 (size_t)2 * c->H * ((c->plan.nnode + 255) / 256) * c->M * 2 * sizeof(double)));
     }
     return 0;
 }
@@ -728,7 +726,8 @@ static int reduce_nodes(fds_ctx* c, long long step0, long long nsteps) {
         return 0;
     }
     const size_t row = (size_t)c->plan.nnode * c->M * 2;
-    FDS_CK(c, launch_tree_reduce_batched(c->jnode + (size_t)step0 * row, c->plan.nnode, 2 * c->M, nsteps,
+    (void)row;
+    FDS_CK(c, launch_tree_reduce_batched(c->jnode, c->plan.nnode, 2 * c->M, nsteps,
                                          c->jsum + (size_t)step0 * c->M * 2, c->jnode_scratch, c->stream, &c->ls));
     return 0;
 }
@@ -835,13 +834,13 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
         return 0;
     }
     const double F0 = s + 8.0, Flast = (s + eps) + 8.0;   // fds/segment.py:64: parameter + epsilon
-    if (c->nb > 1 && nsteps > c->H) return fail(c, "fds_segment_advance: a batch advances at most halo_steps per call");
+    if (nsteps > c->H) return fail(c, "fds_segment_advance: at most fds_halo_steps() steps per call");
     if (int r = upload_forcing(c, s, eps)) return r;
     for (long long j = 0; j < nsteps;) {
         if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
         const bool two = c->fuse2 && nsteps - j >= 2 && c->ens_halo_valid >= 2;
         if (int r = one_step(c, c->E_all(c->cur), c->E_all(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, step0 + j,
-                             c->nb > 1 ? j : step0 + j, two)) return r;
+                             j, two)) return r;
         c->cur ^= 1;
         c->ens_halo_valid -= two ? 2 : 1;
         j += two ? 2 : 1;
