@@ -95,7 +95,7 @@ struct fds_ctx {
     const BatchDesc* batch() const { return nb > 1 ? &bd : nullptr; }
 };
 
-static std::string g_create_err;
+static thread_local std::string g_create_err;   // creation / context-free errors, per calling thread
 
 #define FDS_CK(ctx, call)                                                                      \
     do {                                                                                       \
