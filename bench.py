@@ -344,9 +344,10 @@ def run_ours(args):
         kms = float(kern.item())
         alg_bytes = 16.0 * n_local * M * steps_per_launch
         achieved = alg_bytes / (kms * 1e-3) / 1e9
-        traffic = None
+        traffic = fp64_pct = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')))['dram_bytes_per_launch']
+            prof = json.load(open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')))
+            traffic, fp64_pct = prof['dram_bytes_per_launch'], prof.get('fp64_pipe_busy_pct')
         except Exception:
             pass
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -359,6 +360,7 @@ def run_ours(args):
                              'algorithmic_bytes_per_launch': alg_bytes, 'time_steps_per_launch': steps_per_launch,
                              'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s',
                              'frac_of_nominal_8TBs': achieved / 8000.0,
+                             'fp64_pipe_busy_pct_ncu': fp64_pct,
                              'step_kernel_share_of_time': kms * (S / steps_per_launch) * args.steps / total_ms,
                              'note': ('temporal blocking: one launch advances %g time steps, so DRAM traffic per launch '
                                       '(`traffic`) is 1/%g of the algorithmic bytes and `frac` can exceed 1; the kernel is '

@@ -50,7 +50,7 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio']
 
-traffic = {}
+traffic, fp64 = {}, {}
 for spec in reps:
     name, rep = spec.split('=')
     raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
@@ -71,11 +71,14 @@ for spec in reps:
     for r in data:
         k = r[ki].split('(')[0].replace('void ', '').replace('fds::', '')
         traffic.setdefault(k, []).append(val(r, 'dram__bytes_read.sum') + val(r, 'dram__bytes_write.sum'))
-out = {k: {'dram_bytes_per_launch': sum(v) / len(v)} for k, v in traffic.items()}
+        fp64.setdefault(k, []).append(float(r[hdr.index('sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active')]))
+out = {k: {'dram_bytes_per_launch': sum(v) / len(v), 'fp64_pipe_busy_pct': sum(fp64[k]) / len(fp64[k])}
+       for k, v in traffic.items()}
 if out:
     step = [k for k in out if 'l96_rk4_stream' in k]
     doc = {'kernel': 'l96_rk4_stream_kernel',
            'dram_bytes_per_launch': out[step[0]]['dram_bytes_per_launch'] if step else None,
+           'fp64_pipe_busy_pct': out[step[0]]['fp64_pipe_busy_pct'] if step else None,
            'source': 'profiles/%s_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)' % tag,
            'workload': 'N=2^24 sites, m=32 (34 trajectories)', 'all_kernels': out}
     json.dump(doc, open('profiles/step_kernel_traffic.json', 'w'), indent=1)
