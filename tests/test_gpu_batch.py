@@ -115,3 +115,17 @@ def test_batched_euler_segment_bitwise():
         ru, rV, rv, rJ0, rG, rg = port.run_segment(plugins.run_l96_euler, U[p], V[p], v[p], params[p], steps, eps)
         assert np.array_equal(Ub[p], ru) and np.array_equal(Vb[p], rV) and np.array_equal(vb[p], rv)
         assert np.array_equal(Jb[:, p, 0] / N, rJ0)
+
+
+@gpu
+def test_sweep_sensitivities_are_consistent_with_the_slope_of_the_averages():
+    """Physics check of the whole batched loop (the point of shadowing): over a sweep of forcings the
+    mean dJ/ds must match the slope of the long-time averages J(F) themselves."""
+    B, N, m, K, steps = 256, 64, 32, 50, 100
+    params = np.linspace(-1.0, 1.0, B)
+    np.random.seed(1)
+    Jb, Gb = fds_b200.shadowing_batch(fds_b200.L96(N), np.random.rand(N), params, m, K, steps, 2000, 1e-4)
+    assert np.isfinite(Jb).all() and np.isfinite(Gb).all()
+    for q, tol in ((1, 0.2), (0, 0.5)):                  # <x^2> is the well-resolved objective, <x> is noisier
+        slope = np.polyfit(params, Jb[:, q], 1)[0]
+        assert abs(Gb[:, q].mean() - slope) < tol * abs(slope), (q, Gb[:, q].mean(), slope)
