@@ -17,6 +17,7 @@ FDS_MATH_EXACT, FDS_MATH_FAST = 0, 1
 FDS_FLAG_SIMPLE_KERNELS = 1
 FDS_FLAG_EXTERNAL_STREAM = 2
 FDS_BUILD_ENSEMBLE, FDS_BUILD_KEEP_TANGENTS = 1, 2
+FDS_DILATION_OFF, FDS_DILATION_FD, FDS_DILATION_ANALYTIC, FDS_DILATION_GIVEN = range(4)
 FDS_BUF_ENSEMBLE, FDS_BUF_PRIMAL, FDS_BUF_GRAM, FDS_BUF_JSUM, FDS_BUF_TANGENT, FDS_BUF_DXDT = range(6)
 
 
@@ -49,6 +50,7 @@ SIGNATURES = {
     'fds_set_primal_history': (_I32, [_CTX, _I32, c_double_p]),
     'fds_set_dxdt_weights': (_I32, [_CTX, c_double_p]),
     'fds_set_time_dilation': (_I32, [_CTX, _I32]),
+    'fds_set_dxdt': (_I32, [_CTX, c_double_p]),
     'fds_set_qr_passes': (_I32, [_CTX, _I32]),
     'fds_last_condition': (_D, [_CTX]),
     'fds_run': (_I32, [_CTX, _D, _I64, c_double_p]),

@@ -71,6 +71,7 @@ struct fds_ctx {
     bool state_in_ensemble = false;   // newest primal state is column 0 of the ensemble
     bool tangents_implicit = false;   // newest tangents are (E_k - E_0)/eps_last
     bool time_dilation = true;
+    int dil_mode = 1;                 // FDS_DILATION_*: 0 off, 1 finite differences, 2 analytic (dt * f(u)), 3 given by the host
     // CholeskyQR: 0 = one pass when the first factor certifies cond^2 u negligible, else two; 2 = always two
     int qr_mode = 0;
     bool qr_single = false;           // a certified single-pass factor is waiting for fds_boundary_finish
@@ -415,7 +416,22 @@ int fds_set_dxdt_weights(fds_ctx* c, const double w[4]) {
     return 0;
 }
 
-int fds_set_time_dilation(fds_ctx* c, int enabled) { c->time_dilation = enabled != 0; return 0; }
+int fds_set_time_dilation(fds_ctx* c, int mode) {
+    if (mode < 0 || mode > 3) return fail(c, "fds_set_time_dilation: mode must be 0 .. 3");
+    if (mode == FDS_DILATION_ANALYTIC && (c->toy || c->host_sys))
+        return fail(c, "fds_set_time_dilation: the analytic derivative exists for the Lorenz-96 systems only");
+    c->dil_mode = mode;
+    c->time_dilation = mode != 0;
+    return 0;
+}
+
+int fds_set_dxdt(fds_ctx* c, const double* d_host) {
+    FDS_CK(c, cudaMemcpy2DAsync(c->d, (size_t)(c->nb > 1 ? c->slot : c->n) * sizeof(double), d_host,
+                                (size_t)c->n * sizeof(double), (size_t)c->n * sizeof(double), c->nb,
+                                cudaMemcpyHostToDevice, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
 
 int fds_set_qr_passes(fds_ctx* c, int passes) {
     if (passes != 0 && passes != 2) return fail(c, "fds_set_qr_passes: 0 (adaptive) or 2 (always CholeskyQR2)");
@@ -883,7 +899,16 @@ int fds_boundary_begin(fds_ctx* c, int from_ensemble) {
 }
 
 int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
-    if (c->time_dilation && c->host_sys) {
+    if (c->dil_mode == FDS_DILATION_GIVEN) {
+        // d was put there by fds_set_dxdt (run_ddt callable of the reference, fds/timedilation.py:54-61)
+    } else if (c->dil_mode == FDS_DILATION_ANALYTIC) {
+        if (c->pri_halo_valid < 1) return fail(c, "fds_boundary_dxdt: primal halo must be valid");
+        if (int r = upload_forcing(c, s, 0.0)) return r;
+        FDS_CK(c, launch_l96_ddt(c->P_all(0), c->d_alloc, c->nall, s + 8.0, c->cfg.dt, c->cfg.math == FDS_MATH_EXACT,
+                                 c->cfg.system == FDS_SYS_L96_EULER, c->nb > 1 ? c->Fpp : nullptr, c->slot,
+                                 c->stream, &c->ls));
+        c->pri_halo_valid = 0;
+    } else if (c->time_dilation && c->host_sys) {
         // u1, u2, u3 were put into P(1..3) by fds_set_primal_history
         FDS_CK(c, launch_dxdt(c->P(0), c->P(1), c->P(2), c->P(3), c->c4, c->d, c->n, c->stream, &c->ls));
     } else if (c->time_dilation && c->toy) {

@@ -48,6 +48,9 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
                                   int euler = 0);
 // one thread per element, global loads (RK4 or Euler); no objective sums
 cudaError_t launch_l96_simple(const StepArgs& a, int euler, cudaStream_t st, LaunchStats* ls);
+// d[i] = dt * f(X)_i for i in [0, n) of a single-column state with valid ghosts (2 left, 1 right)
+cudaError_t launch_l96_ddt(const double* X, double* d, long long n, double F0, double dt, int exact, int euler,
+                           const double2* Fpp, long long slot, cudaStream_t st, LaunchStats* ls);
 // 64-site leaf partials of an array: jpart[leaf][M][2]
 cudaError_t launch_stats_leaf(const double* Y, int M, long long n, double* jpart, long long nleaf,
                               cudaStream_t st, LaunchStats* ls);

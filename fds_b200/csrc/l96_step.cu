@@ -401,6 +401,30 @@ cudaError_t launch_l96_simple(const StepArgs& a, int euler, cudaStream_t st, Lau
     return cudaGetLastError();
 }
 
+// per-step time derivative of a single-column state, d_i = dt * f(x)_i (analytic time dilation)
+template <class MP, int EULER>
+__global__ void __launch_bounds__(256) l96_ddt_kernel(const double* __restrict__ X, double* __restrict__ d, long long n,
+                                                      double F0, double dt, const double2* __restrict__ Fpp,
+                                                      long long slot) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double F = Fpp != nullptr ? Fpp[i / slot].x : F0;
+    const double k = EULER ? l96_rhs_fun3d<MP>(X[i - 2], X[i - 1], X[i], X[i + 1], F)
+                           : l96_rhs<MP>(X[i - 2], X[i - 1], X[i], X[i + 1], F);
+    d[i] = MP::mul(dt, k);
+}
+
+cudaError_t launch_l96_ddt(const double* X, double* d, long long n, double F0, double dt, int exact, int euler,
+                           const double2* Fpp, long long slot, cudaStream_t st, LaunchStats* ls) {
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (exact) { if (euler) l96_ddt_kernel<ExactMath, 1><<<grid, 256, 0, st>>>(X, d, n, F0, dt, Fpp, slot);
+                 else l96_ddt_kernel<ExactMath, 0><<<grid, 256, 0, st>>>(X, d, n, F0, dt, Fpp, slot); }
+    else       { if (euler) l96_ddt_kernel<FastMath, 1><<<grid, 256, 0, st>>>(X, d, n, F0, dt, Fpp, slot);
+                 else l96_ddt_kernel<FastMath, 0><<<grid, 256, 0, st>>>(X, d, n, F0, dt, Fpp, slot); }
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
 // ------------------------------ objective sums ------------------------------- //
 __global__ void __launch_bounds__(256) stats_leaf_kernel(const double* __restrict__ Y, int M, long long n,
                                                          double* __restrict__ jpart, long long nleaf) {

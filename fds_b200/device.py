@@ -139,8 +139,14 @@ class Context:
         assert c.shape == (4,)
         self._ck(self.lib.fds_set_dxdt_weights(self.h, dptr(c)))
 
-    def set_time_dilation(self, enabled):
-        self._ck(self.lib.fds_set_time_dilation(self.h, int(bool(enabled))))
+    def set_time_dilation(self, mode):
+        """False / 0: off; True / 1: finite differences; 2: analytic dt*f(u); 3: given (set_dxdt)."""
+        self._ck(self.lib.fds_set_time_dilation(self.h, int(mode)))
+
+    def set_dxdt(self, d):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        assert d.shape == self.lead + (self.n,)
+        self._ck(self.lib.fds_set_dxdt(self.h, dptr(d)))
 
     def set_qr_passes(self, passes):
         """0: adaptive (one CholeskyQR pass when certified well conditioned), 2: always CholeskyQR2."""

@@ -64,6 +64,8 @@ class Engine:
                            max_halo_steps=max_halo_steps, simple_kernels=simple_kernels, stream=stream,
                            batch=self.batch)
         self.time_dilation = True
+        self.dil_mode = 1
+        self.run_ddt = None
 
     # -- sharding of host arrays --------------------------------------------- #
     def local(self, a):
@@ -103,9 +105,30 @@ class Engine:
     def set_dxdt_weights(self, w):
         self.ctx.set_dxdt_weights(w)
 
-    def set_time_dilation(self, enabled):
-        self.time_dilation = bool(enabled)
-        self.ctx.set_time_dilation(enabled)
+    def set_time_dilation(self, mode):
+        """How the time-dilation vector is obtained: True / 1 finite differences of three primal steps
+        (the reference's TimeDilation), False / 0 none (``run_ddt=0``), ``'analytic'`` / 2 the built-in
+        system's ``dt * f(u)``, or a callable ``run_ddt(u0, parameter) -> du per step`` evaluated on the
+        host (the reference's TimeDilationExact, fds/timedilation.py:54-61)."""
+        self.run_ddt = mode if callable(mode) else None
+        if callable(mode):
+            m = _lib.FDS_DILATION_GIVEN
+        elif isinstance(mode, str):
+            m = {'analytic': _lib.FDS_DILATION_ANALYTIC, 'fd': _lib.FDS_DILATION_FD, 'off': _lib.FDS_DILATION_OFF}[mode]
+        else:
+            m = int(mode)
+        self.dil_mode = m
+        self.time_dilation = m != 0
+        if getattr(self, 'ctx', None) is not None:
+            self.ctx.set_time_dilation(m)
+
+    def _dilation_input(self, s):
+        """Before fds_boundary_dxdt: the primal halo (finite differences / analytic) or the host's d."""
+        if self.run_ddt is not None:
+            d = np.asarray(self.run_ddt(self.get_state(), s), dtype=np.float64)
+            self.ctx.set_dxdt(self.local(d))
+        elif self.time_dilation:
+            self._halo(_lib.FDS_BUF_PRIMAL, 3)
 
     def run(self, s, steps, want_J=True):
         """Advance the primal; returns J (steps, 2) = [mean x, mean x^2] or None."""
@@ -134,8 +157,7 @@ class Engine:
         c = self.ctx
         build = (_lib.FDS_BUILD_ENSEMBLE if build else 0) | (_lib.FDS_BUILD_KEEP_TANGENTS if keep_tangents else 0)
         c.boundary_begin(from_ensemble)
-        if self.time_dilation:
-            self._halo(_lib.FDS_BUF_PRIMAL, 3)
+        self._dilation_input(s)
         c.boundary_dxdt(s, from_ensemble, eps)
         self._reduce_gram()
         c.boundary_factor(do_qr, from_ensemble, eps)
@@ -200,8 +222,8 @@ class Engine:
             self.ctx.set_tangents(self.local(W), None)
         else:
             self.ctx.random_tangents(seed)
-        td = self.time_dilation
-        self.ctx.set_time_dilation(False)
+        td = getattr(self, 'dil_mode', 1)
+        self.ctx.set_time_dilation(0)
         try:
             c = self.ctx
             c.boundary_begin(0)
@@ -235,6 +257,7 @@ class HostSolverEngine(Engine):
         self.ring = None
         self.batch = 1
         self.time_dilation = True
+        self.dil_mode, self.run_ddt = 1, None
         self.j_div, self.n_qoi = 1.0, None
         self.i_segment = 0
         self._weights = None
@@ -262,7 +285,7 @@ class HostSolverEngine(Engine):
             self.n_global = int(n)
             self.lo, self.hi = 0, self.n_global
             self.ctx = Context(self.n_global, self.m, scheme='host', **self.kw)
-            self.ctx.set_time_dilation(self.time_dilation)
+            self.ctx.set_time_dilation(self.dil_mode)
             if self._weights is not None:
                 self.ctx.set_dxdt_weights(self._weights)
         elif int(n) != self.n_global:
@@ -272,11 +295,6 @@ class HostSolverEngine(Engine):
         self._weights = np.asarray(w, dtype=np.float64)
         if self.ctx is not None:
             self.ctx.set_dxdt_weights(self._weights)
-
-    def set_time_dilation(self, enabled):
-        self.time_dilation = bool(enabled)
-        if self.ctx is not None:
-            self.ctx.set_time_dilation(enabled)
 
     def set_state(self, u):
         u = np.asarray(u, dtype=np.float64).ravel()
@@ -292,7 +310,9 @@ class HostSolverEngine(Engine):
         c = self.ctx
         flags = (_lib.FDS_BUILD_ENSEMBLE if build else 0) | (_lib.FDS_BUILD_KEEP_TANGENTS if keep_tangents else 0)
         c.boundary_begin(from_ensemble)
-        if self.time_dilation:
+        if self.run_ddt is not None:
+            c.set_dxdt(np.asarray(self.run_ddt(c.get_state(), s), dtype=np.float64))
+        elif self.time_dilation:
             u0 = c.get_state()
             rid = 'time_dilation_{0:02d}'.format(self.i_segment)
             res = self._map([(u0, s, k, rid + '_{0}steps'.format(k)) for k in (1, 2, 3)])

@@ -35,6 +35,17 @@ def _engine_of(run, m):
     return eng(m)
 
 
+def _dilation_mode(run_ddt):
+    """run_ddt argument of the reference -> Engine.set_time_dilation mode."""
+    if run_ddt is None:
+        return 1
+    if callable(run_ddt) or isinstance(run_ddt, str):
+        return run_ddt
+    if run_ddt == 0:
+        return 0
+    raise TypeError('run_ddt: None, 0, "analytic" or a callable run_ddt(u0, parameter)')
+
+
 def lss_gradient_series(checkpoint, segment_range=None):
     """Per-segment series (grad_lss, grad_dil) whose means add up to dJ/ds."""
     _, _, _, lss, G_lss, g_lss, J, G_dil, g_dil = checkpoint
@@ -63,16 +74,16 @@ def continue_shadowing(run, parameter, checkpoint, num_segments, steps_per_segme
                        get_host_dir=None, spawn_compute_job=None, verbose=False):
     """Run segments K0 .. num_segments-1 (K0 = segments already in ``checkpoint``);
     ``num_segments`` is the TOTAL target (reference fds/fds.py:92-176).
-    ``run_ddt=0`` switches time dilation off (fds/timedilation.py:59-61); other
-    non-None values are the reference's broken analytic path and are rejected.
+    ``run_ddt``: None = finite-difference time dilation (the reference's default), 0 = off
+    (fds/timedilation.py:59-61), ``'analytic'`` = the built-in system's ``dt * f(u)`` on the device, or a
+    callable ``run_ddt(u0, parameter) -> du per step`` (the reference's TimeDilationExact, whose upstream
+    implementation raises NameError at fds/timedilation.py:58).
     ``simultaneous_runs``, ``get_host_dir``, ``spawn_compute_job`` are inert."""
     assert verify_checkpoint(checkpoint)
     u0, V, v, lss, G_lss, g_lss, J_hist, G_dil, g_dil = checkpoint
-    if run_ddt is not None and run_ddt != 0:
-        raise NotImplementedError('run_ddt: only None (finite-difference time dilation) or 0 (off)')
     V = np.asarray(V)
     eng = _engine_of(run, V.shape[0])
-    eng.set_time_dilation(run_ddt is None)
+    eng.set_time_dilation(_dilation_mode(run_ddt))
     eng.set_dxdt_weights(stencil_weights(3))
     eng.set_state(u0)
     eng.set_tangents(V, v)
@@ -131,10 +142,8 @@ def shadowing(run, u0, parameter, subspace_dimension, num_segments, steps_per_se
     returns             (time-averaged J (n_qoi,), dJ/ds (n_qoi,)) or the Checkpoint
     """
     m = int(subspace_dimension)
-    if run_ddt is not None and run_ddt != 0:
-        raise NotImplementedError('run_ddt: only None (finite-difference time dilation) or 0 (off)')
     eng = _engine_of(run, m)
-    eng.set_time_dilation(run_ddt is None)
+    eng.set_time_dilation(_dilation_mode(run_ddt))
     eng.set_dxdt_weights(stencil_weights(3))
     eng.set_state(u0)
     if runup_steps > 0:
@@ -217,8 +226,8 @@ def _shadowing_batch_local(run, u0, parameters, subspace_dimension, num_segments
                            runup_steps, epsilon, run_ddt, tangent_seed, return_histories, tangents):
     parameters = np.ascontiguousarray(parameters, dtype=np.float64).ravel()
     B, m = parameters.size, int(subspace_dimension)
-    if run_ddt is not None and run_ddt != 0:
-        raise NotImplementedError('run_ddt: only None (finite-difference time dilation) or 0 (off)')
+    if callable(run_ddt):
+        raise NotImplementedError('shadowing_batch: run_ddt may be None, 0 or "analytic"')
     if B < 2:
         raise ValueError('shadowing_batch needs at least two problems; use shadowing() for one')
     be = getattr(run, 'batch_engine', None)
@@ -229,7 +238,7 @@ def _shadowing_batch_local(run, u0, parameters, subspace_dimension, num_segments
     u0 = np.asarray(u0, dtype=np.float64)
     if u0.ndim == 1:
         u0 = np.broadcast_to(u0, (B, N))
-    eng.set_time_dilation(run_ddt is None)
+    eng.set_time_dilation(_dilation_mode(run_ddt))
     eng.set_dxdt_weights(stencil_weights(3))
     eng.ctx.set_batch_params(parameters)          # problem p runs at 0.0 + parameters[p]
     eng.set_state(np.ascontiguousarray(u0))

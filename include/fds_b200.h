@@ -113,8 +113,17 @@ int fds_random_tangents(fds_ctx*, uint64_t seed);  /* uniform[0,1) V (pascal.ran
 /* FD stencil weights of the time-dilation derivative (fds/timedilation.py:16-19 gets them
  * from np.linalg.solve; pass those 4 doubles for bit parity).  Default: -11/6, 3, -3/2, 1/3 */
 int fds_set_dxdt_weights(fds_ctx*, const double c[4]);
-/* run_ddt=0 of the reference (fds/timedilation.py:59-61): no time dilation at boundaries   */
-int fds_set_time_dilation(fds_ctx*, int enabled);
+/* how the time-dilation vector d (per-step du/dt) of a boundary is obtained:                */
+enum {
+    FDS_DILATION_OFF      = 0, /* run_ddt=0 of the reference (fds/timedilation.py:59-61)               */
+    FDS_DILATION_FD       = 1, /* default: 3rd-order one-sided differences of 3 primal steps (:63-82)  */
+    FDS_DILATION_ANALYTIC = 2, /* d = dt * f(u), the right-hand side of the built-in Lorenz-96 system   */
+    FDS_DILATION_GIVEN    = 3  /* the caller's own run_ddt(u0, parameter) (TimeDilationExact, :54-61 --
+                                  broken upstream, NameError at :58): upload it with fds_set_dxdt
+                                  before every fds_boundary_dxdt                                       */
+};
+int fds_set_time_dilation(fds_ctx*, int mode);
+int fds_set_dxdt(fds_ctx*, const double* d_host);   /* [n_local] (batch: [B][n_local]) */
 
 /* thin QR of the tangent block (LssTangent.checkpoint, fds/lsstan.py:20-34): CholeskyQR from the
  * extended Gram.  passes = 0 (default): ONE pass when the first factor certifies that the loss of
