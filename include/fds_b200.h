@@ -159,12 +159,15 @@ int fds_halo_layout(const fds_ctx*, int which_buf, int64_t halo_steps, int64_t o
  *
  *  fds_boundary_begin   : primal <- ensemble col 0 (or the state set by fds_set_state)
  *        [halo: primal, 3 steps]
- *  fds_boundary_dxdt    : u1,u2,u3, d = sum c_i u_i ; Gram of [tangents ; d] -> FDS_BUF_GRAM
+ *  fds_boundary_dxdt    : u1,u2,u3, d = sum c_i u_i (or the analytic / given d, fds_set_time_dilation);
+ *                         Gram of [tangents ; d] -> FDS_BUF_GRAM
  *        [sum-reduce FDS_BUF_GRAM over ranks]
- *  fds_boundary_factor  : G_dil, g_dil, projection (+ CholeskyQR pass 1 if do_qr); applies it;
- *                         if do_qr: Gram of the result -> FDS_BUF_GRAM
- *        [if do_qr: sum-reduce FDS_BUF_GRAM over ranks]
- *  fds_boundary_finish  : (CholeskyQR pass 2 if do_qr) R, b; explicit tangents; next ensemble
+ *  fds_boundary_factor  : G_dil, g_dil, projection.  do_qr: if the Gram certifies the block well
+ *                         conditioned, the single-pass CholeskyQR factor is kept for _finish and nothing
+ *                         else happens here; otherwise CholeskyQR pass 1 is applied and the Gram of the
+ *                         result goes to FDS_BUF_GRAM
+ *        [if do_qr: sum-reduce FDS_BUF_GRAM over ranks (harmless after a single-pass factor)]
+ *  fds_boundary_finish  : R, b (single pass, or CholeskyQR pass 2); explicit tangents; next ensemble
  *        [halo: ensemble, halo_steps]
  */
 int fds_boundary_begin(fds_ctx*, int from_ensemble);
@@ -177,7 +180,9 @@ int fds_boundary_results(fds_ctx*, double* R, double* b, double* G_dil, double* 
 /* ---- one segment: advance all m+2 trajectories `steps` steps ------------------ */
 /* reference: run_segment's m+2 solver calls (fds/segment.py:56-64).  The host
  * refreshes halos every fds_halo_steps() steps: call fds_segment_advance() in
- * chunks (step0 = index of the first step of the chunk within the segment).       */
+ * chunks of at most that many steps (step0 = index of the first step of the chunk
+ * within the segment).  Inside a chunk the Lorenz-96 RK4 system advances TWO time
+ * steps per kernel pass (temporal blocking; bit-identical to single steps).        */
 int64_t fds_halo_steps(const fds_ctx*, int64_t steps);
 int fds_segment_advance(fds_ctx*, double s, double eps, int64_t step0, int64_t nsteps);
 /* objective sums of the last segment, J_host[steps][m+2][2] = [sum x, sum x^2]    */
