@@ -262,7 +262,7 @@ struct StripPlan {
     long long nnode;    // nodes covering [0, n)
 };
 
-inline long long floor_div(long long a, long long b) {
+FDS_HD long long floor_div(long long a, long long b) {
     long long q = a / b;
     return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
 }

@@ -131,13 +131,24 @@ FDS_HD void l96_rk4_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef
     const long long jhi = g.n < shi ? g.n : shi;
     const long long nfl = g.n & ~(long long)(kLeafSites - 1);
     const long long ncl = (g.n + kLeafSites - 1) & ~(long long)(kLeafSites - 1);
+    // Blocks b in [bfl, bfh] take the unchecked path: the 8 step-2 outputs (sites a + 8b - 11 ..) are stored by
+    // this strip and neither they nor the 8 step-1 values (a + 8b - 3 ..) lie in the partial leaf that contains
+    // site n (leaves wholly outside [0, n) are zeroed as a whole).  Computed once: the loop compares two ints.
+    int bfl = 2, bfh = g.nblk;                                  // j2 >= slo  <=>  b >= 2 ;  j2 + 8 <= shi  <=>  b <= nblk
+    if (nfl != ncl) {                                           // a partial leaf [nfl, ncl) exists
+        // clean blocks: j1 + 8 <= nfl  (b <= (nfl - a - 5) / 8)   or   j2 >= ncl  (b >= (ncl - a + 11) / 8, rounded up)
+        const long long below = floor_div(nfl - g.a - 5, 8), above = -floor_div(-(ncl - g.a + 11), 8);
+        if (below >= bfl && below < bfh) {
+            // the strip straddles the partial leaf: keep the longer clean side unchecked
+            if (above > bfh || (below - bfl) >= (bfh - above)) bfh = (int)below; else bfl = (int)above;
+        } else if (below < bfl) {
+            if (above > bfl) bfl = (int)(above < (long long)bfh + 1 ? above : (long long)bfh + 1);
+        }
+    }
 #pragma unroll 1
     for (int b = kFuse2First; b <= g.nblk + 1; ++b) {
-        const long long j1 = g.a + 8LL * b - 3, j2 = g.a + 8LL * b - 11;
         io.begin_block(b);
-        // unchecked path: the 8 step-2 outputs are stored by this strip and neither they nor the 8
-        // step-1 values lie in the partial leaf (leaves wholly outside [0, n) are zeroed as a whole)
-        const bool fast = j2 >= slo && j2 + 8 <= shi && (j1 + 8 <= nfl || j2 >= ncl);
+        const bool fast = b >= bfl && b <= bfh;
         if (io.all(fast))
             march2_block<MP, true, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
         else
