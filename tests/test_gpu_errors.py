@@ -69,3 +69,18 @@ def test_python_side_shape_checks():
         c.set_tangents(np.zeros((3, 64)))
     c.close()
     assert _lib.load().fds_last_error(None) is not None
+
+
+@gpu
+def test_empty_run_and_minimum_sizes():
+    """Degenerate but legal inputs: zero steps (reference RunWrapper reshapes J to (0, n_qoi)), the
+    smallest ring the stencil allows, a single tangent."""
+    u0 = np.array([1.0, 2.0, 3.0, 4.0])
+    run = fds_b200.L96(4)
+    u1, J = run(u0, 0.1, 0)
+    assert np.array_equal(u1, u0) and J.shape == (0, 2)
+    u1, J = run(u0, 0.1, 1)
+    assert J.shape == (1, 2) and np.isfinite(u1).all()
+    np.random.seed(0)
+    Jm, G = fds_b200.shadowing(run, u0, 0.1, 1, 2, 2, 0, epsilon=1e-5)      # m = 1, 2 segments of 2 steps
+    assert Jm.shape == (2,) and G.shape == (2,) and np.isfinite(G).all()
