@@ -129,3 +129,21 @@ def test_sweep_sensitivities_are_consistent_with_the_slope_of_the_averages():
     for q, tol in ((1, 0.2), (0, 0.5)):                  # <x^2> is the well-resolved objective, <x> is noisier
         slope = np.polyfit(params, Jb[:, q], 1)[0]
         assert abs(Gb[:, q].mean() - slope) < tol * abs(slope), (q, Gb[:, q].mean(), slope)
+
+
+@gpu
+def test_batched_fast_math_is_close_to_exact():
+    B, N, m, steps, eps = 3, 256, 6, 10, 1e-4
+    rng = np.random.RandomState(8)
+    params = np.array([0.0, 0.3, -0.3])
+    U = np.stack([plugins.run_l96_rk4(rng.rand(N), s, 30)[0] for s in params])
+    V, v = rng.randn(B, m, N) / np.sqrt(N), rng.randn(B, N) / np.sqrt(N)
+    out = []
+    for math in ('exact', 'fast'):
+        bc = Context(N, m, batch=B, math=math)
+        bc.set_batch_params(params)
+        out.append(bc.run_segment_host(U, V, v, 0.0, eps, steps))
+        bc.close()
+    (ue, Ve, ve, Je), (uf, Vf, vf, Jf) = out
+    assert maxrel(uf, ue) < 1e-13 and maxrel(Jf, Je) < 1e-13 and not np.array_equal(uf, ue)
+    assert maxrel(Vf, Ve) < 1e-6            # FD tangents amplify rounding by 1 / eps
