@@ -271,7 +271,9 @@ inline StripPlan make_strip_plan(long long n, long long H, long long max_strips)
     StripPlan p;
     if (max_strips < 1) max_strips = 1;
     const long long lo = -8 * (H - 1), hi = n + 4 * (H - 1);
-    // the coarsest node (fewest partials to reduce afterwards) that lengthens a strip by <= 2 %
+    // the coarsest node (fewest partials to reduce afterwards) that lengthens a strip by <= 0.5 %
+    // (the march is serial along a strip, so its length IS the kernel time: at N = 2^24, M = 34 nodes of 1024
+    // sites round 14.7 nodes up to 15 = +1.7 %, nodes of 256 sites give the same length as 64-site leaves)
     long long ls6 = 0;
     for (int e = kLeafShift + kMaxNodeLevels; e >= kLeafShift; --e) {
         const long long g = 1LL << e;
@@ -286,7 +288,7 @@ inline StripPlan make_strip_plan(long long n, long long H, long long max_strips)
                 ls6 = ((s6 + max_strips - 1) / max_strips + kLeafSites - 1) / kLeafSites * kLeafSites;
                 if (ls6 < kLeafSites) ls6 = kLeafSites;
             }
-            if (ls * 50 > ls6 * 51) continue;
+            if (ls * 200 > ls6 * 201) continue;
         }
         p.a0 = a0;
         p.ls = ls;

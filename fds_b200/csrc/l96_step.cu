@@ -15,6 +15,7 @@
 //   coalesced across the columns of a site.  Objective sums (sum x, sum x^2 per
 //   column) are accumulated on the fly in a specified binary tree.
 #include <algorithm>
+#include <cstdlib>
 #include "kernels.h"
 #include "l96_march.cuh"
 #include "l96_march2.cuh"
@@ -39,6 +40,7 @@ struct StreamParams {
     int fuse2;                                 // 1: two steps per pass (l96_march2.cuh)
     const double2* Fpp;                        // per-problem (F0, Flast) of a batch, or nullptr
     int spp;                                   // strips per problem (batch)
+    int skew;                                  // two steps per pass: clocks by which the upper half of the warps starts late
     Rk4Coef c;
 };
 
@@ -257,6 +259,14 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
         const double2 f = p.Fpp[strip / p.spp];
         F = (k == p.M - 1) ? f.y : f.x;
     }
+    if (MODE == 2 && p.skew > 0 && (warp & 4)) {
+        // The two warps of a scheduler (w, w + 4) alternate between a long FP64-bound phase (the 8 pushes of a block)
+        // and a short FP64-free one (leaf counters, barriers, copies).  Sharing the FP64 pipe fairly keeps them in
+        // step, so the FP64-free phases coincide and the pipe idles; half a block of skew lets one warp's FP64-free
+        // phase hide behind the other's pushes, and fair sharing preserves the offset.
+        const long long t0 = clock64();
+        while (clock64() - t0 < p.skew) { }
+    }
     if (MODE == 1) l96_march_t<MP, STATS, EulerPipe<MP>>(io, g, F, p.c);
     else if (MODE == 2) l96_rk4_march2_t<MP, STATS>(io, g, F, p.c);
     else l96_march_t<MP, STATS, Rk4Pipe<MP>>(io, g, F, p.c);
@@ -267,6 +277,11 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
 static int producer_dedicated() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("FDS_PRODUCER"); v = (e && e[0] == 'i') ? 0 : 1; }
+    return v;
+}
+static int two_step_skew() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FDS_SKEW"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
     return v;
 }
 int two_step_runs_per_cta(int M) { return M <= 256 ? 256 / M : 0; }
@@ -326,6 +341,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
     p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
     p.jpart2 = a.jpart2; p.fuse2 = fuse2;
+    p.skew = fuse2 ? two_step_skew() : 0;
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = p.pack ? (int)((plan.nstrips * a.M + p.nconsumer - 1) / p.nconsumer)
                             : (int)((plan.nstrips + p.R - 1) / p.R);
