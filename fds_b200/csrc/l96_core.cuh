@@ -198,6 +198,21 @@ struct LeafStack {
         leaf = t2;
         return b0 && b1 && b2;
     }
+    // The same counter without the leaf output: the eighth push (b == 7) leaves s0, s1, s2 untouched, so the
+    // leaf sum can be formed LATER from the unchanged state by leaf(p) -- the hot loop then carries no branch
+    // and no live leaf value between the push and the (rare) node update.
+    FDS_HD void push_state(double p, int b) {
+        const bool b0 = (b & 1) != 0, b1 = (b & 2) != 0, b2 = (b & 4) != 0;
+        const double t0 = s0 + p;
+        const double p1 = b0 ? t0 : p;
+        s0 = b0 ? s0 : p;
+        const double t1 = s1 + p1;
+        const double p2 = b1 ? t1 : p1;
+        s1 = (b0 && !b1) ? p1 : s1;
+        s2 = (b0 && b1 && !b2) ? p2 : s2;
+    }
+    // leaf sum after the eighth push_state(p, 7): s2 + (s1 + (s0 + p)), the operation order of push()
+    FDS_HD double leaf(double p) const { return s2 + (s1 + (s0 + p)); }
 };
 
 template <int MAXL>

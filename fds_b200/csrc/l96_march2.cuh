@@ -59,6 +59,21 @@ FDS_HD void march2_leaf(IO& io, StepStats& s, const MarchGeom& g, int step, int 
     }
 }
 
+// Unchecked blocks: the leaf counters advance branch-free right after site 2 (march2_block) and the leaf that
+// completed in this block -- one block in eight per step -- is folded into the node counter at the END of the
+// block, from the counter state the eighth push left untouched.  Same operations in the same order as
+// march2_leaf, but the eight pushes and the counter updates form ONE basic block, so the integer/select work
+// of the counters issues in the slots the FP64 pipe leaves free instead of stalling behind four branches.
+template <class IO>
+FDS_HD void march2_node(IO& io, StepStats& s, const MarchGeom& g, int step, int k) {
+    double s1 = s.l1.leaf(s.b1), s2 = s.l2.leaf(s.b2);
+    const long long leaf = (g.a + 8LL * k) >> kLeafShift;
+    if (leaf < 0 || leaf * kLeafSites >= g.n) { s1 = 0.0; s2 = 0.0; }
+    NsStep<IO> view{io, step};
+    if (s.ns.push(view, s1, s2, g.node_shift - kLeafShift))
+        io.emit_node2(step, leaf >> (g.node_shift - kLeafShift), s1, s2);
+}
+
 template <class MP, int P, bool FAST, bool STATS, class IO>
 FDS_HD void march2_site(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_prev, StepStats& sa, StepStats& sb,
                         long long j1, long long j2, long long slo, long long shi, long long jlo, long long jhi,
@@ -105,16 +120,33 @@ FDS_HD void march2_block(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_pr
     FDS_M2(0);
     FDS_M2(1);
     FDS_M2(2);
-    // step 2: sites a + 8(b-2) .. a + 8(b-2) + 7 are complete (Q2 == 7 at P == 2)
-    if (STATS && b >= 2 && b - 2 < g.nblk) march2_leaf(io, sb, g, 1, b - 2);
-    // step 1: sites a + 8(b-1) .. a + 8(b-1) + 7 are complete (Q1 == 7 at P == 2)
-    if (STATS && b >= 1 && b - 1 < g.nblk) march2_leaf(io, sa, g, 0, b - 1);
+    if (FAST) {
+        // unchecked blocks have 2 <= b <= nblk: both leaves exist
+        if (STATS) {
+            sb.l1.push_state(sb.b1, (b - 2) & 7);
+            sb.l2.push_state(sb.b2, (b - 2) & 7);
+            sa.l1.push_state(sa.b1, (b - 1) & 7);
+            sa.l2.push_state(sa.b2, (b - 1) & 7);
+        }
+    } else {
+        // step 2: sites a + 8(b-2) .. a + 8(b-2) + 7 are complete (Q2 == 7 at P == 2)
+        if (STATS && b >= 2 && b - 2 < g.nblk) march2_leaf(io, sb, g, 1, b - 2);
+        // step 1: sites a + 8(b-1) .. a + 8(b-1) + 7 are complete (Q1 == 7 at P == 2)
+        if (STATS && b >= 1 && b - 1 < g.nblk) march2_leaf(io, sa, g, 0, b - 1);
+    }
     FDS_M2(3);
     FDS_M2(4);
     FDS_M2(5);
     FDS_M2(6);
     FDS_M2(7);
 #undef FDS_M2
+    if (FAST && STATS) {
+        const int k2 = (b - 2) & 7, k1 = (b - 1) & 7;
+        if (k2 == 7 || k1 == 7) {
+            if (k2 == 7) march2_node(io, sb, g, 1, b - 2);
+            if (k1 == 7) march2_node(io, sa, g, 0, b - 1);
+        }
+    }
 }
 
 template <class MP, bool STATS, class IO>

@@ -40,6 +40,7 @@ struct StreamParams {
     int fuse2;                                 // 1: two steps per pass (l96_march2.cuh)
     const double2* Fpp;                        // per-problem (F0, Flast) of a batch, or nullptr
     int spp;                                   // strips per problem (batch)
+    int prefetch;                              // shared-producer mode: blocks in flight ahead of the consumers (<= nstages - 2)
     int skew;                                  // two steps per pass: clocks by which the upper half of the warps starts late
     Rk4Coef c;
 };
@@ -113,8 +114,7 @@ struct StreamIO {
     int M;
     FDS_D int cols() const { return MC > 0 ? MC : M; }
     int nstages;
-    uint64_t* full;
-    uint64_t* empty;
+    uint32_t full_s;         // shared-window address of full[0]; empty[s] = full[kMaxStages + s]
     double* yrow;            // output cursor: site a + 8b - 3 of this thread's column
     double* jp;              // node 0, already offset by column (or nullptr)
     double* jp2;             // the same for the second step of a two-step pass
@@ -131,14 +131,14 @@ struct StreamIO {
     const double* cur;
 
     FDS_D void begin_block(int) {
-        mbar_wait(&full[st], par);
+        mbar_wait_s(full_s + 8u * (uint32_t)st, par);
         cur = sdata + (size_t)st * stage_stride;
     }
     FDS_D double load(int p) const { return cur[p * cols()]; }
     FDS_D void store(int p, double v) { yrow[p * cols()] = v; }
     FDS_D void end_block(int) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
+        if (lane == 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + st));
         if (prod != nullptr) {
             if (!prod->done()) {
                 if (turn == warp) prod->issue();
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
         }
     } else {
         // prologue: warp 0 fills all but two stages; every warp tracks the producer position
-        for (int j = 0; j < p.nstages - 2 && !prod.done(); ++j) {
+        for (int j = 0; j < p.prefetch && !prod.done(); ++j) {
             if (warp == 0) prod.issue();
             prod.advance();
         }
@@ -237,8 +237,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.stage_stride = stage_stride;
     io.M = p.M;
     io.nstages = p.nstages;
-    io.full = full;
-    io.empty = empty;
+    io.full_s = smem_u32(full);
     // output cursor of the first block: site a - 16 - 3 (b = -2), or a - 24 - 11 (b = -3, two steps per pass)
     io.yrow = p.Y + (MODE == 2 ? g.a - 8 * 3 - 11 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
@@ -277,6 +276,15 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
 static int producer_dedicated() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("FDS_PRODUCER"); v = (e && e[0] == 'i') ? 0 : 1; }
+    return v;
+}
+// Blocks the shared producer keeps in flight.  A block of the two-step kernel takes ~1.4 us, far above the HBM
+// latency, so a short distance is enough -- and every stage NOT in flight is slack between the fastest and
+// the slowest warp of the CTA (the producer of block c + d reuses the stage of block c + d - nstages, which
+// every warp must have left): d = 6 of 8 stages made the fetching warp wait ~1000 clocks for a straggler.
+static int stream_prefetch() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("FDS_PREFETCH"); v = e ? atoi(e) : 6; if (v < 1) v = 1; }
     return v;
 }
 static int two_step_skew() {
@@ -342,6 +350,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
     p.jpart2 = a.jpart2; p.fuse2 = fuse2;
     p.skew = fuse2 ? two_step_skew() : 0;
+    p.prefetch = std::max(1, std::min(nst - 2, stream_prefetch()));
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = p.pack ? (int)((plan.nstrips * a.M + p.nconsumer - 1) / p.nconsumer)
                             : (int)((plan.nstrips + p.R - 1) / p.R);
