@@ -95,6 +95,18 @@ FDS_D void mbar_wait_s(uint32_t bar, uint32_t parity) {
             : "memory");
     } while (ok == 0);
 }
+// non-blocking probe of a phase (never suspends the thread)
+FDS_D bool mbar_test_s(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 FDS_D void mbar_arrive_s(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }

@@ -60,6 +60,9 @@ struct HostIO2 {
         }
     }
     bool all(bool v) const { return v; }
+    void mid_block() {}
+    int warp_max(int v) const { return v; }
+    int warp_min(int v) const { return v; }
     double ns[2][kMaxNodeLevels + 1][2];
     double ns_get2(int st, int l, int q) const { return ns[st][l][q]; }
     void ns_put2(int st, int l, int q, double v) { ns[st][l][q] = v; }

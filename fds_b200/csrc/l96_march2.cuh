@@ -14,7 +14,9 @@
 // on) to b = nblk + 1 (drain of the 15-site lag).
 //
 // IO policy: as in l96_march.cuh, with the output cursor at site a + 8b - 11 and the per-step
-// variants   emit_node2(step, node, s1, s2),   ns_get2(step, level, which),   ns_put2(step, level, which, v).
+// variants   emit_node2(step, node, s1, s2),   ns_get2(step, level, which),   ns_put2(step, level, which, v),
+// plus   mid_block()  (called once inside every unchecked block; may probe the next block's input)   and
+// warp_max(int) / warp_min(int)  (reductions over the lanes that share a code path; identity for one thread).
 #pragma once
 #include "l96_march.cuh"
 
@@ -136,6 +138,7 @@ FDS_HD void march2_block(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_pr
     }
     FDS_M2(3);
     FDS_M2(4);
+    if (FAST) io.mid_block();      // probe the next block's input early: the answer is there when the loop comes round
     FDS_M2(5);
     FDS_M2(6);
     FDS_M2(7);
@@ -177,15 +180,30 @@ FDS_HD void l96_rk4_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef
             if (above > bfl) bfl = (int)(above < (long long)bfh + 1 ? above : (long long)bfh + 1);
         }
     }
+    // a warp stays on ONE code path: the unchecked range common to all its lanes (they may sit on two strips),
+    // computed once, so the loops below compare warp-uniform integers and carry no vote
+    bfl = io.warp_max(bfl);
+    bfh = io.warp_min(bfh);
+    const int last = g.nblk + 1;
+    int b = kFuse2First;
+    // checked head [first, bfl), unchecked body [bfl, bfh], checked tail (bfh, last]: pass 0 = head + body, pass 1 = tail
 #pragma unroll 1
-    for (int b = kFuse2First; b <= g.nblk + 1; ++b) {
-        io.begin_block(b);
-        const bool fast = b >= bfl && b <= bfh;
-        if (io.all(fast))
-            march2_block<MP, true, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
-        else
+    for (int pass = 0; pass < 2; ++pass) {
+        const int stop = pass == 0 ? (bfl < last + 1 ? bfl : last + 1) : last + 1;
+#pragma unroll 1
+        for (; b < stop; ++b) {
+            io.begin_block(b);
             march2_block<MP, false, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
-        io.end_block(b);
+            io.end_block(b);
+        }
+        if (pass == 0) {
+#pragma unroll 1
+            for (; b <= bfh; ++b) {
+                io.begin_block(b);
+                march2_block<MP, true, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
+                io.end_block(b);
+            }
+        }
     }
 }
 

@@ -126,26 +126,37 @@ struct StreamIO {
     StreamProducer* prod;    // shared-producer mode: every consumer warp carries the producer state
     int warp, nwarps, turn;  // whose turn it is to fetch
     // ring position
-    int st;
+    int st, prev_st;         // prev_st: stage of the previous block, not yet released (-1: none)
     uint32_t par;
+    bool ready;              // this block's `full` phase was already seen complete by mid_block()
     const double* cur;
 
+    // The stage of block c is released at the START of block c + 1 and the `full` barrier of block c + 1 is
+    // probed in the MIDDLE of block c (mid_block): both then sit inside straight-line code, where their
+    // latencies hide behind the FP64 stream, instead of serialising at the loop boundary.
     FDS_D void begin_block(int) {
-        mbar_wait_s(full_s + 8u * (uint32_t)st, par);
+        if (!ready) mbar_wait_s(full_s + 8u * (uint32_t)st, par);
+        ready = false;
         cur = sdata + (size_t)st * stage_stride;
+        __syncwarp();                    // every lane has consumed the previous block's stage
+        if (lane == 0 && prev_st >= 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + prev_st));
     }
+    FDS_D void mid_block() {
+        const bool wrap = st + 1 == nstages;
+        ready = mbar_test_s(full_s + 8u * (uint32_t)(wrap ? 0 : st + 1), wrap ? par ^ 1u : par);
+    }
+    FDS_D int warp_max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
+    FDS_D int warp_min(int v) const { return __reduce_min_sync(0xffffffffu, v); }
     FDS_D double load(int p) const { return cur[p * cols()]; }
     FDS_D void store(int p, double v) { yrow[p * cols()] = v; }
     FDS_D void end_block(int) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + st));
         if (prod != nullptr) {
-            if (!prod->done()) {
-                if (turn == warp) prod->issue();
-                prod->advance();
-            }
+            const bool more = !prod->done();
+            if (more && turn == warp) prod->issue();
+            if (more) prod->advance();
             if (++turn == nwarps) turn = 0;
         }
+        prev_st = st;
         if (++st == nstages) { st = 0; par ^= 1u; }
         yrow += 8 * cols();
     }
@@ -249,8 +260,9 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.lane = lane;
     io.prod = p.dedicated ? nullptr : &prod;
     io.warp = warp; io.nwarps = nwarps; io.turn = 0;
-    io.st = 0;
+    io.st = 0; io.prev_st = -1;
     io.par = 0;
+    io.ready = false;
     io.cur = io.sdata;
 
     double F = (k == p.M - 1) ? p.Flast : p.F0;
@@ -284,7 +296,7 @@ static int producer_dedicated() {
 // every warp must have left): d = 6 of 8 stages made the fetching warp wait ~1000 clocks for a straggler.
 static int stream_prefetch() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("FDS_PREFETCH"); v = e ? atoi(e) : 6; if (v < 1) v = 1; }
+    if (v < 0) { const char* e = getenv("FDS_PREFETCH"); v = e ? atoi(e) : 4; if (v < 1) v = 1; }
     return v;
 }
 static int two_step_skew() {
