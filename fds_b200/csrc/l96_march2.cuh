@@ -15,7 +15,7 @@
 //
 // IO policy: as in l96_march.cuh, with the output cursor at site a + 8b - 11 and the per-step
 // variants   emit_node2(step, node, s1, s2),   ns_get2(step, level, which),   ns_put2(step, level, which, v),
-// plus   mid_block()  (called once inside every unchecked block; may probe the next block's input)   and
+// plus   mid_block()  (called once inside EVERY block: ring bookkeeping, probe of the next block's input)   and
 // warp_max(int) / warp_min(int)  (reductions over the lanes that share a code path; identity for one thread).
 #pragma once
 #include "l96_march.cuh"
@@ -138,7 +138,7 @@ FDS_HD void march2_block(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_pr
     }
     FDS_M2(3);
     FDS_M2(4);
-    if (FAST) io.mid_block();      // probe the next block's input early: the answer is there when the loop comes round
+    io.mid_block();                // ring bookkeeping + early probe of the next block's input, hidden in the FP64 stream
     FDS_M2(5);
     FDS_M2(6);
     FDS_M2(7);

@@ -41,7 +41,6 @@ struct StreamParams {
     const double2* Fpp;                        // per-problem (F0, Flast) of a batch, or nullptr
     int spp;                                   // strips per problem (batch)
     int prefetch;                              // shared-producer mode: blocks in flight ahead of the consumers (<= nstages - 2)
-    int skew;                                  // two steps per pass: clocks by which the upper half of the warps starts late
     Rk4Coef c;
 };
 
@@ -82,7 +81,8 @@ struct StreamProducer {
     }
     FDS_D bool done() const { return it >= nit; }
     // fetch block `it` (8 input sites of every strip) into stage `st`
-    FDS_D void issue() {
+    FDS_D void issue() { issue_at(it, st, par); }
+    FDS_D void issue_at(int it, int st, uint32_t par) {
         uint64_t* empty = full + kMaxStages;
         const int R = P->R, M = P->M, stage_stride = R * P->run_stride;
         const uint32_t chunk_bytes = (uint32_t)(8 * M * sizeof(double));
@@ -107,7 +107,9 @@ struct StreamProducer {
 
 // MC = number of columns when known at compile time (every p*M offset becomes an immediate),
 // 0 = use the run-time value
-template <int MC>
+// MID = the march calls mid_block() once in EVERY block (two-steps-per-pass kernel): all ring bookkeeping then
+// happens there, inside straight-line code, and the block boundary carries only the (rare) copy issue.
+template <int MC, bool MID = false>
 struct StreamIO {
     const double* sdata;     // this thread's (run, column) slot in stage 0
     int stage_stride;        // doubles per stage
@@ -126,38 +128,70 @@ struct StreamIO {
     StreamProducer* prod;    // shared-producer mode: every consumer warp carries the producer state
     int warp, nwarps, turn;  // whose turn it is to fetch
     // ring position
-    int st, prev_st;         // prev_st: stage of the previous block, not yet released (-1: none)
+    int st;
     uint32_t par;
-    bool ready;              // this block's `full` phase was already seen complete by mid_block()
     const double* cur;
+    // MID only
+    int prev_st;             // stage of the previous block, not yet released (-1: none)
+    int blk, ahead;          // blocks begun so far; blocks the copies run ahead of the consumers
+    int pst;                 // stage and parity of the copy this warp owes at the end of the block (if `mine`)
+    uint32_t ppar;
+    bool mine;
+    bool ready;              // this block's `full` phase was already seen complete by mid_block()
 
-    // The stage of block c is released at the START of block c + 1 and the `full` barrier of block c + 1 is
-    // probed in the MIDDLE of block c (mid_block): both then sit inside straight-line code, where their
-    // latencies hide behind the FP64 stream, instead of serialising at the loop boundary.
+    // Two-steps-per-pass kernel (MID): the ring bookkeeping of block c -- probe of block c + 1's `full` barrier,
+    // whose turn it is to fetch, stage / parity of the next block -- runs in the
+    // MIDDLE of block c (mid_block), inside straight-line code where its latencies hide behind the FP64 stream.
+    // The producer position is a function of the consumer's (block c + `ahead` goes into stage st + ahead), so
+    // no separate producer state is carried.  The other kernels keep everything at the block boundary.
     FDS_D void begin_block(int) {
-        if (!ready) mbar_wait_s(full_s + 8u * (uint32_t)st, par);
-        ready = false;
+        if (MID) {
+            if (!ready) mbar_wait_s(full_s + 8u * (uint32_t)st, par);
+            // release the previous block's stage (a warp-wide sync ends a basic block: keep it at the boundary)
+            __syncwarp();                // every lane has consumed it
+            if (lane == 0 && prev_st >= 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + prev_st));
+        } else {
+            mbar_wait_s(full_s + 8u * (uint32_t)st, par);
+        }
         cur = sdata + (size_t)st * stage_stride;
-        __syncwarp();                    // every lane has consumed the previous block's stage
-        if (lane == 0 && prev_st >= 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + prev_st));
     }
     FDS_D void mid_block() {
+        if (!MID) return;
+        // copy duty of this block: block blk + ahead into stage st + ahead (mod nstages)
+        const int pit = blk + ahead;
+        int pst_ = st + ahead;
+        const bool pwrap = pst_ >= nstages;
+        pst = pwrap ? pst_ - nstages : pst_;
+        ppar = pwrap ? par ^ 1u : par;
+        mine = (turn == warp) & (pit < prod->nit);
+        turn = (turn + 1 == nwarps) ? 0 : turn + 1;
+        // next block
         const bool wrap = st + 1 == nstages;
-        ready = mbar_test_s(full_s + 8u * (uint32_t)(wrap ? 0 : st + 1), wrap ? par ^ 1u : par);
+        prev_st = st;
+        st = wrap ? 0 : st + 1;
+        par = wrap ? par ^ 1u : par;
+        ++blk;
+        ready = mbar_test_s(full_s + 8u * (uint32_t)st, par);
     }
     FDS_D int warp_max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
     FDS_D int warp_min(int v) const { return __reduce_min_sync(0xffffffffu, v); }
     FDS_D double load(int p) const { return cur[p * cols()]; }
     FDS_D void store(int p, double v) { yrow[p * cols()] = v; }
     FDS_D void end_block(int) {
-        if (prod != nullptr) {
-            const bool more = !prod->done();
-            if (more && turn == warp) prod->issue();
-            if (more) prod->advance();
-            if (++turn == nwarps) turn = 0;
+        if (MID) {
+            if (mine) prod->issue_at(blk - 1 + ahead, pst, ppar);
+        } else {
+            __syncwarp();
+            if (lane == 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + st));
+            if (prod != nullptr) {
+                if (!prod->done()) {
+                    if (turn == warp) prod->issue();
+                    prod->advance();
+                }
+                if (++turn == nwarps) turn = 0;
+            }
+            if (++st == nstages) { st = 0; par ^= 1u; }
         }
-        prev_st = st;
-        if (++st == nstages) { st = 0; par ^= 1u; }
         yrow += 8 * cols();
     }
     FDS_D void emit_node(long long node, double s1, double s2) {
@@ -243,7 +277,7 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     g.stats = p.jpart != nullptr;
     g.node_shift = p.node_shift;
 
-    StreamIO<MC> io;
+    StreamIO<MC, MODE == 2> io;
     io.sdata = sdata + r * p.run_stride + k;
     io.stage_stride = stage_stride;
     io.M = p.M;
@@ -262,21 +296,14 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.warp = warp; io.nwarps = nwarps; io.turn = 0;
     io.st = 0; io.prev_st = -1;
     io.par = 0;
-    io.ready = false;
+    io.ready = false; io.mine = false;
+    io.blk = 0; io.ahead = p.prefetch; io.pst = 0; io.ppar = 0;
     io.cur = io.sdata;
 
     double F = (k == p.M - 1) ? p.Flast : p.F0;
     if (p.Fpp != nullptr) {
         const double2 f = p.Fpp[strip / p.spp];
         F = (k == p.M - 1) ? f.y : f.x;
-    }
-    if (MODE == 2 && p.skew > 0 && (warp & 4)) {
-        // The two warps of a scheduler (w, w + 4) alternate between a long FP64-bound phase (the 8 pushes of a block)
-        // and a short FP64-free one (leaf counters, barriers, copies).  Sharing the FP64 pipe fairly keeps them in
-        // step, so the FP64-free phases coincide and the pipe idles; half a block of skew lets one warp's FP64-free
-        // phase hide behind the other's pushes, and fair sharing preserves the offset.
-        const long long t0 = clock64();
-        while (clock64() - t0 < p.skew) { }
     }
     if (MODE == 1) l96_march_t<MP, STATS, EulerPipe<MP>>(io, g, F, p.c);
     else if (MODE == 2) l96_rk4_march2_t<MP, STATS>(io, g, F, p.c);
@@ -297,11 +324,6 @@ static int producer_dedicated() {
 static int stream_prefetch() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("FDS_PREFETCH"); v = e ? atoi(e) : 4; if (v < 1) v = 1; }
-    return v;
-}
-static int two_step_skew() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("FDS_SKEW"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
     return v;
 }
 int two_step_runs_per_cta(int M) { return M <= 256 ? 256 / M : 0; }
@@ -361,7 +383,6 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
     p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
     p.jpart2 = a.jpart2; p.fuse2 = fuse2;
-    p.skew = fuse2 ? two_step_skew() : 0;
     p.prefetch = std::max(1, std::min(nst - 2, stream_prefetch()));
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = p.pack ? (int)((plan.nstrips * a.M + p.nconsumer - 1) / p.nconsumer)
