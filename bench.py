@@ -126,12 +126,17 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.power, self.power_limit = [], None
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            try:
+                self.power_limit = pynvml.nvmlDeviceGetEnforcedPowerLimit(self.h) / 1000.0
+            except Exception:
+                pass
         except Exception:
             self.nv = None
 
@@ -146,6 +151,10 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
                 for k, bit in names.items():
                     if r & bit:
@@ -158,7 +167,8 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         self.join(timeout=1.0)
         return {'sm_mhz': float(np.median(self.samples)) if self.samples else None,
-                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'power_w': float(np.median(self.power)) if self.power else None, 'power_limit_w': self.power_limit}
 
 
 # --------------------------------------------------------------------------- #
@@ -350,6 +360,15 @@ def run_ours(args):
             traffic, fp64_pct = prof['dram_bytes_per_launch'], prof.get('fp64_pipe_busy_pct')
         except Exception:
             pass
+        # FP64-pipe utilisation of the step kernel from the live numbers: FP64 warp-instructions per launch
+        # (static count of the hot loop, DESIGN 4.1: 484 per 8-site block of two steps = 30.25 per update in exact
+        # mode with the objective sums) over what 4 schedulers x 1 instruction per 2 clocks issue at the SM clock
+        # sampled during the timed region
+        fp64_live = None
+        if clocks.get('sm_mhz') and args.math == 'exact' and steps_per_launch == 2 and torch.cuda.is_available():
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            winst = n_local * M * steps_per_launch * 30.25 / 32.0
+            fp64_live = 100.0 * winst / (kms * 1e-3 * clocks['sm_mhz'] * 1e6 * sms * 4 * 0.5)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
@@ -360,7 +379,7 @@ def run_ours(args):
                              'algorithmic_bytes_per_launch': alg_bytes, 'time_steps_per_launch': steps_per_launch,
                              'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s',
                              'frac_of_nominal_8TBs': achieved / 8000.0,
-                             'fp64_pipe_busy_pct_ncu': fp64_pct,
+                             'fp64_pipe_busy_pct_ncu': fp64_pct, 'fp64_pipe_busy_pct_live': fp64_live,
                              'step_kernel_share_of_time': kms * (S / steps_per_launch) * args.steps / total_ms,
                              'note': ('temporal blocking: one launch advances %g time steps, so DRAM traffic per launch '
                                       '(`traffic`) is 1/%g of the algorithmic bytes and `frac` can exceed 1; the kernel is '
