@@ -227,7 +227,8 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         if (const char* e = getenv("FDS_BATCH_CTAS_PER_SM")) c->ctas_per_sm = atoi(e) == 1 ? 1 : 2;
         {   // two RK4 steps per pass (one 256-thread CTA per SM), as for a single problem
             const char* e = getenv("FDS_FUSE2");
-            c->fuse2 = (e ? e[0] != '0' : true) && cfg->system == FDS_SYS_L96_RK4 && two_step_runs_per_cta(c->M) >= 1;
+            c->fuse2 = (e ? e[0] != '0' : true) && (cfg->system == FDS_SYS_L96_RK4 || cfg->system == FDS_SYS_L96_EULER) &&
+                       two_step_runs_per_cta(c->M) >= 1;
             if (c->fuse2) c->ctas_per_sm = 1;
         }
         // strips per CTA: two CTAs of <= 256 threads per SM, or one of <= 480 with a producer warp
@@ -269,7 +270,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         {
             const char* e = getenv("FDS_FUSE2");
             const bool want = e ? e[0] != '0' : true;
-            c->fuse2 = want && c->stream_ok && cfg->system == FDS_SYS_L96_RK4 && two_step_runs_per_cta(c->M) >= 1 && H >= 2;
+            c->fuse2 = want && c->stream_ok && two_step_runs_per_cta(c->M) >= 1 && H >= 2;   // RK4 and forward Euler
             if (c->fuse2) { R = two_step_runs_per_cta(c->M); c->runs_per_cta = R; }
         }
         long long max_strips = (long long)c->num_sms * (R >= 1 ? R : 1);

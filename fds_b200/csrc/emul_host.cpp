@@ -113,6 +113,23 @@ int emul_l96_rk4_step2(const double* X, double* Y, int M, long long n, long long
     return 0;
 }
 
+// two forward-Euler steps in one pass
+int emul_l96_euler_step2(const double* X, double* Y, int M, long long n, long long H,
+                         const double* F /*[M]*/, double dt, int exact, long long max_strips, double* jpart1,
+                         double* jpart2) {
+    StripPlan plan = make_strip_plan(n, H, max_strips);
+    Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+    for (long long s = 0; s < plan.nstrips; ++s) {
+        for (int k = 0; k < M; ++k) {
+            HostIO2 io{X, Y, {jpart1, jpart2}, plan.nnode, plan.a0 + s * plan.ls, M, k};
+            MarchGeom g{io.a, n, plan.nblk, jpart1 != nullptr, plan.node_shift};
+            if (exact) l96_euler_march2<ExactMath>(io, g, F[k], c);
+            else       l96_euler_march2<FastMath>(io, g, F[k], c);
+        }
+    }
+    return 0;
+}
+
 // the same with the forward-Euler pipe
 int emul_l96_euler_step(const double* X, double* Y, int M, long long n, long long H,
                         const double* F /*[M]*/, double dt, int exact, long long max_strips, double* jpart) {

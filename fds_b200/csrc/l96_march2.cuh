@@ -1,6 +1,7 @@
-// Two RK4 steps per pass: the per-thread body of the temporally blocked streaming kernel.
+// Two time steps per pass: the per-thread body of the temporally blocked streaming kernel (RK4, or forward
+// Euler through the same push/lag interface).
 //
-// A second Rk4Pipe is chained behind the first: the step-1 value that leaves pipe 1 (site i-7 for a
+// A second pipe (Rk4Pipe / EulerPipe) is chained behind the first: the step-1 value that leaves pipe 1 (site i-7 for a
 // push of site i) is pushed into pipe 2 ONE PUSH LATER (so that the eight stage computations of a push
 // -- four per pipe -- are all independent), whose output is the step-2 value at site i-15.  The
 // intermediate state never touches shared or global memory, so a site is read once and written once
@@ -76,8 +77,8 @@ FDS_HD void march2_node(IO& io, StepStats& s, const MarchGeom& g, int step, int 
         io.emit_node2(step, leaf >> (g.node_shift - kLeafShift), s1, s2);
 }
 
-template <class MP, int P, bool FAST, bool STATS, class IO>
-FDS_HD void march2_site(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_prev, StepStats& sa, StepStats& sb,
+template <class MP, class PIPE, int P, bool FAST, bool STATS, class IO>
+FDS_HD void march2_site(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats& sa, StepStats& sb,
                         long long j1, long long j2, long long slo, long long shi, long long jlo, long long jhi,
                         double F, const Rk4Coef& c) {
     // pipe 2 is fed the step-1 value of the PREVIOUS push (site i - 8 for pipe 1's index i = P mod 8):
@@ -113,12 +114,12 @@ FDS_HD void march2_site(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_pre
     }
 }
 
-template <class MP, bool FAST, bool STATS, class IO>
-FDS_HD void march2_block(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_prev, StepStats& sa, StepStats& sb,
+template <class MP, class PIPE, bool FAST, bool STATS, class IO>
+FDS_HD void march2_block(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats& sa, StepStats& sb,
                          const MarchGeom& g, int b, long long slo, long long shi, long long jlo, long long jhi,
                          double F, const Rk4Coef& c) {
     const long long j1 = g.a + 8LL * b - 3, j2 = g.a + 8LL * b - 11;
-#define FDS_M2(P) march2_site<MP, P, FAST, STATS>(io, p1, p2, x1_prev, sa, sb, j1, j2, slo, shi, jlo, jhi, F, c)
+#define FDS_M2(P) march2_site<MP, PIPE, P, FAST, STATS>(io, p1, p2, x1_prev, sa, sb, j1, j2, slo, shi, jlo, jhi, F, c)
     FDS_M2(0);
     FDS_M2(1);
     FDS_M2(2);
@@ -152,9 +153,11 @@ FDS_HD void march2_block(IO& io, Rk4Pipe<MP>& p1, Rk4Pipe<MP>& p2, double& x1_pr
     }
 }
 
-template <class MP, bool STATS, class IO>
-FDS_HD void l96_rk4_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
-    Rk4Pipe<MP> p1, p2;
+// PIPE: Rk4Pipe<MP> or EulerPipe<MP> (any pipe with push x[i+4] -> x'[i-3]: the chaining below only uses the lag)
+template <class MP, class PIPE, bool STATS, class IO>
+FDS_HD void l96_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
+    static_assert(PIPE::kLag == 3, "the two-step chaining assumes a lag of 3 sites per pipe");
+    PIPE p1, p2;
     p1.reset();
     p2.reset();
     StepStats sa, sb;
@@ -193,24 +196,36 @@ FDS_HD void l96_rk4_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef
 #pragma unroll 1
         for (; b < stop; ++b) {
             io.begin_block(b);
-            march2_block<MP, false, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
+            march2_block<MP, PIPE, false, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
             io.end_block(b);
         }
         if (pass == 0) {
 #pragma unroll 1
             for (; b <= bfh; ++b) {
                 io.begin_block(b);
-                march2_block<MP, true, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
+                march2_block<MP, PIPE, true, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
                 io.end_block(b);
             }
         }
     }
 }
 
+template <class MP, bool STATS, class IO>
+FDS_HD void l96_rk4_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
+    l96_march2_t<MP, Rk4Pipe<MP>, STATS>(io, g, F, c);
+}
+
 template <class MP, class IO>
 FDS_HD void l96_rk4_march2(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
-    if (g.stats) l96_rk4_march2_t<MP, true>(io, g, F, c);
-    else l96_rk4_march2_t<MP, false>(io, g, F, c);
+    if (g.stats) l96_march2_t<MP, Rk4Pipe<MP>, true>(io, g, F, c);
+    else l96_march2_t<MP, Rk4Pipe<MP>, false>(io, g, F, c);
+}
+
+// two forward-Euler steps per pass (the reference's own Lorenz-96 solver, tests/solvers/mock_fun3d/fun3d:48-57)
+template <class MP, class IO>
+FDS_HD void l96_euler_march2(IO& io, const MarchGeom& g, double F, const Rk4Coef& c) {
+    if (g.stats) l96_march2_t<MP, EulerPipe<MP>, true>(io, g, F, c);
+    else l96_march2_t<MP, EulerPipe<MP>, false>(io, g, F, c);
 }
 
 }  // namespace fds

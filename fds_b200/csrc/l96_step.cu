@@ -211,15 +211,15 @@ struct StreamIO {
     FDS_D bool all(bool v) const { return __all_sync(0xffffffffu, v); }
 };
 
-// MODE 0: RK4, 1: forward Euler, 2: RK4, two steps per pass (<= 256 threads = 2 warps per scheduler: twice the pipeline state in up to 255 registers)
+// MODE 0: RK4, 1: forward Euler, 2: RK4, two steps per pass, 3: forward Euler, two steps per pass (<= 256 threads = 2 warps per scheduler: twice the pipeline state in up to 255 registers)
 template <class MP, int MC, bool STATS, int MODE>
-__global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kernel(const __grid_constant__ StreamParams p) {
+__global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kernel(const __grid_constant__ StreamParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
     double* nsm = reinterpret_cast<double*>(smem_raw + 128);
     const int levels = p.node_shift - kLeafShift;
-    double* sdata = nsm + (size_t)(MODE == 2 ? 4 : 2) * levels * (blockDim.x - 32 * p.dedicated);
+    double* sdata = nsm + (size_t)(MODE >= 2 ? 4 : 2) * levels * (blockDim.x - 32 * p.dedicated);
 
     const int tid = threadIdx.x;
     const int nwarps = (blockDim.x >> 5) - p.dedicated;   // consumer warps
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
 
     const long long last_strip = p.nstrips - 1;
     StreamProducer prod;
-    prod.init(&p, sdata, full, lane, MODE == 2 ? -20 : -12,
-              MODE == 2 ? march2_iterations(p.nblk) : march_iterations(p.nblk));   // blocks b = -2 .. nblk (-3 .. nblk + 1)
+    prod.init(&p, sdata, full, lane, MODE >= 2 ? -20 : -12,
+              MODE >= 2 ? march2_iterations(p.nblk) : march_iterations(p.nblk));   // blocks b = -2 .. nblk (-3 .. nblk + 1)
     if (p.dedicated) {
         if (warp == nwarps) {
             while (!prod.done()) { prod.issue(); prod.advance(); }
@@ -277,14 +277,14 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     g.stats = p.jpart != nullptr;
     g.node_shift = p.node_shift;
 
-    StreamIO<MC, MODE == 2> io;
+    StreamIO<MC, MODE >= 2> io;
     io.sdata = sdata + r * p.run_stride + k;
     io.stage_stride = stage_stride;
     io.M = p.M;
     io.nstages = p.nstages;
     io.full_s = smem_u32(full);
     // output cursor of the first block: site a - 16 - 3 (b = -2), or a - 24 - 11 (b = -3, two steps per pass)
-    io.yrow = p.Y + (MODE == 2 ? g.a - 8 * 3 - 11 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
+    io.yrow = p.Y + (MODE >= 2 ? g.a - 8 * 3 - 11 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
     io.jp2 = p.jpart2 != nullptr ? p.jpart2 + 2 * k : nullptr;
     io.levels = levels;
@@ -306,7 +306,8 @@ __global__ void __launch_bounds__(MODE == 2 ? 256 : 512, 1) l96_rk4_stream_kerne
         F = (k == p.M - 1) ? f.y : f.x;
     }
     if (MODE == 1) l96_march_t<MP, STATS, EulerPipe<MP>>(io, g, F, p.c);
-    else if (MODE == 2) l96_rk4_march2_t<MP, STATS>(io, g, F, p.c);
+    else if (MODE == 2) l96_march2_t<MP, Rk4Pipe<MP>, STATS>(io, g, F, p.c);
+    else if (MODE == 3) l96_march2_t<MP, EulerPipe<MP>, STATS>(io, g, F, p.c);
     else l96_march_t<MP, STATS, Rk4Pipe<MP>>(io, g, F, p.c);
 }
 
@@ -335,7 +336,6 @@ int stream_runs_per_cta(int M) {
 cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls,
                                   int euler) {
     const int fuse2 = a.jpart2 != nullptr || a.two_steps;
-    if (fuse2 && euler) return cudaErrorInvalidValue;
     StreamParams p;
     p.X = a.X; p.Y = a.Y; p.jpart = a.jpart; p.nnode = plan.nnode;   // a.jpart: [nnode][M][2]
     p.n = a.n;
@@ -397,7 +397,8 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
         l96_rk4_stream_kernel<MP, MC, ST, EU><<<grid, block, smem, st>>>(p);                                       \
     } while (0)
 #define FDS_STREAM_LAUNCH(MP, MC, ST) \
-    do { if (euler) FDS_STREAM_LAUNCH2(MP, MC, ST, 1); else if (fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 2); \
+    do { if (euler && fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 3); else if (euler) FDS_STREAM_LAUNCH2(MP, MC, ST, 1); \
+         else if (fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 2); \
          else FDS_STREAM_LAUNCH2(MP, MC, ST, 0); } while (0)
 #define FDS_STREAM_MC(MP, ST)                                      \
     do {                                                           \

@@ -96,12 +96,16 @@ def test_streaming_march_matches_oracle(emul, N, M, H, max_strips, exact, scheme
         assert np.abs(got - Xo).max() < 1e-13 and (scheme == 'euler' or not np.array_equal(got, Xo))
 
 
+@pytest.mark.parametrize('scheme', ['rk4', 'euler'])
 @pytest.mark.parametrize('N,M,H,max_strips,exact', [
     (200, 5, 4, 7, 1), (40, 18, 2, 4, 1), (37, 3, 2, 64, 1), (1024, 4, 4, 16, 1), (4096, 2, 2, 37, 1),
     (333, 1, 3, 1, 1), (200, 5, 4, 7, 0), (4, 2, 3, 5, 1), (640, 3, 6, 3, 1), (5000, 2, 2, 2, 1),
     (64, 2, 2, 1, 1), (128, 1, 2, 2, 1), (70000, 1, 2, 5, 1)])
-def test_two_steps_per_pass_march_matches_oracle(emul, N, M, H, max_strips, exact):
-    """l96_march2.cuh: two chained RK4 pipes, both steps' objective partials -- bit for bit two oracle steps."""
+def test_two_steps_per_pass_march_matches_oracle(emul, N, M, H, max_strips, exact, scheme):
+    """l96_march2.cuh: two chained pipes (RK4, or the reference's forward Euler), both steps' objective
+    partials -- bit for bit two oracle steps."""
+    step_fn = plugins.l96_rk4_step if scheme == 'rk4' else plugins.l96_euler_step
+    emul_fn = emul.emul_l96_rk4_step2 if scheme == 'rk4' else emul.emul_l96_euler_step2
     rng = np.random.RandomState(N + M + 1)
     U = rng.rand(M, N) * 6 - 1
     F = 8.0 + np.r_[np.zeros(M - 1), 1e-4] if M > 1 else np.array([8.1])
@@ -112,12 +116,12 @@ def test_two_steps_per_pass_march_matches_oracle(emul, N, M, H, max_strips, exac
     bufB = np.full_like(bufA, np.nan)
     nleaf = pl['nnode']
     npass = H // 2
-    Xo, Jo = plugins.run_l96_ensemble(plugins.l96_rk4_step, U, F, 2 * npass)
+    Xo, Jo = plugins.run_l96_ensemble(step_fn, U, F, 2 * npass)
     for j in range(npass):
         jp = [np.full((nleaf, M, 2), np.nan) for _ in range(2)]
         with np.errstate(all='ignore'):
-            emul.emul_l96_rk4_step2(ptr(bufA, -alo * M), ptr(bufB, -alo * M), M, LL(N), LL(H), ptr(F),
-                                    ctypes.c_double(0.01), exact, LL(max_strips), ptr(jp[0]), ptr(jp[1]))
+            emul_fn(ptr(bufA, -alo * M), ptr(bufB, -alo * M), M, LL(N), LL(H), ptr(F),
+                    ctypes.c_double(0.01), exact, LL(max_strips), ptr(jp[0]), ptr(jp[1]))
         done = 2 * (j + 1)
         lo, hi = -8 * (H - done), N + 4 * (H - done)
         assert not np.isnan(bufB[lo - alo:hi - alo]).any()
