@@ -22,7 +22,8 @@ struct fds_ctx {
     long long alo = 0, ahi = 0;    // allocated site range of ensemble / primal arrays
     StripPlan plan{};              // fixed strip decomposition of the ensemble step kernel
     bool stream_ok = false;
-    bool fuse2 = false;            // two RK4 steps per pass of the streaming kernel (l96_march2.cuh)
+    bool fuse2 = false;            // two time steps per pass of the streaming kernel (l96_march2.cuh)
+    bool fuse4 = false;            // forward Euler: four (l96_marchk.cuh)
     long long prof_steps = 0;      // time steps covered by the profiled launches
     bool toy = false;              // small ODE system (toy_ode.cu) or host solver: no stencil, no halos
     bool host_sys = false;         // FDS_SYS_HOST: the solver runs on the host, only the algebra lives here
@@ -230,6 +231,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
             c->fuse2 = (e ? e[0] != '0' : true) && (cfg->system == FDS_SYS_L96_RK4 || cfg->system == FDS_SYS_L96_EULER) &&
                        two_step_runs_per_cta(c->M) >= 1;
             if (c->fuse2) c->ctas_per_sm = 1;
+            c->fuse4 = c->fuse2 && cfg->system == FDS_SYS_L96_EULER && H >= 4 && !(e && e[0] == '2');
         }
         // strips per CTA: two CTAs of <= 256 threads per SM, or one of <= 480 with a producer warp
         const int R2 = c->fuse2 ? two_step_runs_per_cta(c->M) : (c->ctas_per_sm == 2 ? 256 / c->M : stream_runs_per_cta(c->M));
@@ -257,7 +259,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         c->stream_ok = true;
         StripPlan& pl = c->plan;
         pl.a0 = 0; pl.ls = c->slot / c->spp; pl.nstrips = nstrips; pl.nblk = (int)(pl.ls / 8);
-        pl.alo = -20; pl.ahi = c->nall + 20; pl.node_shift = kLeafShift; pl.nnode = c->nall / kLeafSites;
+        pl.alo = -kPlanPad; pl.ahi = c->nall + kPlanPad; pl.node_shift = kLeafShift; pl.nnode = c->nall / kLeafSites;
         c->alo = pl.alo; c->ahi = pl.ahi;
         c->ds.assign(c->nb, 0.0);
         c->Fhost.assign(c->nb, make_double2(8.0, 8.0));
@@ -272,6 +274,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
             const bool want = e ? e[0] != '0' : true;
             c->fuse2 = want && c->stream_ok && two_step_runs_per_cta(c->M) >= 1 && H >= 2;   // RK4 and forward Euler
             if (c->fuse2) { R = two_step_runs_per_cta(c->M); c->runs_per_cta = R; }
+            c->fuse4 = c->fuse2 && cfg->system == FDS_SYS_L96_EULER && H >= 4 && !(e && e[0] == '2');   // FDS_FUSE2=2: at most two
         }
         long long max_strips = (long long)c->num_sms * (R >= 1 ? R : 1);
         // the two-step kernel packs (strip, column) pairs over all 256 lanes of a CTA (l96_step.cu)
@@ -696,7 +699,8 @@ static int ensure_jsum(fds_ctx* c, long long steps) {
 // (streaming kernel: node partials into jnode[jstep], reduced later in one batch by
 // reduce_nodes(); simple kernels: reduced right away into jsum[jstep])
 static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, double Flast, long long valid,
-                    long long jstep, long long jslot, bool two = false) {
+                    long long jstep, long long jslot, int nfuse = 1) {
+    const bool two = nfuse >= 2;
     double* jsum_slot = c->jsum + (size_t)jstep * M_ * 2;
     StepArgs a;
     a.X = X; a.Y = Y; a.M = M_; a.n = c->nall;
@@ -709,7 +713,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
     const bool euler = c->cfg.system == FDS_SYS_L96_EULER;
     if (c->stream_ok && M_ == c->M) {
         a.jpart = c->jnode + (size_t)jslot * c->plan.nnode * c->M * 2;
-        if (two) { a.two_steps = 1; a.jpart2 = a.jpart + (size_t)c->plan.nnode * c->M * 2; }
+        if (two) { a.two_steps = 1; a.jpart2 = a.jpart + (size_t)c->plan.nnode * c->M * 2; a.nfuse = nfuse; }
         cudaEvent_t e1 = nullptr;
         if (c->profiling) {
             if (c->prof_used == c->prof_events.size()) {
@@ -721,7 +725,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
             FDS_CK(c, cudaEventRecord(c->prof_events[c->prof_used].first, c->stream));
             e1 = c->prof_events[c->prof_used].second;
             c->prof_used++;
-            c->prof_steps += two ? 2 : 1;
+            c->prof_steps += nfuse;
         }
         FDS_CK(c, launch_l96_rk4_stream(a, c->plan, c->stream, &c->ls, euler ? 1 : 0));
         if (e1) FDS_CK(c, cudaEventRecord(e1, c->stream));
@@ -855,12 +859,17 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
     if (int r = upload_forcing(c, s, eps)) return r;
     for (long long j = 0; j < nsteps;) {
         if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
-        const bool two = c->fuse2 && nsteps - j >= 2 && c->ens_halo_valid >= 2;
+        // steps per pass: 4 (forward Euler: four chained pipes fit the register file), 2 (RK4), 1 (remainder)
+        int k = 1;
+        if (c->fuse2) {
+            if (c->fuse4 && nsteps - j >= 4 && c->ens_halo_valid >= 4) k = 4;
+            else if (nsteps - j >= 2 && c->ens_halo_valid >= 2) k = 2;
+        }
         if (int r = one_step(c, c->E_all(c->cur), c->E_all(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, step0 + j,
-                             j, two)) return r;
+                             j, k)) return r;
         c->cur ^= 1;
-        c->ens_halo_valid -= two ? 2 : 1;
-        j += two ? 2 : 1;
+        c->ens_halo_valid -= k;
+        j += k;
     }
     if (int r = reduce_nodes(c, step0, nsteps)) return r;
     c->state_in_ensemble = true;

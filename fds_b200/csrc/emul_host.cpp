@@ -6,6 +6,7 @@
 #include <vector>
 #include "l96_march.cuh"
 #include "l96_march2.cuh"
+#include "l96_marchk.cuh"
 
 using namespace fds;
 
@@ -67,6 +68,37 @@ struct HostIO2 {
     double ns_get2(int st, int l, int q) const { return ns[st][l][q]; }
     void ns_put2(int st, int l, int q, double v) { ns[st][l][q] = v; }
 };
+// K steps per pass (l96_marchk.cuh): output cursor at site a + 8b - 3 - 8(K-1), K sets of objective partials
+template <int K>
+struct HostIOK {
+    const double* X;
+    double* Y;
+    double* const* jpart;   // [K] -> [nnode][M][2]
+    long long nleaf;
+    long long a;
+    int M, k;
+    long long cs = 0, j0 = 0;
+    void begin_block(int b) {
+        cs = a + 8LL * b + 4;
+        j0 = a + 8LL * b - 3 - 8LL * (K - 1);
+    }
+    void end_block(int) {}
+    double load(int p) const { return X[(cs + p) * M + k]; }
+    void store(int p, double v) { Y[(j0 + p) * M + k] = v; }
+    void emit_node2(int step, long long node, double s1, double s2) {
+        if (node >= 0 && node < nleaf) {
+            jpart[step][(node * M + k) * 2 + 0] = s1;
+            jpart[step][(node * M + k) * 2 + 1] = s2;
+        }
+    }
+    bool all(bool v) const { return v; }
+    void mid_block() {}
+    int warp_max(int v) const { return v; }
+    int warp_min(int v) const { return v; }
+    double ns[K][kMaxNodeLevels + 1][2];
+    double ns_get2(int st, int l, int q) const { return ns[st][l][q]; }
+    void ns_put2(int st, int l, int q, double v) { ns[st][l][q] = v; }
+};
 }  // namespace
 
 extern "C" {
@@ -125,6 +157,38 @@ int emul_l96_euler_step2(const double* X, double* Y, int M, long long n, long lo
             MarchGeom g{io.a, n, plan.nblk, jpart1 != nullptr, plan.node_shift};
             if (exact) l96_euler_march2<ExactMath>(io, g, F[k], c);
             else       l96_euler_march2<FastMath>(io, g, F[k], c);
+        }
+    }
+    return 0;
+}
+
+// FOUR forward-Euler steps in one pass (l96_marchk.cuh); jparts: 4 pointers
+int emul_l96_euler_step4(const double* X, double* Y, int M, long long n, long long H,
+                         const double* F /*[M]*/, double dt, int exact, long long max_strips, double* const* jparts) {
+    StripPlan plan = make_strip_plan(n, H, max_strips);
+    Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+    for (long long s = 0; s < plan.nstrips; ++s) {
+        for (int k = 0; k < M; ++k) {
+            HostIOK<4> io{X, Y, jparts, plan.nnode, plan.a0 + s * plan.ls, M, k};
+            MarchGeom g{io.a, n, plan.nblk, jparts != nullptr, plan.node_shift};
+            if (exact) l96_euler_march4<ExactMath>(io, g, F[k], c);
+            else       l96_euler_march4<FastMath>(io, g, F[k], c);
+        }
+    }
+    return 0;
+}
+
+// the generic K-step march with K = 2 and the RK4 pipe (must equal emul_l96_rk4_step2)
+int emul_l96_rk4_stepk2(const double* X, double* Y, int M, long long n, long long H,
+                        const double* F /*[M]*/, double dt, int exact, long long max_strips, double* const* jparts) {
+    StripPlan plan = make_strip_plan(n, H, max_strips);
+    Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+    for (long long s = 0; s < plan.nstrips; ++s) {
+        for (int k = 0; k < M; ++k) {
+            HostIOK<2> io{X, Y, jparts, plan.nnode, plan.a0 + s * plan.ls, M, k};
+            MarchGeom g{io.a, n, plan.nblk, jparts != nullptr, plan.node_shift};
+            if (exact) l96_rk4_marchk2<ExactMath>(io, g, F[k], c);
+            else       l96_rk4_marchk2<FastMath>(io, g, F[k], c);
         }
     }
     return 0;

@@ -37,6 +37,9 @@ struct StepArgs {
     // partials of the first and jpart2 those of the second step; needs runs_per_cta * M <= 256 threads and the in-between producer
     int two_steps = 0;
     double* jpart2 = nullptr;
+    // K time steps in one pass (2: as two_steps; 4: forward Euler only, l96_marchk.cuh): step j's node partials go to
+    // jpart + j * nnode * M * 2
+    int nfuse = 0;
 };
 
 // streaming TMA-fed kernel (RK4 only); `plan` = make_strip_plan(n, H, num_sms * stream_runs_per_cta(M)),

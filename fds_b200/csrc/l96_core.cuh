@@ -265,8 +265,12 @@ struct NodeCounter {
 // that are never used), so the kernel needs no range checks, and the arrays are
 // allocated for sites [alo, ahi) = [a0 - 12, a0 + nstrips*ls + 12): exactly the
 // input chunks the strips read (both bounds == 4 mod 8); the two-steps-per-pass kernel
-// (l96_march2.cuh) starts one block earlier and drains one block later, hence 20 instead of 12.
+// (l96_march2.cuh) starts one block earlier and drains one block later (20 instead of 12), a pass of K steps
+// (l96_marchk.cuh) K - 1 blocks: the plan pads for kMaxFuse steps per pass.
 // --------------------------------------------------------------------------- //
+constexpr int kMaxFuse = 4;                          // most time steps one pass of the streaming kernel advances
+constexpr int kPlanPad = 12 + 8 * (kMaxFuse - 1);    // sites the arrays extend beyond the strips on either side
+
 struct StripPlan {
     long long a0;       // first strip starts here (multiple of the node size)
     long long ls;       // strip length (multiple of the node size)
@@ -312,8 +316,8 @@ inline StripPlan make_strip_plan(long long n, long long H, long long max_strips)
         break;
     }
     p.nblk = (int)(p.ls / 8);
-    p.alo = p.a0 - 20;
-    p.ahi = p.a0 + p.nstrips * p.ls + 20;
+    p.alo = p.a0 - kPlanPad;
+    p.ahi = p.a0 + p.nstrips * p.ls + kPlanPad;
     p.nnode = (n + (1LL << p.node_shift) - 1) >> p.node_shift;
     return p;
 }

@@ -19,6 +19,7 @@
 #include "kernels.h"
 #include "l96_march.cuh"
 #include "l96_march2.cuh"
+#include "l96_marchk.cuh"
 
 namespace fds {
 
@@ -37,6 +38,8 @@ struct StreamParams {
     int dedicated;                             // 1: the last warp only produces; 0: warp 0 produces in between its blocks
     double F0, Flast;
     double* jpart2;                            // two steps per pass: node partials of the second step
+    long long jstride;                         // K steps per pass: step j writes its node partials at jpart + j * jstride
+    int nfuse;                                 // time steps per pass (1, 2 or 4)
     int fuse2;                                 // 1: two steps per pass (l96_march2.cuh)
     const double2* Fpp;                        // per-problem (F0, Flast) of a batch, or nullptr
     int spp;                                   // strips per problem (batch)
@@ -119,7 +122,7 @@ struct StreamIO {
     uint32_t full_s;         // shared-window address of full[0]; empty[s] = full[kMaxStages + s]
     double* yrow;            // output cursor: site a + 8b - 3 of this thread's column
     double* jp;              // node 0, already offset by column (or nullptr)
-    double* jp2;             // the same for the second step of a two-step pass
+    long long jstride;       // K steps per pass: step j's partials at jp + j * jstride
     int levels;              // node levels above the leaf (stride of the second step's counter storage)
     long long nnode;
     double* nsm;             // node-counter storage of this thread: nsm[(2*level + which) * nthr]
@@ -202,7 +205,7 @@ struct StreamIO {
     FDS_D void ns_put(int l, int q, double v) { nsm[(2 * l + q) * nthr] = v; }
     // two steps per pass: step 1 uses the first `levels` slots, step 2 the next
     FDS_D void emit_node2(int step, long long node, double s1, double s2) {
-        double* j = step ? jp2 : jp;
+        double* j = jp != nullptr ? jp + step * jstride : nullptr;
         if (j != nullptr && node >= 0 && node < nnode)
             *reinterpret_cast<double2*>(j + node * (2LL * cols())) = make_double2(s1, s2);
     }
@@ -211,15 +214,17 @@ struct StreamIO {
     FDS_D bool all(bool v) const { return __all_sync(0xffffffffu, v); }
 };
 
-// MODE 0: RK4, 1: forward Euler, 2: RK4, two steps per pass, 3: forward Euler, two steps per pass (<= 256 threads = 2 warps per scheduler: twice the pipeline state in up to 255 registers)
+// MODE 0: RK4, 1: forward Euler, 2: RK4, two steps per pass, 3: forward Euler, two steps per pass, 4: forward Euler, four
+// steps per pass (l96_marchk.cuh) (<= 256 threads = 2 warps per scheduler: twice the pipeline state in up to 255 registers)
 template <class MP, int MC, bool STATS, int MODE>
 __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kernel(const __grid_constant__ StreamParams p) {
+    constexpr int KF = MODE == 4 ? 4 : (MODE >= 2 ? 2 : 1);     // time steps per pass
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
     double* nsm = reinterpret_cast<double*>(smem_raw + 128);
     const int levels = p.node_shift - kLeafShift;
-    double* sdata = nsm + (size_t)(MODE >= 2 ? 4 : 2) * levels * (blockDim.x - 32 * p.dedicated);
+    double* sdata = nsm + (size_t)(2 * KF) * levels * (blockDim.x - 32 * p.dedicated);
 
     const int tid = threadIdx.x;
     const int nwarps = (blockDim.x >> 5) - p.dedicated;   // consumer warps
@@ -237,8 +242,8 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
 
     const long long last_strip = p.nstrips - 1;
     StreamProducer prod;
-    prod.init(&p, sdata, full, lane, MODE >= 2 ? -20 : -12,
-              MODE >= 2 ? march2_iterations(p.nblk) : march_iterations(p.nblk));   // blocks b = -2 .. nblk (-3 .. nblk + 1)
+    prod.init(&p, sdata, full, lane, KF >= 2 ? -8 * (KF + 1) + 4 : -12,
+              KF >= 2 ? p.nblk + 2 * KF + 1 : march_iterations(p.nblk));   // blocks b = -2 .. nblk (-3 .. nblk + 1)
     if (p.dedicated) {
         if (warp == nwarps) {
             while (!prod.done()) { prod.issue(); prod.advance(); }
@@ -284,9 +289,9 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.nstages = p.nstages;
     io.full_s = smem_u32(full);
     // output cursor of the first block: site a - 16 - 3 (b = -2), or a - 24 - 11 (b = -3, two steps per pass)
-    io.yrow = p.Y + (MODE >= 2 ? g.a - 8 * 3 - 11 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
+    io.yrow = p.Y + (KF >= 2 ? g.a - 16 * KF - 3 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
-    io.jp2 = p.jpart2 != nullptr ? p.jpart2 + 2 * k : nullptr;
+    io.jstride = p.jstride;
     io.levels = levels;
     io.nnode = p.nnode;
     io.nsm = nsm + tid;
@@ -308,6 +313,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     if (MODE == 1) l96_march_t<MP, STATS, EulerPipe<MP>>(io, g, F, p.c);
     else if (MODE == 2) l96_march2_t<MP, Rk4Pipe<MP>, STATS>(io, g, F, p.c);
     else if (MODE == 3) l96_march2_t<MP, EulerPipe<MP>, STATS>(io, g, F, p.c);
+    else if (MODE == 4) l96_marchk_t<MP, EulerPipe<MP>, 4, STATS>(io, g, F, p.c);
     else l96_march_t<MP, STATS, Rk4Pipe<MP>>(io, g, F, p.c);
 }
 
@@ -335,7 +341,9 @@ int stream_runs_per_cta(int M) {
 
 cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cudaStream_t st, LaunchStats* ls,
                                   int euler) {
-    const int fuse2 = a.jpart2 != nullptr || a.two_steps;
+    const int nfuse = a.nfuse > 1 ? a.nfuse : ((a.jpart2 != nullptr || a.two_steps) ? 2 : 1);
+    if (nfuse != 1 && nfuse != 2 && !(nfuse == 4 && euler)) return cudaErrorInvalidValue;
+    const int fuse2 = nfuse >= 2;
     StreamParams p;
     p.X = a.X; p.Y = a.Y; p.jpart = a.jpart; p.nnode = plan.nnode;   // a.jpart: [nnode][M][2]
     p.n = a.n;
@@ -374,7 +382,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     const int block = cthreads + 32 * p.dedicated;
     const size_t stage_bytes = (size_t)p.R * p.run_stride * sizeof(double);
     if (fuse2 && block > 256) return cudaErrorInvalidValue;
-    const size_t ns_bytes = (size_t)(fuse2 ? 4 : 2) * (plan.node_shift - kLeafShift) * cthreads * sizeof(double);
+    const size_t ns_bytes = (size_t)(2 * nfuse) * (plan.node_shift - kLeafShift) * cthreads * sizeof(double);
     const size_t budget = smem_budget - 128 - ns_bytes;
     int nst = (int)std::min<size_t>(kMaxStages, budget / stage_bytes);
     if (nst < 2) return cudaErrorInvalidValue;
@@ -383,6 +391,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
     p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
     p.jpart2 = a.jpart2; p.fuse2 = fuse2;
+    p.nfuse = nfuse; p.jstride = (long long)plan.nnode * a.M * 2;
     p.prefetch = std::max(1, std::min(nst - 2, stream_prefetch()));
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = p.pack ? (int)((plan.nstrips * a.M + p.nconsumer - 1) / p.nconsumer)
@@ -397,7 +406,8 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
         l96_rk4_stream_kernel<MP, MC, ST, EU><<<grid, block, smem, st>>>(p);                                       \
     } while (0)
 #define FDS_STREAM_LAUNCH(MP, MC, ST) \
-    do { if (euler && fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 3); else if (euler) FDS_STREAM_LAUNCH2(MP, MC, ST, 1); \
+    do { if (euler && nfuse == 4) FDS_STREAM_LAUNCH2(MP, MC, ST, 4); else if (euler && fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 3); \
+         else if (euler) FDS_STREAM_LAUNCH2(MP, MC, ST, 1); \
          else if (fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 2); \
          else FDS_STREAM_LAUNCH2(MP, MC, ST, 0); } while (0)
 #define FDS_STREAM_MC(MP, ST)                                      \

@@ -20,7 +20,7 @@ c_dp = ctypes.POINTER(ctypes.c_double)
 @pytest.fixture(scope='module')
 def emul():
     deps = [SRC] + [os.path.join(ROOT, 'fds_b200', 'csrc', f)
-                    for f in ('l96_core.cuh', 'l96_march.cuh', 'l96_march2.cuh', 'common.cuh')]
+                    for f in ('l96_core.cuh', 'l96_march.cuh', 'l96_march2.cuh', 'l96_marchk.cuh', 'common.cuh')]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-x', 'c++',
                                SRC, '-o', SO])
@@ -132,6 +132,51 @@ def test_two_steps_per_pass_march_matches_oracle(emul, N, M, H, max_strips, exac
                     for q in range(2):
                         col = np.ascontiguousarray(jp[st][:, k, q])
                         assert emul.emul_tree_reduce(ptr(col), LL(nleaf), LL(1)) / N == Jo[2 * j + st, k, q]
+        bufA, bufB = bufB, bufA
+    got = bufA[-alo:-alo + N].T
+    if exact:
+        assert np.array_equal(got, Xo)
+    else:
+        assert np.abs(got - Xo).max() < 1e-13
+
+
+@pytest.mark.parametrize('scheme,K', [('euler', 4), ('rk4', 2)])
+@pytest.mark.parametrize('N,M,H,max_strips,exact', [
+    (200, 5, 4, 7, 1), (40, 18, 4, 4, 1), (37, 3, 4, 64, 1), (1024, 4, 8, 16, 1), (4096, 2, 4, 37, 1),
+    (333, 1, 5, 1, 1), (200, 5, 4, 7, 0), (8, 2, 4, 5, 1), (640, 3, 8, 3, 1), (5000, 2, 4, 2, 1),
+    (64, 2, 4, 1, 1), (128, 1, 4, 2, 1), (70000, 1, 4, 5, 1)])
+def test_k_steps_per_pass_march_matches_oracle(emul, N, M, H, max_strips, exact, scheme, K):
+    """l96_marchk.cuh: a chain of K pipes (four forward-Euler steps per pass; the generic march with K = 2
+    on the RK4 pipe), all K steps' objective partials -- bit for bit K oracle steps."""
+    step_fn = plugins.l96_rk4_step if scheme == 'rk4' else plugins.l96_euler_step
+    emul_fn = emul.emul_l96_rk4_stepk2 if scheme == 'rk4' else emul.emul_l96_euler_step4
+    rng = np.random.RandomState(N + M + 1)
+    U = rng.rand(M, N) * 6 - 1
+    F = 8.0 + np.r_[np.zeros(M - 1), 1e-4] if M > 1 else np.array([8.1])
+    pl = plan_of(emul, N, H, max_strips)
+    alo, ahi = pl['alo'], pl['ahi']
+    assert alo <= pl['a0'] - 12 - 8 * (K - 1) and ahi >= pl['a0'] + pl['nstrips'] * pl['ls'] + 12 + 8 * (K - 1)
+    bufA = padded(U, alo, ahi, 8 * H, 4 * H)
+    bufB = np.full_like(bufA, np.nan)
+    nleaf = pl['nnode']
+    npass = H // K
+    Xo, Jo = plugins.run_l96_ensemble(step_fn, U, F, K * npass)
+    for j in range(npass):
+        jp = [np.full((nleaf, M, 2), np.nan) for _ in range(K)]
+        jpp = (ctypes.POINTER(ctypes.c_double) * K)(*[ptr(a) for a in jp])
+        with np.errstate(all='ignore'):
+            emul_fn(ptr(bufA, -alo * M), ptr(bufB, -alo * M), M, LL(N), LL(H), ptr(F),
+                    ctypes.c_double(0.01), exact, LL(max_strips), jpp)
+        done = K * (j + 1)
+        lo, hi = -8 * (H - done), N + 4 * (H - done)
+        assert not np.isnan(bufB[lo - alo:hi - alo]).any()
+        for st in range(K):
+            assert not np.isnan(jp[st]).any()
+            if exact:
+                for k in range(M):
+                    for q in range(2):
+                        col = np.ascontiguousarray(jp[st][:, k, q])
+                        assert emul.emul_tree_reduce(ptr(col), LL(nleaf), LL(1)) / N == Jo[K * j + st, k, q]
         bufA, bufB = bufB, bufA
     got = bufA[-alo:-alo + N].T
     if exact:
