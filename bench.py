@@ -231,6 +231,16 @@ def run_ours(args):
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # one process per GPU on a multi-socket host: run on the CPUs next to this rank's GPU, so that the
+        # page-locked host buffers of the end-to-end leg (allocated below) sit on the GPU's own NUMA node and
+        # eight 4.6 GB uploads do not all cross the socket interconnect.  (Not at N = 1: the cpu_baseline leg
+        # that follows uses every core.)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception as e:      # affinity is an optimisation, never a requirement
+            print('bench: no NUMA affinity (%s)' % e, file=sys.stderr)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     assert world == args.gpus, 'launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus)
 
