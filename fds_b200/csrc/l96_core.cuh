@@ -211,6 +211,19 @@ struct LeafStack {
         s1 = (b0 && !b1) ? p1 : s1;
         s2 = (b0 && b1 && !b2) ? p2 : s2;
     }
+    // The same with the lowest bit of b known at compile time (the unchecked loop of the two-step march handles two
+    // blocks per iteration): an even block only parks its sum (no add, no select), an odd block pairs it with the
+    // parked one and runs the two upper levels of the counter -- 2 adds and 3 selects instead of 2 and 5.
+    template <int PAR>
+    FDS_HD void push_state_p(double p, int b) {
+        if (PAR == 0) { s0 = p; return; }
+        const bool b1 = (b & 2) != 0, b2 = (b & 4) != 0;
+        const double p1 = s0 + p;
+        const double t1 = s1 + p1;
+        const double p2 = b1 ? t1 : p1;
+        s1 = b1 ? s1 : p1;
+        s2 = (b1 && !b2) ? p2 : s2;
+    }
     // leaf sum after the eighth push_state(p, 7): s2 + (s1 + (s0 + p)), the operation order of push()
     FDS_HD double leaf(double p) const { return s2 + (s1 + (s0 + p)); }
 };

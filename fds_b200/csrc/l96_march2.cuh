@@ -114,7 +114,8 @@ FDS_HD void march2_site(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats& 
     }
 }
 
-template <class MP, class PIPE, bool FAST, bool STATS, class IO>
+// BP: parity of b when known at compile time (unchecked blocks only), -1 otherwise
+template <class MP, class PIPE, bool FAST, bool STATS, int BP = -1, class IO>
 FDS_HD void march2_block(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats& sa, StepStats& sb,
                          const MarchGeom& g, int b, long long slo, long long shi, long long jlo, long long jhi,
                          double F, const Rk4Coef& c) {
@@ -126,10 +127,18 @@ FDS_HD void march2_block(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats&
     if (FAST) {
         // unchecked blocks have 2 <= b <= nblk: both leaves exist
         if (STATS) {
-            sb.l1.push_state(sb.b1, (b - 2) & 7);
-            sb.l2.push_state(sb.b2, (b - 2) & 7);
-            sa.l1.push_state(sa.b1, (b - 1) & 7);
-            sa.l2.push_state(sa.b2, (b - 1) & 7);
+            if (BP >= 0) {
+                // step 2 counts 8-block b - 2 (parity BP), step 1 counts 8-block b - 1 (the other parity)
+                sb.l1.template push_state_p<BP>(sb.b1, (b - 2) & 7);
+                sb.l2.template push_state_p<BP>(sb.b2, (b - 2) & 7);
+                sa.l1.template push_state_p<1 - BP>(sa.b1, (b - 1) & 7);
+                sa.l2.template push_state_p<1 - BP>(sa.b2, (b - 1) & 7);
+            } else {
+                sb.l1.push_state(sb.b1, (b - 2) & 7);
+                sb.l2.push_state(sb.b2, (b - 2) & 7);
+                sa.l1.push_state(sa.b1, (b - 1) & 7);
+                sa.l2.push_state(sa.b2, (b - 1) & 7);
+            }
         }
     } else {
         // step 2: sites a + 8(b-2) .. a + 8(b-2) + 7 are complete (Q2 == 7 at P == 2)
@@ -187,6 +196,7 @@ FDS_HD void l96_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c)
     // computed once, so the loops below compare warp-uniform integers and carry no vote
     bfl = io.warp_max(bfl);
     bfh = io.warp_min(bfh);
+    bfl += bfl & 1;                 // the unchecked body starts on an even block (the checked path is valid for every block)
     const int last = g.nblk + 1;
     int b = kFuse2First;
     // checked head [first, bfl), unchecked body [bfl, bfh], checked tail (bfh, last]: pass 0 = head + body, pass 1 = tail
@@ -200,11 +210,16 @@ FDS_HD void l96_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c)
             io.end_block(b);
         }
         if (pass == 0) {
+            // Unchecked body, two blocks per iteration so that the lowest bit of the leaf counters' position is a
+            // compile-time constant (b is even here; a single last block is left to the checked tail).
 #pragma unroll 1
-            for (; b <= bfh; ++b) {
+            for (; b + 1 <= bfh; b += 2) {
                 io.begin_block(b);
-                march2_block<MP, PIPE, true, STATS>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
+                march2_block<MP, PIPE, true, STATS, 0>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
                 io.end_block(b);
+                io.begin_block(b + 1);
+                march2_block<MP, PIPE, true, STATS, 1>(io, p1, p2, x1_prev, sa, sb, g, b + 1, slo, shi, jlo, jhi, F, c);
+                io.end_block(b + 1);
             }
         }
     }
