@@ -137,9 +137,8 @@ struct StreamIO {
     // MID only
     int prev_st;             // stage of the previous block, not yet released (-1: none)
     int blk, ahead;          // blocks begun so far; blocks the copies run ahead of the consumers
-    int pst;                 // stage and parity of the copy this warp owes at the end of the block (if `mine`)
-    uint32_t ppar;
-    bool mine;
+    int nit;                 // blocks per strip
+    bool mine;               // this warp issues the copies of block blk - 1 + ahead at the end of the block
     bool ready;              // this block's `full` phase was already seen complete by mid_block()
 
     // Two-steps-per-pass kernel (MID): the ring bookkeeping of block c -- probe of block c + 1's `full` barrier,
@@ -150,9 +149,9 @@ struct StreamIO {
     FDS_D void begin_block(int) {
         if (MID) {
             if (!ready) mbar_wait_s(full_s + 8u * (uint32_t)st, par);
-            // release the previous block's stage (a warp-wide sync ends a basic block: keep it at the boundary)
-            __syncwarp();                // every lane has consumed it
-            if (lane == 0 && prev_st >= 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + prev_st));
+            // release the previous block's stage: EVERY lane arrives for itself (the barrier counts lanes), so no
+            // warp-wide sync is needed -- fewer instructions between the FP64 streams of two blocks
+            if (prev_st >= 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + prev_st));
         } else {
             mbar_wait_s(full_s + 8u * (uint32_t)st, par);
         }
@@ -160,13 +159,8 @@ struct StreamIO {
     }
     FDS_D void mid_block() {
         if (!MID) return;
-        // copy duty of this block: block blk + ahead into stage st + ahead (mod nstages)
-        const int pit = blk + ahead;
-        int pst_ = st + ahead;
-        const bool pwrap = pst_ >= nstages;
-        pst = pwrap ? pst_ - nstages : pst_;
-        ppar = pwrap ? par ^ 1u : par;
-        mine = (turn == warp) & (pit < prod->nit);
+        // copy duty of this block: block blk + ahead (its stage and parity are worked out in end_block, only when due)
+        mine = (turn == warp) & (blk + ahead < nit);
         turn = (turn + 1 == nwarps) ? 0 : turn + 1;
         // next block
         const bool wrap = st + 1 == nstages;
@@ -182,7 +176,13 @@ struct StreamIO {
     FDS_D void store(int p, double v) { yrow[p * cols()] = v; }
     FDS_D void end_block(int) {
         if (MID) {
-            if (mine) prod->issue_at(blk - 1 + ahead, pst, ppar);
+            if (mine) {
+                // this block sat in stage prev_st with parity (st == 0 ? par ^ 1 : par): mid_block() has moved on
+                const uint32_t cpar = st == 0 ? par ^ 1u : par;
+                const int q = prev_st + ahead;
+                const bool w = q >= nstages;
+                prod->issue_at(blk - 1 + ahead, w ? q - nstages : q, w ? cpar ^ 1u : cpar);
+            }
         } else {
             __syncwarp();
             if (lane == 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + st));
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     if (tid == 0) {
         for (int s = 0; s < p.nstages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], nwarps);
+            mbar_init(&empty[s], MODE >= 2 ? nwarps * 32 : nwarps);      // two / four steps per pass: every lane arrives
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.st = 0; io.prev_st = -1;
     io.par = 0;
     io.ready = false; io.mine = false;
-    io.blk = 0; io.ahead = p.prefetch; io.pst = 0; io.ppar = 0;
+    io.blk = 0; io.ahead = p.prefetch; io.nit = prod.nit;
     io.cur = io.sdata;
 
     double F = (k == p.M - 1) ? p.Flast : p.F0;
