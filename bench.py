@@ -371,13 +371,13 @@ def run_ours(args):
         except Exception:
             pass
         # FP64-pipe utilisation of the step kernel from the live numbers: FP64 warp-instructions per launch
-        # (static count of the hot loop, DESIGN 4.1: 484 per 8-site block of two steps = 30.25 per update in exact
+        # (static count of the hot loop, DESIGN 4.1: 476 per 8-site block of two steps = 29.75 per update in exact
         # mode with the objective sums) over what 4 schedulers x 1 instruction per 2 clocks issue at the SM clock
         # sampled during the timed region
         fp64_live = None
         if clocks.get('sm_mhz') and args.math == 'exact' and steps_per_launch == 2 and torch.cuda.is_available():
             sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-            winst = n_local * M * steps_per_launch * 30.25 / 32.0
+            winst = n_local * M * steps_per_launch * 29.75 / 32.0
             fp64_live = 100.0 * winst / (kms * 1e-3 * clocks['sm_mhz'] * 1e6 * sms * 4 * 0.5)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
