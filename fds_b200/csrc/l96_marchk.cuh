@@ -59,7 +59,8 @@ FDS_HD void marchk_site(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&st
     }
 }
 
-template <class MP, class PIPE, int K, bool FAST, bool STATS, class IO>
+// BP: parity of b when known at compile time (unchecked blocks only), -1 otherwise
+template <class MP, class PIPE, int K, bool FAST, bool STATS, int BP = -1, class IO>
 FDS_HD void marchk_block(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&st)[K], const MarchGeom& g, int b,
                          long long slo, long long shi, long long jlo, long long jhi, double F, const Rk4Coef& c) {
     const long long jb = g.a + 8LL * b - 3;      // first step-1 site of this block
@@ -72,8 +73,20 @@ FDS_HD void marchk_block(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&s
         if (STATS) {
 #pragma unroll
             for (int j = K - 1; j >= 0; --j) {
-                st[j].l1.push_state(st[j].b1, (b - 1 - j) & 7);
-                st[j].l2.push_state(st[j].b2, (b - 1 - j) & 7);
+                if (BP >= 0) {
+                    // 8-block b - 1 - j has parity BP ^ ((1 + j) & 1): an even block parks its sum, an odd one pairs it
+                    constexpr int PAR = (BP >= 0 ? BP : 0) ^ 1;       // parity of b - 1
+                    if (j & 1) {
+                        st[j].l1.template push_state_p<PAR ^ 1>(st[j].b1, (b - 1 - j) & 7);
+                        st[j].l2.template push_state_p<PAR ^ 1>(st[j].b2, (b - 1 - j) & 7);
+                    } else {
+                        st[j].l1.template push_state_p<PAR>(st[j].b1, (b - 1 - j) & 7);
+                        st[j].l2.template push_state_p<PAR>(st[j].b2, (b - 1 - j) & 7);
+                    }
+                } else {
+                    st[j].l1.push_state(st[j].b1, (b - 1 - j) & 7);
+                    st[j].l2.push_state(st[j].b2, (b - 1 - j) & 7);
+                }
             }
         }
     } else if (STATS) {
@@ -129,6 +142,7 @@ FDS_HD void l96_marchk_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c)
     }
     bfl = io.warp_max(bfl);
     bfh = io.warp_min(bfh);
+    bfl += bfl & 1;                 // the unchecked body starts on an even block and handles two blocks per iteration
     const int last = g.nblk + K - 1;
     int b = FuseGeom<K>::kFirst;
 #pragma unroll 1
@@ -142,10 +156,13 @@ FDS_HD void l96_marchk_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c)
         }
         if (pass == 0) {
 #pragma unroll 1
-            for (; b <= bfh; ++b) {
+            for (; b + 1 <= bfh; b += 2) {
                 io.begin_block(b);
-                marchk_block<MP, PIPE, K, true, STATS>(io, p, xprev, st, g, b, slo, shi, jlo, jhi, F, c);
+                marchk_block<MP, PIPE, K, true, STATS, 0>(io, p, xprev, st, g, b, slo, shi, jlo, jhi, F, c);
                 io.end_block(b);
+                io.begin_block(b + 1);
+                marchk_block<MP, PIPE, K, true, STATS, 1>(io, p, xprev, st, g, b + 1, slo, shi, jlo, jhi, F, c);
+                io.end_block(b + 1);
             }
         }
     }
