@@ -110,8 +110,9 @@ struct StreamProducer {
 
 // MC = number of columns when known at compile time (every p*M offset becomes an immediate),
 // 0 = use the run-time value
-// MID = the march calls mid_block() once in EVERY block (two-steps-per-pass kernel): all ring bookkeeping then
-// happens there, inside straight-line code, and the block boundary carries only the (rare) copy issue.
+// MID = the march calls mid_block() once in EVERY block (the kernels that advance two or four steps per pass): the
+// ring bookkeeping then happens there, inside straight-line code, and the block boundary carries only the barrier
+// fallback, the stage release and the (rare) copy issue.
 template <int MC, bool MID = false>
 struct StreamIO {
     const double* sdata;     // this thread's (run, column) slot in stage 0
@@ -141,9 +142,9 @@ struct StreamIO {
     bool mine;               // this warp issues the copies of block blk - 1 + ahead at the end of the block
     bool ready;              // this block's `full` phase was already seen complete by mid_block()
 
-    // Two-steps-per-pass kernel (MID): the ring bookkeeping of block c -- probe of block c + 1's `full` barrier,
-    // whose turn it is to fetch, stage / parity of the next block -- runs in the
-    // MIDDLE of block c (mid_block), inside straight-line code where its latencies hide behind the FP64 stream.
+    // MID: the ring bookkeeping of block c -- probe of block c + 1's `full` barrier, whose turn it is to fetch,
+    // stage / parity of the next block -- runs in the MIDDLE of block c (mid_block), inside straight-line code
+    // where its latencies hide behind the FP64 stream.
     // The producer position is a function of the consumer's (block c + `ahead` goes into stage st + ahead), so
     // no separate producer state is carried.  The other kernels keep everything at the block boundary.
     FDS_D void begin_block(int) {
