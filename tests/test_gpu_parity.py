@@ -183,6 +183,35 @@ def test_segment_then_boundary_device_resident(name):
 
 
 @gpu
+@pytest.mark.parametrize('scheme', ['rk4', 'euler'])
+@pytest.mark.parametrize('H,steps', [(3, 7), (5, 11), (6, 13), (8, 8), (128, 10)])
+def test_mixed_pass_depths_bitwise(scheme, H, steps):
+    """Temporal blocking under a small halo capacity: a segment is cut into halo chunks of at most H steps, and a
+    chunk into passes of four (forward Euler), two and one time steps -- every mixture gives the oracle's ensemble
+    and objective sums bit for bit."""
+    N, m, s, eps = 4096, 4, 0.1, 1e-4
+    rng = np.random.RandomState(11)
+    u0 = plugins.run_l96_rk4(rng.rand(N), s, 40)[0]
+    V = np.linalg.qr(rng.rand(m, N).T)[0].T
+    v = rng.randn(N) / np.sqrt(N)
+    eng = fds_b200.L96(N, scheme=scheme, max_halo_steps=H).engine(m)
+    eng.set_time_dilation(False)
+    eng.set_state(u0)
+    eng.set_tangents(V, v)
+    eng.boundary(s, eps, from_ensemble=0, do_qr=0, build=1)      # no dilation, no QR: just builds u0 + eps [V; v]
+    J = eng.segment(s, eps, steps)
+    U = np.vstack([u0, u0 + eps * V, u0 + eps * v])
+    F = np.r_[np.full(m + 1, s + 8.0), (s + eps) + 8.0]         # fds/segment.py:64: parameter + epsilon, then F = s + 8
+    step = plugins.l96_euler_step if scheme == 'euler' else plugins.l96_rk4_step
+    Xo, Jo = plugins.run_l96_ensemble(step, U, F, steps)
+    assert np.array_equal(J, Jo)
+    assert np.array_equal(eng.get_state(), Xo[0])
+    Vd, vd = eng.get_tangents()
+    assert np.array_equal(Vd, (Xo[1:m + 1] - Xo[0]) / eps) and np.array_equal(vd, (Xo[m + 1] - Xo[0]) / eps)
+    eng.close()
+
+
+@gpu
 def test_boundary_projection_only_matches_reference():
     g = golden('seg_l96rk4_N1024_m8')
     eng = fds_b200.L96(1024).engine(8)
