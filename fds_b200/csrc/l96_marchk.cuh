@@ -26,6 +26,12 @@ struct FuseGeom {
     static constexpr int kOutOff = -16 * K - 3;        // output cursor of the first block, relative to the strip start
     static constexpr int kPad = 12 + 8 * (K - 1);      // sites the arrays extend beyond the strips on either side
 };
+// the one-step march (l96_march.cuh: b = -2 .. nblk) and the two-step march (l96_march2.cuh: b = -3 .. nblk + 1)
+static_assert(FuseGeom<1>::kFirst == -2 && FuseGeom<1>::kExtra == 3 && FuseGeom<1>::kInOff == -12 &&
+              FuseGeom<1>::kOutOff == -19, "one step per pass");
+static_assert(FuseGeom<2>::kFirst == kFuse2First && FuseGeom<2>::kInOff == -20 && FuseGeom<2>::kOutOff == -35 &&
+              FuseGeom<2>::kPad == 20, "two steps per pass");
+static_assert(FuseGeom<kMaxFuse>::kPad == kPlanPad, "the strip plan pads for the deepest pass");
 
 template <class MP, class PIPE, int K, int P, bool FAST, bool STATS, class IO>
 FDS_HD void marchk_site(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&st)[K], long long jb, long long slo,

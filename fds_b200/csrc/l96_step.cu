@@ -243,8 +243,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
 
     const long long last_strip = p.nstrips - 1;
     StreamProducer prod;
-    prod.init(&p, sdata, full, lane, KF >= 2 ? -8 * (KF + 1) + 4 : -12,
-              KF >= 2 ? p.nblk + 2 * KF + 1 : march_iterations(p.nblk));   // blocks b = -2 .. nblk (-3 .. nblk + 1)
+    prod.init(&p, sdata, full, lane, FuseGeom<KF>::kInOff, p.nblk + FuseGeom<KF>::kExtra);   // blocks b = -2 .. nblk (-3 .. nblk + 1)
     if (p.dedicated) {
         if (warp == nwarps) {
             while (!prod.done()) { prod.issue(); prod.advance(); }
@@ -290,7 +289,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.nstages = p.nstages;
     io.full_s = smem_u32(full);
     // output cursor of the first block: site a - 16 - 3 (b = -2), or a - 24 - 11 (b = -3, two steps per pass)
-    io.yrow = p.Y + (KF >= 2 ? g.a - 16 * KF - 3 : g.a - 8 * 2 - 3) * p.M + k;   // block b = -2
+    io.yrow = p.Y + (g.a + FuseGeom<KF>::kOutOff) * p.M + k;   // block b = -2
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
     io.jstride = p.jstride;
     io.levels = levels;
