@@ -53,6 +53,7 @@ SIGNATURES = {
     'fds_set_dxdt': (_I32, [_CTX, c_double_p]),
     'fds_set_qr_passes': (_I32, [_CTX, _I32]),
     'fds_last_condition': (_D, [_CTX]),
+    'fds_single_pass_pending': (_I32, [_CTX]),
     'fds_run': (_I32, [_CTX, _D, _I64, c_double_p]),
     'fds_primal_advance': (_I32, [_CTX, _D, _I64, _I64, _I32]),
     'fds_halo_mark_valid': (_I32, [_CTX, _I32, _I64]),
@@ -75,6 +76,20 @@ SIGNATURES = {
     'fds_set_batch_params': (_I32, [_CTX, c_double_p]),
     'fds_batch_count': (_I32, [_CTX]),
     'fds_segment_sensitivities': (_I32, [_CTX, _I64, _D, c_double_p, c_double_p]),
+    'fds_boundary_out_doubles': (_I64, [_CTX]),
+    'fds_boundary_enqueue': (_I32, [_CTX, _D, _D, _I32, _I32, _I32, _I64, c_double_p]),
+    'fds_boundary_check': (_I32, [_CTX, c_double_p, _I32]),
+    'fds_segment_enqueue': (_I32, [_CTX, _D, _D, _I64, c_double_p]),
+    'fds_comm_unique_id': (_I32, [ctypes.c_void_p]),
+    'fds_comm_init': (_I32, [_CTX, ctypes.c_void_p]),
+    'fds_comm_attach': (_I32, [_CTX, ctypes.c_void_p]),
+    'fds_comm_attached': (_I32, [_CTX]),
+    'fds_host_alloc_wc': (ctypes.c_void_p, [ctypes.c_size_t]),
+    'fds_collectives': (_I64, [_CTX]),
+    'fds_get_ensemble_rows': (_I32, [_CTX, _I64, _I64, c_double_p]),
+    'fds_get_ensemble_column': (_I32, [_CTX, _I32, c_double_p]),
+    'fds_strip_plan': (_I32, [_CTX, c_int64_p]),
+    'fds_fp64_issue_rate': (_I32, [_I32, c_double_p, c_double_p]),
     'fds_buffer_ptr': (ctypes.c_void_p, [_CTX, _I32]),
     'fds_kernel_launches': (_I64, [_CTX]),
     'fds_sync': (_I32, [_CTX]),

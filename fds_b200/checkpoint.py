@@ -17,8 +17,13 @@ def _filename(cp):
 
 
 def save_checkpoint(checkpoint_path, cp):
-    with open(os.path.join(checkpoint_path, _filename(cp)), 'wb') as f:
+    """Written to a temporary name and renamed, so that a concurrent load_last_checkpoint never sees a
+    truncated file (and never picks the temporary up: its name does not parse as m{m}_segment{K})."""
+    final = os.path.join(checkpoint_path, _filename(cp))
+    tmp = os.path.join(checkpoint_path, '.tmp_{0}_{1}'.format(_filename(cp), os.getpid()))
+    with open(tmp, 'wb') as f:
         pickle.dump(cp, f)
+    os.replace(tmp, final)
 
 
 def load_checkpoint(checkpoint_file):

@@ -466,7 +466,9 @@ FDS_D SmallBufs small_of(SmallBufs B, long long stride, int p) {
 }
 
 // pass 1: G_dil/g_dil, projection, (optionally) first Cholesky factor; builds A1
-__global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use_d, int do_qr, long long bstride) {
+__global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use_d, int do_qr, long long bstride,
+                                                     const int* gate, int gate_want) {
+    if (gate != nullptr && *gate != gate_want) return;
     B = small_of(B, bstride, blockIdx.x);
     extern __shared__ __align__(16) double sm[];
     const int MX = m + 2, MO = m + 1, D = m + 1;
@@ -523,12 +525,16 @@ __global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use
         B.A[e] = v;
     }
     __syncthreads();
-    if (tid == 0) *B.status = fail;
+    if (tid == 0) *B.status = fail ? kSmallPass1 + fail : 0;
 }
 
 // pass 2: second Cholesky factor on the Gram of [Q1; p_w], b, R = (L1 L2)^T; builds A2
-__global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long long bstride) {
+__global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long long bstride, const double* gram2,
+                                                     const int* gate, int gate_want) {
+    if (gate != nullptr && *gate != gate_want) return;
+    if (gram2 != nullptr) gram2 += (size_t)blockIdx.x * bstride;
     B = small_of(B, bstride, blockIdx.x);
+    if (gram2 != nullptr) B.gram = const_cast<double*>(gram2);
     extern __shared__ __align__(16) double sm[];
     const int MX = m + 2, MO = m + 1, D = m + 1;
     double* G = sm;                      // MX*MX
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long lo
     }
     (void)D;
     __syncthreads();
-    if (tid == 0) *B.status = fail;
+    if (tid == 0 && fail) *B.status = kSmallPass2 + fail;      // only ever raised: a pass-1 failure stays visible
 }
 
 // Single-pass CholeskyQR with its own certificate: everything the boundary needs -- G_dil, g_dil,
@@ -583,7 +589,8 @@ __global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long lo
 // with G = P P^T the projected Gram; for the symmetric G, |G|_2 <= |G|_inf, so
 // sqrt(|G|_inf |G^-1|_inf) >= cond_2(P).  The kernel reports that bound next to the status so that
 // the host can fall back to the two-pass CholeskyQR2 (small1 / small2) whenever it is not negligible.
-__global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, int use_d, long long bstride) {
+__global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, int use_d, long long bstride,
+                                                           int* two_pass_flag, int force_two) {
     B = small_of(B, bstride, blockIdx.x);
     extern __shared__ __align__(16) double sm[];
     const int MX = m + 2, MO = m + 1, D = m + 1;
@@ -676,17 +683,22 @@ __global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, i
     }
     __syncthreads();
     if (tid == 0) {
+        const double cond = sqrt(nrm[0] * nrm[1]);
         *B.status = fail;
-        reinterpret_cast<double*>(B.status)[1] = sqrt(nrm[0] * nrm[1]);
+        reinterpret_cast<double*>(B.status)[1] = cond;
+        // one Cholesky pass loses orthogonality like cond^2 u: CholeskyQR2 takes over unless that is negligible
+        if (two_pass_flag != nullptr && (force_two || fail != 0 || !(cond * cond * 2.3e-16 < kSinglePassTol)))
+            atomicMax(two_pass_flag, 1);
     }
 }
 
 cudaError_t launch_small_single(const SmallBufs& B, int m, int use_d, cudaStream_t st, LaunchStats* ls,
-                                const BatchDesc* batch) {
+                                const BatchDesc* batch, int* two_pass_flag, int force_two) {
     const size_t smem = small_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(small_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    small_single_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, batch ? batch->small_stride : 0);
+    small_single_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, batch ? batch->small_stride : 0,
+                                                                     two_pass_flag, force_two);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
@@ -696,15 +708,18 @@ cudaError_t launch_small1(const SmallBufs& B, int m, int use_d, int do_qr, cudaS
     const size_t smem = small_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(small1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    small1_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, do_qr, batch ? batch->small_stride : 0);
+    small1_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, do_qr, batch ? batch->small_stride : 0,
+                                                               batch ? batch->gate : nullptr, batch ? batch->gate_want : 0);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
-cudaError_t launch_small2(const SmallBufs& B, int m, cudaStream_t st, LaunchStats* ls, const BatchDesc* batch) {
+cudaError_t launch_small2(const SmallBufs& B, int m, cudaStream_t st, LaunchStats* ls, const BatchDesc* batch,
+                          const double* gram2) {
     const size_t smem = small_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(small2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    small2_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, batch ? batch->small_stride : 0);
+    small2_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, batch ? batch->small_stride : 0, gram2,
+                                                               batch ? batch->gate : nullptr, batch ? batch->gate_want : 0);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }

@@ -8,6 +8,7 @@
 
 #include "../../include/fds_b200.h"
 #include "kernels.h"
+#include "nccl_dl.h"
 
 using namespace fds;
 
@@ -83,6 +84,17 @@ struct fds_ctx {
     long long ens_halo_valid = 0, pri_halo_valid = 0;
     LaunchStats ls;
     std::string err;
+    // in-library communicator (fds_comm_*): NCCL on the context's stream -- halo send/recv, Gram
+    // all-reduce, all-gather + fixed-order sum of the objective partials; nothing returns to the host
+    const NcclApi* nccl = nullptr;
+    NcclComm comm = nullptr;
+    bool own_comm = false;
+    double* jgather = nullptr;        // [world][len] gathered objective partials
+    size_t jgather_cap = 0;
+    // device-gated boundary (adaptive CholeskyQR decided on the device, results fetched asynchronously)
+    bool gated = false;
+    double* gram2 = nullptr;          // Gram of the CholeskyQR2 second pass (kept apart from small.gram)
+    double* out_host = nullptr;       // pinned mirror of [R, b, G_dil, g_dil, status, cond] of the last boundary
     // optional per-launch timing of the step kernel (fds_profile_*)
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -121,7 +133,7 @@ static int check_small_status(fds_ctx* c, const char* what) {
         FDS_CK(c, cudaStreamSynchronize(c->stream));
         c->cond_last = 0.0;
         for (int p = 0; p < c->nb; ++p) {
-            if (all[p].st != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(all[p].st) +
+            if (all[p].st != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(all[p].st % 1000) +
                                                " of problem " + std::to_string(p) + " (tangent block numerically rank deficient)");
             c->cond_last = std::max(c->cond_last, all[p].cond);      // the worst problem decides
         }
@@ -135,10 +147,24 @@ static int check_small_status(fds_ctx* c, const char* what) {
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     st = sc.st;
     c->cond_last = sc.cond;
-    if (st != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(st) +
+    if (st != 0) return fail(c, std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(st % 1000) +
                                     " (tangent block numerically rank deficient)");
     return 0;
 }
+
+// RAII: make the context's GPU current for the duration of an entry point and restore the caller's
+// afterwards (a process may hold contexts on several GPUs, and torch may have changed the current device)
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define FDS_ON_DEVICE(c) DeviceGuard guard__((c)->cfg.device)
 
 static cudaError_t do_gram(fds_ctx* c, int src, double inv_eps) {
     if (c->mma_boundary || (c->fast_boundary && gram_mma_supported(c->m)))
@@ -160,6 +186,61 @@ static cudaError_t do_apply(fds_ctx* c, int src, double inv_eps, double* Tout, d
                                  eps, c->num_sms, c->stream, &c->ls);
     return launch_apply(src, c->Ecur(), c->T, c->d, c->small.A, c->m, inv_eps, c->n, Tout != nullptr ? Tout : c->T,
                         E_out, c->P(0), eps, c->stream, &c->ls, c->batch());
+}
+
+
+// ----------------------- in-library communicator (NCCL) ---------------------- //
+#define FDS_NCCL(ctx, call)                                                                        \
+    do {                                                                                           \
+        int r__ = (ctx)->nccl->call;                                                               \
+        if (r__ != 0) {                                                                            \
+            (ctx)->err = std::string("nccl" #call ": ") + (ctx)->nccl->GetErrorString(r__);        \
+            return 5;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+// ring halo exchange on the context's stream: the last 8h sites go to the right neighbour, the first 4h
+// to the left one (tests/solvers/mock_fun3d/fun3d:29-37 does the same per RHS evaluation over MPI).
+// With two ranks both neighbours are the same peer: sends and receives pair up in issue order.
+static int halo_exchange(fds_ctx* c, int which, long long hs) {
+    int64_t off[4], cnt[4];
+    if (fds_halo_layout(c, which, hs, off, cnt) != 0) return fail(c, "halo_steps out of range");
+    double* base = which == FDS_BUF_ENSEMBLE ? c->Ecur() : c->P(0);
+    const int world = c->cfg.world, right = (c->cfg.rank + 1) % world, left = (c->cfg.rank + world - 1) % world;
+    FDS_NCCL(c, GroupStart());
+    FDS_NCCL(c, Send(base + off[0], (size_t)cnt[0], kNcclFloat64, right, c->comm, c->stream));
+    FDS_NCCL(c, Send(base + off[1], (size_t)cnt[1], kNcclFloat64, left, c->comm, c->stream));
+    FDS_NCCL(c, Recv(base + off[2], (size_t)cnt[2], kNcclFloat64, left, c->comm, c->stream));
+    FDS_NCCL(c, Recv(base + off[3], (size_t)cnt[3], kNcclFloat64, right, c->comm, c->stream));
+    FDS_NCCL(c, GroupEnd());
+    c->ls.collectives++;
+    if (which == FDS_BUF_ENSEMBLE) c->ens_halo_valid = hs; else c->pri_halo_valid = hs;
+    return 0;
+}
+
+// sum of an (m+2)^2 Gram over the ranks (pascal_lite/operators/plinalg.py:19-44 reduces over MPI)
+static int allreduce_gram(fds_ctx* c, double* g) {
+    if (!c->comm) return 0;
+    FDS_NCCL(c, AllReduce(g, g, (size_t)c->MX * c->MX, kNcclFloat64, kNcclSum, c->comm, c->stream));
+    c->ls.collectives++;
+    return 0;
+}
+
+// objective partials of the ranks -> global sums in c->jsum on every rank: all-gather, then the canonical
+// tree continued over the ranks in a FIXED order (J does not depend on the number of GPUs)
+static int reduce_jsum_ranks(fds_ctx* c, size_t len) {
+    if (!c->comm || len == 0) return 0;
+    const size_t need = len * (size_t)c->cfg.world;
+    if (c->jgather_cap < need) {
+        cudaFree(c->jgather);
+        c->jgather = nullptr; c->jgather_cap = 0;
+        FDS_CK(c, cudaMalloc(&c->jgather, need * sizeof(double)));
+        c->jgather_cap = need;
+    }
+    FDS_NCCL(c, AllGather(c->jsum, c->jgather, len, kNcclFloat64, c->comm, c->stream));
+    c->ls.collectives++;
+    FDS_CK(c, launch_rank_tree_sum(c->jgather, c->cfg.world, (long long)len, c->jsum, c->stream, &c->ls));
+    return 0;
 }
 
 extern "C" {
@@ -206,7 +287,11 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
             return 1;                                                            \
         }                                                                        \
     } while (0)
-    CK0(cudaSetDevice(cfg->device));
+    DeviceGuard guard__(cfg->device);
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != cfg->device) CK0(cudaSetDevice(cfg->device));   // reports a bad ordinal
+    }
     CK0(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
     if (cfg->stream || (cfg->flags & FDS_FLAG_EXTERNAL_STREAM)) c->stream = (cudaStream_t)cfg->stream;
     else { CK0(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
@@ -304,7 +389,7 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
     if (c->nb > 1) CK0(cudaMalloc(&c->Fpp, (size_t)c->nb * sizeof(double2)));
     {   // small matrices in one block (per problem)
         const size_t mm = (size_t)c->m * c->m;
-        const size_t tot = ((size_t)c->MX * c->MX + (size_t)c->MO * c->MX + 2 * mm + c->m + c->MO + 4 + 1) & ~(size_t)1;
+        const size_t tot = (2 * (size_t)c->MX * c->MX + (size_t)c->MO * c->MX + 2 * mm + c->m + c->MO + 4 + 1) & ~(size_t)1;
         c->small_stride = (long long)tot;
         CK0(cudaMalloc(&c->small_block, tot * c->nb * sizeof(double)));
         CK0(cudaMemsetAsync(c->small_block, 0, tot * c->nb * sizeof(double), c->stream));
@@ -315,7 +400,8 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
         c->small.R = p;    p += mm;
         c->small.b = p;    p += c->m;
         c->small.gdil = p; p += c->MO;
-        c->small.status = reinterpret_cast<int*>(p);
+        c->small.status = reinterpret_cast<int*>(p); p += 4;      // [int status, int two_pass][double cond][2 spare]
+        c->gram2 = p;                                             // second-pass Gram of the gated CholeskyQR2
     }
     c->bd.count = c->nb; c->bd.slot = c->slot; c->bd.small_stride = c->small_stride;
     c->bd.part_stride = (long long)c->max_part * c->MX * c->MX;
@@ -323,6 +409,12 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
     c->mma_boundary = gram_mma_supported(c->m) && apply_mma_supported(c->m) && !(cfg->flags & FDS_FLAG_SIMPLE_KERNELS) &&
                       !c->toy;
     CK0(cudaMallocHost(&c->A_host, (size_t)c->MO * c->MX * sizeof(double)));
+    CK0(cudaMallocHost(&c->out_host, (size_t)c->nb * ((size_t)c->m * c->m + 2 * c->m + 3) * sizeof(double)));
+    // the boundary runs without a host round trip when both big passes are tensor-core kernels (m = 16, 32)
+    {
+        const char* e = getenv("FDS_GATED");
+        c->gated = c->mma_boundary && !(e && e[0] == '0');
+    }
     CK0(cudaMalloc(&c->c4, 4 * sizeof(double)));
     {
         const double w[4] = {-11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0};
@@ -345,8 +437,11 @@ int fds_ctx_create(const fds_config* cfg, fds_ctx** out) {
 
 void fds_ctx_destroy(fds_ctx* c) {
     if (!c) return;
-    cudaSetDevice(c->cfg.device);
+    FDS_ON_DEVICE(c);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm && c->own_comm && c->nccl) c->nccl->CommDestroy(c->comm);
+    cudaFree(c->jgather);
+    if (c->out_host) cudaFreeHost(c->out_host);
     for (int j = 0; j < 2; ++j) cudaFree(c->Ebase[j]);
     for (int j = 0; j < 4; ++j) cudaFree(c->Pbase[j]);
     cudaFree(c->T_alloc); cudaFree(c->d_alloc); cudaFree(c->Fpp); cudaFree(c->sens); cudaFree(c->gram_part); cudaFree(c->small_block); cudaFree(c->c4);
@@ -373,8 +468,98 @@ void* fds_host_alloc(size_t bytes) {
 void fds_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int fds_sync(fds_ctx* c) {
+    FDS_ON_DEVICE(c);
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
+}
+
+// ------------------------------- communicator -------------------------------- //
+int fds_comm_unique_id(void* id128) {
+    std::string err;
+    const NcclApi* api = nccl_api(&err);
+    if (!api) { g_create_err = err; return 5; }
+    const int r = api->GetUniqueId(reinterpret_cast<NcclUniqueId*>(id128));
+    if (r != 0) { g_create_err = std::string("ncclGetUniqueId: ") + api->GetErrorString(r); return 5; }
+    return 0;
+}
+
+int fds_comm_init(fds_ctx* c, const void* id128) {
+    FDS_ON_DEVICE(c);
+    if (c->cfg.world < 2) return fail(c, "fds_comm_init: the context was created with world = 1");
+    if (c->comm) return fail(c, "fds_comm_init: a communicator is already attached");
+    c->nccl = nccl_api(&c->err);
+    if (!c->nccl) return 5;
+    NcclUniqueId id;
+    std::memcpy(&id, id128, sizeof(id));
+    FDS_NCCL(c, CommInitRank(&c->comm, c->cfg.world, id, c->cfg.rank));
+    c->own_comm = true;
+    return 0;
+}
+
+int fds_comm_attach(fds_ctx* c, void* nccl_comm) {
+    FDS_ON_DEVICE(c);
+    if (c->cfg.world < 2) return fail(c, "fds_comm_attach: the context was created with world = 1");
+    if (c->comm) return fail(c, "fds_comm_attach: a communicator is already attached");
+    c->nccl = nccl_api(&c->err);
+    if (!c->nccl) return 5;
+    int count = 0, rank = -1;
+    FDS_NCCL(c, CommCount(nccl_comm, &count));
+    FDS_NCCL(c, CommUserRank(nccl_comm, &rank));
+    if (count != c->cfg.world || rank != c->cfg.rank) return fail(c, "fds_comm_attach: communicator size / rank differ from the context's");
+    c->comm = nccl_comm;
+    c->own_comm = false;
+    return 0;
+}
+
+int fds_comm_attached(const fds_ctx* c) { return c->comm != nullptr; }
+int64_t fds_collectives(const fds_ctx* c) { return c->ls.collectives; }
+
+// ------------------------------- introspection ------------------------------- //
+int fds_get_ensemble_rows(fds_ctx* c, int64_t site0, int64_t nsites, double* out) {
+    FDS_ON_DEVICE(c);
+    if (c->nb > 1) return fail(c, "fds_get_ensemble_rows: not available for a batch");
+    if (nsites < 0 || site0 < c->alo || site0 + nsites > c->ahi) return fail(c, "fds_get_ensemble_rows: range outside the allocated sites");
+    FDS_CK(c, cudaMemcpyAsync(out, c->Ecur() + site0 * c->M, (size_t)nsites * c->M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fds_get_ensemble_column(fds_ctx* c, int k, double* out) {
+    FDS_ON_DEVICE(c);
+    if (c->nb > 1) return fail(c, "fds_get_ensemble_column: not available for a batch");
+    if (k < 0 || k >= c->M) return fail(c, "fds_get_ensemble_column: column out of range");
+    // P(3) is scratch outside fds_boundary_dxdt (the third look-ahead state of the time-dilation stencil)
+    FDS_CK(c, launch_extract_col0(c->Ecur() + k, c->M, c->P(3), c->n, c->stream, &c->ls));
+    FDS_CK(c, cudaMemcpyAsync(out, c->P(3), (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int fds_strip_plan(const fds_ctx* c, int64_t out[8]) {
+    if (!c->stream_ok) return 2;
+    out[0] = c->plan.a0; out[1] = c->plan.ls; out[2] = c->plan.nstrips; out[3] = c->plan.nblk;
+    out[4] = c->plan.node_shift; out[5] = c->plan.nnode;
+    out[6] = (c->fuse2 && c->M >= 9 && c->nb == 1) ? 256 : 0;    // lanes a CTA packs (strip, column) pairs over; 0 = whole strips per CTA
+    out[7] = c->fuse4 ? 4 : (c->fuse2 ? 2 : 1);
+    return 0;
+}
+
+int fds_fp64_issue_rate(int device, double* winst_per_s, double* seconds) {
+    int ndev = 0, sms = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) { g_create_err = "fds_fp64_issue_rate: no such CUDA device"; return 3; }
+    DeviceGuard guard__(device);
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = fp64_issue_rate(sms, nullptr, winst_per_s, seconds);
+    if (e != cudaSuccess) { g_create_err = std::string("fds_fp64_issue_rate: ") + cudaGetErrorString(e); return 1; }
+    return 0;
+}
+
+// write-combined page-locked memory: for buffers the host only WRITES and the device reads (uploads)
+void* fds_host_alloc_wc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
 }
 
 int64_t fds_kernel_launches(const fds_ctx* c) { return c->ls.launches; }
@@ -389,6 +574,7 @@ int fds_profile_enable(fds_ctx* c, int enabled) {
 }
 
 int fds_profile_read(fds_ctx* c, double* total_ms, int64_t* launches) {
+    FDS_ON_DEVICE(c);
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     double tot = 0.0;
     for (size_t j = 0; j < c->prof_used; ++j) {
@@ -415,6 +601,7 @@ void* fds_buffer_ptr(const fds_ctx* c, int which) {
 }
 
 int fds_set_dxdt_weights(fds_ctx* c, const double w[4]) {
+    FDS_ON_DEVICE(c);
     FDS_CK(c, cudaMemcpyAsync(c->c4, w, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
@@ -430,6 +617,7 @@ int fds_set_time_dilation(fds_ctx* c, int mode) {
 }
 
 int fds_set_dxdt(fds_ctx* c, const double* d_host) {
+    FDS_ON_DEVICE(c);
     FDS_CK(c, cudaMemcpy2DAsync(c->d, (size_t)(c->nb > 1 ? c->slot : c->n) * sizeof(double), d_host,
                                 (size_t)c->n * sizeof(double), (size_t)c->n * sizeof(double), c->nb,
                                 cudaMemcpyHostToDevice, c->stream));
@@ -445,6 +633,8 @@ int fds_set_qr_passes(fds_ctx* c, int passes) {
 
 double fds_last_condition(const fds_ctx* c) { return c->cond_last; }
 
+int fds_single_pass_pending(const fds_ctx* c) { return c->qr_single ? 1 : 0; }
+
 // ------------------------------- state in / out ------------------------------ //
 static int sync_primal_from_ensemble(fds_ctx* c) {
     if (c->state_in_ensemble) {
@@ -456,6 +646,7 @@ static int sync_primal_from_ensemble(fds_ctx* c) {
 }
 
 int fds_set_state(fds_ctx* c, const double* u) {
+    FDS_ON_DEVICE(c);
     // batch: u is [nb][n]; rows land `slot` sites apart
     FDS_CK(c, cudaMemcpy2DAsync(c->P(0), (size_t)(c->nb > 1 ? c->slot : c->n) * sizeof(double), u,
                                 (size_t)c->n * sizeof(double), (size_t)c->n * sizeof(double), c->nb,
@@ -467,6 +658,7 @@ int fds_set_state(fds_ctx* c, const double* u) {
 }
 
 int fds_get_state(fds_ctx* c, double* u) {
+    FDS_ON_DEVICE(c);
     if (int r = sync_primal_from_ensemble(c)) return r;
     FDS_CK(c, cudaMemcpy2DAsync(u, (size_t)c->n * sizeof(double), c->P(0),
                                 (size_t)(c->nb > 1 ? c->slot : c->n) * sizeof(double), (size_t)c->n * sizeof(double),
@@ -499,6 +691,7 @@ static int materialize_tangents(fds_ctx* c) {
 // copy stream uploads chunk i+1 while the context's stream transposes chunk i.
 // batch: V is [nb][m][n], v is [nb][n]
 int fds_set_tangents(fds_ctx* c, const double* Vall, const double* vall) {
+    FDS_ON_DEVICE(c);
     if (int r = ensure_stage(c)) return r;
     FDS_CK(c, cudaStreamSynchronize(c->stream));       // T and the stages are free
     long long i = 0;
@@ -530,6 +723,7 @@ int fds_set_tangents(fds_ctx* c, const double* Vall, const double* vall) {
 }
 
 int fds_get_tangents(fds_ctx* c, double* Vall, double* vall) {
+    FDS_ON_DEVICE(c);
     if (int r = materialize_tangents(c)) return r;
     if (int r = ensure_stage(c)) return r;
     long long i = 0;
@@ -561,6 +755,7 @@ int fds_get_tangents(fds_ctx* c, double* Vall, double* vall) {
 // ---- host-solver mode: the ensemble itself crosses the boundary --------------------------- //
 // E_host[M][n] (row k = trajectory k) <-> device [n][M], same staged transposes as the tangents
 int fds_get_ensemble(fds_ctx* c, double* Eh) {
+    FDS_ON_DEVICE(c);
     if (c->nb > 1) return fail(c, "fds_get_ensemble: not available for a batch");
     if (int r = ensure_stage(c)) return r;
     long long i = 0;
@@ -584,6 +779,7 @@ int fds_get_ensemble(fds_ctx* c, double* Eh) {
 // the advanced ensemble comes back: column 0 is the new primal state, the tangents are implicit
 // in it, (E_k - E_0) / eps, exactly as after fds_segment_advance
 int fds_set_ensemble(fds_ctx* c, const double* Eh, double eps) {
+    FDS_ON_DEVICE(c);
     if (c->nb > 1) return fail(c, "fds_set_ensemble: not available for a batch");
     if (int r = ensure_stage(c)) return r;
     FDS_CK(c, cudaStreamSynchronize(c->stream));
@@ -610,6 +806,7 @@ int fds_set_ensemble(fds_ctx* c, const double* Eh, double eps) {
 
 // time dilation of the host-solver mode: the states after 1, 2, 3 steps (fds/timedilation.py:63-82)
 int fds_set_primal_history(fds_ctx* c, int j, const double* u_host) {
+    FDS_ON_DEVICE(c);
     if (j < 1 || j > 3) return fail(c, "fds_set_primal_history: j must be 1, 2 or 3");
     FDS_CK(c, cudaMemcpyAsync(c->P(j), u_host, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
@@ -617,6 +814,7 @@ int fds_set_primal_history(fds_ctx* c, int j, const double* u_host) {
 }
 
 int fds_random_tangents(fds_ctx* c, uint64_t seed) {
+    FDS_ON_DEVICE(c);
     if (c->nb > 1) FDS_CK(c, launch_fill_random(c->T_alloc, c->nall, c->MO, c->m, 0, c->nall, seed, c->stream, &c->ls));
     else FDS_CK(c, launch_fill_random(c->T, c->n, c->MO, c->m, c->cfg.site_offset, c->cfg.n_global, seed, c->stream, &c->ls));
     c->tangents_implicit = false;
@@ -627,8 +825,10 @@ int fds_random_tangents(fds_ctx* c, uint64_t seed) {
 int64_t fds_halo_steps(const fds_ctx* c, int64_t steps) { return c->toy ? steps : std::min<long long>(steps, c->H); }
 
 int fds_halo_wrap_ensemble(fds_ctx* c, int64_t hs) {
+    FDS_ON_DEVICE(c);
     if (c->toy) { c->ens_halo_valid = hs; return 0; }
-    if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_ensemble: world > 1, exchange halos between ranks instead");
+    if (c->cfg.world != 1 && c->comm) return halo_exchange(c, FDS_BUF_ENSEMBLE, hs);
+    if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_ensemble: world > 1, attach a communicator (fds_comm_init) or exchange halos between ranks yourself");
     if (hs < 1 || hs > c->H) return fail(c, "halo_steps out of range");
     if (c->nb > 1) FDS_CK(c, launch_halo_wrap_batch(c->Ecur(), c->M, c->n, 8 * hs, 4 * hs, c->nb, c->slot, c->stream, &c->ls));
     else
@@ -638,8 +838,10 @@ int fds_halo_wrap_ensemble(fds_ctx* c, int64_t hs) {
 }
 
 int fds_halo_wrap_primal(fds_ctx* c, int64_t hs) {
+    FDS_ON_DEVICE(c);
     if (c->toy) { c->pri_halo_valid = hs; return 0; }
-    if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_primal: world > 1, exchange halos between ranks instead");
+    if (c->cfg.world != 1 && c->comm) return halo_exchange(c, FDS_BUF_PRIMAL, hs);
+    if (c->cfg.world != 1) return fail(c, "fds_halo_wrap_primal: world > 1, attach a communicator (fds_comm_init) or exchange halos between ranks yourself");
     if (hs < 1 || hs > c->H) return fail(c, "halo_steps out of range");
     if (c->nb > 1) FDS_CK(c, launch_halo_wrap_batch(c->P(0), 1, c->n, 8 * hs, 4 * hs, c->nb, c->slot, c->stream, &c->ls));
     else
@@ -784,6 +986,7 @@ int fds_set_batch_params(fds_ctx* c, const double* ds) {
 int fds_batch_count(const fds_ctx* c) { return c->nb; }
 
 int fds_segment_sensitivities(fds_ctx* c, int64_t steps, double eps, double* J0_host, double* G_host) {
+    FDS_ON_DEVICE(c);
     if (steps > c->jsum_cap || steps < 2) return fail(c, "fds_segment_sensitivities: needs 2 <= steps <= steps run");
     const size_t nj = (size_t)c->nb * steps * 2, ng = (size_t)c->nb * c->MO * 2;
     if (c->sens_cap < nj + ng) {
@@ -801,6 +1004,7 @@ int fds_segment_sensitivities(fds_ctx* c, int64_t steps, double eps, double* J0_
 }
 
 int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int record) {
+    FDS_ON_DEVICE(c);
     if (int r = sync_primal_from_ensemble(c)) return r;
     if (record) if (int r = ensure_jsum(c, step0 + nsteps)) return r;
     if (c->host_sys) return fail(c, "host-solver system: the solver runs on the host (fds_set_state / fds_set_ensemble)");
@@ -828,7 +1032,9 @@ int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int 
 }
 
 int fds_run(fds_ctx* c, double s, int64_t steps, double* Jsum_host) {
-    if (c->cfg.world != 1) return fail(c, "fds_run: world > 1, drive fds_primal_advance with halo exchanges");
+    FDS_ON_DEVICE(c);
+    if (c->cfg.world != 1 && !c->comm)
+        return fail(c, "fds_run: world > 1, attach a communicator (fds_comm_init) or drive fds_primal_advance with halo exchanges");
     if (int r = sync_primal_from_ensemble(c)) return r;
     for (long long t = 0; t < steps;) {
         const long long hs = fds_halo_steps(c, steps - t);
@@ -836,6 +1042,7 @@ int fds_run(fds_ctx* c, double s, int64_t steps, double* Jsum_host) {
         if (int r = fds_primal_advance(c, s, t, hs, Jsum_host != nullptr)) return r;
         t += hs;
     }
+    if (Jsum_host && steps > 0) if (int r = reduce_jsum_ranks(c, (size_t)steps * 2)) return r;
     if (Jsum_host && steps > 0)
         FDS_CK(c, cudaMemcpyAsync(Jsum_host, c->jsum, (size_t)steps * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
@@ -843,6 +1050,7 @@ int fds_run(fds_ctx* c, double s, int64_t steps, double* Jsum_host) {
 }
 
 int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t nsteps) {
+    FDS_ON_DEVICE(c);
     if (c->host_sys) return fail(c, "host-solver system: advance the ensemble on the host (fds_get_ensemble / fds_set_ensemble)");
     if (int r = ensure_jsum(c, step0 + nsteps)) return r;
     if (c->toy) {
@@ -879,26 +1087,42 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
 }
 
 int fds_segment_jsums(fds_ctx* c, int64_t steps, double* out) {
+    FDS_ON_DEVICE(c);
     if (steps > c->jsum_cap) return fail(c, "fds_segment_jsums: more steps than were run");
     FDS_CK(c, cudaMemcpyAsync(out, c->jsum, (size_t)steps * c->nb * c->M * 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
-int fds_segment(fds_ctx* c, double s, double eps, int64_t steps, double* Jsum_host) {
-    if (c->cfg.world != 1) return fail(c, "fds_segment: world > 1, drive fds_segment_advance with halo exchanges");
+// the whole segment on the stream: halo refreshes (wrap / NCCL), the step kernels, the objective reduction
+// (over the ranks too) and, if asked for, the copy of the sums to the host -- nothing is waited for
+int fds_segment_enqueue(fds_ctx* c, double s, double eps, int64_t steps, double* Jsum_host) {
+    FDS_ON_DEVICE(c);
+    if (c->cfg.world != 1 && !c->comm)
+        return fail(c, "fds_segment: world > 1, attach a communicator (fds_comm_init) or drive fds_segment_advance with halo exchanges");
     for (long long t = 0; t < steps;) {
         const long long hs = fds_halo_steps(c, steps - t);
         if (int r = fds_halo_wrap_ensemble(c, hs)) return r;
         if (int r = fds_segment_advance(c, s, eps, t, hs)) return r;
         t += hs;
     }
-    if (Jsum_host) return fds_segment_jsums(c, steps, Jsum_host);
+    const size_t len = (size_t)steps * c->nb * c->M * 2;
+    if (int r = reduce_jsum_ranks(c, len)) return r;
+    if (Jsum_host && steps > 0)
+        FDS_CK(c, cudaMemcpyAsync(Jsum_host, c->jsum, len * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+int fds_segment(fds_ctx* c, double s, double eps, int64_t steps, double* Jsum_host) {
+    FDS_ON_DEVICE(c);
+    if (int r = fds_segment_enqueue(c, s, eps, steps, Jsum_host)) return r;
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 // ---------------------------------- boundary --------------------------------- //
 int fds_boundary_begin(fds_ctx* c, int from_ensemble) {
+    FDS_ON_DEVICE(c);
     if (from_ensemble) {
         c->state_in_ensemble = true;   // column 0 of the ensemble is the state of record
         if (int r = sync_primal_from_ensemble(c)) return r;
@@ -909,6 +1133,7 @@ int fds_boundary_begin(fds_ctx* c, int from_ensemble) {
 }
 
 int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
+    FDS_ON_DEVICE(c);
     if (c->dil_mode == FDS_DILATION_GIVEN) {
         // d was put there by fds_set_dxdt (run_ddt callable of the reference, fds/timedilation.py:54-61)
     } else if (c->dil_mode == FDS_DILATION_ANALYTIC) {
@@ -948,6 +1173,7 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
 }
 
 int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
+    FDS_ON_DEVICE(c);
     c->qr_single = false;
     if (do_qr && (c->fast_boundary || c->mma_boundary) && c->qr_mode == 0) {
         // one Cholesky pass loses orthogonality like cond^2 u: take it when that is below 2e-13
@@ -973,6 +1199,7 @@ int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
 }
 
 int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
+    FDS_ON_DEVICE(c);
     const bool ens = (build & FDS_BUILD_ENSEMBLE) != 0;
     // explicit tangents are written unless the caller only wants the next ensemble (hot loop)
     const bool keepT = !ens || (build & FDS_BUILD_KEEP_TANGENTS) != 0 || !(c->fast_boundary || c->mma_boundary);
@@ -995,6 +1222,7 @@ int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
 }
 
 int fds_boundary_results(fds_ctx* c, double* R, double* b, double* G_dil, double* g_dil) {
+    FDS_ON_DEVICE(c);
     // batch: one row per problem -- R[nb][m][m], b[nb][m], G_dil[nb][m], g_dil[nb]
     const size_t pitch = (size_t)c->small_stride * sizeof(double);
     auto fetch = [&](double* dst, const double* src, size_t count) {
@@ -1009,20 +1237,129 @@ int fds_boundary_results(fds_ctx* c, double* R, double* b, double* G_dil, double
     return 0;
 }
 
-int fds_boundary(fds_ctx* c, double s, double eps, int from_ensemble, int do_qr, int build, int64_t halo_steps,
-                 double* R, double* b, double* G_dil, double* g_dil) {
-    if (c->cfg.world != 1) return fail(c, "fds_boundary: world > 1, drive the phases with reductions in between");
+// ---- the device-gated boundary: no host round trip between its kernels ------------------------ //
+// factor + finish of a boundary whose big passes are tensor-core kernels.  The adaptive CholeskyQR
+// decision is taken by small_single_kernel on the device (two_pass flag next to the status word); the
+// CholeskyQR2 kernels and both variants of the final apply are enqueued behind it, gated on that flag.
+// With a communicator the second Gram is all-reduced unconditionally (9 KB; the ranks hold identical
+// all-reduced first Grams, so they take the same branch).
+static int gated_factor_finish(fds_ctx* c, int do_qr, int from_ensemble, double eps, int build) {
+    const bool ens = (build & FDS_BUILD_ENSEMBLE) != 0;
+    const bool keepT = !ens || (build & FDS_BUILD_KEEP_TANGENTS) != 0;
+    const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
+    const double inv_eps = from_ensemble ? 1.0 / eps : 0.0;
+    const int use_d = c->time_dilation ? 1 : 0;
+    c->qr_single = false;
+    if (!do_qr) {
+        FDS_CK(c, launch_small1(c->small, c->m, use_d, 0, c->stream, &c->ls, c->batch()));
+        FDS_CK(c, do_apply(c, src, inv_eps, c->T, nullptr, 0.0));
+        c->tangents_implicit = false;
+        if (ens) FDS_CK(c, launch_make_ensemble(c->P_all(0), c->T_alloc, c->M, eps, c->E_all(c->cur), c->nall, c->stream, &c->ls));
+    } else {
+        int* flag = c->small.status + 1;          // one flag for the whole batch: the worst problem decides
+        FDS_CK(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
+        FDS_CK(c, launch_small_single(c->small, c->m, use_d, c->stream, &c->ls, c->batch(), flag, c->qr_mode == 2));
+        BatchDesc two = c->bd, one = c->bd;
+        two.gate = flag; two.gate_want = 1;
+        one.gate = flag; one.gate_want = 0;
+        // CholeskyQR2 (gate = 1): pass 1 -> T, Gram of T -> gram2, pass 2
+        FDS_CK(c, launch_small1(c->small, c->m, use_d, 1, c->stream, &c->ls, &two));
+        FDS_CK(c, launch_apply_mma(src, c->Ecur(), c->T, c->d, c->small.A, c->m, inv_eps, c->n, c->T, nullptr, c->P(0),
+                                   0.0, c->num_sms, c->stream, &c->ls, &two));
+        FDS_CK(c, launch_gram_mma(SRC_TANGENT, c->Ecur(), c->T, c->d, c->m, 0.0, c->n, c->gram_part, c->max_part,
+                                  c->gram2, c->num_sms, c->stream, &c->ls, &two));
+        if (int r = allreduce_gram(c, c->gram2)) return r;
+        FDS_CK(c, launch_small2(c->small, c->m, c->stream, &c->ls, &two, c->gram2));
+        // the last pass: from the source with the single-pass factor (gate = 0), or from T with the second factor
+        double* Tout = keepT ? c->T : nullptr;
+        double* Eout = ens ? c->Ecur() : nullptr;
+        FDS_CK(c, launch_apply_mma(src, c->Ecur(), c->T, c->d, c->small.A, c->m, inv_eps, c->n, Tout, Eout, c->P(0), eps,
+                                   c->num_sms, c->stream, &c->ls, &one));
+        FDS_CK(c, launch_apply_mma(SRC_TANGENT, c->Ecur(), c->T, c->d, c->small.A, c->m, 0.0, c->n, Tout, Eout, c->P(0), eps,
+                                   c->num_sms, c->stream, &c->ls, &two));
+        c->tangents_implicit = !keepT;            // without T the new ensemble is the record of the tangents
+    }
+    if (ens) { c->ens_halo_valid = 0; c->eps_last = eps; }
+    c->state_in_ensemble = false;
+    return 0;
+}
+
+int64_t fds_boundary_out_doubles(const fds_ctx* c) { return (int64_t)c->m * c->m + 2 * c->m + 3; }
+
+// layout of one problem's block: R[m*m], b[m], G_dil[m], g_dil, {int32 status, int32 two_pass}, cond
+static int decode_boundary_block(fds_ctx* c, const double* blk, int problem) {
+    const size_t o = (size_t)c->m * c->m + 2 * c->m + 1;
+    int st[2];
+    std::memcpy(st, blk + o, sizeof(st));
+    if (st[0] != 0) {
+        const char* what = st[0] >= kSmallPass2 ? "CholeskyQR pass 2" : (st[0] >= kSmallPass1 ? "CholeskyQR pass 1" : "CholeskyQR");
+        std::string msg = std::string(what) + ": Cholesky pivot <= 0 at column " + std::to_string(st[0] % 1000);
+        if (c->nb > 1) msg += " of problem " + std::to_string(problem);
+        return fail(c, msg + " (tangent block numerically rank deficient)");
+    }
+    return 0;
+}
+
+int fds_boundary_check(fds_ctx* c, const double* out, int do_qr) {
+    if (!do_qr) return 0;
+    const size_t len = (size_t)fds_boundary_out_doubles(c);
+    double cond = 0.0;
+    for (int p = 0; p < c->nb; ++p) {
+        if (int r = decode_boundary_block(c, out + p * len, p)) return r;
+        cond = std::max(cond, out[p * len + len - 1]);
+    }
+    c->cond_last = cond;
+    return 0;
+}
+
+// One whole boundary enqueued on the stream (world > 1: with the context's communicator).  `out` receives
+// fds_boundary_out_doubles() doubles per problem once the stream has reached this point (page-locked memory
+// keeps the copy asynchronous); check it with fds_boundary_check() after fds_sync().  Contexts whose boundary
+// cannot run gated (m other than 16 / 32, small ODE systems) do the same work with their host round trips.
+int fds_boundary_enqueue(fds_ctx* c, double s, double eps, int from_ensemble, int do_qr, int build, int64_t halo_steps,
+                         double* out) {
+    FDS_ON_DEVICE(c);
+    if (c->cfg.world != 1 && !c->comm)
+        return fail(c, "fds_boundary: world > 1, attach a communicator (fds_comm_init) or drive the phases with reductions in between");
     if (int r = fds_boundary_begin(c, from_ensemble)) return r;
     if (c->time_dilation) if (int r = fds_halo_wrap_primal(c, 3)) return r;
     if (int r = fds_boundary_dxdt(c, s, from_ensemble, eps)) return r;
-    if (int r = fds_boundary_factor(c, do_qr, from_ensemble, eps)) return r;
-    if (int r = fds_boundary_finish(c, do_qr, eps, build)) return r;
+    if (int r = allreduce_gram(c, c->small.gram)) return r;
+    const size_t len = (size_t)fds_boundary_out_doubles(c);
+    if (c->gated) {
+        if (int r = gated_factor_finish(c, do_qr, from_ensemble, eps, build)) return r;
+    } else {
+        if (int r = fds_boundary_factor(c, do_qr, from_ensemble, eps)) return r;
+        if (do_qr && !c->qr_single) if (int r = allreduce_gram(c, c->small.gram)) return r;
+        if (int r = fds_boundary_finish(c, do_qr, eps, build)) return r;
+    }
     if (build && halo_steps > 0) if (int r = fds_halo_wrap_ensemble(c, halo_steps)) return r;
-    return fds_boundary_results(c, do_qr ? R : nullptr, do_qr ? b : nullptr, G_dil, g_dil);
+    if (out != nullptr)
+        FDS_CK(c, cudaMemcpy2DAsync(out, len * sizeof(double), c->small.R, (size_t)c->small_stride * sizeof(double),
+                                    len * sizeof(double), c->nb, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+int fds_boundary(fds_ctx* c, double s, double eps, int from_ensemble, int do_qr, int build, int64_t halo_steps,
+                 double* R, double* b, double* G_dil, double* g_dil) {
+    FDS_ON_DEVICE(c);
+    if (int r = fds_boundary_enqueue(c, s, eps, from_ensemble, do_qr, build, halo_steps, c->out_host)) return r;
+    FDS_CK(c, cudaStreamSynchronize(c->stream));
+    if (int r = fds_boundary_check(c, c->out_host, do_qr)) return r;
+    const size_t len = (size_t)fds_boundary_out_doubles(c), mm = (size_t)c->m * c->m, m = (size_t)c->m;
+    for (int p = 0; p < c->nb; ++p) {
+        const double* blk = c->out_host + p * len;
+        if (do_qr && R) std::memcpy(R + p * mm, blk, mm * sizeof(double));
+        if (do_qr && b) std::memcpy(b + p * m, blk + mm, m * sizeof(double));
+        if (G_dil) std::memcpy(G_dil + p * m, blk + mm + m, m * sizeof(double));
+        if (g_dil) g_dil[p] = blk[mm + 2 * m];
+    }
+    return 0;
 }
 
 int fds_run_segment_host(fds_ctx* c, double* u, double* V, double* v, double s, double eps, int64_t steps,
                          double* Jsum_host) {
+    FDS_ON_DEVICE(c);
     if (c->cfg.world != 1) return fail(c, "fds_run_segment_host: world == 1 only");
     if (int r = fds_set_state(c, u)) return r;
     if (int r = fds_set_tangents(c, V, v)) return r;
@@ -1040,8 +1377,11 @@ int fds_lss_solve(int device, const double* R, const double* b, int64_t K, int m
 
 int fds_lss_solve_batch(int device, const double* R, const double* b, int64_t K, int m, int64_t nbatch, double* alpha) {
     if (K < 1 || m < 1 || nbatch < 1 || lss_smem_bytes(m) > 220 * 1024) { g_create_err = "fds_lss_solve: bad K, m or batch"; return 2; }
-    cudaError_t e = cudaSetDevice(device);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e == cudaSuccess && (device < 0 || device >= ndev)) e = cudaErrorInvalidDevice;
     if (e != cudaSuccess) { g_create_err = std::string("fds_lss_solve: ") + cudaGetErrorString(e) + " -- no CPU fallback"; return 3; }
+    DeviceGuard guard__(device);
     const size_t mm = (size_t)m * m;
     double *dR = nullptr, *db = nullptr, *da = nullptr, *dw = nullptr;
     int* dst = nullptr;

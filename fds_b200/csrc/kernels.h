@@ -6,7 +6,7 @@
 
 namespace fds {
 
-struct LaunchStats { long long launches = 0; };
+struct LaunchStats { long long launches = 0; long long collectives = 0; };
 
 // ---- l96_step.cu ------------------------------------------------------------ //
 struct StepArgs {
@@ -75,6 +75,11 @@ cudaError_t launch_batch_jreduce(const double* leaves, long long nleaf_total, lo
                                  long long leaves_pp, int C, int batch, long long steps, double* out,
                                  cudaStream_t st, LaunchStats* ls);
 
+// cross-rank continuation of the canonical tree: gathered[world][len] (rank-major) -> out[len], balanced binary
+// tree over the ranks, zero padded to a power of two, lower rank on the left (fds_b200/ring.py tree_sum_leading)
+cudaError_t launch_rank_tree_sum(const double* gathered, int world, long long len, double* out, cudaStream_t st,
+                                 LaunchStats* ls);
+
 // batch: J0[p][steps][2] (means) and G[p][m+1][2] (trapezoid-mean FD sensitivities / eps) from jsum[steps][nb][M][2]
 cudaError_t launch_batch_sens(const double* jsum, int nb, int M, long long steps, double n_sites, double eps,
                               double* J0, double* G, cudaStream_t st, LaunchStats* ls);
@@ -105,6 +110,12 @@ struct BatchDesc {
     long long slot = 0;          // sites between consecutive problems
     long long small_stride = 0;  // doubles between consecutive SmallBufs blocks
     long long part_stride = 0;   // doubles between consecutive Gram partial blocks
+    // device-side gate: when set, the kernel returns at once unless *gate == gate_want.  The adaptive
+    // CholeskyQR decision (one pass or two) is taken ON the device by small_single_kernel, so both
+    // variants of a boundary are enqueued without a host round trip and the untaken one costs an
+    // empty launch.
+    const int* gate = nullptr;
+    int gate_want = 0;
 };
 // Gram of X_i = [t_0..t_m, d_i]  (MX = m+2), t from the ensemble ((E_k - E_0) * inv_eps) or from T.
 // part: [grid][MX*MX] scratch; out: MX*MX (deterministic fixed-order sum of the partials)
@@ -126,12 +137,21 @@ struct SmallBufs {          // all device pointers
     double* gdil;           // m+1  (G_dil[0..m-1], g_dil)
     int* status;            // 0 ok, >0 Cholesky pivot failure (1-based column)
 };
+// status word: 0 ok; 1000 + column: Cholesky pivot <= 0 in pass 1; 2000 + column: in pass 2 (kSmallPass*).
+// small2 only ever RAISES the status (a pass-1 failure stays visible when both are enqueued back to back).
+// `gram2`: small2 factors this Gram instead of B.gram (the gated boundary keeps the two Grams apart).
+constexpr int kSmallPass1 = 1000, kSmallPass2 = 2000;
 cudaError_t launch_small1(const SmallBufs&, int m, int use_d, int do_qr, cudaStream_t, LaunchStats*,
                           const BatchDesc* batch = nullptr);
-cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr);
-// single-pass CholeskyQR from one Gram; writes sqrt(|G|_inf |G^-1|_inf) >= cond_2 to ((double*)status)[1]
+cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr,
+                          const double* gram2 = nullptr);
+// single-pass CholeskyQR from one Gram; writes sqrt(|G|_inf |G^-1|_inf) >= cond_2 to ((double*)status)[1].
+// two_pass_flag (optional, zeroed by the caller): raised to 1 (atomicMax, so the worst problem of a batch
+// decides) when the factor failed or cond^2 u >= kSinglePassTol, or when force_two is set -- the gate of
+// the CholeskyQR2 kernels enqueued behind it.
+constexpr double kSinglePassTol = 2e-13;
 cudaError_t launch_small_single(const SmallBufs&, int m, int use_d, cudaStream_t, LaunchStats*,
-                                const BatchDesc* batch = nullptr);
+                                const BatchDesc* batch = nullptr, int* two_pass_flag = nullptr, int force_two = 0);
 size_t small_smem_bytes(int m);
 
 // ---- boundary_fast.cu ---------------------------------------------------------- //
@@ -157,6 +177,12 @@ bool apply_mma_supported(int m);
 cudaError_t launch_apply_mma(int src, const double* E, const double* Tin, const double* d, const double* A, int m,
                              double inv_eps, long long n, double* Tout, double* E_out, const double* u, double eps,
                              int num_sms, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr);
+
+// ---- diag.cu ----------------------------------------------------------------- //
+// FP64 issue-rate microbenchmark: the roof of the exact-mode step kernel.  Runs the step kernel's own
+// instruction mix (2 DADD : 1 DMUL, 8 independent chains per thread, 2 warps per scheduler, one CTA per SM)
+// and returns FP64 warp-instructions per second for the whole GPU at the clock the board sustains.
+cudaError_t fp64_issue_rate(int num_sms, cudaStream_t st, double* winst_per_s, double* seconds);
 
 // ---- toy_ode.cu -------------------------------------------------------------- //
 // small ODE systems (Lorenz-63, Van der Pol, circular): state dimension, 0 for the L96 systems

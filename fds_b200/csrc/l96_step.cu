@@ -610,6 +610,28 @@ cudaError_t launch_tree_reduce_batched(const double* in, long long n_in, int C, 
     return cudaSuccess;
 }
 
+// cross-rank part of the canonical tree (see kernels.h)
+__global__ void __launch_bounds__(256) rank_tree_sum_kernel(const double* __restrict__ g, int world, int P,
+                                                            long long len, double* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    double v[64];
+    for (int r = 0; r < P; ++r) v[r] = r < world ? g[(size_t)r * len + e] : 0.0;
+    for (int s = 1; s < P; s <<= 1)
+        for (int j = 0; j < P; j += 2 * s) v[j] = __dadd_rn(v[j], v[j + s]);
+    out[e] = v[0];
+}
+
+cudaError_t launch_rank_tree_sum(const double* gathered, int world, long long len, double* out, cudaStream_t st,
+                                 LaunchStats* ls) {
+    int P = 1;
+    while (P < world) P *= 2;
+    if (P > 64 || len < 1) return cudaErrorInvalidValue;
+    rank_tree_sum_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(gathered, world, P, len, out);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
 // --------------------------------- halo wrap --------------------------------- //
 __global__ void __launch_bounds__(256) halo_wrap_kernel(double* __restrict__ A, int M, long long n,
                                                         long long gl, long long gr) {

@@ -156,6 +156,11 @@ class Context:
     def last_condition(self):
         return float(self.lib.fds_last_condition(self.h))
 
+    @property
+    def single_pass_pending(self):
+        """Split-phase API: the certified single CholeskyQR pass was accepted by boundary_factor."""
+        return bool(self.lib.fds_single_pass_pending(self.h))
+
     def set_batch_params(self, ds):
         """Problem p of a batched context runs at parameter s + ds[p]."""
         ds = np.ascontiguousarray(ds, dtype=np.float64)
@@ -226,16 +231,79 @@ class Context:
         self._ck(self.lib.fds_segment_sensitivities(self.h, int(steps), float(eps), dptr(J0), dptr(G)))
         return J0, G[..., :self.m, :], G[..., self.m, :]
 
-    # -- world == 1 conveniences --------------------------------------------- #
+    # -- whole boundary / segment in one call (world == 1, or a communicator attached) -------- #
     def boundary(self, s, eps, from_ensemble, do_qr, build, halo_steps=0):
         """One segment boundary; returns (R, b, G_dil, g_dil) (R, b None unless do_qr)."""
-        m = self.m
-        R = np.empty((m, m)) if do_qr else None
-        b = np.empty(m) if do_qr else None
-        Gd, gd = np.empty(m), np.empty(1)
+        m, L = self.m, self.lead
+        R = np.empty(L + (m, m)) if do_qr else None
+        b = np.empty(L + (m,)) if do_qr else None
+        Gd, gd = np.empty(L + (m,)), np.empty(L + (1,))
         self._ck(self.lib.fds_boundary(self.h, float(s), float(eps), int(from_ensemble), int(do_qr),
                                        int(build), int(halo_steps), dptr(R), dptr(b), dptr(Gd), dptr(gd)))
-        return R, b, Gd, float(gd[0])
+        return R, b, Gd, (gd[:, 0] if L else float(gd[0]))
+
+    # -- the same without waiting for the device ------------------------------------------------ #
+    @property
+    def boundary_out_doubles(self):
+        return int(self.lib.fds_boundary_out_doubles(self.h))
+
+    def boundary_enqueue(self, s, eps, from_ensemble, do_qr, build, halo_steps, out):
+        """Put one boundary on the stream; ``out`` (page-locked, batch x boundary_out_doubles) is filled
+        when the stream gets there.  Decode with ``boundary_unpack`` after ``sync()``."""
+        assert out is None or (out.size == max(1, self.batch) * self.boundary_out_doubles and out.flags['C_CONTIGUOUS'])
+        self._ck(self.lib.fds_boundary_enqueue(self.h, float(s), float(eps), int(from_ensemble), int(do_qr),
+                                               int(build), int(halo_steps), dptr(out)))
+
+    def boundary_unpack(self, out, do_qr):
+        """(R, b, G_dil, g_dil, two_passes, cond) from a filled ``out`` block; raises on a failed Cholesky pivot."""
+        self._ck(self.lib.fds_boundary_check(self.h, dptr(out), int(do_qr)))
+        m, nb = self.m, max(1, self.batch)
+        blk = out.reshape(nb, -1)
+        R = blk[:, :m * m].reshape(self.lead + (m, m)).copy() if do_qr else None
+        b = blk[:, m * m:m * m + m].reshape(self.lead + (m,)).copy() if do_qr else None
+        Gd = blk[:, m * m + m:m * m + 2 * m].reshape(self.lead + (m,)).copy()
+        gd = blk[:, m * m + 2 * m].copy()
+        st = blk[:, m * m + 2 * m + 1].copy().view(np.int32).reshape(nb, 2)
+        cond = blk[:, m * m + 2 * m + 2].copy()
+        return R, b, Gd, (gd if self.lead else float(gd[0])), bool(st[:, 1].any()), float(cond.max())
+
+    def segment_enqueue(self, s, eps, steps, Jout):
+        """Put one segment on the stream; ``Jout`` (page-locked, (steps,) + lead + (m+2, 2)) gets the objective sums."""
+        assert Jout is None or (Jout.shape == (int(steps),) + self.lead + (self.M, 2) and Jout.flags['C_CONTIGUOUS'])
+        self._ck(self.lib.fds_segment_enqueue(self.h, float(s), float(eps), int(steps), dptr(Jout)))
+
+    # -- in-library communicator ------------------------------------------------------------------ #
+    def comm_init(self, unique_id):
+        """Join the NCCL communicator identified by the 128 bytes rank 0 got from ``comm_unique_id()``."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.fds_comm_init(self.h, buf))
+
+    @property
+    def comm_attached(self):
+        return bool(self.lib.fds_comm_attached(self.h))
+
+    @property
+    def collectives(self):
+        return int(self.lib.fds_collectives(self.h))
+
+    # -- introspection ---------------------------------------------------------------------------- #
+    def ensemble_rows(self, site0, nsites):
+        """Rows [site0, site0 + nsites) of the current ensemble, (nsites, m+2); ghost sites allowed."""
+        out = np.empty((int(nsites), self.M))
+        self._ck(self.lib.fds_get_ensemble_rows(self.h, int(site0), int(nsites), dptr(out)))
+        return out
+
+    def ensemble_column(self, k):
+        out = _lib.host_empty((self.n,))
+        self._ck(self.lib.fds_get_ensemble_column(self.h, int(k), dptr(out)))
+        return out
+
+    def strip_plan(self):
+        out = (ctypes.c_int64 * 8)()
+        if self.lib.fds_strip_plan(self.h, out) != 0:
+            raise FdsError('fds_strip_plan: this context does not use the streaming step kernel')
+        keys = ('a0', 'strip_sites', 'strips', 'blocks_per_strip', 'node_shift', 'nodes', 'lanes_per_cta', 'steps_per_pass')
+        return dict(zip(keys, (int(x) for x in out)))
 
     def segment(self, s, eps, steps, want_J=True):
         """Advance all m+2 trajectories ``steps`` steps; objective SUMS [steps][m+2][2]."""
@@ -253,6 +321,25 @@ class Context:
         J = self.segment(s, eps, steps)
         V1, v1 = self.get_tangents()
         return self.get_state(), V1, v1, J
+
+
+def comm_unique_id():
+    """128-byte NCCL id (call on ONE rank, distribute to the others, then ``Context.comm_init``)."""
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(128)
+    if lib.fds_comm_unique_id(buf) != 0:
+        raise FdsError(lib.fds_last_error(None).decode())
+    return buf.raw
+
+
+def fp64_issue_rate(device=0):
+    """(FP64 warp-instructions per second of the whole GPU, seconds the probe ran): the measured roof
+    of the exact-mode step kernel (same CTA shape and instruction mix, no memory traffic)."""
+    lib = _lib.load()
+    r, t = ctypes.c_double(), ctypes.c_double()
+    if lib.fds_fp64_issue_rate(int(device), ctypes.byref(r), ctypes.byref(t)) != 0:
+        raise FdsError(lib.fds_last_error(None).decode())
+    return r.value, t.value
 
 
 def lss_solve(R, b, device=0):

@@ -10,7 +10,7 @@ fds/segment.py:43-79).
 import numpy as np
 
 from . import _lib
-from .device import Context, TOY_SYSTEMS
+from .device import Context, TOY_SYSTEMS, comm_unique_id
 from .ring import Ring, shard_range
 
 
@@ -24,7 +24,13 @@ class _DevView:
 
 class Engine:
     def __init__(self, n_global, m, scheme='rk4', math='exact', dt=0.01, device=None,
-                 group=None, distributed=None, max_halo_steps=0, simple_kernels=False, stream=None, batch=1):
+                 group=None, distributed=None, max_halo_steps=0, simple_kernels=False, stream=None, batch=1,
+                 comm='nccl'):
+        """``comm`` (sharded state only): ``'nccl'`` -- the library holds its own NCCL communicator and a
+        boundary / segment is ONE enqueue on the context's stream (halo send/recv, Gram all-reduce and the
+        fixed-order objective sum inside, no host round trip); ``'torch'`` -- the host drives the phases and
+        fills the reduction points with ``torch.distributed`` calls (``Ring``; also what the gloo CPU tests
+        exercise)."""
         self.n_global = int(n_global)
         self.batch = int(batch)
         if self.batch > 1:
@@ -66,6 +72,14 @@ class Engine:
         self.time_dilation = True
         self.dil_mode = 1
         self.run_ddt = None
+        self._dq = None
+        # whole boundaries / segments inside the library: one GPU, or ranks joined by the library's communicator
+        self.lib_comm = self.ring is not None and comm != 'torch'
+        if self.lib_comm:
+            ids = [comm_unique_id() if rank == 0 else None]
+            self.ring.dist.broadcast_object_list(ids, src=self.ring._global(0), group=self.ring.group)
+            self.ctx.comm_init(ids[0])
+        self.in_library = self.ring is None or self.lib_comm
 
     # -- sharding of host arrays --------------------------------------------- #
     def local(self, a):
@@ -133,7 +147,7 @@ class Engine:
     def run(self, s, steps, want_J=True):
         """Advance the primal; returns J (steps, 2) = [mean x, mean x^2] or None."""
         steps = int(steps)
-        if self.ring is None:
+        if self.in_library:
             Js = self.ctx.run(s, steps, want_J)
         else:
             self.ctx.boundary_begin(0)
@@ -156,31 +170,67 @@ class Engine:
         tangents explicitly when the ensemble is built.  Returns (R, b, G_dil, g_dil)."""
         c = self.ctx
         build = (_lib.FDS_BUILD_ENSEMBLE if build else 0) | (_lib.FDS_BUILD_KEEP_TANGENTS if keep_tangents else 0)
+        if self.in_library:
+            if self.run_ddt is not None:
+                self._dilation_input(s)
+            return c.boundary(s, eps, from_ensemble, do_qr, build, 0)
         c.boundary_begin(from_ensemble)
         self._dilation_input(s)
         c.boundary_dxdt(s, from_ensemble, eps)
         self._reduce_gram()
         c.boundary_factor(do_qr, from_ensemble, eps)
-        if do_qr:
+        if do_qr and not c.single_pass_pending:      # the certified single pass launched no second Gram
             self._reduce_gram()
         c.boundary_finish(do_qr, eps, build)
         return c.boundary_results(do_qr)
+
+    # -- the loop without host round trips ---------------------------------------- #
+    def deferred_ok(self):
+        """Can boundaries and segments be enqueued back to back, their KB-sized results fetched at the end?"""
+        return self.in_library and self.run_ddt is None
+
+    def begin_deferred(self, nseg, steps):
+        """Page-locked landing area for ``nseg`` boundaries and ``nseg`` segments of ``steps`` steps."""
+        L = self.ctx.boundary_out_doubles * max(1, self.batch)
+        self._dq = dict(out=_lib.pinned_empty((int(nseg), L)),
+                        J=_lib.pinned_empty((int(nseg), int(steps)) + self.ctx.lead + (self.M, 2)),
+                        nb=0, ns=0, steps=int(steps))
+
+    def boundary_deferred(self, s, eps, from_ensemble, do_qr, build, keep_tangents=True):
+        q = self._dq
+        build = (_lib.FDS_BUILD_ENSEMBLE if build else 0) | (_lib.FDS_BUILD_KEEP_TANGENTS if keep_tangents else 0)
+        assert do_qr
+        self.ctx.boundary_enqueue(s, eps, from_ensemble, do_qr, build, 0, q['out'][q['nb']])
+        q['nb'] += 1
+
+    def segment_deferred(self, s, eps, steps):
+        q = self._dq
+        assert int(steps) == q['steps']
+        self.ctx.segment_enqueue(s, eps, steps, q['J'][q['ns']])
+        q['ns'] += 1
+
+    def end_deferred(self):
+        """Wait for the stream; returns ([(R, b, G_dil, g_dil)] per boundary, [J (steps, m+2, n_qoi)] per segment)."""
+        q, self._dq = self._dq, None
+        self.ctx.sync()
+        bnd = [self.ctx.boundary_unpack(q['out'][i], 1)[:4] for i in range(q['nb'])]
+        Js = [q['J'][i][..., :self.n_qoi] / self.j_div for i in range(q['ns'])]
+        return bnd, Js
 
     # -- one segment ------------------------------------------------------------ #
     def segment(self, s, eps, steps):
         """Advance the m+2 trajectories; returns J (steps, m+2, 2)."""
         steps = int(steps)
+        if self.in_library:
+            return self.ctx.segment(s, eps, steps)[..., :self.n_qoi] / self.j_div
         t = 0
         while t < steps:
             hs = self.ctx.halo_steps(steps - t)
             self._halo(_lib.FDS_BUF_ENSEMBLE, hs)
             self.ctx.segment_advance(s, eps, t, hs)
             t += hs
-        if self.ring is None:
-            Js = self.ctx.segment_jsums(steps)
-        else:
-            part = self._view(_lib.FDS_BUF_JSUM, 0, steps * self.M * 2).clone()
-            Js = self.ring.ordered_sum(part).reshape(steps, self.M, 2)
+        part = self._view(_lib.FDS_BUF_JSUM, 0, steps * self.M * 2).clone()
+        Js = self.ring.ordered_sum(part).reshape(steps, self.M, 2)
         return Js[..., :self.n_qoi] / self.j_div
 
     def segment_sens(self, s, eps, steps):
@@ -188,12 +238,7 @@ class Engine:
         the (steps, m+2, n_qoi) objective block never crosses PCIe."""
         assert self.ring is None
         steps = int(steps)
-        t = 0
-        while t < steps:
-            hs = self.ctx.halo_steps(steps - t)
-            self._halo(_lib.FDS_BUF_ENSEMBLE, hs)
-            self.ctx.segment_advance(s, eps, t, hs)
-            t += hs
+        self.ctx.segment_enqueue(s, eps, steps, None)
         return self.ctx.segment_sensitivities(steps, eps)
 
     # -- state in / out (global host arrays) ------------------------------------ #
@@ -226,12 +271,16 @@ class Engine:
         self.ctx.set_time_dilation(0)
         try:
             c = self.ctx
-            c.boundary_begin(0)
-            c.boundary_dxdt(0.0, 0, 1.0)
-            self._reduce_gram()
-            c.boundary_factor(1, 0, 1.0)
-            self._reduce_gram()
-            c.boundary_finish(1, 1.0, 0)
+            if self.in_library:
+                c.boundary(0.0, 1.0, 0, 1, 0, 0)
+            else:
+                c.boundary_begin(0)
+                c.boundary_dxdt(0.0, 0, 1.0)
+                self._reduce_gram()
+                c.boundary_factor(1, 0, 1.0)
+                if not c.single_pass_pending:
+                    self._reduce_gram()
+                c.boundary_finish(1, 1.0, 0)
         finally:
             self.ctx.set_time_dilation(td)
 
@@ -247,14 +296,20 @@ class HostSolverEngine(Engine):
     ensemble crosses PCIe once in each direction, as it would cross the reference's process pool.
     The run_id strings are the reference's (fds/segment.py:38-49, fds/fds.py:109,131)."""
 
-    def __init__(self, run, m, math='exact', device=None, simultaneous_runs=1):
+    def __init__(self, run, m, math='exact', device=None, simultaneous_runs=None):
+        import threading
         self.user_run = run
         self.m, self.M = int(m), int(m) + 2
         self.kw = dict(math=math, device=0 if device is None else int(device))
         self.device = self.kw['device']
-        self.simultaneous_runs = max(1, int(simultaneous_runs or 1))
+        self.set_simultaneous_runs(simultaneous_runs)
+        # what the reference hands to every run: (Manager().Lock(), Manager().dict()) (fds/fds.py:203-204,
+        # used by apps/vida.py and apps/openfoam4_pitzdaily/pisofoam.py to allocate nodes).  The runs here are
+        # threads of this process, so a thread lock and a plain dict give the same semantics.
+        self.interprocess = (threading.Lock(), {})
         self.ctx = None
         self.ring = None
+        self.lib_comm, self.in_library, self._dq = False, True, None
         self.batch = 1
         self.time_dilation = True
         self.dil_mode, self.run_ddt = 1, None
@@ -262,10 +317,18 @@ class HostSolverEngine(Engine):
         self.i_segment = 0
         self._weights = None
 
+    def set_simultaneous_runs(self, n):
+        """``simultaneous_runs`` of the reference (fds/segment.py:37): None = as many workers as cores."""
+        import os
+        self.simultaneous_runs = max(1, int(n)) if n else (os.cpu_count() or 1)
+
+    def deferred_ok(self):
+        return False
+
     # -- the reference's RunWrapper (fds/fds.py:53-90): 3-, 4- or 5-argument plugins -------------- #
     def _call(self, u0, parameter, steps, run_id):
-        run, last = self.user_run, None
-        for kw in (dict(run_id=run_id, interprocess=None), dict(run_id=run_id), dict(interprocess=None), {}):
+        run, last, ip = self.user_run, None, self.interprocess
+        for kw in (dict(run_id=run_id, interprocess=ip), dict(run_id=run_id), dict(interprocess=ip), {}):
             try:
                 u1, J = run(np.array(u0), parameter, steps, **kw)
                 return np.asarray(u1, dtype=np.float64), np.array(J, dtype=np.float64).reshape([steps, -1])
@@ -302,7 +365,7 @@ class HostSolverEngine(Engine):
         self.ctx.set_state(u)
 
     def run(self, s, steps, want_J=True):
-        u1, J = self._call(self.ctx.get_state(), s, int(steps), 'run_up')
+        u1, J = self._call(self.ctx.get_state(), s, int(steps), 'runup')       # fds/fds.py:207
         self.ctx.set_state(u1)
         return J if want_J else None
 

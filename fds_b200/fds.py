@@ -78,7 +78,8 @@ def continue_shadowing(run, parameter, checkpoint, num_segments, steps_per_segme
     (fds/timedilation.py:59-61), ``'analytic'`` = the built-in system's ``dt * f(u)`` on the device, or a
     callable ``run_ddt(u0, parameter) -> du per step`` (the reference's TimeDilationExact, whose upstream
     implementation raises NameError at fds/timedilation.py:58).
-    ``simultaneous_runs``, ``get_host_dir``, ``spawn_compute_job`` are inert."""
+    ``simultaneous_runs`` sets the worker count of a ``HostSolver`` (fds/segment.py:37) and is inert for
+    device plugins; ``get_host_dir``, ``spawn_compute_job`` are inert."""
     assert verify_checkpoint(checkpoint)
     u0, V, v, lss, G_lss, g_lss, J_hist, G_dil, g_dil = checkpoint
     V = np.asarray(V)
@@ -89,38 +90,76 @@ def continue_shadowing(run, parameter, checkpoint, num_segments, steps_per_segme
     eng.set_tangents(V, v)
     if hasattr(eng, 'i_segment'):
         eng.i_segment = lss.K_segments()       # run_id numbering of a host solver continues
+    if simultaneous_runs is not None and hasattr(eng, 'set_simultaneous_runs'):
+        eng.set_simultaneous_runs(simultaneous_runs)
     return _segment_loop(eng, parameter, lss, G_lss, g_lss, J_hist, G_dil, g_dil, num_segments,
                          steps_per_segment, epsilon, checkpoint_path, checkpoint_interval,
                          return_checkpoint, verbose)
 
 
+def _is_writer(eng):
+    """Rank that writes checkpoints (every rank holds the same gathered arrays)."""
+    ring = getattr(eng, 'ring', None)
+    return ring is None or ring.rank == 0
+
+
+def _save(eng, checkpoint_path, cp):
+    """Checkpoint written once (rank 0), atomically, and visible to every rank when this returns."""
+    if _is_writer(eng):
+        save_checkpoint(checkpoint_path, cp)
+    ring = getattr(eng, 'ring', None)
+    if ring is not None:
+        ring.dist.barrier(group=ring.group)
+
+
 def _segment_loop(eng, parameter, lss, G_lss, g_lss, J_hist, G_dil, g_dil, num_segments,
                   steps, epsilon, checkpoint_path, checkpoint_interval, return_checkpoint, verbose):
-    def record_segment():
-        J0, G, g = sensitivities(eng.segment(parameter, epsilon, steps), epsilon)
+    def record(J):
+        J0, G, g = sensitivities(J, epsilon)
         J_hist.append(J0), G_lss.append(G), g_lss.append(g)
 
     def snapshot():
         V, v = eng.get_tangents()
         return Checkpoint(eng.get_state(), V, v, lss, G_lss, g_lss, J_hist, G_dil, g_dil)
 
+    K0 = lss.K_segments()
     # first boundary of this call: time dilation + projection only (fds/fds.py:113-126)
     eng.boundary(parameter, epsilon, from_ensemble=0, do_qr=0, build=1)
-    record_segment()
-    for i in range(lss.K_segments() + 1, num_segments + 1):
-        last = i == num_segments
-        save = bool(checkpoint_path) and i % checkpoint_interval == 0
-        R, b, Gd, gd = eng.boundary(parameter, epsilon, from_ensemble=1, do_qr=1, build=not last,
-                                    keep_tangents=save)
-        lss.append(R, b)
-        G_dil.append(Gd), g_dil.append(gd)
-        if verbose:
-            print(lss_gradient(Checkpoint(None, None, None, lss, G_lss, g_lss, J_hist, G_dil, g_dil)))
-            sys.stdout.flush()
-        if save:
-            save_checkpoint(checkpoint_path, snapshot())
-        if not last:
-            record_segment()
+    nq = num_segments - K0
+    if nq >= 1 and not verbose and not checkpoint_path and getattr(eng, 'deferred_ok', lambda: False)():
+        # Device-resident loop without host round trips: every boundary and segment of this call is put on
+        # the stream back to back (adaptive CholeskyQR decided on the device, halo exchange / reductions
+        # over the library's communicator), the KB-sized per-segment results land in page-locked memory and
+        # are read once at the end.  Same arithmetic as the step-by-step loop below.
+        eng.begin_deferred(nq, steps)
+        eng.segment_deferred(parameter, epsilon, steps)
+        for i in range(K0 + 1, num_segments + 1):
+            last = i == num_segments
+            eng.boundary_deferred(parameter, epsilon, from_ensemble=1, do_qr=1, build=not last,
+                                  keep_tangents=last and return_checkpoint)
+            if not last:
+                eng.segment_deferred(parameter, epsilon, steps)
+        bnd, Js = eng.end_deferred()
+        for (R, b, Gd, gd), J in zip(bnd, Js):
+            record(J)
+            lss.append(R, b)
+            G_dil.append(Gd), g_dil.append(gd)
+    else:
+        record(eng.segment(parameter, epsilon, steps))
+        for i in range(K0 + 1, num_segments + 1):
+            last = i == num_segments
+            save = bool(checkpoint_path) and i % checkpoint_interval == 0
+            R, b, Gd, gd = eng.boundary(parameter, epsilon, from_ensemble=1, do_qr=1, build=not last,
+                                        keep_tangents=save or (last and return_checkpoint))
+            lss.append(R, b)
+            G_dil.append(Gd), g_dil.append(gd)
+            if verbose:
+                print(lss_gradient(Checkpoint(None, None, None, lss, G_lss, g_lss, J_hist, G_dil, g_dil)))
+                sys.stdout.flush()
+            if save:
+                _save(eng, checkpoint_path, snapshot())
+            if not last:
+                record(eng.segment(parameter, epsilon, steps))
     if return_checkpoint:
         return snapshot()
     cp = Checkpoint(None, None, None, lss, G_lss, g_lss, J_hist, G_dil, g_dil)
@@ -146,6 +185,10 @@ def shadowing(run, u0, parameter, subspace_dimension, num_segments, steps_per_se
     eng.set_time_dilation(_dilation_mode(run_ddt))
     eng.set_dxdt_weights(stencil_weights(3))
     eng.set_state(u0)
+    if hasattr(eng, 'i_segment'):
+        eng.i_segment = 0                      # run_id numbering of a host solver starts over (fds/segment.py:38-49)
+    if simultaneous_runs is not None and hasattr(eng, 'set_simultaneous_runs'):
+        eng.set_simultaneous_runs(simultaneous_runs)
     if runup_steps > 0:
         eng.run(parameter, runup_steps, want_J=False)
     # random orthonormal tangents, v = 0 (fds/fds.py:21-27)

@@ -12,11 +12,31 @@ import numpy as np
 from . import device
 
 
+def _solve_device():
+    """GPU of the KKT solve: this process's current device under torch.distributed (one process per
+    GPU), else device 0.  Resolved at call time, never stored: a checkpoint written by rank 5 of an
+    8-GPU run must load and solve on a one-GPU box."""
+    try:
+        import torch
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
+            return torch.cuda.current_device()
+    except ImportError:
+        pass
+    return 0
+
+
 class LssTangent:
-    def __init__(self, Rs=None, bs=None, device_ordinal=0):
+    def __init__(self, Rs=None, bs=None, device_ordinal=None):
         self.Rs = list(Rs) if Rs is not None else []
         self.bs = list(bs) if bs is not None else []
-        self.device_ordinal = device_ordinal
+        self.device_ordinal = device_ordinal      # explicit override for this process only (not pickled)
+
+    def __getstate__(self):
+        return {'Rs': self.Rs, 'bs': self.bs}
+
+    def __setstate__(self, st):
+        self.Rs, self.bs = list(st['Rs']), list(st['bs'])
+        self.device_ordinal = None
 
     def K_segments(self):
         assert len(self.Rs) == len(self.bs)
@@ -35,7 +55,8 @@ class LssTangent:
         (fds/lsstan.py:36-50), on the device."""
         R, b = np.array(self.Rs), np.array(self.bs)
         assert R.ndim == 3 and b.ndim == 2 and R.shape == (b.shape[0], b.shape[1], b.shape[1])
-        return device.lss_solve(R, b, self.device_ordinal)
+        dev = self.device_ordinal if self.device_ordinal is not None else _solve_device()
+        return device.lss_solve(R, b, dev)
 
     def lyapunov_exponents(self, segment_range=None):
         """log |diag R_i| per segment (fds/lsstan.py:58-64)."""

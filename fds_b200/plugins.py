@@ -75,7 +75,7 @@ class HostSolver:
     algebra of the segment loop runs on the device (``HostSolverEngine``).  A bare Python callable is
     still rejected: nothing in this package runs the hot path on the CPU behind the user's back."""
 
-    def __init__(self, run, math='exact', device=None, simultaneous_runs=1):
+    def __init__(self, run, math='exact', device=None, simultaneous_runs=None):
         self.user_run = run
         self.kw = dict(math=math, device=device, simultaneous_runs=simultaneous_runs)
         self._engines = {}

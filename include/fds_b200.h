@@ -107,6 +107,7 @@ int fds_get_tangents(fds_ctx*, double* V_host, double* v_host);
 /* page-locked host memory (cudaHostAlloc) for the buffers above: optional -- any host pointer is
  * accepted -- but pinned buffers move at full PCIe rate and let uploads overlap the transposes  */
 void* fds_host_alloc(size_t bytes);                                  /* NULL on failure */
+void* fds_host_alloc_wc(size_t bytes);  /* write-combined: for buffers the host only writes (uploads) */
 void  fds_host_free(void* p);
 int fds_random_tangents(fds_ctx*, uint64_t seed);  /* uniform[0,1) V (pascal.random, fds/fds.py:23), v = 0 */
 
@@ -132,6 +133,9 @@ int fds_set_dxdt(fds_ctx*, const double* d_host);   /* [n_local] (batch: [B][n_l
  * fds_last_condition: the bound sqrt(|G|_inf |G^-1|_inf) >= cond_2 of the last single-pass attempt. */
 int    fds_set_qr_passes(fds_ctx*, int passes);
 double fds_last_condition(const fds_ctx*);
+/* split-phase API: after fds_boundary_factor, 1 if the certified single pass was accepted -- no second
+ * Gram was launched, so the caller skips the second sum-reduce of FDS_BUF_GRAM                          */
+int    fds_single_pass_pending(const fds_ctx*);
 
 /* ---- the solver plugin itself: u1, J = run(u0, s, steps), fds/fds.py:184-200 -- */
 /* single trajectory on the context's primal array (world == 1; halos wrapped inside);
@@ -188,10 +192,41 @@ int fds_segment_advance(fds_ctx*, double s, double eps, int64_t step0, int64_t n
 /* objective sums of the last segment, J_host[steps][m+2][2] = [sum x, sum x^2]    */
 int fds_segment_jsums(fds_ctx*, int64_t steps, double* Jsum_host);
 
-/* ---- convenience for world == 1 (all phases + halos inside) ------------------- */
+/* ---- whole boundary / whole segment in one call (all phases, halos and reductions inside) -----
+ * world == 1, or world > 1 with a communicator attached (fds_comm_init below).                  */
 int fds_boundary(fds_ctx*, double s, double eps, int from_ensemble, int do_qr, int build_ensemble,
                  int64_t halo_steps, double* R, double* b, double* G_dil, double* g_dil);
 int fds_segment(fds_ctx*, double s, double eps, int64_t steps, double* Jsum_host);
+/* The same WITHOUT waiting for the device: everything one iteration of the reference's loop does
+ * (fds/fds.py:128-170) is put on the context's stream and the call returns.  For m = 16 / 32 the adaptive
+ * CholeskyQR decision (one pass or two) is taken on the device, so a boundary has no host round trip at
+ * all; the results land in caller-owned (preferably page-locked, fds_host_alloc) memory when the stream
+ * gets there:
+ *   out[fds_boundary_out_doubles()] per problem = R[m*m], b[m], G_dil[m], g_dil,
+ *                                                 {int32 status, int32 two_passes_taken}, cond bound
+ *   Jsum_host[steps][m+2][2]
+ * Call fds_sync(), then fds_boundary_check(out, do_qr) (non-zero = a Cholesky pivot failed, message in
+ * fds_last_error).  out / Jsum_host may be NULL.                                       */
+int64_t fds_boundary_out_doubles(const fds_ctx*);
+int fds_boundary_enqueue(fds_ctx*, double s, double eps, int from_ensemble, int do_qr, int build_ensemble,
+                         int64_t halo_steps, double* out);
+int fds_boundary_check(fds_ctx*, const double* out, int do_qr);
+int fds_segment_enqueue(fds_ctx*, double s, double eps, int64_t steps, double* Jsum_host);
+
+/* ---- multi-GPU inside the library: NCCL on the context's stream ---------------------------------
+ * The reference shards the state over MPI ranks (fds/compute.py:87-89) and exchanges halos / reduces
+ * dot products over MPI (tests/solvers/mock_fun3d/fun3d:29-37, pascal_lite/operators/plinalg.py:19-64).
+ * Here rank 0 obtains a 128-byte id (fds_comm_unique_id), the host distributes it by whatever means it
+ * has (MPI_Bcast, torch.distributed, a file), and every rank calls fds_comm_init on its context (created
+ * with cfg.rank / cfg.world).  From then on fds_halo_wrap_*, fds_run, fds_boundary*, fds_segment* work for
+ * world > 1: ring send/recv of the halos, one all-reduce of the (m+2)^2 Gram per CholeskyQR pass, and an
+ * all-gather + FIXED-order tree sum of the objective partials (J is bitwise independent of the number of
+ * ranks for power-of-two shard sizes).  NCCL is bound at run time (dlopen of libnccl.so.2, or $FDS_NCCL_LIB).
+ * fds_comm_attach: use an existing ncclComm_t (not owned) instead.                                  */
+int fds_comm_unique_id(void* id128);
+int fds_comm_init(fds_ctx*, const void* id128);
+int fds_comm_attach(fds_ctx*, void* nccl_comm);
+int fds_comm_attached(const fds_ctx*);
 /* host-buffer form of one reference run_segment call (fds/segment.py:14-82):
  * u, V, v in -> advanced u, V, v out, Jsum[steps][m+2][2]; H2D and D2H inside     */
 int fds_run_segment_host(fds_ctx*, double* u, double* V, double* v, double s, double eps,
@@ -231,6 +266,18 @@ int fds_lss_solve(int device, const double* R, const double* b, int64_t K, int m
 /* ---- introspection ------------------------------------------------------------ */
 void*   fds_buffer_ptr(const fds_ctx*, int which_buf);   /* device pointer of site/elem 0 */
 int64_t fds_kernel_launches(const fds_ctx*);              /* kernels launched so far        */
+int64_t fds_collectives(const fds_ctx*);                  /* NCCL operations enqueued so far */
+/* a slab of the current ensemble, rows [site0, site0 + nsites) of E[site][m+2] (ghost sites allowed), and
+ * one whole column k (0 = primal, fds/segment.py:43; m+1 = the parameter-perturbed run, :64): what a test
+ * needs to compare any window of a large state with the reference's run() on the same window            */
+int fds_get_ensemble_rows(fds_ctx*, int64_t site0, int64_t nsites, double* out);   /* [nsites][m+2] */
+int fds_get_ensemble_column(fds_ctx*, int k, double* out);                         /* [n_local]     */
+/* strip decomposition of the step kernel: out = {a0, strip length, strips, 8-blocks per strip, log2 sites
+ * per objective node, nodes, lanes a CTA packs (strip, column) pairs over (0 = whole strips), steps per pass} */
+int fds_strip_plan(const fds_ctx*, int64_t out[8]);
+/* measured roof of the exact-mode step kernel: FP64 warp-instructions per second of the whole GPU with the
+ * kernel's own shape and instruction mix (~0.25 s of load, so at the clock the board sustains)          */
+int fds_fp64_issue_rate(int device, double* winst_per_s, double* seconds);
 int     fds_sync(fds_ctx*);
 /* per-launch device timing of the ensemble step kernel (CUDA events on the context's stream):
  * enable, run, then read the summed duration and the number of launches since enabling   */
