@@ -1,30 +1,37 @@
 #!/usr/bin/env python
 """Benchmark of the shadowing segment loop (BASELINE.json metric) on 1..8 B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
 
-Workload (BASELINE.json configs[3]): Lorenz-96, F = 8, RK4 dt = 0.01,
-N = 2^24 sites PER GPU (weak scaling, state sharded along N with halo exchange),
-m = 32 homogeneous tangents -> 34 trajectories, 100 time steps per segment,
-epsilon = 1e-6 sqrt(N), synthetic data (u0 = RandomState(0).rand(N) + run-up).
+Workload (BASELINE.json configs[3]): Lorenz-96, F = 8, RK4 dt = 0.01, m = 32 homogeneous
+tangents -> 34 trajectories, 100 time steps per segment, epsilon = 1e-6 sqrt(N), synthetic data
+(u0 = RandomState(rank).rand(n) + run-up).  The state is sharded along N over the ranks (halo exchange +
+Gram all-reduce on the library's own NCCL communicator).  --scaling weak (default): N = 2^24 sites PER GPU;
+--scaling strong: N = 2^24 sites in TOTAL (BASELINE configs[3] read literally).  Every N > 1 weak line also
+carries the strong-scaling measurement as the side key `strong_cfg4`.
 
-One bench "step" = one shadowing segment: the boundary (time dilation, projection,
-CholeskyQR2, next perturbed ensemble) + 100 ensemble time steps + the objective
-sums / sensitivities brought back to the host.  metric = state-updates/s =
-N_total * (m+1) * steps_per_segment * K / time.
+One bench "step" = one shadowing segment: the boundary (time dilation, projection, adaptive CholeskyQR,
+next perturbed ensemble) + 100 ensemble time steps + the objective sums / R / b brought back to the host.
+metric = state-updates/s = N_total * (m+1) * steps_per_segment * K / time.
 
-`value`   device-resident loop (inputs in HBM when the clock starts).
-`e2e`     the public API call continue_shadowing(run, s, checkpoint, ...) on HOST
-          numpy buffers: u0/V/v uploaded, K segments, u0/V/v + histories downloaded.
-`roofline` the ensemble step kernel: algorithmic bytes 16 B * N_local * (m+2) per
-          launch / mean launch duration (CUDA events around every launch in the
-          timed region) vs the measured HBM copy peak (MEASURED_PEAKS.json).
-`cpu_baseline` / --impl reference: the numpy restatement of the reference's loop
-          (oracle/shadowing_port.py, pinned against /root/reference by
-          oracle/gen_golden.py) on the host cores, process pool of os.cpu_count()
-          workers like the reference (fds/segment.py:37), on a bounded sample.
+`value`     device-resident loop (inputs in HBM when the clock starts): K boundaries + K segments put on the
+            stream back to back (no host round trip), results read once -- the product loop of
+            fds_b200/fds.py:_segment_loop.
+`e2e`       the public API call continue_shadowing(run, s, checkpoint, ...) on HOST numpy buffers:
+            u0/V/v uploaded, K segments, u0/V/v + histories downloaded.
+`roofline`  the ensemble step kernel.  Exact mode is bound by the FP64 pipe (two time steps per pass halve
+            the HBM traffic): achieved FP64 warp-instructions/s vs the rate measured in this run by the
+            library's probe (fds_fp64_issue_rate: same CTA shape and instruction mix, no memory traffic).
+            The HBM view rides along: algorithmic bytes (16 B per trajectory-site-step) per launch / mean
+            launch duration vs the measured copy peak, and the real DRAM traffic of an ncu capture.
+`dist_check` (N > 1) sharded vs single-GPU bit-equality on a small problem, run before the timed region;
+            the process exits non-zero when it fails.
+`cpu_baseline` / --impl reference: the UNMODIFIED reference (oracle/_ref, installed from /root/reference by
+            oracle/build_ref.py) when present, else the numpy port (oracle/shadowing_port.py), on the host
+            cores with the reference's own process pool, on a bounded sample that its `config` names.
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -38,6 +45,10 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'L96 shadowing state-updates/s (N*(m+1)*steps*K / time)'
 UNIT = 'state-updates/s'
+# FP64 warp-instructions of the exact-mode two-step kernel per 8-site block of two steps (static count of
+# the hot loop with the objective tree): 476 -> 29.75 per trajectory-site-step
+FP64_INST_PER_UPDATE = {('exact', 2): 29.75}
+STEP_KERNEL_SOURCES = ['l96_step.cu', 'l96_core.cuh', 'l96_march.cuh', 'l96_march2.cuh', 'l96_marchk.cuh', 'common.cuh']
 
 
 def parse():
@@ -46,77 +57,117 @@ def parse():
     ap.add_argument('--steps', type=int, default=5, help='timed segments')
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--logn', type=int, default=24, help='log2 of sites per GPU')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--logn', type=int, default=24, help='log2 of sites per GPU (weak) / in total (strong)')
     ap.add_argument('--m', type=int, default=32)
     ap.add_argument('--seg-steps', type=int, default=100)
     ap.add_argument('--math', default='exact', choices=['exact', 'fast'])
-    ap.add_argument('--cpu-logn', type=int, default=20, help='log2 N of the CPU-baseline sample')
+    ap.add_argument('--cpu-logn', type=int, default=18, help='log2 N of the CPU sample (reference arm / cpu_baseline)')
     ap.add_argument('--cpu-seg-steps', type=int, default=10)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-sweep', action='store_true', help='skip the batched-sweep side measurement')
+    ap.add_argument('--no-fast', action='store_true', help='skip the fast-math side measurement')
+    ap.add_argument('--no-strong', action='store_true', help='skip the strong-scaling side measurement (N > 1)')
+    ap.add_argument('--no-distcheck', action='store_true')
+    ap.add_argument('--no-djds', action='store_true')
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------- #
-# CPU leg: the oracle port (the only place bench.py executes oracle/)
+# CPU leg: the reference itself (oracle/_ref) or the oracle port -- the only place bench.py executes oracle/
 # --------------------------------------------------------------------------- #
-def cpu_port_run(logn, m, seg_steps, K):
+def reference_module():
+    """The unmodified reference package, installed into oracle/_ref by oracle/build_ref.py (git-ignored,
+    travels to the GPU box); None when it is not there."""
+    p = os.path.join(ROOT, 'oracle', '_ref')
+    if os.path.isdir(os.path.join(p, 'fds')) and os.path.isdir(os.path.join(p, 'pascal_lite')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+        try:
+            import fds
+            return fds
+        except Exception as e:                       # a missing dependency (scipy, dill) on the box
+            print('bench: oracle/_ref present but not importable (%s); timing the port' % e, file=sys.stderr)
+    return None
+
+
+def cpu_run(logn, m, seg_steps, K):
+    """One bounded sample on the host cores; returns (updates/s, seconds, cores, kind)."""
     from oracle import plugins, shadowing_port as port
     N = 1 << logn
     cores = os.cpu_count() or 1
     u0 = np.random.RandomState(0).rand(N)
     u0 = plugins.run_l96_rk4(u0, 0.0, 20)[0]
     np.random.seed(0)
+    ref = reference_module()
     t0 = time.perf_counter()
-    port.shadowing(plugins.run_l96_rk4, u0, 0.0, m, K, seg_steps, 0,
-                   epsilon=1e-6 * np.sqrt(N), workers=cores)
+    if ref is not None:
+        # fds/fds.py:178-220; simultaneous_runs=None -> Pool(None) = one worker per core (fds/segment.py:37)
+        ref.shadowing(plugins.run_l96_rk4, u0, 0.0, m, K, seg_steps, 0, epsilon=1e-6 * np.sqrt(N))
+    else:
+        port.shadowing(plugins.run_l96_rk4, u0, 0.0, m, K, seg_steps, 0, epsilon=1e-6 * np.sqrt(N), workers=cores)
     dt = time.perf_counter() - t0
-    return N * (m + 1) * seg_steps * K / dt, dt, cores
+    return N * (m + 1) * seg_steps * K / dt, dt, cores, 'reference' if ref is not None else 'port'
+
+
+def cpu_sample_text(args, K, cores, kind, dt=None):
+    what = ('fds.shadowing() of the unmodified reference (oracle/_ref)' if kind == 'reference'
+            else 'oracle/shadowing_port.py shadowing()')
+    return ('%s, L96-RK4 N=2^%d m=%d, %d segments x %d steps per sample, pool of %d processes%s'
+            % (what, args.cpu_logn, args.m, K, args.cpu_seg_steps, cores, '' if dt is None else ', %.1f s' % dt))
 
 
 def cpu_baseline(args):
     K = 2
-    v, dt, cores = cpu_port_run(args.cpu_logn, args.m, args.cpu_seg_steps, K)
-    return {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': 'oracle/shadowing_port.py shadowing(), L96-RK4 N=2^%d m=%d, %d segments x %d steps, '
-                      'pool of %d processes, %.1f s' % (args.cpu_logn, args.m, K, args.cpu_seg_steps, cores, dt)}
+    v, dt, cores, kind = cpu_run(args.cpu_logn, args.m, args.cpu_seg_steps, K)
+    return {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': cpu_sample_text(args, K, cores, kind, dt)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (numpy port; the Python reference
-    itself cannot travel to the GPU box) on the host cores, same metric."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores, same metric.
+    Each bench step is one bounded sample (named in `config`): N = 2^cpu_logn, 2 segments x cpu_seg_steps."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     K = 2
     vals, times = [], []
+    cores, kind = os.cpu_count() or 1, 'port'
     for it in range(args.warmup + args.steps):
-        v, dt, cores = cpu_port_run(args.cpu_logn, args.m, args.cpu_seg_steps, K)
+        v, dt, cores, kind = cpu_run(args.cpu_logn, args.m, args.cpu_seg_steps, K)
         if it >= args.warmup:
             vals.append(v), times.append(dt)
     value = float(np.mean(vals))
-    sample = ('bounded sample of the workload: N=2^%d (not 2^%d) m=%d, %d segments x %d steps per bench step, '
-              'pool of %d processes' % (args.cpu_logn, args.logn, args.m, K, args.cpu_seg_steps, cores))
+    cfg = {'workload': 'bounded sample of the headline workload: Lorenz-96 F=8 RK4 dt=0.01 shadowing, N=2^%d sites '
+                       '(headline: 2^%d per GPU), m=%d (%d trajectories), %d segments x %d steps per bench step '
+                       '(headline: 1 segment x %d steps), eps=1e-6*sqrt(N), host cores only'
+                       % (args.cpu_logn, args.logn, args.m, args.m + 2, K, args.cpu_seg_steps, args.seg_steps),
+           'N': 1 << args.cpu_logn, 'm': args.m, 'segments_per_step': K, 'steps_per_segment': args.cpu_seg_steps,
+           'sample_of': workload_config(args)['workload'],
+           'parallelism': 'multiprocessing.Pool(%d) as the reference does (fds/segment.py:37)' % cores}
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(times) * 1e3),
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic', 'config': workload_config(args),
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                             'sample': cpu_sample_text(args, K, cores, kind)},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     emit(line)
 
 
-def workload_config(args):
-    return {'workload': 'Lorenz-96 F=8 RK4 dt=0.01 shadowing, N=2^%d sites per GPU, m=%d (%d trajectories), '
-                        '%d steps/segment, eps=1e-6*sqrt(N)' % (args.logn, args.m, args.m + 2, args.seg_steps),
-            'N_per_gpu': 1 << args.logn, 'm': args.m, 'steps_per_segment': args.seg_steps, 'math': args.math,
-            'bench_step': 'one segment = boundary (time dilation + projection + CholeskyQR2 + next ensemble) '
-                          '+ %d ensemble time steps' % args.seg_steps,
-            'l2': 'ensemble %.1f GB per GPU >> 126 MB L2 (no flush needed)'
-                  % ((1 << args.logn) * (args.m + 2) * 8 / 1e9),
-            'parallelism': 'N-sharded ring, %d GPU(s)' % args.gpus}
+def workload_config(args, world=None):
+    world = args.gpus if world is None else world
+    per = 'per GPU' if args.scaling == 'weak' else 'in total (sharded over the GPUs)'
+    n_local = (1 << args.logn) if args.scaling == 'weak' else (1 << args.logn) // world
+    return {'workload': 'Lorenz-96 F=8 RK4 dt=0.01 shadowing, N=2^%d sites %s, m=%d (%d trajectories), '
+                        '%d steps/segment, eps=1e-6*sqrt(N)' % (args.logn, per, args.m, args.m + 2, args.seg_steps),
+            'N_per_gpu': n_local, 'm': args.m, 'steps_per_segment': args.seg_steps, 'math': args.math,
+            'bench_step': 'one segment = boundary (time dilation + projection + adaptive CholeskyQR: one certified '
+                          'pass, CholeskyQR2 otherwise -- see qr_two_pass_segments + next ensemble) + %d ensemble time steps'
+                          % args.seg_steps,
+            'l2': 'ensemble %.1f GB per GPU >> 126 MB L2 (no flush needed)' % (n_local * (args.m + 2) * 8 / 1e9),
+            'parallelism': 'N-sharded ring, %d GPU(s), library NCCL communicator' % world}
 
 
 # --------------------------------------------------------------------------- #
@@ -172,33 +223,40 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------- #
-def djds_check(device):
+def djds_check(device, math='exact'):
     """Third part of the BASELINE metric: dJ/ds of config 3 (Lorenz-96 N=40, m=16, 100 segments)
     on the GPU next to the reference's value and its own error bar (committed fixture generated
-    from the reference by oracle/gen_golden.py); pass = ratio <= 1."""
+    from the reference by oracle/gen_golden.py); pass = ratio <= 1.  Fast math follows a
+    different trajectory, so its own statistical error is added to the bar."""
     import fds_b200
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'cfg3_l96rk4_N40_m16_K100.npz'))
     np.random.seed(int(g['seed']))
-    run = fds_b200.L96(40, device=device, distributed=False)
-    J, G = fds_b200.shadowing(run, g['u0'], float(g['s']), int(g['m']), int(g['K']), int(g['steps']),
-                              int(g['runup']), epsilon=float(g['eps']))
+    run = fds_b200.L96(40, device=device, distributed=False, math=math)
+    cp = fds_b200.shadowing(run, g['u0'], float(g['s']), int(g['m']), int(g['K']), int(g['steps']),
+                            int(g['runup']), epsilon=float(g['eps']), return_checkpoint=True)
     run.close()
+    a, b = fds_b200.lss_gradient_series(cp)
+    G, own = fds_b200.timeseries.mean_std(a + b)
     err = np.abs(G - g['G_ref'])
-    return {'config': 'Lorenz-96 N=40 F=8.1 RK4, m=16, 100 segments x 100 steps (BASELINE configs[2])',
+    bar = g['G_err'] if math == 'exact' else g['G_err'] + own
+    return {'config': 'Lorenz-96 N=40 F=8.1 RK4, m=16, 100 segments x 100 steps (BASELINE configs[2])', 'math': math,
             'G': G.tolist(), 'G_ref': g['G_ref'].tolist(), 'sigma_ref': g['G_err'].tolist(),
-            'abs_err': err.tolist(), 'ratio': (err / g['G_err']).tolist(),
-            'pass': bool((err <= g['G_err']).all())}
+            'abs_err': err.tolist(), 'ratio': (err / bar).tolist(), 'pass': bool((err <= bar).all())}
 
 
-def sweep_check(device, B=4096, N=4096, m=16, K=2, steps=100):
-    """BASELINE configs[4] measured beside the headline: B independent Lorenz-96 problems (F swept
-    over [6, 10]) in one batched context; whole segments (boundary + 100 steps), device resident."""
+def sweep_check(device, dist, world, B_total=4096, N=4096, m=16, K=2, steps=100):
+    """BASELINE configs[4] measured beside the headline: 4096 independent Lorenz-96 problems (F swept over
+    [6, 10]), split over the ranks (replicas only, no collective), one batched context per GPU; whole
+    segments (boundary + 100 steps), device resident.  Time = max over ranks."""
+    import torch
     import fds_b200
     eps = 1e-4
+    rank = dist.get_rank() if world > 1 else 0
+    B = B_total // world
     run = fds_b200.L96(N, device=device, distributed=False)
     eng = run.batch_engine(m, B)
-    eng.ctx.set_batch_params(np.linspace(-2.0, 2.0, B))
-    eng.set_state(np.random.RandomState(0).rand(B, N))
+    eng.ctx.set_batch_params(np.linspace(-2.0, 2.0, B_total)[rank * B:(rank + 1) * B])
+    eng.set_state(np.random.RandomState(rank).rand(B, N))
     eng.run(0.0, 200, want_J=False)
     eng.orthonormal_random_tangents(seed=1)
     eng.boundary(0.0, eps, 0, 0, 1)
@@ -209,6 +267,8 @@ def sweep_check(device, B=4096, N=4096, m=16, K=2, steps=100):
         return R, eng.segment_sens(0.0, eps, steps)[1]
     seg()
     eng.ctx.sync()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(K):
         R, J = seg()
@@ -216,83 +276,132 @@ def sweep_check(device, B=4096, N=4096, m=16, K=2, steps=100):
     dt = time.perf_counter() - t0
     ok = bool(np.isfinite(J).all() and np.isfinite(R).all())
     run.close()
-    return {'config': '%d independent Lorenz-96 N=%d problems, m=%d, one batched context on one GPU' % (B, N, m),
-            'value': B * N * (m + 1) * steps * K / dt, 'unit': UNIT, 'segments': K, 'seconds': dt, 'finite': ok}
+    if world > 1:
+        t = torch.tensor([dt, 0.0 if ok else 1.0], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, ok = float(t[0].item()), t[1].item() == 0.0
+    return {'config': '%d independent Lorenz-96 N=%d problems, m=%d, %d per GPU in one batched context each '
+                      '(replicas only, no data-path collective)' % (B_total, N, m, B),
+            'value': B_total * N * (m + 1) * steps * K / dt, 'unit': UNIT, 'segments': K, 'seconds': dt, 'finite': ok}
+
+
+def step_sources_sha():
+    h = hashlib.sha256()
+    for f in STEP_KERNEL_SOURCES:
+        with open(os.path.join(ROOT, 'fds_b200', 'csrc', f), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+class Loop:
+    """One context + the device-resident segment loop of the product (enqueue-only, results read at the end)."""
+
+    def __init__(self, fds_b200, N, m, S, math, device, stream, rank):
+        self.N, self.m, self.S = N, m, S
+        self.eps, self.s = 1e-6 * np.sqrt(N), 0.0
+        self.run = fds_b200.L96(N, math=math, device=device, stream=stream)
+        self.eng = eng = self.run.engine(m)
+        eng.ctx.set_state(np.random.RandomState(rank).rand(eng.hi - eng.lo))
+        eng.run(self.s, 200, want_J=False)
+        eng.orthonormal_random_tangents(seed=1)
+        eng.boundary(self.s, self.eps, from_ensemble=0, do_qr=0, build=1)
+        eng.segment(self.s, self.eps, S)
+
+    def segments(self, K):
+        """K x (boundary + segment); returns the per-segment results (R, b, Gd, gd, J0, G, g) and how many
+        boundaries took the two-pass CholeskyQR2."""
+        from fds_b200.segment import sensitivities
+        eng, s, eps, S = self.eng, self.s, self.eps, self.S
+        eng.begin_deferred(K, S)
+        for _ in range(K):
+            eng.boundary_deferred(s, eps, from_ensemble=1, do_qr=1, build=1, keep_tangents=False)
+            eng.segment_deferred(s, eps, S)
+        q = eng._dq
+        bnd, Js = eng.end_deferred()
+        two = sum(int(eng.ctx.boundary_unpack(q['out'][i], 1)[4]) for i in range(K))
+        return [b + sensitivities(J, eps) for b, J in zip(bnd, Js)], two
+
+    def close(self):
+        self.run.close()
+
+
+def timed(loop, K, W, barrier, torch, dist, world):
+    """W warm-up + K timed segments; device time (CUDA events on the context's stream = torch's current
+    stream), max over ranks."""
+    loop.segments(max(W, 1))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    hist, two = loop.segments(K)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    R = hist[-1][0]
+    assert np.isfinite(R).all() and (np.diag(R) > 0).all() and np.isfinite(hist[-1][4]).all()
+    return float(ms.item()), hist, two
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import fds_b200
-    from fds_b200.segment import sensitivities
+    from fds_b200 import device as fdev
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # one process per GPU on a multi-socket host: run on the CPUs next to this rank's GPU, so that the
-        # page-locked host buffers of the end-to-end leg (allocated below) sit on the GPU's own NUMA node and
-        # eight 4.6 GB uploads do not all cross the socket interconnect.  (Not at N = 1: the cpu_baseline leg
-        # that follows uses every core.)
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-        except Exception as e:      # affinity is an optimisation, never a requirement
-            print('bench: no NUMA affinity (%s)' % e, file=sys.stderr)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     assert world == args.gpus, 'launch with torchrun --nproc-per-node %d for --gpus %d' % (args.gpus, args.gpus)
-
-    n_local = 1 << args.logn
-    N = n_local * world
-    m, M, S = args.m, args.m + 2, args.seg_steps
-    eps = 1e-6 * np.sqrt(N)
-    s = 0.0
-    stream = torch.cuda.current_stream().cuda_stream
-    run = fds_b200.L96(N, math=args.math, device=local_rank, stream=stream)
-    eng = run.engine(m)
-    lo, hi = eng.lo, eng.hi
-
-    # synthetic initial state on the attractor; random orthonormal tangents (device RNG)
-    eng.ctx.set_state(np.random.RandomState(rank).rand(n_local))
-    eng.run(s, 200, want_J=False)
-    eng.orthonormal_random_tangents(seed=1)
-    eng.boundary(s, eps, from_ensemble=0, do_qr=0, build=1)
-    eng.segment(s, eps, S)
-
-    def one_segment():
-        R, b, Gd, gd = eng.boundary(s, eps, from_ensemble=1, do_qr=1, build=1, keep_tangents=False)
-        J0, G, g = sensitivities(eng.segment(s, eps, S), eps)
-        return R, b, Gd, gd, J0, G, g
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_segment()
+    # ---- multi-GPU parity first: sharded vs one GPU, bit for bit, on a small problem ----------- #
+    dist_check = None
+    if world > 1 and not args.no_distcheck:
+        from fds_b200.selfcheck import sharded_vs_single
+        dist_check = sharded_vs_single(local_rank)
+        if not dist_check['pass']:
+            if rank == 0:
+                emit({'metric': METRIC, 'value': None, 'unit': UNIT, 'n_gpus': world, 'dist_check': dist_check,
+                      'error': 'sharded run differs from the single-GPU run'})
+            dist.destroy_process_group()
+            sys.exit(3)
+
+    n_local = (1 << args.logn) if args.scaling == 'weak' else (1 << args.logn) // world
+    N = n_local * world
+    m, M, S = args.m, args.m + 2, args.seg_steps
+    stream = torch.cuda.current_stream().cuda_stream
+    loop = Loop(fds_b200, N, m, S, args.math, local_rank, stream, rank)
+    eng, run, s, eps = loop.eng, loop.run, loop.s, loop.eps
+
+    loop.segments(max(args.warmup, 1))
     sampler = ClockSampler(local_rank)
     eng.ctx.profile_enable(True)
-    l0 = eng.ctx.launches
+    l0, c0 = eng.ctx.launches, eng.ctx.collectives
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    hist = [one_segment() for _ in range(args.steps)]
+    hist, two_pass = loop.segments(args.steps)
     e1.record()
     barrier()
     clocks = sampler.result()
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
-    launches = torch.tensor([eng.ctx.launches - l0], device='cuda', dtype=torch.float64)
+    counts = torch.tensor([eng.ctx.launches - l0, eng.ctx.collectives - c0], device='cuda', dtype=torch.float64)
     kern_ms, kern_n = eng.ctx.profile_read()
     steps_per_launch = eng.ctx.profile_steps / max(kern_n, 1)     # 2 with temporal blocking
     eng.ctx.profile_enable(False)
     kern = torch.tensor([kern_ms / max(kern_n, 1)], device='cuda', dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
         dist.all_reduce(kern, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     value = N * (m + 1) * S * args.steps / (total_ms * 1e-3)
@@ -301,6 +410,15 @@ def run_ours(args):
     R = hist[-1][0]
     assert np.isfinite(R).all() and (np.diag(R) > 0).all()
     assert np.isfinite(hist[-1][4]).all()
+
+    # ---- the measured FP64 roof (the board still warm from the timed region) -------------------- #
+    fp64_peak, fp64_clk = None, None
+    if rank == 0:
+        probe_clk = ClockSampler(local_rank)
+        probe_clk.start()
+        fp64_peak, _ = fdev.fp64_issue_rate(local_rank)
+        fp64_clk = probe_clk.result()
+    barrier()
 
     # ---- end to end through the public API on host buffers ----------------- #
     e2e = per_seg = None
@@ -329,6 +447,7 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
         assert out.lss.K_segments() == args.steps and np.isfinite(out.V).all()
+        del out
         # strictest reading: the reference's run_segment(u0, V, v) -> (u0, V, v, J0, G, g) on host arrays, i.e.
         # the whole ensemble state crosses PCIe in both directions EVERY segment (single GPU only)
         bytes_in_1 = M * n_local * 8
@@ -344,6 +463,7 @@ def run_ours(args):
             barrier()
             dt1 = (time.perf_counter() - t1) / 2
             assert np.isfinite(res[1]).all()
+            res = None
             per_seg = {'value': N * (m + 1) * S / dt1, 'unit': UNIT, 'seconds_per_segment': dt1,
                        'h2d_bytes_per_step': float(bytes_in_1), 'd2h_bytes_per_step': float(bytes_in_1 + S * M * 16),
                        'call': 'segment.run_segment(run, u0, V, v, s, 0, %d, eps) on pinned host arrays, one call per segment' % S}
@@ -353,62 +473,143 @@ def run_ours(args):
                'h2d_bytes_per_step': bytes_in / args.steps, 'd2h_bytes_per_step': (bytes_in + small) / args.steps,
                'call': 'continue_shadowing(run, s, checkpoint(host u0,V,v), %d segments, return_checkpoint=True); '
                        'one call = %d bench steps, %.3f s' % (args.steps, args.steps, dt)}
+        del u, V, v
+
+    roof_main = roofline(args, args.math, n_local, M, float(kern.item()), steps_per_launch, S, args.steps, total_ms,
+                         clocks, fp64_peak, fp64_clk) if rank == 0 else None
+    loop.close()
+    fds_b200._lib.pool_release()
+
+    # ---- side measurements ---------------------------------------------------------------------- #
+    fast = None
+    if args.math == 'exact' and not args.no_fast:
+        # FMA-contracted arithmetic (north-star criterion 2 admits it: dJ/ds within the error bar): 22 instead of
+        # 30 FP64 instructions per update, so the kernel leans on DRAM -- its own roofline line
+        lf = Loop(fds_b200, N, m, S, 'fast', local_rank, stream, rank)
+        lf.segments(2)
+        lf.eng.ctx.profile_enable(True)
+        fclk = ClockSampler(local_rank)
+        fclk.start()
+        Kf = min(args.steps, 5)
+        fms, _, _ = timed(lf, Kf, 1, barrier, torch, dist, world)
+        fclocks = fclk.result()
+        fk_ms, fk_n = lf.eng.ctx.profile_read()
+        fspl = lf.eng.ctx.profile_steps / max(fk_n, 1)
+        fkern = torch.tensor([fk_ms / max(fk_n, 1)], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(fkern, op=dist.ReduceOp.MAX)
+        lf.close()
+        if rank == 0:
+            # the timed() call ran its own warm-up segment with profiling on: launches / steps ratios are unaffected
+            fast = {'value': N * (m + 1) * S * Kf / (fms * 1e-3), 'unit': UNIT, 'ms_per_step': fms / Kf, 'segments': Kf,
+                    'roofline': roofline(args, 'fast', n_local, M, float(fkern.item()), fspl, S, Kf, fms, fclocks,
+                                         fp64_peak, fp64_clk)}
+
+    strong = None
+    if world > 1 and args.scaling == 'weak' and not args.no_strong:
+        # BASELINE configs[3] read literally: N = 2^logn sites in TOTAL, sharded over the ranks
+        ls = Loop(fds_b200, 1 << args.logn, m, S, args.math, local_rank, stream, rank)
+        Ks = max(args.steps, 5)
+        sms, _, stwo = timed(ls, Ks, 2, barrier, torch, dist, world)
+        ls.close()
+        strong = {'config': 'N = 2^%d sites in total over %d GPUs (2^%d... per GPU), m=%d, %d steps/segment'
+                            % (args.logn, world, args.logn, m, S),
+                  'N_per_gpu': (1 << args.logn) // world, 'value': (1 << args.logn) * (m + 1) * S * Ks / (sms * 1e-3),
+                  'unit': UNIT, 'ms_per_step': sms / Ks, 'segments': Ks, 'qr_two_pass_segments': stwo,
+                  'scaling': 'strong', 'note': 'efficiency = value / (the 1-GPU headline value of the same run series)'}
+
+    sweep = None
+    if not args.no_sweep and 4096 % world == 0:
+        sweep = sweep_check(local_rank, dist, world)
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:
-            pass
-        peak = float(peaks.get('hbm_gbs', 6650.0))
-        kms = float(kern.item())
-        alg_bytes = 16.0 * n_local * M * steps_per_launch
-        achieved = alg_bytes / (kms * 1e-3) / 1e9
-        traffic = fp64_pct = None
-        try:
-            prof = json.load(open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')))
-            traffic, fp64_pct = prof['dram_bytes_per_launch'], prof.get('fp64_pipe_busy_pct')
-        except Exception:
-            pass
-        # FP64-pipe utilisation of the step kernel from the live numbers: FP64 warp-instructions per launch
-        # (static count of the hot loop, DESIGN 4.1: 476 per 8-site block of two steps = 29.75 per update in exact
-        # mode with the objective sums) over what 4 schedulers x 1 instruction per 2 clocks issue at the SM clock
-        # sampled during the timed region
-        fp64_live = None
-        if clocks.get('sm_mhz') and args.math == 'exact' and steps_per_launch == 2 and torch.cuda.is_available():
-            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-            winst = n_local * M * steps_per_launch * 29.75 / 32.0
-            fp64_live = 100.0 * winst / (kms * 1e-3 * clocks['sm_mhz'] * 1e6 * sms * 4 * 0.5)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': workload_config(args),
-                'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                             'frac': achieved / peak, 'traffic': traffic,
-                             'kernel': 'l96_rk4_stream_kernel', 'kernel_ms': kms,
-                             'algorithmic_bytes_per_launch': alg_bytes, 'time_steps_per_launch': steps_per_launch,
-                             'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s',
-                             'frac_of_nominal_8TBs': achieved / 8000.0,
-                             'fp64_pipe_busy_pct_ncu': fp64_pct, 'fp64_pipe_busy_pct_live': fp64_live,
-                             'step_kernel_share_of_time': kms * (S / steps_per_launch) * args.steps / total_ms,
-                             'note': ('temporal blocking: one launch advances %g time steps, so DRAM traffic per launch '
-                                      '(`traffic`) is 1/%g of the algorithmic bytes and `frac` can exceed 1; the kernel is '
-                                      'then bound by the FP64 pipe (profiles/)' % (steps_per_launch, steps_per_launch))
-                                     if steps_per_launch > 1 else 'one time step per launch'},
-                'clocks': clocks, 'gpu_launches': int(launches.item())}
+                'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': workload_config(args, world), 'roofline': roof_main, 'clocks': clocks,
+                'gpu_launches': int(counts[0].item()), 'nccl_ops': int(counts[1].item()),
+                'qr_two_pass_segments': int(two_pass)}
         if e2e is not None:
             line['e2e'] = e2e
             if per_seg is not None:
                 line['e2e_run_segment'] = per_seg
-        line['djds'] = djds_check(local_rank)
-        if world == 1 and not args.no_sweep:
-            line['sweep_cfg5'] = sweep_check(local_rank)
+        if dist_check is not None:
+            line['dist_check'] = dist_check
+        if fast is not None:
+            line['value_fast'] = fast['value']
+            line['fast_math'] = fast
+        if strong is not None:
+            line['strong_cfg4'] = strong
+        if not args.no_djds:
+            line['djds'] = djds_check(local_rank)
+            if fast is not None:
+                line['fast_math']['djds'] = djds_check(local_rank, 'fast')
+        if sweep is not None:
+            line['sweep_cfg5'] = sweep
         if not args.no_cpu and world == 1:
             line['cpu_baseline'] = cpu_baseline(args)
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def roofline(args, math, n_local, M, kms, steps_per_launch, S, K, total_ms, clocks, fp64_peak, fp64_clk):
+    """Roofline object of the step kernel.  Exact math: FP64-issue bound (measured peak); fast math: HBM
+    bound on the REAL traffic (8 B per trajectory-site-step with two steps per pass)."""
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    alg_bytes = 16.0 * n_local * M * steps_per_launch
+    alg_gbs = alg_bytes / (kms * 1e-3) / 1e9
+    traffic = ncu_fp64 = None
+    note = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'step_kernel_traffic.json')))
+        ent = prof.get(math, prof if math == 'exact' else {})
+        if ent.get('src_sha16') == step_sources_sha() and n_local == (1 << 24) and M == 34:
+            traffic, ncu_fp64 = ent.get('dram_bytes_per_launch'), ent.get('fp64_pipe_busy_pct')
+        else:
+            note = 'ncu capture under profiles/ is of other kernel sources or another size: traffic not quoted'
+    except Exception:
+        pass
+    hbm = {'achieved_algorithmic': alg_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac_algorithmic': alg_gbs / hbm_peak,
+           'frac_of_nominal_8TBs': alg_gbs / 8000.0, 'algorithmic_bytes_per_launch': alg_bytes,
+           'dram_bytes_per_launch_ncu': traffic,
+           'frac_dram_real': (traffic / (kms * 1e-3) / 1e9 / hbm_peak) if traffic else None,
+           'peak_source': 'MEASURED_PEAKS.json hbm_gbs (measured copy)' if peaks else 'fallback 6650 GB/s'}
+    common = {'kernel': 'l96_rk4_stream_kernel', 'kernel_ms': kms, 'time_steps_per_launch': steps_per_launch,
+              'step_kernel_share_of_time': kms * (S / steps_per_launch) * K / total_ms, 'traffic': traffic,
+              'fp64_pipe_busy_pct_ncu': ncu_fp64, 'hbm': hbm}
+    if note:
+        common['note'] = note
+    ipu = FP64_INST_PER_UPDATE.get((math, int(round(steps_per_launch))))
+    if math == 'exact' and ipu and fp64_peak:
+        winst = n_local * M * steps_per_launch * ipu / 32.0
+        ach = winst / (kms * 1e-3)
+        out = {'bound': 'fp64', 'achieved': ach / 1e9, 'peak': fp64_peak / 1e9, 'unit': 'G FP64 warp-inst/s',
+               'frac': ach / fp64_peak,
+               'peak_source': 'fds_fp64_issue_rate() measured in this run (one 256-thread CTA per SM, 2 DADD : 1 DMUL, '
+                              '8 chains per thread, no memory traffic) at %s MHz' % (fp64_clk or {}).get('sm_mhz'),
+               'fp64_warp_inst_per_update': ipu,
+               'why': 'two time steps per pass: DRAM traffic per launch is half the algorithmic bytes, the FP64 pipe '
+                      '(%g exact-mode instructions per update) is what is saturated' % ipu}
+        if clocks.get('sm_mhz') and fp64_clk and fp64_clk.get('sm_mhz'):
+            # per-clock view: removes the clock difference between the probe (no DRAM power) and the step kernel
+            out['frac_per_clock'] = out['frac'] * fp64_clk['sm_mhz'] / clocks['sm_mhz']
+        out.update(common)
+        return out
+    # HBM bound: report against the REAL traffic when known, else the algorithmic bytes
+    real = traffic / (kms * 1e-3) / 1e9 if traffic else None
+    out = {'bound': 'hbm', 'achieved': real if real else alg_gbs, 'peak': hbm_peak, 'unit': 'GB/s',
+           'frac': (real if real else alg_gbs) / hbm_peak,
+           'basis': 'measured DRAM bytes (ncu)' if real else 'algorithmic bytes (16 B per trajectory-site-step; the kernel '
+                    'moves half of that with two steps per pass)'}
+    out.update(common)
+    return out
 
 
 class _LocalShardPlugin:

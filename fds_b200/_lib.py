@@ -49,11 +49,14 @@ SIGNATURES = {
     'fds_set_ensemble': (_I32, [_CTX, c_double_p, _D]),
     'fds_set_primal_history': (_I32, [_CTX, _I32, c_double_p]),
     'fds_set_dxdt_weights': (_I32, [_CTX, c_double_p]),
+    'fds_set_dxdt_stencil': (_I32, [_CTX, _I32, c_double_p]),
+    'fds_dilation_order': (_I32, [_CTX]),
     'fds_set_time_dilation': (_I32, [_CTX, _I32]),
     'fds_set_dxdt': (_I32, [_CTX, c_double_p]),
     'fds_set_qr_passes': (_I32, [_CTX, _I32]),
     'fds_last_condition': (_D, [_CTX]),
     'fds_single_pass_pending': (_I32, [_CTX]),
+    'fds_last_qr_passes': (_I32, [_CTX]),
     'fds_run': (_I32, [_CTX, _D, _I64, c_double_p]),
     'fds_primal_advance': (_I32, [_CTX, _D, _I64, _I64, _I32]),
     'fds_halo_mark_valid': (_I32, [_CTX, _I32, _I64]),

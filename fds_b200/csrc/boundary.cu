@@ -47,6 +47,78 @@ cudaError_t launch_dxdt(const double* P0, const double* P1, const double* P2, co
     return cudaGetLastError();
 }
 
+// ---- time dilation, fused: u_1 .. u_order and d in one pass (see kernels.h) ---------------------------------- //
+constexpr int kDilTile = 1024;      // sites of d per CTA
+constexpr int kDilThreads = 256;
+
+template <class MP, int EULER>
+__global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const double* __restrict__ P0, double* __restrict__ d,
+                                                                     long long n, DilationStencil st, double F0, Rk4Coef c,
+                                                                     const double2* __restrict__ Fpp, long long slot) {
+    constexpr int GL = EULER ? 2 : 8, GR = EULER ? 1 : 4;          // dependency cone of one step
+    extern __shared__ __align__(16) double sm[];
+    const int p = st.order;
+    const int W0 = kDilTile + p * (GL + GR);                         // widest level (u_0)
+    double* buf[2] = {sm, sm + W0};
+    const long long t0 = (long long)blockIdx.x * kDilTile;
+    const int cnt = (int)((n - t0) < kDilTile ? (n - t0) : kDilTile);
+    const int tid = threadIdx.x;
+    // level 0: u_0 on [t0 - p GL, t0 + cnt + p GR); buffer index j <-> site t0 - p GL + j
+    const int w0 = cnt + p * (GL + GR);
+    for (int j = tid; j < w0; j += kDilThreads) buf[0][j] = P0[t0 - p * GL + j];
+    __syncthreads();
+    constexpr int PER = kDilTile / kDilThreads;
+    double acc[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid + q * kDilThreads;
+        acc[q] = i < cnt ? __dmul_rn(st.c[0], buf[0][i + p * GL]) : 0.0;
+    }
+    for (int k = 1; k <= p; ++k) {
+        // level k: u_k on [t0 - (p-k) GL, t0 + cnt + (p-k) GR); index j <-> site t0 - (p-k) GL + j.
+        // site s sits at index s - t0 + (p-k+1) GL in level k-1
+        const double* src = buf[(k - 1) & 1];
+        double* dst = buf[k & 1];
+        const int wk = cnt + (p - k) * (GL + GR);
+        for (int j = tid; j < wk; j += kDilThreads) {
+            const long long site = t0 - (long long)(p - k) * GL + j;
+            double F = F0;
+            if (Fpp != nullptr) {
+                long long q = site / slot;                         // ghosts left of stacked site 0 belong to problem 0
+                F = Fpp[q < 0 ? 0 : q].x;
+            }
+            const double* x = src + j;                             // = index of site - GL in level k-1
+            dst[j] = EULER ? l96_euler_point<MP>(x, F, c.h) : l96_rk4_point<MP>(x, F, c);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int i = tid + q * kDilThreads;
+            if (i < cnt) acc[q] = __dadd_rn(acc[q], __dmul_rn(st.c[k], dst[i + (p - k) * GL]));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int i = tid + q * kDilThreads;
+        if (i < cnt) d[t0 + i] = acc[q];
+    }
+}
+
+cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, const DilationStencil& st, double F0, double dt,
+                                  int exact, int euler, const double2* Fpp, long long slot, cudaStream_t stream,
+                                  LaunchStats* ls) {
+    if (st.order < 1 || st.order > kMaxDilationOrder || n < 1) return cudaErrorInvalidValue;
+    const unsigned grid = (unsigned)((n + kDilTile - 1) / kDilTile);
+    const size_t smem = 2 * (size_t)(kDilTile + st.order * 12) * sizeof(double);
+    const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+#define FDS_DIL(MP, E) dilation_fused_kernel<MP, E><<<grid, kDilThreads, smem, stream>>>(P0, d, n, st, F0, c, Fpp, slot)
+    if (exact) { if (euler) FDS_DIL(ExactMath, 1); else FDS_DIL(ExactMath, 0); }
+    else       { if (euler) FDS_DIL(FastMath, 1);  else FDS_DIL(FastMath, 0); }
+#undef FDS_DIL
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
 // T[i][j] = (E[i][j+1] - E[i][0]) / eps   (fds/segment.py:74,77; true IEEE division)
 __global__ void diff_tangents_kernel(const double* __restrict__ E, int M, double eps, double* __restrict__ T,
                                      long long total) {

@@ -53,6 +53,7 @@ struct fds_ctx {
     double* small_block = nullptr;
     SmallBufs small{};
     double* c4 = nullptr;
+    DilationStencil stencil{3, {-11.0 / 6.0, 3.0, -1.5, 1.0 / 3.0, 0, 0, 0, 0, 0}};   // fds/timedilation.py:64: order 3
     double* A_host = nullptr;      // pinned copy of small.A (+ status): A travels to apply_fast as a kernel parameter
     bool fast_boundary = false;    // register-blocked gram / apply kernels (boundary_fast.cu)
     bool mma_boundary = false;     // tensor-core gram / apply kernels (boundary_mma.cu): single problem or batch
@@ -80,6 +81,7 @@ struct fds_ctx {
     int pend_src = 0;
     double pend_inv_eps = 0.0;
     double cond_last = 0.0;           // upper bound of cond_2 from the last single-pass attempt
+    int passes_last = 0;              // CholeskyQR passes the last boundary with QR took (1 or 2)
     double eps_last = 0.0;
     long long ens_halo_valid = 0, pri_halo_valid = 0;
     LaunchStats ls;
@@ -604,8 +606,23 @@ int fds_set_dxdt_weights(fds_ctx* c, const double w[4]) {
     FDS_ON_DEVICE(c);
     FDS_CK(c, cudaMemcpyAsync(c->c4, w, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
+    c->stencil.order = 3;
+    for (int j = 0; j < 4; ++j) c->stencil.c[j] = w[j];
     return 0;
 }
+
+// TimeDilation.order_of_accuracy (fds/timedilation.py:8-12,64): `order` look-ahead steps, order + 1 weights
+int fds_set_dxdt_stencil(fds_ctx* c, int order, const double* w) {
+    if (order == 3) return fds_set_dxdt_weights(c, w);
+    if (order < 1 || order > kMaxDilationOrder) return fail(c, "fds_set_dxdt_stencil: order must be 1 .. 8");
+    if (c->toy || c->host_sys) return fail(c, "fds_set_dxdt_stencil: small ODE systems and host solvers implement order 3 only");
+    if (order > c->H) return fail(c, "fds_set_dxdt_stencil: order exceeds the halo capacity (max_halo_steps)");
+    c->stencil.order = order;
+    for (int j = 0; j <= order; ++j) c->stencil.c[j] = w[j];
+    return 0;
+}
+
+int fds_dilation_order(const fds_ctx* c) { return c->stencil.order; }
 
 int fds_set_time_dilation(fds_ctx* c, int mode) {
     if (mode < 0 || mode > 3) return fail(c, "fds_set_time_dilation: mode must be 0 .. 3");
@@ -634,6 +651,8 @@ int fds_set_qr_passes(fds_ctx* c, int passes) {
 double fds_last_condition(const fds_ctx* c) { return c->cond_last; }
 
 int fds_single_pass_pending(const fds_ctx* c) { return c->qr_single ? 1 : 0; }
+
+int fds_last_qr_passes(const fds_ctx* c) { return c->passes_last; }
 
 // ------------------------------- state in / out ------------------------------ //
 static int sync_primal_from_ensemble(fds_ctx* c) {
@@ -1152,17 +1171,26 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
                                          nullptr, c->stream, &c->ls));
         FDS_CK(c, launch_dxdt(c->P(0), c->P(1), c->P(2), c->P(3), c->c4, c->d, c->n, c->stream, &c->ls));
     } else if (c->time_dilation) {
-        if (c->pri_halo_valid < 3) return fail(c, "fds_boundary_dxdt: primal halo must be valid for 3 steps");
+        if (c->pri_halo_valid < c->stencil.order)
+            return fail(c, "fds_boundary_dxdt: primal halo must be valid for " + std::to_string(c->stencil.order) + " steps");
         if (int r = upload_forcing(c, s, 0.0)) return r;
-        long long valid = 3;
-        for (int j = 1; j <= 3; ++j) {
-            StepArgs a;
-            primal_step_args(c, a, j - 1, j, valid, s);
-            FDS_CK(c, launch_l96_simple(a, c->cfg.system == FDS_SYS_L96_EULER, c->stream, &c->ls));
-            --valid;
+        static const bool split = getenv("FDS_DILATION_SPLIT") != nullptr;     // cross-check path: one kernel per step
+        if (split && c->stencil.order == 3) {
+            long long valid = 3;
+            for (int j = 1; j <= 3; ++j) {
+                StepArgs a;
+                primal_step_args(c, a, j - 1, j, valid, s);
+                FDS_CK(c, launch_l96_simple(a, c->cfg.system == FDS_SYS_L96_EULER, c->stream, &c->ls));
+                --valid;
+            }
+            FDS_CK(c, launch_dxdt(c->P_all(0), c->P_all(1), c->P_all(2), c->P_all(3), c->c4, c->d_alloc, c->nall, c->stream, &c->ls));
+        } else {
+            // u_1 .. u_order and d = sum c_k u_k in one pass, nothing but d written
+            FDS_CK(c, launch_dilation_fused(c->P_all(0), c->d_alloc, c->nall, c->stencil, s + 8.0, c->cfg.dt,
+                                            c->cfg.math == FDS_MATH_EXACT, c->cfg.system == FDS_SYS_L96_EULER,
+                                            c->nb > 1 ? c->Fpp : nullptr, c->slot, c->stream, &c->ls));
         }
         c->pri_halo_valid = 0;
-        FDS_CK(c, launch_dxdt(c->P_all(0), c->P_all(1), c->P_all(2), c->P_all(3), c->c4, c->d_alloc, c->nall, c->stream, &c->ls));
     } else {
         FDS_CK(c, cudaMemsetAsync(c->d_alloc, 0, (size_t)c->nall * sizeof(double), c->stream));
     }
@@ -1180,8 +1208,9 @@ int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
         FDS_CK(c, launch_small_single(c->small, c->m, c->time_dilation ? 1 : 0, c->stream, &c->ls, c->batch()));
         const std::string keep = c->err;
         const int r = check_small_status(c, "CholeskyQR");
-        if (r == 0 && c->cond_last * c->cond_last * 2.3e-16 < 2e-13) {
+        if (r == 0 && c->cond_last * c->cond_last * 2.3e-16 < kSinglePassTol) {
             c->qr_single = true;
+            c->passes_last = 1;
             c->pend_src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
             c->pend_inv_eps = from_ensemble ? 1.0 / eps : 0.0;
             return 0;
@@ -1209,6 +1238,7 @@ int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
         FDS_CK(c, do_apply(c, c->pend_src, c->pend_inv_eps, keepT ? c->T : nullptr, ens ? c->Ecur() : nullptr, eps));
         if (!keepT) c->tangents_implicit = true;    // the new ensemble is the record of the tangents
     } else if (do_qr) {
+        c->passes_last = 2;
         FDS_CK(c, launch_small2(c->small, c->m, c->stream, &c->ls, c->batch()));
         if (int r = check_small_status(c, "CholeskyQR pass 2")) return r;
         FDS_CK(c, do_apply(c, SRC_TANGENT, 0.0, keepT ? c->T : nullptr, ens ? c->Ecur() : nullptr, eps));
@@ -1304,11 +1334,16 @@ int fds_boundary_check(fds_ctx* c, const double* out, int do_qr) {
     if (!do_qr) return 0;
     const size_t len = (size_t)fds_boundary_out_doubles(c);
     double cond = 0.0;
+    int two = 0;
     for (int p = 0; p < c->nb; ++p) {
         if (int r = decode_boundary_block(c, out + p * len, p)) return r;
         cond = std::max(cond, out[p * len + len - 1]);
+        int st[2];
+        std::memcpy(st, out + p * len + len - 2, sizeof(st));
+        two |= st[1];
     }
     c->cond_last = cond;
+    if (c->gated) c->passes_last = two ? 2 : 1;
     return 0;
 }
 
@@ -1322,7 +1357,7 @@ int fds_boundary_enqueue(fds_ctx* c, double s, double eps, int from_ensemble, in
     if (c->cfg.world != 1 && !c->comm)
         return fail(c, "fds_boundary: world > 1, attach a communicator (fds_comm_init) or drive the phases with reductions in between");
     if (int r = fds_boundary_begin(c, from_ensemble)) return r;
-    if (c->time_dilation) if (int r = fds_halo_wrap_primal(c, 3)) return r;
+    if (c->time_dilation) if (int r = fds_halo_wrap_primal(c, c->stencil.order)) return r;
     if (int r = fds_boundary_dxdt(c, s, from_ensemble, eps)) return r;
     if (int r = allreduce_gram(c, c->small.gram)) return r;
     const size_t len = (size_t)fds_boundary_out_doubles(c);

@@ -88,6 +88,15 @@ cudaError_t launch_batch_sens(const double* jsum, int nb, int M, long long steps
 cudaError_t launch_extract_col0(const double* E, int M, double* P, long long n, cudaStream_t, LaunchStats*);
 cudaError_t launch_dxdt(const double* P0, const double* P1, const double* P2, const double* P3,
                         const double* c4_dev, double* d, long long n, cudaStream_t, LaunchStats*);
+// Time dilation in ONE pass (fds/timedilation.py:14-35,63-82): the `order` look-ahead states u_1 .. u_order of the
+// primal (each one solver step, same arithmetic as launch_l96_simple) are formed tile by tile in shared memory and
+// d = sum_k c_k u_k is accumulated in the reference's left-to-right order -- no intermediate state touches HBM.
+// P0: site 0 of the single-column primal with ghosts valid for `order` steps; d: site 0.  Batch: stacked array + Fpp.
+constexpr int kMaxDilationOrder = 8;
+struct DilationStencil { int order; double c[kMaxDilationOrder + 1]; };
+cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, const DilationStencil& st, double F0,
+                                  double dt, int exact, int euler, const double2* Fpp, long long slot,
+                                  cudaStream_t, LaunchStats*);
 cudaError_t launch_diff_tangents(const double* E, int M, double eps, double* T, long long n,
                                  cudaStream_t, LaunchStats*);
 cudaError_t launch_make_ensemble(const double* u, const double* T, int M, double eps, double* E,

@@ -135,9 +135,14 @@ class Context:
         self._ck(self.lib.fds_random_tangents(self.h, ctypes.c_uint64(int(seed) & (2 ** 64 - 1))))
 
     def set_dxdt_weights(self, c):
+        """One-sided first-derivative weights on order + 1 nodes (order 3 unless len(c) says otherwise)."""
         c = np.ascontiguousarray(c, dtype=np.float64)
-        assert c.shape == (4,)
-        self._ck(self.lib.fds_set_dxdt_weights(self.h, dptr(c)))
+        assert c.ndim == 1 and c.size >= 2
+        self._ck(self.lib.fds_set_dxdt_stencil(self.h, c.size - 1, dptr(c)))
+
+    @property
+    def dilation_order(self):
+        return int(self.lib.fds_dilation_order(self.h))
 
     def set_time_dilation(self, mode):
         """False / 0: off; True / 1: finite differences; 2: analytic dt*f(u); 3: given (set_dxdt)."""
@@ -155,6 +160,11 @@ class Context:
     @property
     def last_condition(self):
         return float(self.lib.fds_last_condition(self.h))
+
+    @property
+    def last_qr_passes(self):
+        """CholeskyQR passes (1 or 2) the last boundary with QR took."""
+        return int(self.lib.fds_last_qr_passes(self.h))
 
     @property
     def single_pass_pending(self):

@@ -142,7 +142,7 @@ class Engine:
             d = np.asarray(self.run_ddt(self.get_state(), s), dtype=np.float64)
             self.ctx.set_dxdt(self.local(d))
         elif self.time_dilation:
-            self._halo(_lib.FDS_BUF_PRIMAL, 3)
+            self._halo(_lib.FDS_BUF_PRIMAL, self.ctx.dilation_order)
 
     def run(self, s, steps, want_J=True):
         """Advance the primal; returns J (steps, 2) = [mean x, mean x^2] or None."""

@@ -18,6 +18,7 @@ import numpy as np
 from .checkpoint import Checkpoint, verify_checkpoint, save_checkpoint
 from .lsstan import LssTangent
 from .segment import trapez_mean, sensitivities
+from . import timedilation
 from .timedilation import stencil_weights
 from .timeseries import windowed_mean
 
@@ -85,7 +86,7 @@ def continue_shadowing(run, parameter, checkpoint, num_segments, steps_per_segme
     V = np.asarray(V)
     eng = _engine_of(run, V.shape[0])
     eng.set_time_dilation(_dilation_mode(run_ddt))
-    eng.set_dxdt_weights(stencil_weights(3))
+    eng.set_dxdt_weights(stencil_weights(timedilation.ORDER_OF_ACCURACY))
     eng.set_state(u0)
     eng.set_tangents(V, v)
     if hasattr(eng, 'i_segment'):
@@ -183,7 +184,7 @@ def shadowing(run, u0, parameter, subspace_dimension, num_segments, steps_per_se
     m = int(subspace_dimension)
     eng = _engine_of(run, m)
     eng.set_time_dilation(_dilation_mode(run_ddt))
-    eng.set_dxdt_weights(stencil_weights(3))
+    eng.set_dxdt_weights(stencil_weights(timedilation.ORDER_OF_ACCURACY))
     eng.set_state(u0)
     if hasattr(eng, 'i_segment'):
         eng.i_segment = 0                      # run_id numbering of a host solver starts over (fds/segment.py:38-49)
@@ -282,7 +283,7 @@ def _shadowing_batch_local(run, u0, parameters, subspace_dimension, num_segments
     if u0.ndim == 1:
         u0 = np.broadcast_to(u0, (B, N))
     eng.set_time_dilation(_dilation_mode(run_ddt))
-    eng.set_dxdt_weights(stencil_weights(3))
+    eng.set_dxdt_weights(stencil_weights(timedilation.ORDER_OF_ACCURACY))
     eng.ctx.set_batch_params(parameters)          # problem p runs at 0.0 + parameters[p]
     eng.set_state(np.ascontiguousarray(u0))
     s = 0.0

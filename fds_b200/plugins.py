@@ -45,7 +45,7 @@ class _DevicePlugin:
         key = (m, int(batch))
         if key not in self._engines:
             kw = dict(self.kw)
-            kw.pop('group', None), kw.pop('distributed', None)
+            kw.pop('group', None), kw.pop('distributed', None), kw.pop('comm', None)
             if kw.get('device') is None:
                 kw['device'] = _current_device()
             self._engines[key] = Engine(self.N, m, batch=int(batch), **kw)
@@ -135,7 +135,10 @@ class L96(_DevicePlugin):
     n_qoi = 2
 
     def __init__(self, N, scheme='rk4', dt=0.01, math='exact', device=None, group=None,
-                 max_halo_steps=0, simple_kernels=False, stream=None, distributed=None):
+                 max_halo_steps=0, simple_kernels=False, stream=None, distributed=None, comm='nccl'):
+        """Under an initialised ``torch.distributed`` (one process per GPU) the state is sharded along N over
+        the ranks of ``group``; ``comm='nccl'`` (default) lets the library run halo exchange and reductions on
+        its own NCCL communicator, ``comm='torch'`` drives them from the host (``fds_b200/ring.py``)."""
         self._init(N, scheme=scheme, math=math, dt=dt, device=device, group=group,
                    max_halo_steps=max_halo_steps, simple_kernels=simple_kernels, stream=stream,
-                   distributed=distributed)
+                   distributed=distributed, comm=comm)

@@ -14,12 +14,15 @@ ORDER_OF_ACCURACY = 3     # reference fds/timedilation.py:64
 
 
 def set_order_of_accuracy(order_of_accuracy):
-    """The device path implements the reference default (3) only."""
+    """Order of the one-sided difference used for the time-dilation vector: that many look-ahead steps of the
+    primal per boundary (reference fds/timedilation.py:8-12, incl. its clamp at 2).  Takes effect at the next
+    ``shadowing`` / ``continue_shadowing`` call; Lorenz-96 device plugins support 2 .. 8, the small ODE systems
+    and host solvers 3."""
     global ORDER_OF_ACCURACY
-    if order_of_accuracy != 3:
-        sys.stderr.write('fds_b200: device time dilation is 3rd order; ignoring %r\n'
-                         % (order_of_accuracy,))
-    ORDER_OF_ACCURACY = 3
+    if order_of_accuracy < 2:
+        order_of_accuracy = 2
+        sys.stderr.write('Order of accuracy too low, setting to 2 instead\n')
+    ORDER_OF_ACCURACY = int(order_of_accuracy)
 
 
 def stencil_weights(order):

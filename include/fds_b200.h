@@ -114,6 +114,10 @@ int fds_random_tangents(fds_ctx*, uint64_t seed);  /* uniform[0,1) V (pascal.ran
 /* FD stencil weights of the time-dilation derivative (fds/timedilation.py:16-19 gets them
  * from np.linalg.solve; pass those 4 doubles for bit parity).  Default: -11/6, 3, -3/2, 1/3 */
 int fds_set_dxdt_weights(fds_ctx*, const double c[4]);
+/* any order of accuracy (TimeDilation.order_of_accuracy, fds/timedilation.py:8-12,64): `order` look-ahead steps
+ * (1 .. 8, at most the halo capacity), order + 1 weights; Lorenz-96 device systems only for order != 3    */
+int fds_set_dxdt_stencil(fds_ctx*, int order, const double* c);
+int fds_dilation_order(const fds_ctx*);
 /* how the time-dilation vector d (per-step du/dt) of a boundary is obtained:                */
 enum {
     FDS_DILATION_OFF      = 0, /* run_ddt=0 of the reference (fds/timedilation.py:59-61)               */
@@ -136,6 +140,7 @@ double fds_last_condition(const fds_ctx*);
 /* split-phase API: after fds_boundary_factor, 1 if the certified single pass was accepted -- no second
  * Gram was launched, so the caller skips the second sum-reduce of FDS_BUF_GRAM                          */
 int    fds_single_pass_pending(const fds_ctx*);
+int    fds_last_qr_passes(const fds_ctx*);   /* 1 or 2: what the last boundary with QR took (after its results were read) */
 
 /* ---- the solver plugin itself: u1, J = run(u0, s, steps), fds/fds.py:184-200 -- */
 /* single trajectory on the context's primal array (world == 1; halos wrapped inside);

@@ -176,8 +176,31 @@ def kkt_known_answer():
     np.savez_compressed(os.path.join(GOLD, 'kkt_K50_m16.npz'), R=R, b=b, alpha=alpha)
 
 
+def clv_fixture():
+    """Covariant Lyapunov vectors (fds/lsstan.py:66-85; consumed by apps/**/drawCLV.py, shape-checked
+    upstream in tests/test_lyapunov_vector.py:47-48): the reference's LssTangent fed with the R history of
+    two reference runs already stored as fixtures -> vectors, magnitudes and sines of the angles."""
+    out = {}
+    for tag, name in (('cfg1', 'cfg1_lorenz63_m2_K20'), ('cfg3', 'cfg3_l96rk4_N40_m16_K100')):
+        g = np.load(os.path.join(GOLD, name + '.npz'))
+        lss = RefLss()
+        lss.Rs, lss.bs = list(g['Rs']), list(g['bs'])
+        v = lss.lyapunov_covariant_vectors()
+        mag, sin = lss.lyapunov_covariant_magnitude_and_sin_angle()
+        assert v.shape == (g['Rs'].shape[1], g['Rs'].shape[0] + 1, g['Rs'].shape[1])
+        out[tag + '_src'] = name
+        out[tag + '_v'], out[tag + '_mag'], out[tag + '_sin'] = v, mag, sin
+        out[tag + '_exponents'] = lss.lyapunov_exponents()
+        out[tag + '_exponents_range'] = lss.lyapunov_exponents((2, 11))
+    np.savez_compressed(os.path.join(GOLD, 'clv_from_reference.npz'), **out)
+    print('clv fixture:', {k: np.shape(v) for k, v in out.items()})
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ['clv']:
+        clv_fixture()
+        return
     if sys.argv[1:] == ['vdp']:
         full_run('cfg2_vanderpol_m1_K20', plugins.run_vanderpol, np.array([1.0, 1.0]), 4.0,
                  1, 20, 50000, 2000, 1e-6, 0, pin_tol=1e-6)
@@ -206,6 +229,7 @@ def main():
     # BASELINE config 2: Van der Pol, m=1 (tests/test_vanderpol.py:33-36)
     full_run('cfg2_vanderpol_m1_K20', plugins.run_vanderpol, np.array([1.0, 1.0]), 4.0, 1,
              20, 50000, 2000, 1e-6, 0, pin_tol=1e-6)
+    clv_fixture()
 
 
 if __name__ == '__main__':

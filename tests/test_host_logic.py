@@ -7,6 +7,7 @@ import fds_b200
 from fds_b200 import checkpoint as ckpt, device, fds as core
 from fds_b200.lsstan import LssTangent
 from oracle import shadowing_port as port
+from conftest import golden
 
 
 def oracle_solve(R, b, dev=0):
@@ -79,3 +80,24 @@ def test_device_plugins_are_picklable_like_the_reference_requires():
     for run in (fds_b200.L96(128, scheme='euler'), fds_b200.Lorenz63(), fds_b200.VanDerPol(), fds_b200.Circular()):
         r2 = pickle.loads(pickle.dumps(run))
         assert type(r2) is type(run) and r2.N == run.N and r2.kw == run.kw and r2._engines == {}
+
+
+@pytest.mark.parametrize('tag', ['cfg1', 'cfg3'])
+def test_covariant_lyapunov_vectors_match_the_reference_values(tag):
+    """lyapunov_covariant_vectors / ..._magnitude_and_sin_angle / lyapunov_exponents (reference
+    fds/lsstan.py:58-85) on the R history of two reference runs: VALUES against the reference's own outputs
+    (fixture written by oracle/gen_golden.py clv), not just shapes.  Host-only post-processing."""
+    from fds_b200.lsstan import LssTangent
+    g = golden('clv_from_reference')
+    src = golden(str(g[tag + '_src']))
+    lss = LssTangent(list(src['Rs']), list(src['bs']))
+    v = lss.lyapunov_covariant_vectors()
+    mag, sin = lss.lyapunov_covariant_magnitude_and_sin_angle()
+    assert v.shape == g[tag + '_v'].shape
+    scale = np.abs(g[tag + '_v']).max()
+    assert np.abs(v - g[tag + '_v']).max() <= 1e-12 * scale
+    assert np.abs(mag - g[tag + '_mag']).max() <= 1e-12 * np.abs(g[tag + '_mag']).max()
+    # sin = sqrt(1 - cos^2) amplifies rounding where the vectors are nearly parallel: compare sin^2
+    assert np.allclose(sin ** 2, g[tag + '_sin'] ** 2, rtol=0, atol=1e-10, equal_nan=True)
+    assert np.array_equal(lss.lyapunov_exponents(), g[tag + '_exponents'])
+    assert np.array_equal(lss.lyapunov_exponents((2, 11)), g[tag + '_exponents_range'])

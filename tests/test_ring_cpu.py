@@ -76,7 +76,15 @@ def _worker(rank, world, port, N, q):
         ok_sum = True
         if world & (world - 1) == 0 and (N // world) & (N // world - 1) == 0:
             ok_sum = tot[0] == plugins.tree_sum(x) and tot[1] == plugins.tree_sum(x * x)
-        q.put((rank, ok_state, ok_gram, ok_sum, tot.tolist()))
+        # ---- bootstrap of the library's own NCCL communicator (fds_comm_unique_id on rank 0, handed to every
+        # rank through the process group -- the host side of Engine(comm='nccl'); the id is opaque bytes) ----
+        from fds_b200.device import comm_unique_id
+        ids = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=ring._global(0), group=ring.group)
+        chk = torch.tensor([float(sum(ids[0]))], dtype=torch.float64)
+        ring.allreduce_sum(chk)
+        ok_id = len(ids[0]) == 128 and chk.item() == world * float(sum(ids[0]))
+        q.put((rank, ok_state, ok_gram, ok_sum and ok_id, tot.tolist()))
     finally:
         dist.destroy_process_group()
 
