@@ -1174,7 +1174,7 @@ int fds_boundary_dxdt(fds_ctx* c, double s, int from_ensemble, double eps) {
         if (c->pri_halo_valid < c->stencil.order)
             return fail(c, "fds_boundary_dxdt: primal halo must be valid for " + std::to_string(c->stencil.order) + " steps");
         if (int r = upload_forcing(c, s, 0.0)) return r;
-        static const bool split = getenv("FDS_DILATION_SPLIT") != nullptr;     // cross-check path: one kernel per step
+        const bool split = getenv("FDS_DILATION_SPLIT") != nullptr;            // cross-check path: one kernel per step
         if (split && c->stencil.order == 3) {
             long long valid = 3;
             for (int j = 1; j <= 3; ++j) {

@@ -91,3 +91,59 @@ def test_batch_and_host_solver_accept_the_variants():
     assert np.array_equal(Jh, Jd) and maxrel(Gh, Gd) < 1e-6
     with pytest.raises(fds_b200.FdsError, match='analytic'):
         fds_b200.shadowing(fds_b200.Lorenz63(), np.array([1.0, 1.0, 28.0]), 28.0, 2, 2, 100, 0, run_ddt='analytic')
+
+
+@gpu
+@pytest.mark.parametrize('N,m,scheme', [(40, 5, 'rk4'), (5000, 16, 'rk4'), (1 << 16, 32, 'rk4'), (3000, 8, 'euler')])
+def test_fused_time_dilation_equals_one_kernel_per_step(monkeypatch, N, m, scheme):
+    """The one-pass kernel (u_1, u_2, u_3 and d in shared memory tiles) against the cross-check path (three
+    single-column solver steps + the stencil kernel, FDS_DILATION_SPLIT): same arithmetic, same bits in everything
+    that depends on d."""
+    rng = np.random.RandomState(N)
+    step = plugins.run_l96_rk4 if scheme == 'rk4' else plugins.run_l96_euler
+    u = step(rng.rand(N), 0.1, 100)[0]
+    V, v = rng.rand(m, N), rng.randn(N)
+    res = []
+    for split in (False, True):
+        if split:
+            monkeypatch.setenv('FDS_DILATION_SPLIT', '1')
+        else:
+            monkeypatch.delenv('FDS_DILATION_SPLIT', raising=False)
+        eng = fds_b200.L96(N, scheme=scheme).engine(m)
+        eng.set_state(u)
+        eng.set_tangents(V, v)
+        R, b, Gd, gd = eng.boundary(0.1, 1e-4, from_ensemble=0, do_qr=1, build=0)
+        res.append((R, b, Gd, gd) + tuple(eng.get_tangents()))
+        eng.close()
+    for a, c in zip(*res):
+        assert np.array_equal(np.asarray(a), np.asarray(c))
+
+
+@gpu
+@pytest.mark.parametrize('order', [2, 4, 6])
+def test_other_orders_of_accuracy_match_the_oracle(order):
+    """set_order_of_accuracy (reference fds/timedilation.py:8-12): `order` look-ahead steps and order + 1 weights;
+    contribution and projection against the oracle's TimeDilation with the same order."""
+    from oracle import shadowing_port as port
+    N, m, s = 777, 6, 0.1
+    rng = np.random.RandomState(order)
+    u = plugins.run_l96_rk4(rng.rand(N), s, 200)[0]
+    V, v = rng.rand(m, N), rng.randn(N)
+    old_port, old_dev = port.TimeDilation.ORDER, fds_b200.timedilation.ORDER_OF_ACCURACY
+    try:
+        port.TimeDilation.ORDER = order
+        td = port.TimeDilation(plugins.run_l96_rk4, u, s)
+        fds_b200.timedilation.set_order_of_accuracy(order)
+        eng = fds_b200.L96(N).engine(m)
+        eng.set_dxdt_weights(fds_b200.timedilation.stencil_weights(fds_b200.timedilation.ORDER_OF_ACCURACY))
+        assert eng.ctx.dilation_order == order
+        eng.set_state(u)
+        eng.set_tangents(V, v)
+        _, _, Gd, gd = eng.boundary(s, 1e-4, from_ensemble=0, do_qr=0, build=0)
+        Vp, vp = eng.get_tangents()
+        eng.close()
+    finally:
+        port.TimeDilation.ORDER = old_port
+        fds_b200.timedilation.ORDER_OF_ACCURACY = old_dev
+    assert maxrel(Gd, td.contribution(V)) < 1e-11 and abs(gd - td.contribution(v)) < 1e-11 * abs(gd) + 1e-14
+    assert maxrel(Vp, td.project(V)) < 1e-11 and maxrel(vp, td.project(v)) < 1e-11
