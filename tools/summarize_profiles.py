@@ -12,10 +12,14 @@ tag, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
 
 # ---- launch list: per-kernel totals and shares -------------------------------
 lines = [l for l in open(launches) if not l.startswith('==')]
+rows = [r for r in csv.DictReader(lines) if r.get('Metric Name') == 'gpu__time_duration.sum']
+# the timed region of `bench.py --steps 2`: the two segments (each opens with extract_col0_kernel) before the FP64 probe
+names = [r['Kernel Name'].split('(')[0] for r in rows]
+end = names.index('fp64_rate_kernel') if 'fp64_rate_kernel' in names else len(names)
+starts = [i for i, k in enumerate(names[:end]) if k == 'extract_col0_kernel']
+rows = rows[starts[-2] if len(starts) >= 2 else 0:end]
 agg = collections.OrderedDict()
-for row in csv.DictReader(lines):
-    if row.get('Metric Name') != 'gpu__time_duration.sum':
-        continue
+for row in rows:
     v = float(row['Metric Value'].replace(',', ''))
     u = row['Metric Unit']
     v *= {'ns': 1e-6, 'us': 1e-3, 'usecond': 1e-3, 'ms': 1.0, 'msecond': 1.0, 'nsecond': 1e-6}[u]
@@ -25,8 +29,8 @@ for row in csv.DictReader(lines):
     a[1] += v
 tot = sum(v[1] for v in agg.values())
 with open('profiles/%s_launches_summary.txt' % tag, 'w') as f:
-    f.write('# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-sweep\n')
-    f.write('# launches of the timed region (set-up skipped with -s); times are cold-cache and serialised: compare SHARES\n')
+    f.write('# ncu --metrics gpu__time_duration.sum --clock-control none : python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-sweep --no-fast --no-djds\n')
+    f.write('# launches of the timed region (the two timed segments, cut out of the full launch list); times are cold-cache and serialised: compare SHARES\n')
     f.write('%-58s %7s %12s %10s %7s\n' % ('kernel', 'n', 'total_ms', 'avg_ms', 'share'))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write('%-58s %7d %12.3f %10.4f %6.1f%%\n' % (k[:58], v[0], v[1], v[1] / v[0], 100 * v[1] / tot))
@@ -75,11 +79,15 @@ for spec in reps:
 out = {k: {'dram_bytes_per_launch': sum(v) / len(v), 'fp64_pipe_busy_pct': sum(fp64[k]) / len(fp64[k])}
        for k, v in traffic.items()}
 if out:
-    step = [k for k in out if 'l96_rk4_stream' in k]
-    doc = {'kernel': 'l96_rk4_stream_kernel',
-           'dram_bytes_per_launch': out[step[0]]['dram_bytes_per_launch'] if step else None,
-           'fp64_pipe_busy_pct': out[step[0]]['fp64_pipe_busy_pct'] if step else None,
-           'source': 'profiles/%s_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)' % tag,
+    # what bench.py quotes as roofline.traffic: keyed by math mode, tied to the kernel sources by their hash
+    sys.path.insert(0, '.')
+    import bench
+    sha = bench.step_sources_sha()
+    doc = {'source': 'profiles/%s_*_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full)' % tag,
            'workload': 'N=2^24 sites, m=32 (34 trajectories)', 'all_kernels': out}
+    for k, v in out.items():
+        if 'l96_rk4_stream' in k:
+            mode = 'fast' if 'FastMath' in k else 'exact'
+            doc[mode] = dict(v, kernel=k, src_sha16=sha)
     json.dump(doc, open('profiles/step_kernel_traffic.json', 'w'), indent=1)
 print('ok', list(out))
