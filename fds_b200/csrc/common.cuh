@@ -110,6 +110,15 @@ FDS_D bool mbar_test_s(uint32_t bar, uint32_t parity) {
 FDS_D void mbar_arrive_s(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// 8-byte load from a shared-window address (ordered after the mbarrier waits: all are volatile)
+FDS_D double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+FDS_D void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+template <int OFF>
+FDS_D void sts_f64_off(uint32_t a, double v) { asm volatile("st.shared.f64 [%0+%2], %1;" ::"r"(a), "d"(v), "n"(OFF)); }
 FDS_D void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))

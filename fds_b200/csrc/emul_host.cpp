@@ -67,6 +67,14 @@ struct HostIO2 {
     double ns[2][kMaxNodeLevels + 1][2];
     double ns_get2(int st, int l, int q) const { return ns[st][l][q]; }
     void ns_put2(int st, int l, int q, double v) { ns[st][l][q] = v; }
+    double pl[2 * kMaxFuse][4];
+    void pl_put(int sum, int slot, double v) { pl[sum][slot] = v; }
+    double pl_get(int sum, int slot) const { return pl[sum][slot]; }
+    int plc = 0;
+    void pl_cur_set(int slot) { plc = slot; }
+    void pl_cur_next() { ++plc; }
+    template <int SUM>
+    void pl_cur_put(double v) { pl[SUM][plc] = v; }
 };
 // K steps per pass (l96_marchk.cuh): output cursor at site a + 8b - 3 - 8(K-1), K sets of objective partials
 template <int K>
@@ -98,6 +106,14 @@ struct HostIOK {
     double ns[K][kMaxNodeLevels + 1][2];
     double ns_get2(int st, int l, int q) const { return ns[st][l][q]; }
     void ns_put2(int st, int l, int q, double v) { ns[st][l][q] = v; }
+    double pl[2 * kMaxFuse][4];
+    void pl_put(int sum, int slot, double v) { pl[sum][slot] = v; }
+    double pl_get(int sum, int slot) const { return pl[sum][slot]; }
+    int plc = 0;
+    void pl_cur_set(int slot) { plc = slot; }
+    void pl_cur_next() { ++plc; }
+    template <int SUM>
+    void pl_cur_put(double v) { pl[SUM][plc] = v; }
 };
 }  // namespace
 

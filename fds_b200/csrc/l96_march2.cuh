@@ -34,49 +34,70 @@ struct NsStep {            // NodeCounter storage view of one of the two steps
     FDS_HD void ns_put(int l, int q, double v) { io.ns_put2(step, l, q, v); }
 };
 
+// 64-site leaf of one objective sum, kept as the four pair sums q_j = (block 2j) + (block 2j + 1) of its eight
+// 8-site blocks: an even block parks its sum in a register, the odd block adds its own and stores the pair in
+// per-thread storage of the IO policy (shared memory in the CUDA kernel); the leaf (q0 + q1) + (q2 + q3) -- the
+// balanced tree of oracle/plugins.py tree_sum -- is formed when the eighth block completes.  Compared with a
+// binary counter in registers (LeafStack) the hot loop carries no select instructions: one add and one store
+// per pair of blocks and sum.
+//   void pl_put(int sum, int slot, double v) / double pl_get(int sum, int slot)      sum = 2 * step + which
 struct StepStats {         // objective accumulators of one step
     Tree8 t1, t2;
-    LeafStack l1, l2;
+    double e1, e2;         // parked 8-site sums of the even block
     NodeCounter ns;
     double b1, b2;
     FDS_HD void reset() {
         t1.t1 = t1.t2 = t1.t4 = 0.0; t2 = t1;
-        l1.s0 = l1.s1 = l1.s2 = 0.0; l2 = l1;
+        e1 = e2 = 0.0;
         ns.reset();
         b1 = b2 = 0.0;
     }
 };
 
-// 8-block k of the strip (sites a + 8k .. a + 8k + 7) of step `step` is complete: fold it into the leaf
-template <class IO>
-FDS_HD void march2_leaf(IO& io, StepStats& s, const MarchGeom& g, int step, int k) {
-    double s1, s2;
-    const bool d1 = s.l1.push(s.b1, k & 7, s1);
-    const bool d2 = s.l2.push(s.b2, k & 7, s2);
-    if (d1 && d2) {
-        const long long leaf = (g.a + 8LL * k) >> kLeafShift;
-        if (leaf < 0 || leaf * kLeafSites >= g.n) { s1 = 0.0; s2 = 0.0; }
-        NsStep<IO> view{io, step};
-        if (s.ns.push(view, s1, s2, g.node_shift - kLeafShift))
-            io.emit_node2(step, leaf >> (g.node_shift - kLeafShift), s1, s2);
+// 8-block j (0 .. 7) of a leaf of step STEP is complete (its sums in s.b1, s.b2); PAR = parity of j if known at
+// compile time.  CUR: the unchecked two-block body keeps a cursor on the slot of the current pair (the two steps
+// pair the SAME 8-block index inside one loop iteration), so the store needs no address arithmetic.
+template <int PAR, int STEP, bool CUR = false, class IO>
+FDS_HD void march2_pair(IO& io, StepStats& s, int j) {
+    if (PAR == 0 || (PAR < 0 && !(j & 1))) { s.e1 = s.b1; s.e2 = s.b2; return; }
+    if (CUR) {
+        io.template pl_cur_put<2 * STEP>(s.e1 + s.b1);
+        io.template pl_cur_put<2 * STEP + 1>(s.e2 + s.b2);
+    } else {
+        io.pl_put(2 * STEP, j >> 1, s.e1 + s.b1);
+        io.pl_put(2 * STEP + 1, j >> 1, s.e2 + s.b2);
     }
 }
 
-// Unchecked blocks: the leaf counters advance branch-free right after site 2 (march2_block) and the leaf that
-// completed in this block -- one block in eight per step -- is folded into the node counter at the END of the
-// block, from the counter state the eighth push left untouched.  Same operations in the same order as
-// march2_leaf, but the eight pushes and the counter updates form ONE basic block, so the integer/select work
-// of the counters issues in the slots the FP64 pipe leaves free instead of stalling behind four branches.
+// the eighth block of a leaf is complete and paired: fold the leaf into the node counter
 template <class IO>
 FDS_HD void march2_node(IO& io, StepStats& s, const MarchGeom& g, int step, int k) {
-    double s1 = s.l1.leaf(s.b1), s2 = s.l2.leaf(s.b2);
+    double s1 = (io.pl_get(2 * step, 0) + io.pl_get(2 * step, 1)) + (io.pl_get(2 * step, 2) + io.pl_get(2 * step, 3));
+    double s2 = (io.pl_get(2 * step + 1, 0) + io.pl_get(2 * step + 1, 1)) +
+                (io.pl_get(2 * step + 1, 2) + io.pl_get(2 * step + 1, 3));
     const long long leaf = (g.a + 8LL * k) >> kLeafShift;
-    if (leaf < 0 || leaf * kLeafSites >= g.n) { s1 = 0.0; s2 = 0.0; }
+    if (leaf < 0 || leaf * kLeafSites >= g.n) { s1 = 0.0; s2 = 0.0; }     // leaves outside [0, n): exact zeros
     NsStep<IO> view{io, step};
     if (s.ns.push(view, s1, s2, g.node_shift - kLeafShift))
         io.emit_node2(step, leaf >> (g.node_shift - kLeafShift), s1, s2);
 }
 
+// 8-block k of the strip (sites a + 8k .. a + 8k + 7) of step `step` is complete: checked path
+template <class IO>
+FDS_HD void march2_leaf(IO& io, StepStats& s, const MarchGeom& g, int step, int k) {
+    // (STEP only selects the storage of the pair sums: dispatch the run-time step of the K-step march)
+    switch (step) {
+        case 0: march2_pair<-1, 0>(io, s, k & 7); break;
+        case 1: march2_pair<-1, 1>(io, s, k & 7); break;
+        case 2: march2_pair<-1, 2>(io, s, k & 7); break;
+        default: march2_pair<-1, 3>(io, s, k & 7); break;
+    }
+    if ((k & 7) == 7) march2_node(io, s, g, step, k);
+}
+
+// Unchecked blocks: the pair sums advance branch-free right after site 2 (march2_block) and the leaf that completed
+// in this block -- one block in eight per step -- is folded into the node counter at the END of the block, so the
+// eight pushes form ONE basic block.
 template <class MP, class PIPE, int P, bool FAST, bool STATS, class IO>
 FDS_HD void march2_site(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats& sa, StepStats& sb,
                         long long j1, long long j2, long long slo, long long shi, long long jlo, long long jhi,
@@ -127,18 +148,9 @@ FDS_HD void march2_block(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats&
     if (FAST) {
         // unchecked blocks have 2 <= b <= nblk: both leaves exist
         if (STATS) {
-            if (BP >= 0) {
-                // step 2 counts 8-block b - 2 (parity BP), step 1 counts 8-block b - 1 (the other parity)
-                sb.l1.template push_state_p<BP>(sb.b1, (b - 2) & 7);
-                sb.l2.template push_state_p<BP>(sb.b2, (b - 2) & 7);
-                sa.l1.template push_state_p<1 - BP>(sa.b1, (b - 1) & 7);
-                sa.l2.template push_state_p<1 - BP>(sa.b2, (b - 1) & 7);
-            } else {
-                sb.l1.push_state(sb.b1, (b - 2) & 7);
-                sb.l2.push_state(sb.b2, (b - 2) & 7);
-                sa.l1.push_state(sa.b1, (b - 1) & 7);
-                sa.l2.push_state(sa.b2, (b - 1) & 7);
-            }
+            // step 2 counts 8-block b - 2 (parity BP), step 1 counts 8-block b - 1 (the other parity)
+            march2_pair<BP, 1, (BP >= 0)>(io, sb, (b - 2) & 7);
+            march2_pair<(BP >= 0 ? 1 - BP : -1), 0, (BP >= 0)>(io, sa, (b - 1) & 7);
         }
     } else {
         // step 2: sites a + 8(b-2) .. a + 8(b-2) + 7 are complete (Q2 == 7 at P == 2)
@@ -153,13 +165,8 @@ FDS_HD void march2_block(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats&
     FDS_M2(6);
     FDS_M2(7);
 #undef FDS_M2
-    if (FAST && STATS) {
-        const int k2 = (b - 2) & 7, k1 = (b - 1) & 7;
-        if (k2 == 7 || k1 == 7) {
-            if (k2 == 7) march2_node(io, sb, g, 1, b - 2);
-            if (k1 == 7) march2_node(io, sa, g, 0, b - 1);
-        }
-    }
+    // (unchecked blocks: the leaves that complete are folded into the node counters by the caller, once per PAIR of
+    // blocks -- l96_march2_t)
 }
 
 // PIPE: Rk4Pipe<MP> or EulerPipe<MP> (any pipe with push x[i+4] -> x'[i-3]: the chaining below only uses the lag)
@@ -212,6 +219,11 @@ FDS_HD void l96_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c)
         if (pass == 0) {
             // Unchecked body, two blocks per iteration so that the lowest bit of the leaf counters' position is a
             // compile-time constant (b is even here; a single last block is left to the checked tail).
+            // In iteration b the two steps pair the same 8-block index b - 1 (step 1 in block b, step 2 in block b + 1),
+            // so one cursor serves both and BOTH leaves complete in the same iteration (b = 0 mod 8): one rare
+            // branch per pair of blocks folds them into the node counters.  (Step 1 parks 8-block b in a register
+            // during block b + 1: the stored pairs are untouched until block b + 2.)
+            if (STATS) io.pl_cur_set(((b - 1) & 7) >> 1);
 #pragma unroll 1
             for (; b + 1 <= bfh; b += 2) {
                 io.begin_block(b);
@@ -220,6 +232,14 @@ FDS_HD void l96_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c)
                 io.begin_block(b + 1);
                 march2_block<MP, PIPE, true, STATS, 1>(io, p1, p2, x1_prev, sa, sb, g, b + 1, slo, shi, jlo, jhi, F, c);
                 io.end_block(b + 1);
+                if (STATS) {
+                    io.pl_cur_next();
+                    if ((b & 7) == 0) {
+                        march2_node(io, sa, g, 0, b - 1);
+                        march2_node(io, sb, g, 1, b - 1);
+                        io.pl_cur_set(0);
+                    }
+                }
             }
         }
     }

@@ -65,6 +65,13 @@ FDS_HD void marchk_site(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&st
     }
 }
 
+// pair sums of steps J + 1, J, .. 1 (compile-time recursion: the step selects the storage of its pair sums)
+template <int BP, int J, class IO, int K>
+FDS_HD void marchk_pair(IO& io, StepStats (&st)[K], int b) {
+    march2_pair<(BP >= 0 ? BP ^ ((J + 1) & 1) : -1), J>(io, st[J], (b - 1 - J) & 7);
+    if constexpr (J > 0) marchk_pair<BP, J - 1>(io, st, b);
+}
+
 // BP: parity of b when known at compile time (unchecked blocks only), -1 otherwise
 template <class MP, class PIPE, int K, bool FAST, bool STATS, int BP = -1, class IO>
 FDS_HD void marchk_block(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&st)[K], const MarchGeom& g, int b,
@@ -77,23 +84,9 @@ FDS_HD void marchk_block(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&s
     // step j + 1: the 8-block b - 1 - j of the strip is complete (Q == 7 at P == 2)
     if (FAST) {
         if (STATS) {
-#pragma unroll
-            for (int j = K - 1; j >= 0; --j) {
-                if (BP >= 0) {
-                    // 8-block b - 1 - j has parity BP ^ ((1 + j) & 1): an even block parks its sum, an odd one pairs it
-                    constexpr int PAR = (BP >= 0 ? BP : 0) ^ 1;       // parity of b - 1
-                    if (j & 1) {
-                        st[j].l1.template push_state_p<PAR ^ 1>(st[j].b1, (b - 1 - j) & 7);
-                        st[j].l2.template push_state_p<PAR ^ 1>(st[j].b2, (b - 1 - j) & 7);
-                    } else {
-                        st[j].l1.template push_state_p<PAR>(st[j].b1, (b - 1 - j) & 7);
-                        st[j].l2.template push_state_p<PAR>(st[j].b2, (b - 1 - j) & 7);
-                    }
-                } else {
-                    st[j].l1.push_state(st[j].b1, (b - 1 - j) & 7);
-                    st[j].l2.push_state(st[j].b2, (b - 1 - j) & 7);
-                }
-            }
+            // 8-block b - 1 - j has parity BP ^ ((1 + j) & 1): an even block parks its sum, an odd one pairs it
+            // and stores the pair (march2_pair)
+            marchk_pair<BP, K - 1>(io, st, b);
         }
     } else if (STATS) {
 #pragma unroll

@@ -48,6 +48,8 @@ struct StreamParams {
 };
 
 constexpr int kMaxStages = 8;
+constexpr uint32_t kPairStride = 256 * 8;   // bytes between two entries of a thread's pair-sum table (one row of 256 threads)
+constexpr int kStreamHdrBytes = 256;      // full[8], empty[8], sink, padding: the per-thread tables start here
 
 // The TMA producer role.  Dedicated mode: one extra warp does nothing else.  Shared mode (all warps
 // compute): the consumer warps take turns -- at the end of consumer block c, warp (c mod nwarps)
@@ -127,6 +129,8 @@ struct StreamIO {
     int levels;              // node levels above the leaf (stride of the second step's counter storage)
     long long nnode;
     double* nsm;             // node-counter storage of this thread: nsm[(2*level + which) * nthr]
+    uint32_t pls_s, plc_s;   // pair sums of the open leaves of this thread (l96_march2.cuh), shared-window address of
+                             // entry (sum, slot) = pls_s + (4 * sum + slot) * kPairStride; plc_s: cursor on a slot
     int nthr;
     int lane;
     StreamProducer* prod;    // shared-producer mode: every consumer warp carries the producer state
@@ -135,54 +139,70 @@ struct StreamIO {
     int st;
     uint32_t par;
     const double* cur;
-    // MID only
-    int prev_st;             // stage of the previous block, not yet released (-1: none)
+    // MID only: the ring position is carried as shared-window addresses (no index arithmetic, no generic->shared
+    // conversion in the loop)
+    uint32_t cur_s, nxt_s;   // this thread's slot in the current block's stage / in the next block's (set by mid_block)
+    uint32_t bar_s, bar_end; // `full` barrier of the current stage; one past the last stage's
+    uint32_t stage_bytes, ring_bytes;
+    uint32_t prev_empty;     // `empty` barrier of the previous block's stage, not yet released (first block: a sink)
     int blk, ahead;          // blocks begun so far; blocks the copies run ahead of the consumers
     int nit;                 // blocks per strip
+    int duty;                // the next block at whose end this warp issues copies (block duty + ahead), INT_MAX: none left
     bool mine;               // this warp issues the copies of block blk - 1 + ahead at the end of the block
     bool ready;              // this block's `full` phase was already seen complete by mid_block()
 
     // MID: the ring bookkeeping of block c -- probe of block c + 1's `full` barrier, whose turn it is to fetch,
-    // stage / parity of the next block -- runs in the MIDDLE of block c (mid_block), inside straight-line code
+    // position of the next block -- runs in the MIDDLE of block c (mid_block), inside straight-line code
     // where its latencies hide behind the FP64 stream.
     // The producer position is a function of the consumer's (block c + `ahead` goes into stage st + ahead), so
     // no separate producer state is carried.  The other kernels keep everything at the block boundary.
     FDS_D void begin_block(int) {
         if (MID) {
-            if (!ready) mbar_wait_s(full_s + 8u * (uint32_t)st, par);
+            if (!ready) mbar_wait_s(bar_s, par);
             // release the previous block's stage: EVERY lane arrives for itself (the barrier counts lanes), so no
             // warp-wide sync is needed -- fewer instructions between the FP64 streams of two blocks
-            if (prev_st >= 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + prev_st));
+            mbar_arrive_s(prev_empty);
+            cur_s = nxt_s;
         } else {
             mbar_wait_s(full_s + 8u * (uint32_t)st, par);
+            cur = sdata + (size_t)st * stage_stride;
         }
-        cur = sdata + (size_t)st * stage_stride;
     }
     FDS_D void mid_block() {
         if (!MID) return;
-        // copy duty of this block: block blk + ahead (its stage and parity are worked out in end_block, only when due)
-        mine = (turn == warp) & (blk + ahead < nit);
-        turn = (turn + 1 == nwarps) ? 0 : turn + 1;
-        // next block
-        const bool wrap = st + 1 == nstages;
-        prev_st = st;
-        st = wrap ? 0 : st + 1;
-        par = wrap ? par ^ 1u : par;
+        mine = blk == duty;          // copy duty of this block (block blk + ahead): every nwarps-th block, while any is left
         ++blk;
-        ready = mbar_test_s(full_s + 8u * (uint32_t)st, par);
+        // next block
+        prev_empty = bar_s + 8u * kMaxStages;
+        bar_s += 8u;
+        nxt_s = cur_s + stage_bytes;          // (the rest of THIS block still loads through cur_s)
+        if (bar_s == bar_end) {      // wrap: step back by the length of the ring (three predicated instructions)
+            bar_s -= 8u * (uint32_t)nstages;
+            nxt_s -= ring_bytes;
+            par ^= 1u;
+        }
+        // all lanes see the same phase: the vote makes the branch on it warp-uniform for the compiler as well
+        ready = __all_sync(0xffffffffu, mbar_test_s(bar_s, par));
     }
     FDS_D int warp_max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
     FDS_D int warp_min(int v) const { return __reduce_min_sync(0xffffffffu, v); }
-    FDS_D double load(int p) const { return cur[p * cols()]; }
+    FDS_D double load(int p) const {
+        if (MID) return lds_f64(cur_s + (uint32_t)(p * cols()) * 8u);
+        return cur[p * cols()];
+    }
     FDS_D void store(int p, double v) { yrow[p * cols()] = v; }
     FDS_D void end_block(int) {
         if (MID) {
             if (mine) {
-                // this block sat in stage prev_st with parity (st == 0 ? par ^ 1 : par): mid_block() has moved on
-                const uint32_t cpar = st == 0 ? par ^ 1u : par;
-                const int q = prev_st + ahead;
+                // this block (blk - 1) sat in the stage of prev_empty; mid_block() has moved on (and flipped the
+                // parity if it wrapped)
+                const int pst = (int)((prev_empty - full_s) >> 3) - kMaxStages;
+                const uint32_t cpar = bar_s == full_s ? par ^ 1u : par;
+                const int q = pst + ahead;
                 const bool w = q >= nstages;
                 prod->issue_at(blk - 1 + ahead, w ? q - nstages : q, w ? cpar ^ 1u : cpar);
+                duty += nwarps;
+                if (duty + ahead >= nit) duty = 0x7fffffff;
             }
         } else {
             __syncwarp();
@@ -210,6 +230,12 @@ struct StreamIO {
         if (j != nullptr && node >= 0 && node < nnode)
             *reinterpret_cast<double2*>(j + node * (2LL * cols())) = make_double2(s1, s2);
     }
+    FDS_D void pl_put(int sum, int slot, double v) { sts_f64(pls_s + (uint32_t)(4 * sum + slot) * kPairStride, v); }
+    FDS_D double pl_get(int sum, int slot) const { return lds_f64(pls_s + (uint32_t)(4 * sum + slot) * kPairStride); }
+    FDS_D void pl_cur_set(int slot) { plc_s = pls_s + (uint32_t)slot * kPairStride; }
+    FDS_D void pl_cur_next() { plc_s += kPairStride; }
+    template <int SUM>
+    FDS_D void pl_cur_put(double v) { sts_f64_off<SUM * 4 * (int)kPairStride>(plc_s, v); }
     FDS_D double ns_get2(int step, int l, int q) const { return nsm[(2 * (step * levels + l) + q) * nthr]; }
     FDS_D void ns_put2(int step, int l, int q, double v) { nsm[(2 * (step * levels + l) + q) * nthr] = v; }
     FDS_D bool all(bool v) const { return __all_sync(0xffffffffu, v); }
@@ -223,13 +249,16 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
     uint64_t* empty = full + kMaxStages;
-    double* nsm = reinterpret_cast<double*>(smem_raw + 128);
+    uint64_t* sink = full + 2 * kMaxStages;        // never waited on: takes the stage release of a strip's first block
+    double* nsm = reinterpret_cast<double*>(smem_raw + kStreamHdrBytes);
     const int levels = p.node_shift - kLeafShift;
-    double* sdata = nsm + (size_t)(2 * KF) * levels * (blockDim.x - 32 * p.dedicated);
+    double* pls = nsm + (size_t)(2 * KF) * levels * (blockDim.x - 32 * p.dedicated);
+    // two / four steps per pass: 2 KF open leaves per thread, four pair sums each
+    double* sdata = pls + (KF >= 2 ? (size_t)(8 * KF) * 256 : 0);
 
     const int tid = threadIdx.x;
     const int nwarps = (blockDim.x >> 5) - p.dedicated;   // consumer warps
-    const int warp = tid >> 5, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // warp-uniform by construction: say so
     const int stage_stride = p.R * p.run_stride;
 
     if (tid == 0) {
@@ -237,6 +266,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], MODE >= 2 ? nwarps * 32 : nwarps);      // two / four steps per pass: every lane arrives
         }
+        mbar_init(sink, 0xfffff);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -295,15 +325,22 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.levels = levels;
     io.nnode = p.nnode;
     io.nsm = nsm + tid;
+    io.pls_s = smem_u32(pls + tid); io.plc_s = io.pls_s;
     io.nthr = nwarps * 32;
     io.lane = lane;
     io.prod = p.dedicated ? nullptr : &prod;
     io.warp = warp; io.nwarps = nwarps; io.turn = 0;
-    io.st = 0; io.prev_st = -1;
+    io.st = 0;
     io.par = 0;
     io.ready = false; io.mine = false;
     io.blk = 0; io.ahead = p.prefetch; io.nit = prod.nit;
+    io.duty = warp + p.prefetch < prod.nit ? warp : 0x7fffffff;
     io.cur = io.sdata;
+    io.cur_s = smem_u32(io.sdata); io.nxt_s = io.cur_s;
+    io.stage_bytes = (uint32_t)stage_stride * 8u;
+    io.ring_bytes = io.stage_bytes * (uint32_t)p.nstages;
+    io.bar_s = io.full_s; io.bar_end = io.full_s + 8u * (uint32_t)p.nstages;
+    io.prev_empty = smem_u32(sink);
 
     double F = (k == p.M - 1) ? p.Flast : p.F0;
     if (p.Fpp != nullptr) {
@@ -382,8 +419,9 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     const int block = cthreads + 32 * p.dedicated;
     const size_t stage_bytes = (size_t)p.R * p.run_stride * sizeof(double);
     if (fuse2 && block > 256) return cudaErrorInvalidValue;
-    const size_t ns_bytes = (size_t)(2 * nfuse) * (plan.node_shift - kLeafShift) * cthreads * sizeof(double);
-    const size_t budget = smem_budget - 128 - ns_bytes;
+    const size_t ns_bytes = (size_t)(2 * nfuse) * (plan.node_shift - kLeafShift) * cthreads * sizeof(double) +
+                            (fuse2 ? (size_t)(8 * nfuse) * 256 * sizeof(double) : 0);
+    const size_t budget = smem_budget - kStreamHdrBytes - ns_bytes;
     int nst = (int)std::min<size_t>(kMaxStages, budget / stage_bytes);
     if (nst < 2) return cudaErrorInvalidValue;
     p.nstages = nst;
@@ -396,7 +434,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = p.pack ? (int)((plan.nstrips * a.M + p.nconsumer - 1) / p.nconsumer)
                             : (int)((plan.nstrips + p.R - 1) / p.R);
-    const size_t smem = 128 + ns_bytes + stage_bytes * nst;
+    const size_t smem = kStreamHdrBytes + ns_bytes + stage_bytes * nst;
     cudaError_t e = cudaSuccess;
 #define FDS_STREAM_LAUNCH2(MP, MC, ST, EU)                                                                         \
     do {                                                                                                           \
@@ -417,8 +455,14 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
         else FDS_STREAM_LAUNCH(MP, 0, ST);                         \
     } while (0)
     const bool stats = p.jpart != nullptr;
+#ifdef FDS_DEV_ONE
+    // development build (tools/sass_hot.py): only the headline instantiation, seconds instead of a minute to compile
+    (void)stats;
+    if (a.exact) FDS_STREAM_LAUNCH2(ExactMath, 34, true, 2); else FDS_STREAM_LAUNCH2(FastMath, 34, true, 2);
+#else
     if (a.exact) { if (stats) FDS_STREAM_MC(ExactMath, true); else FDS_STREAM_MC(ExactMath, false); }
     else         { if (stats) FDS_STREAM_MC(FastMath, true);  else FDS_STREAM_MC(FastMath, false); }
+#endif
 #undef FDS_STREAM_MC
 #undef FDS_STREAM_LAUNCH
 #undef FDS_STREAM_LAUNCH2
