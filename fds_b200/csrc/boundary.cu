@@ -51,6 +51,11 @@ cudaError_t launch_dxdt(const double* P0, const double* P1, const double* P2, co
 constexpr int kDilTile = 1024;      // sites of d per CTA
 constexpr int kDilThreads = 256;
 
+// RK4: the four stages of a step run one after the other over the whole tile (+ its shrinking halo) through
+// shared memory -- y2, y3, y4 and the k-accumulator are arrays, each right-hand side is evaluated ONCE per site
+// and step.  (The single-site form l96_rk4_point evaluates 22 right-hand sides per site and step; with it this
+// kernel was bound by the FP64 pipe at 0.46 ms for N = 2^24.)  Same operations in the same order as
+// l96_rk4_point / Rk4Pipe: bit-identical.
 template <class MP, int EULER>
 __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const double* __restrict__ P0, double* __restrict__ d,
                                                                      long long n, DilationStencil st, double F0, Rk4Coef c,
@@ -59,43 +64,81 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
     extern __shared__ __align__(16) double sm[];
     const int p = st.order;
     const int W0 = kDilTile + p * (GL + GR);                         // widest level (u_0)
-    double* buf[2] = {sm, sm + W0};
+    // RK4: level, two stage arrays, k-accumulator; Euler: two levels
+    double* U = sm;
+    double* Ya = sm + W0;
+    double* Yb = sm + 2 * W0;
+    double* AC = sm + 3 * W0;
     const long long t0 = (long long)blockIdx.x * kDilTile;
     const int cnt = (int)((n - t0) < kDilTile ? (n - t0) : kDilTile);
     const int tid = threadIdx.x;
     // level 0: u_0 on [t0 - p GL, t0 + cnt + p GR); buffer index j <-> site t0 - p GL + j
     const int w0 = cnt + p * (GL + GR);
-    for (int j = tid; j < w0; j += kDilThreads) buf[0][j] = P0[t0 - p * GL + j];
+    for (int j = tid; j < w0; j += kDilThreads) U[j] = P0[t0 - p * GL + j];
     __syncthreads();
     constexpr int PER = kDilTile / kDilThreads;
     double acc[PER];
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
         const int i = tid + q * kDilThreads;
-        acc[q] = i < cnt ? __dmul_rn(st.c[0], buf[0][i + p * GL]) : 0.0;
+        acc[q] = i < cnt ? __dmul_rn(st.c[0], U[i + p * GL]) : 0.0;
     }
     for (int k = 1; k <= p; ++k) {
-        // level k: u_k on [t0 - (p-k) GL, t0 + cnt + (p-k) GR); index j <-> site t0 - (p-k) GL + j.
-        // site s sits at index s - t0 + (p-k+1) GL in level k-1
-        const double* src = buf[(k - 1) & 1];
-        double* dst = buf[k & 1];
-        const int wk = cnt + (p - k) * (GL + GR);
-        for (int j = tid; j < wk; j += kDilThreads) {
-            const long long site = t0 - (long long)(p - k) * GL + j;
+        // level k: u_k on [t0 - (p-k) GL, t0 + cnt + (p-k) GR); index i <-> site t0 - (p-k) GL + i = index i + GL of
+        // level k-1, whose width is w
+        const int w = cnt + (p - k + 1) * (GL + GR);
+        const int wk = w - (GL + GR);
+        const long long site0 = t0 - (long long)(p - k + 1) * GL;     // site of index 0 of level k-1
+        auto forcing = [&](int j) {
             double F = F0;
             if (Fpp != nullptr) {
-                long long q = site / slot;                         // ghosts left of stacked site 0 belong to problem 0
+                long long q = (site0 + j) / slot;                      // ghosts left of stacked site 0 belong to problem 0
                 F = Fpp[q < 0 ? 0 : q].x;
             }
-            const double* x = src + j;                             // = index of site - GL in level k-1
-            dst[j] = EULER ? l96_euler_point<MP>(x, F, c.h) : l96_rk4_point<MP>(x, F, c);
+            return F;
+        };
+        double* out = EULER ? Ya : Yb;
+        if (EULER) {
+            for (int i = tid; i < wk; i += kDilThreads) out[i] = l96_euler_point<MP>(U + i, forcing(i + GL), c.h);
+            __syncthreads();
+        } else {
+            // stage 1 on [2, w-1): k1, y2 = x + h2 k1
+            for (int j = 2 + tid; j < w - 1; j += kDilThreads) {
+                const double k1 = l96_rhs<MP>(U[j - 2], U[j - 1], U[j], U[j + 1], forcing(j));
+                AC[j] = k1;
+                Ya[j] = MP::muladd(c.h2, k1, U[j]);
+            }
+            __syncthreads();
+            // stage 2 on [4, w-2): k2 from y2, y3 = x + h2 k2
+            for (int j = 4 + tid; j < w - 2; j += kDilThreads) {
+                const double k2 = l96_rhs<MP>(Ya[j - 2], Ya[j - 1], Ya[j], Ya[j + 1], forcing(j));
+                AC[j] = MP::twice_plus(k2, AC[j]);
+                Yb[j] = MP::muladd(c.h2, k2, U[j]);
+            }
+            __syncthreads();
+            // stage 3 on [6, w-3): k3 from y3, y4 = x + h k3 (over y2, which is no longer needed)
+            for (int j = 6 + tid; j < w - 3; j += kDilThreads) {
+                const double k3 = l96_rhs<MP>(Yb[j - 2], Yb[j - 1], Yb[j], Yb[j + 1], forcing(j));
+                AC[j] = MP::twice_plus(k3, AC[j]);
+                Ya[j] = MP::muladd(c.h, k3, U[j]);
+            }
+            __syncthreads();
+            // stage 4 on [8, w-4): x' = x + h6 (acc + k4), written as level k (over y3)
+            for (int j = 8 + tid; j < w - 4; j += kDilThreads) {
+                const double k4 = l96_rhs<MP>(Ya[j - 2], Ya[j - 1], Ya[j], Ya[j + 1], forcing(j));
+                Yb[j - 8] = MP::muladd(c.h6, MP::add(AC[j], k4), U[j]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
 #pragma unroll
         for (int q = 0; q < PER; ++q) {
             const int i = tid + q * kDilThreads;
-            if (i < cnt) acc[q] = __dadd_rn(acc[q], __dmul_rn(st.c[k], dst[i + (p - k) * GL]));
+            if (i < cnt) acc[q] = __dadd_rn(acc[q], __dmul_rn(st.c[k], out[i + (p - k) * GL]));
         }
+        // the new level becomes the input of the next step (its old array is free)
+        if (EULER) { double* t = U; U = Ya; Ya = t; }
+        else { double* t = U; U = Yb; Yb = t; }
+        __syncthreads();
     }
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
@@ -109,7 +152,7 @@ cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, cons
                                   LaunchStats* ls) {
     if (st.order < 1 || st.order > kMaxDilationOrder || n < 1) return cudaErrorInvalidValue;
     const unsigned grid = (unsigned)((n + kDilTile - 1) / kDilTile);
-    const size_t smem = 2 * (size_t)(kDilTile + st.order * 12) * sizeof(double);
+    const size_t smem = (euler ? 2 : 4) * (size_t)(kDilTile + st.order * 12) * sizeof(double);
     const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
 #define FDS_DIL(MP, E) dilation_fused_kernel<MP, E><<<grid, kDilThreads, smem, stream>>>(P0, d, n, st, F0, c, Fpp, slot)
     if (exact) { if (euler) FDS_DIL(ExactMath, 1); else FDS_DIL(ExactMath, 0); }
