@@ -3,7 +3,9 @@
 Same 9-field order, file naming (``m{m}_segment{K}``) and load-latest semantics as
 the reference ``fds/checkpoint.py`` (:6-52).  Unlike the reference (which pickles
 un-evaluated lazy graphs with dill), ``u0``, ``V``, ``v`` here are plain numpy
-arrays fetched from the device, so the standard pickle is enough.
+arrays fetched from the device, so the standard pickle is enough.  Files written BY the
+reference are recognised and read too (``refcheckpoint.py``), so a run started with the
+reference can be continued here.
 """
 import os
 import pickle
@@ -27,6 +29,12 @@ def save_checkpoint(checkpoint_path, cp):
 
 
 def load_checkpoint(checkpoint_file):
+    """A checkpoint written by this package (plain pickle of numpy arrays) or by the reference (dill pickle of
+    lazy pascal_lite graphs, fds/checkpoint.py:8-18 -- read by fds_b200/refcheckpoint.py without the reference
+    on the path)."""
+    from . import refcheckpoint
+    if refcheckpoint.is_reference_checkpoint(checkpoint_file):
+        return refcheckpoint.load_reference_checkpoint(checkpoint_file)
     with open(checkpoint_file, 'rb') as f:
         return pickle.load(f)
 

@@ -196,10 +196,43 @@ def clv_fixture():
     print('clv fixture:', {k: np.shape(v) for k, v in out.items()})
 
 
+def reference_checkpoint_fixture():
+    """A checkpoint FILE written by the reference (dill pickle of lazy pascal_lite graphs, fds/checkpoint.py:8-18),
+    what the reference itself reads out of it (V and v evaluated by its own executor), and the reference's
+    continuation from it (restart protocol of tests/test_restart.py:52-64): Lorenz-96 Euler N=40, m=4, 3 segments
+    written, continued to 6.  The file is committed as it is (15 KB): fds_b200/refcheckpoint.py must read it
+    without the reference on the path."""
+    import shutil
+    import tempfile
+    from fds.checkpoint import load_last_checkpoint
+    from fds.compute import run_compute
+    tmp = tempfile.mkdtemp()
+    s, m, K0, K1, steps, eps = 0.1, 4, 3, 6, 20, 1e-4
+    np.random.seed(3)
+    u0 = np.random.rand(40)
+    quiet(ref.shadowing, plugins.run_l96_euler, u0, s, m, K0, steps, 50, epsilon=eps, checkpoint_path=tmp)
+    name = 'm{0}_segment{1}'.format(m, K0)
+    shutil.copy(os.path.join(tmp, name), os.path.join(GOLD, 'refcp_l96euler_' + name))
+    cp = load_last_checkpoint(tmp, m)
+    run_compute([cp.V, cp.v])                          # what the reference's executor makes of the stored graphs
+    out = dict(u0=cp.u0.field, V=cp.V.field, v=cp.v.field, s=s, m=m, K0=K0, K1=K1, steps=steps, eps=eps)
+    out.update({'file_' + k: v for k, v in ref_checkpoint_arrays(cp).items()})
+    cp = load_last_checkpoint(tmp, m)
+    cp2 = quiet(ref.continue_shadowing, plugins.run_l96_euler, s, cp, K1, steps, epsilon=eps, return_checkpoint=True)
+    out.update({'cont_' + k: v for k, v in ref_checkpoint_arrays(cp2).items()})
+    out['cont_G'] = ref.lss_gradient(cp2)
+    shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(GOLD, 'refcp_l96euler_expected.npz'), **out)
+    print('reference checkpoint fixture: file', name, 'continued to', cp2.lss.K_segments(), 'segments, G =', out['cont_G'])
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     if sys.argv[1:] == ['clv']:
         clv_fixture()
+        return
+    if sys.argv[1:] == ['refcp']:
+        reference_checkpoint_fixture()
         return
     if sys.argv[1:] == ['vdp']:
         full_run('cfg2_vanderpol_m1_K20', plugins.run_vanderpol, np.array([1.0, 1.0]), 4.0,
@@ -230,6 +263,7 @@ def main():
     full_run('cfg2_vanderpol_m1_K20', plugins.run_vanderpol, np.array([1.0, 1.0]), 4.0, 1,
              20, 50000, 2000, 1e-6, 0, pin_tol=1e-6)
     clv_fixture()
+    reference_checkpoint_fixture()
 
 
 if __name__ == '__main__':

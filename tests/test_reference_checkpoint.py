@@ -1,0 +1,87 @@
+"""Checkpoints written by the REFERENCE (dill pickles of lazy pascal_lite graphs, fds/checkpoint.py:8-18) are
+read without the reference, dill or pascal_lite importable: tests/golden/refcp_l96euler_m4_segment3 is such a
+file, committed as the reference wrote it (oracle/gen_golden.py reference_checkpoint_fixture), next to what
+the reference's own executor makes of it and the reference's continuation from it."""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+
+FILE = os.path.join(ROOT, 'tests', 'golden', 'refcp_l96euler_m4_segment3')
+
+
+def test_reference_checkpoint_file_reads_bit_for_bit_without_the_reference():
+    # a clean interpreter: nothing of the reference (or dill) may be needed, and nothing of it gets imported
+    code = ("import sys, numpy as np\n"
+            "sys.path.insert(0, %r)\n"
+            "sys.modules['dill'] = None; sys.modules['fds'] = None; sys.modules['pascal_lite'] = None\n"
+            "from fds_b200.checkpoint import load_checkpoint\n"
+            "cp = load_checkpoint(%r)\n"
+            "np.savez(sys.argv[1], u0=cp.u0, V=cp.V, v=cp.v, Rs=np.array(cp.lss.Rs), bs=np.array(cp.lss.bs),\n"
+            "         G_lss=np.array(cp.G_lss), g_lss=np.array(cp.g_lss), J=np.array(cp.J),\n"
+            "         G_dil=np.array(cp.G_dil), g_dil=np.array(cp.g_dil))\n" % (ROOT, FILE))
+    out = os.path.join(ROOT, 'tests', '_refcp_out.npz')
+    try:
+        subprocess.run([sys.executable, '-c', code, out], check=True, capture_output=True, text=True)
+        got, want = np.load(out), golden('refcp_l96euler_expected')
+        for k in ('u0', 'V', 'v'):
+            assert np.array_equal(got[k], want[k]), k                 # V, v: the stored lazy graphs, evaluated
+        for k in ('Rs', 'bs', 'G_lss', 'g_lss', 'J', 'G_dil', 'g_dil'):
+            assert np.array_equal(got[k], want['file_' + k]), k
+    finally:
+        if os.path.exists(out):
+            os.remove(out)
+
+
+def test_load_last_checkpoint_picks_up_a_reference_file(tmp_path):
+    from fds_b200.checkpoint import load_last_checkpoint, verify_checkpoint
+    shutil.copy(FILE, tmp_path / 'm4_segment3')
+    (tmp_path / 'm4_segment_garbage').write_text('x')                  # tests/test_restart.py:46-50
+    cp = load_last_checkpoint(str(tmp_path), 4)
+    assert verify_checkpoint(cp) and cp.lss.K_segments() == 3 and cp.lss.m_modes() == 4
+    assert cp.V.shape == (4, 40) and cp.u0.shape == (40,) and isinstance(cp.V, np.ndarray)
+    assert load_last_checkpoint(str(tmp_path), 5) is None
+
+
+def test_hostile_pickle_is_refused(tmp_path):
+    import pickle
+    from fds_b200.refcheckpoint import load_reference_checkpoint, ReferenceCheckpointError
+    p = tmp_path / 'evil'
+    p.write_bytes(pickle.dumps(os.system))                               # a global outside the whitelist
+    with pytest.raises((ReferenceCheckpointError, pickle.UnpicklingError)):
+        load_reference_checkpoint(str(p))
+
+
+@pytest.mark.gpu
+def test_continue_shadowing_from_a_reference_checkpoint():
+    """The reference's restart protocol (tests/test_restart.py:52-64) across implementations: 3 segments
+    run and written by the reference, 3 more run here on the GPU, against the reference's own continuation.
+    Lorenz-96 forward Euler is the reference's own solver (bit-identical plugin), so the primal objective
+    history of the new segments is identical; R, b and dJ/ds agree up to the QR sign convention / 1e-9."""
+    import fds_b200
+    from fds_b200.checkpoint import load_checkpoint
+    want = golden('refcp_l96euler_expected')
+    cp = load_checkpoint(FILE)
+    run = fds_b200.L96(40, scheme='euler')
+    cp2 = fds_b200.continue_shadowing(run, float(want['s']), cp, int(want['K1']), int(want['steps']),
+                                      epsilon=float(want['eps']), return_checkpoint=True)
+    run.close()
+    assert cp2.lss.K_segments() == int(want['K1'])
+    J = np.array(cp2.J)
+    assert np.array_equal(J, want['cont_J'])                            # all six segments, bit for bit
+    Rd, Rr = np.array(cp2.lss.Rs), want['cont_Rs']
+    assert np.array_equal(Rd[:3], Rr[:3])                               # the reference's own, carried over
+    # first new boundary: same V (from the file), so R agrees up to LAPACK's row signs (CholeskyQR: diag R > 0);
+    # a flipped row is the finite difference in the opposite direction from then on: O(eps) differences
+    eps = float(want['eps'])
+    e3 = np.abs(np.abs(Rd[3]) - np.abs(Rr[3])).max() / np.abs(Rr[3]).max()
+    e45 = np.abs(np.abs(Rd[4:]) - np.abs(Rr[4:])).max() / np.abs(Rr[4:]).max()
+    G = fds_b200.lss_gradient(cp2)
+    eG = np.abs(G - want['cont_G']).max() / np.abs(want['cont_G']).max()
+    print('R3 %.2e  R4,5 %.2e  dJ/ds %.2e' % (e3, e45, eG))
+    assert e3 < 1e-12 and e45 < eps and eG < 0.1 * eps       # measured: 6e-17, 1e-5, 1e-7
