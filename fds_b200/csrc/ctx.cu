@@ -73,6 +73,7 @@ struct fds_ctx {
     // state machine
     bool state_in_ensemble = false;   // newest primal state is column 0 of the ensemble
     bool tangents_implicit = false;   // newest tangents are (E_k - E_0)/eps_last
+    bool primal_synced = false;       // ... and P(0) already holds that column (the last pass of the segment wrote it)
     bool time_dilation = true;
     int dil_mode = 1;                 // FDS_DILATION_*: 0 off, 1 finite differences, 2 analytic (dt * f(u)), 3 given by the host
     // CholeskyQR: 0 = one pass when the first factor certifies cond^2 u negligible, else two; 2 = always two
@@ -657,7 +658,8 @@ int fds_last_qr_passes(const fds_ctx* c) { return c->passes_last; }
 // ------------------------------- state in / out ------------------------------ //
 static int sync_primal_from_ensemble(fds_ctx* c) {
     if (c->state_in_ensemble) {
-        FDS_CK(c, launch_extract_col0(c->E_all(c->cur), c->M, c->P_all(0), c->nall, c->stream, &c->ls));
+        if (!c->primal_synced)
+            FDS_CK(c, launch_extract_col0(c->E_all(c->cur), c->M, c->P_all(0), c->nall, c->stream, &c->ls));
         c->state_in_ensemble = false;
         c->pri_halo_valid = 0;
     }
@@ -672,6 +674,7 @@ int fds_set_state(fds_ctx* c, const double* u) {
                                 cudaMemcpyHostToDevice, c->stream));
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     c->state_in_ensemble = false;
+    c->primal_synced = false;
     c->pri_halo_valid = 0;
     return 0;
 }
@@ -817,6 +820,7 @@ int fds_set_ensemble(fds_ctx* c, const double* Eh, double eps) {
     }
     FDS_CK(c, cudaStreamSynchronize(c->stream));
     c->state_in_ensemble = true;
+    c->primal_synced = false;
     c->tangents_implicit = true;
     c->eps_last = eps;
     c->ens_halo_valid = 0;
@@ -920,7 +924,7 @@ static int ensure_jsum(fds_ctx* c, long long steps) {
 // (streaming kernel: node partials into jnode[jstep], reduced later in one batch by
 // reduce_nodes(); simple kernels: reduced right away into jsum[jstep])
 static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, double Flast, long long valid,
-                    long long jstep, long long jslot, int nfuse = 1) {
+                    long long jstep, long long jslot, int nfuse = 1, double* primal_out = nullptr) {
     const bool two = nfuse >= 2;
     double* jsum_slot = c->jsum + (size_t)jstep * M_ * 2;
     StepArgs a;
@@ -935,6 +939,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
     if (c->stream_ok && M_ == c->M) {
         a.jpart = c->jnode + (size_t)jslot * c->plan.nnode * c->M * 2;
         if (two) { a.two_steps = 1; a.jpart2 = a.jpart + (size_t)c->plan.nnode * c->M * 2; a.nfuse = nfuse; }
+        a.primal_out = primal_out;
         cudaEvent_t e1 = nullptr;
         if (c->profiling) {
             if (c->prof_used == c->prof_events.size()) {
@@ -1045,6 +1050,7 @@ int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int 
             FDS_CK(c, launch_tree_reduce(c->jpart, c->nleaf, 2, c->jsum + (size_t)(step0 + j) * 2, c->jscratch, c->stream, &c->ls));
         }
         std::swap(c->Pbase[0], c->Pbase[1]);
+        c->primal_synced = false;
         c->pri_halo_valid--;
     }
     return 0;
@@ -1077,6 +1083,7 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
         FDS_CK(c, launch_toy_advance(c->cfg.system, c->cfg.math == FDS_MATH_EXACT, c->Ecur(), c->Ecur(), c->M, nsteps,
                                      s, s + eps, c->jsum + (size_t)step0 * c->M * 2, c->stream, &c->ls));
         c->state_in_ensemble = true;
+        c->primal_synced = false;
         c->tangents_implicit = true;
         c->eps_last = eps;
         return 0;
@@ -1084,6 +1091,10 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
     const double F0 = s + 8.0, Flast = (s + eps) + 8.0;   // fds/segment.py:64: parameter + epsilon
     if (nsteps > c->H) return fail(c, "fds_segment_advance: at most fds_halo_steps() steps per call");
     if (int r = upload_forcing(c, s, eps)) return r;
+    static const bool emit_env = [] { const char* e = getenv("FDS_EMIT_PRIMAL"); return !(e && e[0] == '0'); }();
+    const bool emit_ok = emit_env && c->stream_ok && c->cfg.system == FDS_SYS_L96_RK4;
+    bool emitted = false;
+    c->primal_synced = false;
     for (long long j = 0; j < nsteps;) {
         if (c->ens_halo_valid < 1) return fail(c, "fds_segment_advance: ensemble halo exhausted; refresh it first");
         // steps per pass: 4 (forward Euler: four chained pipes fit the register file), 2 (RK4), 1 (remainder)
@@ -1092,8 +1103,12 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
             if (c->fuse4 && nsteps - j >= 4 && c->ens_halo_valid >= 4) k = 4;
             else if (nsteps - j >= 2 && c->ens_halo_valid >= 2) k = 2;
         }
+        // the last pass of the call (RK4, two steps) also writes column 0 to the primal array: the next boundary
+        // finds the state there instead of extracting it from the ensemble with a strided pass
+        const bool emit = emit_ok && k == 2 && j + k >= nsteps;
         if (int r = one_step(c, c->E_all(c->cur), c->E_all(c->cur ^ 1), c->M, F0, Flast, c->ens_halo_valid, step0 + j,
-                             j, k)) return r;
+                             j, k, emit ? c->P_all(0) : nullptr)) return r;
+        emitted = emit;
         c->cur ^= 1;
         c->ens_halo_valid -= k;
         j += k;
@@ -1101,6 +1116,8 @@ int fds_segment_advance(fds_ctx* c, double s, double eps, int64_t step0, int64_t
     if (int r = reduce_nodes(c, step0, nsteps)) return r;
     c->state_in_ensemble = true;
     c->tangents_implicit = true;
+    c->primal_synced = emitted;
+    if (emitted) c->pri_halo_valid = 0;
     c->eps_last = eps;
     return 0;
 }

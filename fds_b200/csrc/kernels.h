@@ -40,6 +40,9 @@ struct StepArgs {
     // K time steps in one pass (2: as two_steps; 4: forward Euler only, l96_marchk.cuh): step j's node partials go to
     // jpart + j * nnode * M * 2
     int nfuse = 0;
+    // RK4, two steps per pass: also write column 0 of the output (the primal state) to this single-column array
+    // (pointer to site 0) -- the last pass of a segment saves the strided extraction pass of the next boundary
+    double* primal_out = nullptr;
 };
 
 // streaming TMA-fed kernel (RK4 only); `plan` = make_strip_plan(n, H, num_sms * stream_runs_per_cta(M)),

@@ -42,6 +42,7 @@ struct StreamParams {
     int nfuse;                                 // time steps per pass (1, 2 or 4)
     int fuse2;                                 // 1: two steps per pass (l96_march2.cuh)
     const double2* Fpp;                        // per-problem (F0, Flast) of a batch, or nullptr
+    double* P0out;                             // EMIT kernels: column 0 of the output goes here as well (site 0)
     int spp;                                   // strips per problem (batch)
     int prefetch;                              // shared-producer mode: blocks in flight ahead of the consumers (<= nstages - 2)
     Rk4Coef c;
@@ -115,7 +116,7 @@ struct StreamProducer {
 // MID = the march calls mid_block() once in EVERY block (the kernels that advance two or four steps per pass): the
 // ring bookkeeping then happens there, inside straight-line code, and the block boundary carries only the barrier
 // fallback, the stage release and the (rare) copy issue.
-template <int MC, bool MID = false>
+template <int MC, bool MID = false, bool EMIT = false>
 struct StreamIO {
     const double* sdata;     // this thread's (run, column) slot in stage 0
     int stage_stride;        // doubles per stage
@@ -124,6 +125,8 @@ struct StreamIO {
     int nstages;
     uint32_t full_s;         // shared-window address of full[0]; empty[s] = full[kMaxStages + s]
     double* yrow;            // output cursor: site a + 8b - 3 of this thread's column
+    double* prow;            // EMIT: the same site in the single-column primal array (column-0 lanes store there too)
+    bool col0;
     double* jp;              // node 0, already offset by column (or nullptr)
     long long jstride;       // K steps per pass: step j's partials at jp + j * jstride
     int levels;              // node levels above the leaf (stride of the second step's counter storage)
@@ -190,7 +193,10 @@ struct StreamIO {
         if (MID) return lds_f64(cur_s + (uint32_t)(p * cols()) * 8u);
         return cur[p * cols()];
     }
-    FDS_D void store(int p, double v) { yrow[p * cols()] = v; }
+    FDS_D void store(int p, double v) {
+        yrow[p * cols()] = v;
+        if (EMIT && col0) prow[p] = v;
+    }
     FDS_D void end_block(int) {
         if (MID) {
             if (mine) {
@@ -217,6 +223,7 @@ struct StreamIO {
             if (++st == nstages) { st = 0; par ^= 1u; }
         }
         yrow += 8 * cols();
+        if (EMIT) prow += 8;
     }
     FDS_D void emit_node(long long node, double s1, double s2) {
         if (jp != nullptr && node >= 0 && node < nnode)
@@ -243,7 +250,7 @@ struct StreamIO {
 
 // MODE 0: RK4, 1: forward Euler, 2: RK4, two steps per pass, 3: forward Euler, two steps per pass, 4: forward Euler, four
 // steps per pass (l96_marchk.cuh) (<= 256 threads = 2 warps per scheduler: twice the pipeline state in up to 255 registers)
-template <class MP, int MC, bool STATS, int MODE>
+template <class MP, int MC, bool STATS, int MODE, bool EMIT = false>
 __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kernel(const __grid_constant__ StreamParams p) {
     constexpr int KF = MODE == 4 ? 4 : (MODE >= 2 ? 2 : 1);     // time steps per pass
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     g.stats = p.jpart != nullptr;
     g.node_shift = p.node_shift;
 
-    StreamIO<MC, MODE >= 2> io;
+    StreamIO<MC, MODE >= 2, EMIT> io;
     io.sdata = sdata + r * p.run_stride + k;
     io.stage_stride = stage_stride;
     io.M = p.M;
@@ -320,6 +327,8 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.full_s = smem_u32(full);
     // output cursor of the first block: site a - 16 - 3 (b = -2), or a - 24 - 11 (b = -3, two steps per pass)
     io.yrow = p.Y + (g.a + FuseGeom<KF>::kOutOff) * p.M + k;   // block b = -2
+    io.prow = EMIT ? p.P0out + (g.a + FuseGeom<KF>::kOutOff) : nullptr;
+    io.col0 = k == 0;
     io.jp = p.jpart != nullptr ? p.jpart + 2 * k : nullptr;
     io.jstride = p.jstride;
     io.levels = levels;
@@ -429,6 +438,9 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.F0 = a.F0; p.Flast = a.M > 1 ? a.Flast : a.F0;
     p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
     p.jpart2 = a.jpart2; p.fuse2 = fuse2;
+    p.P0out = a.primal_out;
+    const bool emit = a.primal_out != nullptr;
+    if (emit && (euler || nfuse != 2 || a.jpart == nullptr)) return cudaErrorInvalidValue;   // RK4, two steps, with objective sums
     p.nfuse = nfuse; p.jstride = (long long)plan.nnode * a.M * 2;
     p.prefetch = std::max(1, std::min(nst - 2, stream_prefetch()));
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
@@ -443,8 +455,16 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
         if (e != cudaSuccess) return e;                                                                            \
         l96_rk4_stream_kernel<MP, MC, ST, EU><<<grid, block, smem, st>>>(p);                                       \
     } while (0)
+#define FDS_STREAM_LAUNCH2E(MP, MC)                                                                               \
+    do {                                                                                                           \
+        e = cudaFuncSetAttribute(l96_rk4_stream_kernel<MP, MC, true, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                                       \
+        if (e != cudaSuccess) return e;                                                                            \
+        l96_rk4_stream_kernel<MP, MC, true, 2, true><<<grid, block, smem, st>>>(p);                                \
+    } while (0)
 #define FDS_STREAM_LAUNCH(MP, MC, ST) \
-    do { if (euler && nfuse == 4) FDS_STREAM_LAUNCH2(MP, MC, ST, 4); else if (euler && fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 3); \
+    do { if (emit) { if (ST) FDS_STREAM_LAUNCH2E(MP, MC); } \
+         else if (euler && nfuse == 4) FDS_STREAM_LAUNCH2(MP, MC, ST, 4); else if (euler && fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 3); \
          else if (euler) FDS_STREAM_LAUNCH2(MP, MC, ST, 1); \
          else if (fuse2) FDS_STREAM_LAUNCH2(MP, MC, ST, 2); \
          else FDS_STREAM_LAUNCH2(MP, MC, ST, 0); } while (0)
@@ -466,6 +486,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
 #undef FDS_STREAM_MC
 #undef FDS_STREAM_LAUNCH
 #undef FDS_STREAM_LAUNCH2
+#undef FDS_STREAM_LAUNCH2E
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
