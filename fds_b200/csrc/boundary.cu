@@ -48,102 +48,99 @@ cudaError_t launch_dxdt(const double* P0, const double* P1, const double* P2, co
 }
 
 // ---- time dilation, fused: u_1 .. u_order and d in one pass (see kernels.h) ---------------------------------- //
-constexpr int kDilTile = 1024;      // sites of d per CTA
+// A CTA owns a WINDOW of kDilThreads * kDilRun consecutive sites, thread t the run [t kDilRun, (t + 1) kDilRun) of
+// it, in registers, for every stage of every step: the state u, the k-accumulator and d never touch memory.  A stage
+// hands its input (u, y2, y3, y4) to the neighbouring threads through shared memory -- one store per site, three
+// halo loads per thread and stage -- so the kernel is bound by neither shared-memory bandwidth (the stage-array form:
+// 9 accesses per site and stage, 0.42 ms at N = 2^24) nor the FP64 pipe (the single-site form l96_rk4_point evaluates
+// 22 right-hand sides per site and step: 0.46 ms).  The dependency cone eats 8 sites on the left and 4 on the right
+// per step, so a window of W sites yields d on its inner W - 12 * order sites.  Same operations in the same order as
+// l96_rk4_point / Rk4Pipe (one right-hand side per site, stage and step): bit-identical.
 constexpr int kDilThreads = 256;
+constexpr int kDilRun = 8;
+constexpr int kDilWindow = kDilThreads * kDilRun;
 
-// RK4: the four stages of a step run one after the other over the whole tile (+ its shrinking halo) through
-// shared memory -- y2, y3, y4 and the k-accumulator are arrays, each right-hand side is evaluated ONCE per site
-// and step.  (The single-site form l96_rk4_point evaluates 22 right-hand sides per site and step; with it this
-// kernel was bound by the FP64 pipe at 0.46 ms for N = 2^24.)  Same operations in the same order as
-// l96_rk4_point / Rk4Pipe: bit-identical.
 template <class MP, int EULER>
 __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const double* __restrict__ P0, double* __restrict__ d,
                                                                      long long n, DilationStencil st, double F0, Rk4Coef c,
                                                                      const double2* __restrict__ Fpp, long long slot) {
-    constexpr int GL = EULER ? 2 : 8, GR = EULER ? 1 : 4;          // dependency cone of one step
-    extern __shared__ __align__(16) double sm[];
+    constexpr int GL = EULER ? 2 : 8, GR = EULER ? 1 : 4, L = kDilRun, W = kDilWindow;
+    __shared__ __align__(16) double sm[2][W + 4];                       // position j of the window at sm[.][j + 2]
     const int p = st.order;
-    const int W0 = kDilTile + p * (GL + GR);                         // widest level (u_0)
-    // RK4: level, two stage arrays, k-accumulator; Euler: two levels
-    double* U = sm;
-    double* Ya = sm + W0;
-    double* Yb = sm + 2 * W0;
-    double* AC = sm + 3 * W0;
-    const long long t0 = (long long)blockIdx.x * kDilTile;
-    const int cnt = (int)((n - t0) < kDilTile ? (n - t0) : kDilTile);
-    const int tid = threadIdx.x;
-    // level 0: u_0 on [t0 - p GL, t0 + cnt + p GR); buffer index j <-> site t0 - p GL + j
-    const int w0 = cnt + p * (GL + GR);
-    for (int j = tid; j < w0; j += kDilThreads) U[j] = P0[t0 - p * GL + j];
-    __syncthreads();
-    constexpr int PER = kDilTile / kDilThreads;
-    double acc[PER];
+    const int tile = W - p * (GL + GR);
+    const long long t0 = (long long)blockIdx.x * tile;                  // first site this CTA writes d for
+    const long long w0 = t0 - (long long)p * GL;                        // site of window position 0
+    const int tid = threadIdx.x, j0 = tid * L;
+    if (tid < 2) { sm[0][tid] = 0.0; sm[1][tid] = 0.0; sm[0][W + 2 + tid] = 0.0; sm[1][W + 2 + tid] = 0.0; }
+    double u[L], dacc[L], F[L];
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int i = tid + q * kDilThreads;
-        acc[q] = i < cnt ? __dmul_rn(st.c[0], U[i + p * GL]) : 0.0;
+    for (int q = 0; q < L; ++q) {
+        const long long site = w0 + j0 + q;
+        u[q] = site < n + (long long)p * GR ? P0[site] : 0.0;          // (the left halo always exists: site >= -p GL)
+        dacc[q] = __dmul_rn(st.c[0], u[q]);
+        F[q] = F0;
+        if (Fpp != nullptr) {
+            long long pr = site / slot;                                  // ghosts left of stacked site 0 belong to problem 0
+            F[q] = Fpp[pr < 0 ? 0 : pr].x;
+        }
     }
-    for (int k = 1; k <= p; ++k) {
-        // level k: u_k on [t0 - (p-k) GL, t0 + cnt + (p-k) GR); index i <-> site t0 - (p-k) GL + i = index i + GL of
-        // level k-1, whose width is w
-        const int w = cnt + (p - k + 1) * (GL + GR);
-        const int wk = w - (GL + GR);
-        const long long site0 = t0 - (long long)(p - k + 1) * GL;     // site of index 0 of level k-1
-        auto forcing = [&](int j) {
-            double F = F0;
-            if (Fpp != nullptr) {
-                long long q = (site0 + j) / slot;                      // ghosts left of stacked site 0 belong to problem 0
-                F = Fpp[q < 0 ? 0 : q].x;
-            }
-            return F;
-        };
-        double* out = EULER ? Ya : Yb;
-        if (EULER) {
-            for (int i = tid; i < wk; i += kDilThreads) out[i] = l96_euler_point<MP>(U + i, forcing(i + GL), c.h);
-            __syncthreads();
-        } else {
-            // stage 1 on [2, w-1): k1, y2 = x + h2 k1
-            for (int j = 2 + tid; j < w - 1; j += kDilThreads) {
-                const double k1 = l96_rhs<MP>(U[j - 2], U[j - 1], U[j], U[j + 1], forcing(j));
-                AC[j] = k1;
-                Ya[j] = MP::muladd(c.h2, k1, U[j]);
-            }
-            __syncthreads();
-            // stage 2 on [4, w-2): k2 from y2, y3 = x + h2 k2
-            for (int j = 4 + tid; j < w - 2; j += kDilThreads) {
-                const double k2 = l96_rhs<MP>(Ya[j - 2], Ya[j - 1], Ya[j], Ya[j + 1], forcing(j));
-                AC[j] = MP::twice_plus(k2, AC[j]);
-                Yb[j] = MP::muladd(c.h2, k2, U[j]);
-            }
-            __syncthreads();
-            // stage 3 on [6, w-3): k3 from y3, y4 = x + h k3 (over y2, which is no longer needed)
-            for (int j = 6 + tid; j < w - 3; j += kDilThreads) {
-                const double k3 = l96_rhs<MP>(Yb[j - 2], Yb[j - 1], Yb[j], Yb[j + 1], forcing(j));
-                AC[j] = MP::twice_plus(k3, AC[j]);
-                Ya[j] = MP::muladd(c.h, k3, U[j]);
-            }
-            __syncthreads();
-            // stage 4 on [8, w-4): x' = x + h6 (acc + k4), written as level k (over y3)
-            for (int j = 8 + tid; j < w - 4; j += kDilThreads) {
-                const double k4 = l96_rhs<MP>(Ya[j - 2], Ya[j - 1], Ya[j], Ya[j + 1], forcing(j));
-                Yb[j - 8] = MP::muladd(c.h6, MP::add(AC[j], k4), U[j]);
-            }
-            __syncthreads();
-        }
+    int buf = 0;
+    // x[0 .. L+2] = stage input at window positions j0 - 2 .. j0 + L: the own run from registers, the halo from the
+    // neighbours' stores
+    auto exchange = [&](const double (&own)[L], double (&x)[L + 3]) {
+        double* row = sm[buf] + 2 + j0;
 #pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            const int i = tid + q * kDilThreads;
-            if (i < cnt) acc[q] = __dadd_rn(acc[q], __dmul_rn(st.c[k], out[i + (p - k) * GL]));
-        }
-        // the new level becomes the input of the next step (its old array is free)
-        if (EULER) { double* t = U; U = Ya; Ya = t; }
-        else { double* t = U; U = Yb; Yb = t; }
+        for (int q = 0; q < L; q += 2) *reinterpret_cast<double2*>(row + q) = make_double2(own[q], own[q + 1]);
         __syncthreads();
+        x[0] = row[-2]; x[1] = row[-1]; x[L + 2] = row[L];
+#pragma unroll
+        for (int q = 0; q < L; ++q) x[q + 2] = own[q];
+        buf ^= 1;                                                        // the next stage writes the other buffer: one barrier per stage
+    };
+    for (int k = 1; k <= p; ++k) {
+        double x[L + 3];
+        if (EULER) {
+            exchange(u, x);
+#pragma unroll
+            for (int q = 0; q < L; ++q) u[q] = l96_euler_point<MP>(x + q, F[q], c.h);
+        } else {
+            double acc[L], y[L];
+            exchange(u, x);
+#pragma unroll
+            for (int q = 0; q < L; ++q) {
+                const double k1 = l96_rhs<MP>(x[q], x[q + 1], x[q + 2], x[q + 3], F[q]);
+                acc[q] = k1;
+                y[q] = MP::muladd(c.h2, k1, u[q]);
+            }
+            exchange(y, x);
+#pragma unroll
+            for (int q = 0; q < L; ++q) {
+                const double k2 = l96_rhs<MP>(x[q], x[q + 1], x[q + 2], x[q + 3], F[q]);
+                acc[q] = MP::twice_plus(k2, acc[q]);
+                y[q] = MP::muladd(c.h2, k2, u[q]);
+            }
+            exchange(y, x);
+#pragma unroll
+            for (int q = 0; q < L; ++q) {
+                const double k3 = l96_rhs<MP>(x[q], x[q + 1], x[q + 2], x[q + 3], F[q]);
+                acc[q] = MP::twice_plus(k3, acc[q]);
+                y[q] = MP::muladd(c.h, k3, u[q]);
+            }
+            exchange(y, x);
+#pragma unroll
+            for (int q = 0; q < L; ++q) {
+                const double k4 = l96_rhs<MP>(x[q], x[q + 1], x[q + 2], x[q + 3], F[q]);
+                u[q] = MP::muladd(c.h6, MP::add(acc[q], k4), u[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < L; ++q) dacc[q] = __dadd_rn(dacc[q], __dmul_rn(st.c[k], u[q]));
     }
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int i = tid + q * kDilThreads;
-        if (i < cnt) d[t0 + i] = acc[q];
+    for (int q = 0; q < L; ++q) {
+        const int j = j0 + q;
+        const long long site = w0 + j;
+        if (j >= p * GL && j < p * GL + tile && site < n) d[site] = dacc[q];
     }
 }
 
@@ -151,10 +148,10 @@ cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, cons
                                   int exact, int euler, const double2* Fpp, long long slot, cudaStream_t stream,
                                   LaunchStats* ls) {
     if (st.order < 1 || st.order > kMaxDilationOrder || n < 1) return cudaErrorInvalidValue;
-    const unsigned grid = (unsigned)((n + kDilTile - 1) / kDilTile);
-    const size_t smem = (euler ? 2 : 4) * (size_t)(kDilTile + st.order * 12) * sizeof(double);
+    const int tile = kDilWindow - st.order * (euler ? 3 : 12);
+    const unsigned grid = (unsigned)((n + tile - 1) / tile);
     const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
-#define FDS_DIL(MP, E) dilation_fused_kernel<MP, E><<<grid, kDilThreads, smem, stream>>>(P0, d, n, st, F0, c, Fpp, slot)
+#define FDS_DIL(MP, E) dilation_fused_kernel<MP, E><<<grid, kDilThreads, 0, stream>>>(P0, d, n, st, F0, c, Fpp, slot)
     if (exact) { if (euler) FDS_DIL(ExactMath, 1); else FDS_DIL(ExactMath, 0); }
     else       { if (euler) FDS_DIL(FastMath, 1);  else FDS_DIL(FastMath, 0); }
 #undef FDS_DIL
