@@ -65,13 +65,18 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
                                                                      long long n, DilationStencil st, double F0, Rk4Coef c,
                                                                      const double2* __restrict__ Fpp, long long slot) {
     constexpr int GL = EULER ? 2 : 8, GR = EULER ? 1 : 4, L = kDilRun, W = kDilWindow;
-    __shared__ __align__(16) double sm[2][W + 4];                       // position j of the window at sm[.][j + 2]
+    // window position j lives at sm[.][j + (j >> 3) + 3]: one unused slot per run of 8, so that the lanes of a warp
+    // (runs 8 positions apart) hit different banks -- with the plain layout every exchange was an 8-way bank conflict
+    // and the kernel spent its time in the shared-memory pipe (0.37 ms at N = 2^24)
+    constexpr int SMW = W + W / L + 4;
+    __shared__ __align__(16) double sm[2][SMW];
     const int p = st.order;
     const int tile = W - p * (GL + GR);
     const long long t0 = (long long)blockIdx.x * tile;                  // first site this CTA writes d for
     const long long w0 = t0 - (long long)p * GL;                        // site of window position 0
     const int tid = threadIdx.x, j0 = tid * L;
-    if (tid < 2) { sm[0][tid] = 0.0; sm[1][tid] = 0.0; sm[0][W + 2 + tid] = 0.0; sm[1][W + 2 + tid] = 0.0; }
+    if (tid < 2) { sm[0][tid] = 0.0; sm[1][tid] = 0.0; }               // positions -2, -1
+    if (tid == 2) { sm[0][W + W / L + 3] = 0.0; sm[1][W + W / L + 3] = 0.0; }   // position W
     double u[L], dacc[L], F[L];
 #pragma unroll
     for (int q = 0; q < L; ++q) {
@@ -88,11 +93,11 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
     // x[0 .. L+2] = stage input at window positions j0 - 2 .. j0 + L: the own run from registers, the halo from the
     // neighbours' stores
     auto exchange = [&](const double (&own)[L], double (&x)[L + 3]) {
-        double* row = sm[buf] + 2 + j0;
+        double* row = sm[buf] + (L + 1) * tid + 3;                      // position j0
 #pragma unroll
-        for (int q = 0; q < L; q += 2) *reinterpret_cast<double2*>(row + q) = make_double2(own[q], own[q + 1]);
+        for (int q = 0; q < L; ++q) row[q] = own[q];
         __syncthreads();
-        x[0] = row[-2]; x[1] = row[-1]; x[L + 2] = row[L];
+        x[0] = row[-3]; x[1] = row[-2]; x[L + 2] = row[L + 1];           // positions j0 - 2, j0 - 1 (previous run), j0 + L (next run)
 #pragma unroll
         for (int q = 0; q < L; ++q) x[q + 2] = own[q];
         buf ^= 1;                                                        // the next stage writes the other buffer: one barrier per stage
@@ -566,7 +571,7 @@ __device__ void cta_tri_inverse(const double* L, int ld, int mm, double* Linv) {
 
 size_t small_smem_bytes(int m) {
     const int MX = m + 2;
-    return sizeof(double) * ((size_t)MX * MX + 2 * (size_t)m * m + 2 * MX) + 16;
+    return sizeof(double) * ((size_t)MX * MX + 2 * (size_t)m * m + 4 * MX) + 16;
 }
 
 // SmallBufs of problem p of a batch
@@ -698,9 +703,9 @@ __global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long lo
 // Single-pass CholeskyQR with its own certificate: everything the boundary needs -- G_dil, g_dil,
 // the projection, Q = L^-1 P, R = L^T, b = Q p_w, w <- p_w - b^T Q -- from ONE extended Gram, as the
 // constant matrix A.  The loss of orthogonality of one Cholesky pass is ~ cond_2(P)^2 u = cond_2(G) u
-// with G = P P^T the projected Gram; for the symmetric G, |G|_2 <= |G|_inf, so
-// sqrt(|G|_inf |G^-1|_inf) >= cond_2(P).  The kernel reports that bound next to the status so that
-// the host can fall back to the two-pass CholeskyQR2 (small1 / small2) whenever it is not negligible.
+// with G = P P^T the projected Gram -- after equilibration (see below).  The kernel reports an upper bound of
+// that condition number next to the status so that the two-pass CholeskyQR2 (small1 / small2) takes over
+// whenever it is not negligible.
 __global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, int use_d, long long bstride,
                                                            int* two_pass_flag, int force_two) {
     B = small_of(B, bstride, blockIdx.x);
@@ -729,27 +734,53 @@ __global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, i
         Gp[e] = use_d ? G[j * MX + l] - c[j] * G[l * MX + D] : G[j * MX + l];
     }
     __syncthreads();
-    for (int j = tid; j < m; j += nthr) {            // row sums of |G| (before it is factored in place)
-        double r = 0.0;
-        for (int l = 0; l < m; ++l) r += fabs(Gp[j * m + l]);
+    // Condition certificate on the EQUILIBRATED Gram H = D G D, D = diag(G)^-1/2 (unit diagonal): Cholesky's backward
+    // error is componentwise relative to sqrt(G_ii G_jj), and Q = P L^-T does not change when the rows of P are
+    // rescaled, so the orthogonality lost by one pass is governed by cond_2(H), not cond_2(G) (the rows of P have
+    // grown by different factors over the segment: diag R spreads by 3 - 5).  |.|_2 <= min(|.|_inf, |.|_F) for the
+    // symmetric H and H^-1 = D^-1 G^-1 D^-1 gives the bound; sq[j] = sqrt(G_jj).
+    double* sq = bb + MX;                // m
+    double* fr = sq + MX;                // m     squared Frobenius row sums
+    for (int j = tid; j < m; j += nthr) sq[j] = sqrt(fmax(Gp[j * m + j], 0.0));
+    __syncthreads();
+    for (int j = tid; j < m; j += nthr) {            // row sums of |H| and H^2 (before G is factored in place)
+        double r = 0.0, f = 0.0;
+        for (int l = 0; l < m; ++l) {
+            const double sc = sq[j] * sq[l];
+            const double h = sc > 0.0 ? Gp[j * m + l] / sc : (j == l ? 1.0 : 0.0);
+            r += fabs(h);
+            f += h * h;
+        }
         bb[j] = r;
+        fr[j] = f;
     }
     __syncthreads();
-    if (tid == 0) { double a = 0.0; for (int j = 0; j < m; ++j) a = fmax(a, bb[j]); nrm[0] = a; }
+    if (tid == 0) {
+        double a = 0.0, f = 0.0;
+        for (int j = 0; j < m; ++j) { a = fmax(a, bb[j]); f += fr[j]; }
+        nrm[0] = fmin(a, sqrt(f));
+    }
     __syncthreads();
     cta_cholesky(Gp, m, m, &fail);
     cta_tri_inverse(Gp, m, m, Li);
-    for (int a = tid; a < m; a += nthr) {            // row sums of |G^-1| = |L^-T L^-1|
-        double r = 0.0;
+    for (int a = tid; a < m; a += nthr) {            // row sums of |H^-1|, H^-1 = D^-1 L^-T L^-1 D^-1
+        double r = 0.0, f = 0.0;
         for (int b = 0; b < m; ++b) {
             double e = 0.0;
             for (int k = a > b ? a : b; k < m; ++k) e += Li[k * m + a] * Li[k * m + b];
+            e *= sq[a] * sq[b];
             r += fabs(e);
+            f += e * e;
         }
         bb[a] = r;
+        fr[a] = f;
     }
     __syncthreads();
-    if (tid == 0) { double a = 0.0; for (int j = 0; j < m; ++j) a = fmax(a, bb[j]); nrm[1] = a; }
+    if (tid == 0) {
+        double a = 0.0, f = 0.0;
+        for (int j = 0; j < m; ++j) { a = fmax(a, bb[j]); f += fr[j]; }
+        nrm[1] = fmin(a, sqrt(f));
+    }
     __syncthreads();
     // b = L^-1 <P_j, p_w>,  <P_j, p_w> = G[j][m] - c_j G[m][D]
     for (int j = tid; j < m; j += nthr) {

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(32 * (kMmaWarps + 1), 1) gram_mma_kernel(
 // four sites of a group (lanes t = 0 .. 3) are folded by two shuffles at the very end.  11 DFMA (352 FMA slots)
 // replace 5 DMMA (1280 FMA slots) per group of 4 sites at MX = 34.
 template <int NBD, int NV, int SRC>
-__global__ void __launch_bounds__(32 * (kMmaWarps + 1), 1) gram_mma2_kernel(
+__global__ void __launch_bounds__(32 * (kMmaWarps + 1), 2) gram_mma2_kernel(
     const double* __restrict__ E, const double* __restrict__ T, const double* __restrict__ d, int MX, double inv_eps,
     long long n, int nst, double* __restrict__ part, BatchDesc bd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -336,11 +336,14 @@ static cudaError_t gram_mma2_launch(int src, const double* E, const double* T, c
     const int W = src == SRC_ENSEMBLE ? MX : MX - 1;
     const size_t stage_doubles = ((size_t)S * W + S + 15) & ~(size_t)15;
     const size_t scratch = (size_t)kMmaWarps * (NP * 64 + NV * 8 * NBD + NS);
-    int nst = (int)std::min<size_t>(kBndMaxStages, (200 * 1024) / (stage_doubles * sizeof(double)));
+    // two CTAs per SM (96 registers, half the ring each): one CTA's tensor-core work overlaps the other's waits --
+    // with one CTA the pass sat at 57 % of the DMMA rate AND 56 % of the DRAM rate (profiles/r2b_boundary_ncu.txt)
+    static const int ctas = [] { const char* e = getenv("FDS_GRAM_CTAS"); return (e && e[0] == '1') ? 1 : 2; }();
+    int nst = (int)std::min<size_t>(kBndMaxStages, ((ctas == 2 ? 104 : 200) * 1024) / (stage_doubles * sizeof(double)));
     if (nst < 2) return cudaErrorInvalidValue;
     const size_t smem = 128 + sizeof(double) * std::max(scratch, (size_t)nst * stage_doubles);
     const long long ntiles = (n + S - 1) / S;
-    int gx = (int)std::min<long long>(ntiles, std::min(max_part, num_sms));
+    int gx = (int)std::min<long long>(ntiles, std::min(max_part, ctas * num_sms));
     if (gx < 1) gx = 1;
     const dim3 grid((unsigned)gx, (unsigned)bd.count);
     const int block = 32 * (kMmaWarps + 1);

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1427,43 +1428,64 @@ int fds_lss_solve(int device, const double* R, const double* b, int64_t K, int m
     return fds_lss_solve_batch(device, R, b, K, m, 1, alpha);
 }
 
+// Device buffers of the context-free LSS solve, kept between calls (one set per GPU, grown on demand): with
+// verbose=True the reference solves after EVERY segment (fds/fds.py:161), which used to cost five cudaMalloc and
+// four blocking copies per call.  One lock: concurrent solves on the same process are serialised.
+namespace {
+struct LssScratch {
+    double* buf = nullptr;      // [R | b | alpha | work]
+    int* status = nullptr;
+    size_t cap = 0, cap_st = 0;
+    cudaStream_t stream = nullptr;
+};
+std::mutex g_lss_mutex;
+LssScratch g_lss[64];
+}  // namespace
+
 int fds_lss_solve_batch(int device, const double* R, const double* b, int64_t K, int m, int64_t nbatch, double* alpha) {
     if (K < 1 || m < 1 || nbatch < 1 || lss_smem_bytes(m) > 220 * 1024) { g_create_err = "fds_lss_solve: bad K, m or batch"; return 2; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e == cudaSuccess && (device < 0 || device >= ndev)) e = cudaErrorInvalidDevice;
+    if (e == cudaSuccess && (device < 0 || device >= ndev || device >= 64)) e = cudaErrorInvalidDevice;
     if (e != cudaSuccess) { g_create_err = std::string("fds_lss_solve: ") + cudaGetErrorString(e) + " -- no CPU fallback"; return 3; }
     DeviceGuard guard__(device);
-    const size_t mm = (size_t)m * m;
-    double *dR = nullptr, *db = nullptr, *da = nullptr, *dw = nullptr;
-    int* dst = nullptr;
-    int rc = 0, st = 0;
+    std::lock_guard<std::mutex> lock(g_lss_mutex);
+    LssScratch& sc = g_lss[device];
+    const size_t mm = (size_t)m * m, nbz = (size_t)nbatch;
+    const size_t nR = nbz * K * mm, nb_ = nbz * K * m, nw = nbz * ((size_t)2 * K * mm + (size_t)2 * K * m);
+    const size_t need = nR + 2 * nb_ + nw;
 #define CKL(call)                                                                          \
     do {                                                                                   \
         cudaError_t e__ = (call);                                                          \
-        if (e__ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__); rc = 1; goto done; } \
+        if (e__ != cudaSuccess) { g_create_err = std::string(#call) + ": " + cudaGetErrorString(e__); return 1; } \
     } while (0)
-    {
-    const size_t nbz = (size_t)nbatch;
-    std::vector<int> sts(nbz, 0);
-    CKL(cudaMalloc(&dR, nbz * K * mm * sizeof(double)));
-    CKL(cudaMalloc(&db, nbz * K * m * sizeof(double)));
-    CKL(cudaMalloc(&da, nbz * K * m * sizeof(double)));
-    CKL(cudaMalloc(&dw, nbz * ((size_t)2 * K * mm + (size_t)2 * K * m) * sizeof(double)));
-    CKL(cudaMalloc(&dst, nbz * sizeof(int)));
-    CKL(cudaMemcpy(dR, R, nbz * K * mm * sizeof(double), cudaMemcpyHostToDevice));
-    CKL(cudaMemcpy(db, b, nbz * K * m * sizeof(double), cudaMemcpyHostToDevice));
-    CKL(launch_lss_solve(dR, db, K, m, da, dw, dst, nullptr, nullptr, (int)nbatch));
-    CKL(cudaMemcpy(alpha, da, nbz * K * m * sizeof(double), cudaMemcpyDeviceToHost));
-    CKL(cudaMemcpy(sts.data(), dst, nbz * sizeof(int), cudaMemcpyDeviceToHost));
-    for (size_t p = 0; p < nbz; ++p)
-        if (sts[p] != 0) { st = sts[p]; g_create_err = "fds_lss_solve: Schur complement not positive definite at row " +
-                                                      std::to_string(st) + " (problem " + std::to_string(p) + ")"; rc = 4; break; }
+    if (!sc.stream) CKL(cudaStreamCreateWithFlags(&sc.stream, cudaStreamNonBlocking));
+    if (sc.cap < need) {
+        cudaFree(sc.buf); sc.buf = nullptr; sc.cap = 0;
+        CKL(cudaMalloc(&sc.buf, need * sizeof(double)));
+        sc.cap = need;
     }
-done:
-    cudaFree(dR); cudaFree(db); cudaFree(da); cudaFree(dw); cudaFree(dst);
-    return rc;
+    if (sc.cap_st < nbz) {
+        cudaFree(sc.status); sc.status = nullptr; sc.cap_st = 0;
+        CKL(cudaMalloc(&sc.status, nbz * sizeof(int)));
+        sc.cap_st = nbz;
+    }
+    double *dR = sc.buf, *db = dR + nR, *da = db + nb_, *dw = da + nb_;
+    std::vector<int> sts(nbz, 0);
+    CKL(cudaMemcpyAsync(dR, R, nR * sizeof(double), cudaMemcpyHostToDevice, sc.stream));
+    CKL(cudaMemcpyAsync(db, b, nb_ * sizeof(double), cudaMemcpyHostToDevice, sc.stream));
+    CKL(launch_lss_solve(dR, db, K, m, da, dw, sc.status, sc.stream, nullptr, (int)nbatch));
+    CKL(cudaMemcpyAsync(alpha, da, nb_ * sizeof(double), cudaMemcpyDeviceToHost, sc.stream));
+    CKL(cudaMemcpyAsync(sts.data(), sc.status, nbz * sizeof(int), cudaMemcpyDeviceToHost, sc.stream));
+    CKL(cudaStreamSynchronize(sc.stream));
 #undef CKL
+    for (size_t p = 0; p < nbz; ++p)
+        if (sts[p] != 0) {
+            g_create_err = "fds_lss_solve: Schur complement not positive definite at row " + std::to_string(sts[p]) +
+                           " (problem " + std::to_string(p) + ")";
+            return 4;
+        }
+    return 0;
 }
 
 }  // extern "C"

@@ -13,10 +13,11 @@ tag, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
 # ---- launch list: per-kernel totals and shares -------------------------------
 lines = [l for l in open(launches) if not l.startswith('==')]
 rows = [r for r in csv.DictReader(lines) if r.get('Metric Name') == 'gpu__time_duration.sum']
-# the timed region of `bench.py --steps 2`: the two segments (each opens with extract_col0_kernel) before the FP64 probe
+# the timed region of `bench.py --steps 2`: the two segments (each opens with the time-dilation kernel of its
+# boundary, after the 3 us halo wrap) before the FP64 probe
 names = [r['Kernel Name'].split('(')[0] for r in rows]
 end = names.index('fp64_rate_kernel') if 'fp64_rate_kernel' in names else len(names)
-starts = [i for i, k in enumerate(names[:end]) if k == 'extract_col0_kernel']
+starts = [i for i, k in enumerate(names[:end]) if 'dilation_fused_kernel' in k]
 rows = rows[starts[-2] if len(starts) >= 2 else 0:end]
 agg = collections.OrderedDict()
 for row in rows:
