@@ -45,9 +45,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'L96 shadowing state-updates/s (N*(m+1)*steps*K / time)'
 UNIT = 'state-updates/s'
-# FP64 warp-instructions of the exact-mode two-step kernel per 8-site block of two steps (static count of
-# the hot loop with the objective tree): 476 -> 29.75 per trajectory-site-step
-FP64_INST_PER_UPDATE = {('exact', 2): 29.75}
+# FP64 warp-instructions of the exact-mode two-step kernel per trajectory-site-step: static count of the hot loop
+# with the objective tree (tools/sass_hot.py): 956 per two 8-site blocks of two steps
+FP64_INST_PER_UPDATE = {('exact', 2): 956.0 / 32.0}
 STEP_KERNEL_SOURCES = ['l96_step.cu', 'l96_core.cuh', 'l96_march.cuh', 'l96_march2.cuh', 'l96_marchk.cuh', 'common.cuh']
 
 
