@@ -534,12 +534,13 @@ cudaError_t launch_apply(int src, const double* E, const double* Tin, const doub
 // ------------------------------ small algebra (1 CTA) ------------------------ //
 // In-place Cholesky G = L L^T of the leading mm x mm block of a matrix with row stride ld
 // (lower triangle holds L on exit).  Returns via *fail the 1-based failing column, else 0.
-__device__ void cta_cholesky(double* G, int ld, int mm, int* fail) {
+// min_pivot: pivots at or below it count as failures (0: only non-positive ones).
+__device__ void cta_cholesky(double* G, int ld, int mm, int* fail, double min_pivot = 0.0) {
     const int tid = threadIdx.x, nthr = blockDim.x;
     for (int j = 0; j < mm; ++j) {
         __syncthreads();
         const double piv = G[j * ld + j];
-        if (!(piv > 0.0)) { if (tid == 0 && *fail == 0) *fail = j + 1; }
+        if (!(piv > min_pivot)) { if (tid == 0 && *fail == 0) *fail = j + 1; }
         const double ljj = sqrt(piv > 0.0 ? piv : 1.0);
         __syncthreads();
         if (tid == 0) G[j * ld + j] = ljj;
@@ -582,9 +583,62 @@ FDS_D SmallBufs small_of(SmallBufs B, long long stride, int p) {
     return B;
 }
 
+// Upper bound of cond_2 of the EQUILIBRATED Gram H = D G D, D = diag(G)^-1/2 (see small_single_kernel), in two parts
+// around the in-place factorisation: |H|_2 <= min(|H|_inf, |H|_F) before, |H^-1|_2 likewise from L^-1 after.
+// sq, rs, fr: m doubles of shared memory each.
+__device__ double cta_eq_norm_before(const double* Gp, int m, double* sq, double* rs, double* fr, double* out) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int j = tid; j < m; j += nthr) sq[j] = sqrt(fmax(Gp[j * m + j], 0.0));
+    __syncthreads();
+    for (int j = tid; j < m; j += nthr) {
+        double r = 0.0, f = 0.0;
+        for (int l = 0; l < m; ++l) {
+            const double sc = sq[j] * sq[l];
+            const double h = sc > 0.0 ? Gp[j * m + l] / sc : (j == l ? 1.0 : 0.0);
+            r += fabs(h);
+            f += h * h;
+        }
+        rs[j] = r;
+        fr[j] = f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, f = 0.0;
+        for (int j = 0; j < m; ++j) { a = fmax(a, rs[j]); f += fr[j]; }
+        *out = fmin(a, sqrt(f));
+    }
+    __syncthreads();
+    return *out;
+}
+__device__ double cta_eq_norm_after(const double* Li, int m, const double* sq, double* rs, double* fr, double* out) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int a = tid; a < m; a += nthr) {            // row sums of |H^-1|, H^-1 = D^-1 L^-T L^-1 D^-1
+        double r = 0.0, f = 0.0;
+        for (int b = 0; b < m; ++b) {
+            double e = 0.0;
+            for (int k = a > b ? a : b; k < m; ++k) e += Li[k * m + a] * Li[k * m + b];
+            e *= sq[a] * sq[b];
+            r += fabs(e);
+            f += e * e;
+        }
+        rs[a] = r;
+        fr[a] = f;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0, f = 0.0;
+        for (int j = 0; j < m; ++j) { a = fmax(a, rs[j]); f += fr[j]; }
+        *out = fmin(a, sqrt(f));
+    }
+    __syncthreads();
+    return *out;
+}
+
 // pass 1: G_dil/g_dil, projection, (optionally) first Cholesky factor; builds A1
+// shift_rel > 0: the projected Gram gets shift_rel * trace added to its diagonal before it is factored (first pass of
+// the shifted CholeskyQR3 below) -- the factor then exists for any numerically rank-deficient block
 __global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use_d, int do_qr, long long bstride,
-                                                     const int* gate, int gate_want) {
+                                                     const int* gate, int gate_want, double shift_rel) {
     if (gate != nullptr && *gate != gate_want) return;
     B = small_of(B, bstride, blockIdx.x);
     extern __shared__ __align__(16) double sm[];
@@ -619,8 +673,28 @@ __global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use
         Gp[e] = use_d ? G[j * MX + l] - c[j] * G[l * MX + D] : G[j * MX + l];
     }
     __syncthreads();
+    if (shift_rel > 0.0) {
+        __shared__ double shift;
+        if (tid == 0) {
+            double tr = 0.0;
+            for (int j = 0; j < m; ++j) tr += Gp[j * m + j];
+            shift = shift_rel * tr;
+        }
+        __syncthreads();
+        for (int j = tid; j < m; j += nthr) Gp[j * m + j] += shift;
+        __syncthreads();
+    }
+    // condition bound of the block as it is factored (equilibrated, see small_single_kernel): beyond ~1e7 the
+    // caller must not trust CholeskyQR2 even when no pivot fails -- it switches to the shifted CholeskyQR3
+    __shared__ double nrm1[2];
+    double* rs = c + MX;
+    double* sq = rs + MX;
+    double* fr = sq + MX;
+    cta_eq_norm_before(Gp, m, sq, rs, fr, &nrm1[0]);
     cta_cholesky(Gp, m, m, &fail);
     cta_tri_inverse(Gp, m, m, Li);
+    cta_eq_norm_after(Li, m, sq, rs, fr, &nrm1[1]);
+    if (tid == 0) reinterpret_cast<double*>(B.status)[1] = sqrt(nrm1[0] * nrm1[1]);
     for (int e = tid; e < m * m; e += nthr) {
         const int i = e / m, k = e % m;
         B.L1[e] = k <= i ? Gp[e] : 0.0;
@@ -639,6 +713,49 @@ __global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use
         } else {                                      // inhomogeneous row: projection only
             v = l == m ? 1.0 : (l == D ? -c[m] : 0.0);
         }
+        B.A[e] = v;
+    }
+    __syncthreads();
+    if (tid == 0) *B.status = fail ? kSmallPass1 + fail : 0;
+}
+
+// Middle pass of the shifted CholeskyQR3 (Fukaya, Kannan, Nakatsukasa, Yamamoto, Yanagisawa 2020): the tangent array
+// holds [Q1; p_w] with Q1 = L1s^-1 P from the SHIFTED first factor -- not orthonormal, but with cond_2 <~ 1e7 whatever
+// cond_2(P) was.  Factor its Gram, Q2 = L2^-1 Q1 (inhomogeneous row untouched), and fold L2 into the accumulated
+// factor: L1 <- L1 L2, so that the ordinary pass 2 (small2) ends with R = (L1s L2 L3)^T.
+__global__ void __launch_bounds__(256) small_mid_kernel(SmallBufs B, int m, long long bstride) {
+    B = small_of(B, bstride, blockIdx.x);
+    extern __shared__ __align__(16) double sm[];
+    const int MX = m + 2, MO = m + 1;
+    double* G = sm;                      // MX*MX
+    double* L2 = G + MX * MX;            // m*m
+    double* Li = L2 + m * m;             // m*m
+    __shared__ int fail;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) fail = 0;
+    for (int e = tid; e < MX * MX; e += nthr) G[e] = B.gram[e];
+    __syncthreads();
+    for (int e = tid; e < m * m; e += nthr) L2[e] = G[(e / m) * MX + e % m];
+    __syncthreads();
+    // The Gram of Q1 has the eigenvalues lambda / (lambda + sigma) of the shifted first pass: tiny but well above
+    // rounding for any block the method can handle, and (rounding aside) ZERO for an exactly rank-deficient block --
+    // which must fail, not pass with a pivot made of rounding noise
+    cta_cholesky(L2, m, m, &fail, 8.0 * m * 1.1102230246251565e-16);
+    cta_tri_inverse(L2, m, m, Li);
+    for (int e = tid; e < m * m; e += nthr) {        // (L1 L2)[i][k] = sum_{j = k .. i} L1[i][j] L2[j][k]   (G is free: scratch)
+        const int i = e / m, k = e % m;
+        double s = 0.0;
+        if (k <= i)
+            for (int j = k; j <= i; ++j) s += B.L1[i * m + j] * L2[j * m + k];
+        G[e] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * m; e += nthr) B.L1[e] = G[e];
+    for (int e = tid; e < MO * MX; e += nthr) {
+        const int o = e / MX, l = e % MX;
+        double v = 0.0;
+        if (o < m) { if (l < m && l <= o) v = Li[o * m + l]; }
+        else if (l == m) v = 1.0;
         B.A[e] = v;
     }
     __syncthreads();
@@ -741,47 +858,10 @@ __global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, i
     // symmetric H and H^-1 = D^-1 G^-1 D^-1 gives the bound; sq[j] = sqrt(G_jj).
     double* sq = bb + MX;                // m
     double* fr = sq + MX;                // m     squared Frobenius row sums
-    for (int j = tid; j < m; j += nthr) sq[j] = sqrt(fmax(Gp[j * m + j], 0.0));
-    __syncthreads();
-    for (int j = tid; j < m; j += nthr) {            // row sums of |H| and H^2 (before G is factored in place)
-        double r = 0.0, f = 0.0;
-        for (int l = 0; l < m; ++l) {
-            const double sc = sq[j] * sq[l];
-            const double h = sc > 0.0 ? Gp[j * m + l] / sc : (j == l ? 1.0 : 0.0);
-            r += fabs(h);
-            f += h * h;
-        }
-        bb[j] = r;
-        fr[j] = f;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double a = 0.0, f = 0.0;
-        for (int j = 0; j < m; ++j) { a = fmax(a, bb[j]); f += fr[j]; }
-        nrm[0] = fmin(a, sqrt(f));
-    }
-    __syncthreads();
+    cta_eq_norm_before(Gp, m, sq, bb, fr, &nrm[0]);
     cta_cholesky(Gp, m, m, &fail);
     cta_tri_inverse(Gp, m, m, Li);
-    for (int a = tid; a < m; a += nthr) {            // row sums of |H^-1|, H^-1 = D^-1 L^-T L^-1 D^-1
-        double r = 0.0, f = 0.0;
-        for (int b = 0; b < m; ++b) {
-            double e = 0.0;
-            for (int k = a > b ? a : b; k < m; ++k) e += Li[k * m + a] * Li[k * m + b];
-            e *= sq[a] * sq[b];
-            r += fabs(e);
-            f += e * e;
-        }
-        bb[a] = r;
-        fr[a] = f;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        double a = 0.0, f = 0.0;
-        for (int j = 0; j < m; ++j) { a = fmax(a, bb[j]); f += fr[j]; }
-        nrm[1] = fmin(a, sqrt(f));
-    }
-    __syncthreads();
+    cta_eq_norm_after(Li, m, sq, bb, fr, &nrm[1]);
     // b = L^-1 <P_j, p_w>,  <P_j, p_w> = G[j][m] - c_j G[m][D]
     for (int j = tid; j < m; j += nthr) {
         double s = 0.0;
@@ -847,12 +927,21 @@ cudaError_t launch_small_single(const SmallBufs& B, int m, int use_d, cudaStream
 }
 
 cudaError_t launch_small1(const SmallBufs& B, int m, int use_d, int do_qr, cudaStream_t st, LaunchStats* ls,
-                          const BatchDesc* batch) {
+                          const BatchDesc* batch, double shift_rel) {
     const size_t smem = small_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(small1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     small1_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, do_qr, batch ? batch->small_stride : 0,
-                                                               batch ? batch->gate : nullptr, batch ? batch->gate_want : 0);
+                                                               batch ? batch->gate : nullptr, batch ? batch->gate_want : 0,
+                                                               shift_rel);
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+cudaError_t launch_small_mid(const SmallBufs& B, int m, cudaStream_t st, LaunchStats* ls, const BatchDesc* batch) {
+    const size_t smem = small_smem_bytes(m);
+    cudaError_t e = cudaFuncSetAttribute(small_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    small_mid_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, batch ? batch->small_stride : 0);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }

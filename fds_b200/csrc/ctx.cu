@@ -83,7 +83,8 @@ struct fds_ctx {
     int pend_src = 0;
     double pend_inv_eps = 0.0;
     double cond_last = 0.0;           // upper bound of cond_2 from the last single-pass attempt
-    int passes_last = 0;              // CholeskyQR passes the last boundary with QR took (1 or 2)
+    int passes_last = 0;              // CholeskyQR passes the last boundary with QR took (1, 2, or 3: shifted CholeskyQR3)
+    bool shifted_last = false;
     double eps_last = 0.0;
     long long ens_halo_valid = 0, pri_halo_valid = 0;
     LaunchStats ls;
@@ -112,6 +113,9 @@ struct fds_ctx {
     double* P(int j) const { return P_all(j) + gl0; }
     const BatchDesc* batch() const { return nb > 1 ? &bd : nullptr; }
 };
+
+// CholeskyQR2 needs cond_2 of the block below ~ u^-1/2 / poly(m, n); past this bound the shifted CholeskyQR3 runs
+constexpr double kShiftedQrCond = 1e6;
 
 static thread_local std::string g_create_err;   // creation / context-free errors, per calling thread
 
@@ -1237,10 +1241,40 @@ int fds_boundary_factor(fds_ctx* c, int do_qr, int from_ensemble, double eps) {
         c->err = keep;                    // ill conditioned or rank deficient: CholeskyQR2 decides
     }
     FDS_CK(c, launch_small1(c->small, c->m, c->time_dilation ? 1 : 0, do_qr, c->stream, &c->ls, c->batch()));
-    if (do_qr || c->fast_boundary) if (int r = check_small_status(c, "CholeskyQR pass 1")) return r;
     const int src = from_ensemble ? SRC_ENSEMBLE : SRC_TANGENT;
-    FDS_CK(c, do_apply(c, src, from_ensemble ? 1.0 / eps : 0.0, c->T, nullptr, 0.0));
+    bool shifted = false;
+    if (do_qr || c->fast_boundary) {
+        const std::string keep = c->err;
+        const int r = check_small_status(c, "CholeskyQR pass 1");
+        // (the bound is garbage-in-garbage-out for a numerically singular Gram: anything that is not a number below
+        // the limit counts, and so does a failed pivot)
+        const bool too_ill = do_qr && r != 1 && (r == 2 || !(c->cond_last < kShiftedQrCond));
+        if (too_ill && (c->cfg.world == 1 || c->comm)) {
+            // The Gram of the tangent block is numerically singular (cond_2 of the block beyond ~1e8: a subspace that
+            // reaches far into the stable directions, e.g. m = N with a wide Lyapunov spectrum -- the reference's
+            // Householder QR, pascal_lite/operators/linalg.py:21, does not care).  Shifted CholeskyQR3: a first
+            // factor of G + sigma I, sigma = 11 (m n + m (m + 1)) u trace(G) >= the bound of Fukaya et al. (2020),
+            // always exists and leaves a block with cond_2 <~ 1e7, on which CholeskyQR2 (middle pass + pass 2) is
+            // accurate; R = (L1s L2 L3)^T.
+            c->err = keep;
+            const double nn = (double)c->cfg.n_global, mm = (double)c->m;
+            const double shift_rel = 11.0 * (mm * nn + mm * (mm + 1.0)) * 1.1102230246251565e-16;
+            FDS_CK(c, launch_small1(c->small, c->m, c->time_dilation ? 1 : 0, 1, c->stream, &c->ls, c->batch(), shift_rel));
+            if (int r2 = check_small_status(c, "shifted CholeskyQR3 pass 1")) return r2;
+            FDS_CK(c, do_apply(c, src, from_ensemble ? 1.0 / eps : 0.0, c->T, nullptr, 0.0));
+            FDS_CK(c, do_gram(c, SRC_TANGENT, 0.0));
+            if (int r2 = allreduce_gram(c, c->small.gram)) return r2;
+            FDS_CK(c, launch_small_mid(c->small, c->m, c->stream, &c->ls, c->batch()));
+            if (int r2 = check_small_status(c, "shifted CholeskyQR3 pass 2")) return r2;
+            FDS_CK(c, do_apply(c, SRC_TANGENT, 0.0, c->T, nullptr, 0.0));
+            shifted = true;
+        } else if (r != 0) {
+            return r;
+        }
+    }
+    if (!shifted) FDS_CK(c, do_apply(c, src, from_ensemble ? 1.0 / eps : 0.0, c->T, nullptr, 0.0));
     c->tangents_implicit = false;
+    c->shifted_last = shifted;
     if (do_qr) FDS_CK(c, do_gram(c, SRC_TANGENT, 0.0));
     return 0;
 }
@@ -1256,7 +1290,7 @@ int fds_boundary_finish(fds_ctx* c, int do_qr, double eps, int build) {
         FDS_CK(c, do_apply(c, c->pend_src, c->pend_inv_eps, keepT ? c->T : nullptr, ens ? c->Ecur() : nullptr, eps));
         if (!keepT) c->tangents_implicit = true;    // the new ensemble is the record of the tangents
     } else if (do_qr) {
-        c->passes_last = 2;
+        c->passes_last = c->shifted_last ? 3 : 2;
         FDS_CK(c, launch_small2(c->small, c->m, c->stream, &c->ls, c->batch()));
         if (int r = check_small_status(c, "CholeskyQR pass 2")) return r;
         FDS_CK(c, do_apply(c, SRC_TANGENT, 0.0, keepT ? c->T : nullptr, ens ? c->Ecur() : nullptr, eps));

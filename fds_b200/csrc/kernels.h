@@ -154,7 +154,9 @@ struct SmallBufs {          // all device pointers
 // `gram2`: small2 factors this Gram instead of B.gram (the gated boundary keeps the two Grams apart).
 constexpr int kSmallPass1 = 1000, kSmallPass2 = 2000;
 cudaError_t launch_small1(const SmallBufs&, int m, int use_d, int do_qr, cudaStream_t, LaunchStats*,
-                          const BatchDesc* batch = nullptr);
+                          const BatchDesc* batch = nullptr, double shift_rel = 0.0);
+// middle pass of the shifted CholeskyQR3 (after a small1 with shift_rel > 0): Gram of [Q1; p_w] -> L2, L1 <- L1 L2, A
+cudaError_t launch_small_mid(const SmallBufs&, int m, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr);
 cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr,
                           const double* gram2 = nullptr);
 // single-pass CholeskyQR from one Gram; writes sqrt(|G|_inf |G^-1|_inf) >= cond_2 to ((double*)status)[1].

@@ -226,8 +226,43 @@ def reference_checkpoint_fixture():
     print('reference checkpoint fixture: file', name, 'continued to', cp2.lss.K_segments(), 'segments, G =', out['cont_G'])
 
 
+def lorenz_vdp_dudt(u, s):
+    """The reference's only pure-Python plugin (tests/test_lyapunov_vector.py:13-22): a Lorenz-63 system driving
+    a Van der Pol-type oscillator."""
+    x, y, z, x0, y0 = u
+    return np.array([10 * (y - x), x * (s - z) - y, x * y - 8. / 3 * z, y0,
+                     (z - x0 ** 2) * y0 - x0 * (2 * np.pi) ** 2])
+
+
+def lorenz_vdp_run(u, s, nsteps, dt=0.05):
+    """run(u, s, steps) of that system with scipy's odeint, objective [z, x0^2] (tests/test_lyapunov_vector.py:24-30)."""
+    from scipy.integrate import odeint
+    J = np.empty([nsteps, 2])
+    for i in range(nsteps):
+        u = odeint(lambda w, t: lorenz_vdp_dudt(w, s), u, [0, dt])[1]
+        J[i] = u[2], u[3] ** 2
+    return u, J
+
+
+def lyapunov_plugin_fixture():
+    """tests/test_lyapunov_vector.py:33-48 run by the reference itself: the five Lyapunov exponents (mean and
+    standard error over the segments, fds/timeseries.py:3-7) of the Lorenz + Van der Pol system, time dilation off
+    (run_ddt=0)."""
+    m, steps, K, dt = 5, 50, 50, 0.05
+    np.random.seed(11)
+    cp = quiet(ref.shadowing, lorenz_vdp_run, np.ones(5), 28, m, K, steps, 100, run_ddt=0, return_checkpoint=True)
+    L = cp.lss.lyapunov_exponents() / (steps * dt)
+    Lm, Le = ref.timeseries.mean_std(L)
+    np.savez_compressed(os.path.join(GOLD, 'lyapunov_lorenz_vdp_from_reference.npz'), L=Lm, L_err=Le, m=m, steps=steps,
+                        K=K, dt=dt, s=28.0, runup=100, clv_shape=np.array(cp.lss.lyapunov_covariant_vectors().shape))
+    print('lyapunov plugin fixture: L =', Lm, '+-', Le)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ['lyap']:
+        lyapunov_plugin_fixture()
+        return
     if sys.argv[1:] == ['clv']:
         clv_fixture()
         return
@@ -264,6 +299,7 @@ def main():
              20, 50000, 2000, 1e-6, 0, pin_tol=1e-6)
     clv_fixture()
     reference_checkpoint_fixture()
+    lyapunov_plugin_fixture()
 
 
 if __name__ == '__main__':

@@ -83,3 +83,39 @@ def test_host_solver_restart_and_plugin_signatures(tmp_path):
 def test_bare_callable_is_still_rejected():
     with pytest.raises(TypeError, match='HostSolver'):
         fds_b200.shadowing(plugins.run_l96_rk4, np.zeros(40), 0.0, 2, 2, 10, 0)
+
+
+def _lorenz_vdp_run(u, s, nsteps, dt=0.05):
+    """A user-style pure-Python plugin: the Lorenz-63 + Van der Pol system of the reference's
+    tests/test_lyapunov_vector.py:13-30, integrated with scipy's odeint, objective [z, x0^2]."""
+    from scipy.integrate import odeint
+
+    def dudt(w, t):
+        x, y, z, x0, y0 = w
+        return [10 * (y - x), x * (s - z) - y, x * y - 8. / 3 * z, y0, (z - x0 ** 2) * y0 - x0 * (2 * np.pi) ** 2]
+    J = np.empty([nsteps, 2])
+    for i in range(nsteps):
+        u = odeint(dudt, u, [0, dt])[1]
+        J[i] = u[2], u[3] ** 2
+    return u, J
+
+
+@gpu
+def test_lyapunov_spectrum_of_a_python_plugin():
+    """The reference's tests/test_lyapunov_vector.py:33-48 through HostSolver: time dilation off (run_ddt=0), five
+    exponents from log|diag R| on the device, asserted against the reference's literal values within 3 sigma (its
+    own criterion) AND against the spectrum the reference itself computes (fixture, oracle/gen_golden.py)."""
+    g = golden('lyapunov_lorenz_vdp_from_reference')
+    m, steps, K, dt = int(g['m']), int(g['steps']), int(g['K']), float(g['dt'])
+    np.random.seed(11)
+    cp = fds_b200.shadowing(fds_b200.HostSolver(_lorenz_vdp_run), np.ones(5), float(g['s']), m, K, steps,
+                            int(g['runup']), run_ddt=0, return_checkpoint=True)
+    L = cp.lss.lyapunov_exponents() / (steps * dt)
+    L, L_err = fds_b200.timeseries.mean_std(L)
+    for lit, lo, hi in zip((0.90, 0.25, 0.0, -4.98, -6.40), L - 3 * L_err, L + 3 * L_err):
+        assert lo < lit < hi
+    assert (np.abs(L - g['L']) < 3 * (L_err + g['L_err'])).all()
+    assert (np.abs(L - g['L']) < 0.05 * np.abs(g['L']).max()).all()      # same trajectory, same seed: far closer than the bars
+    v = cp.lss.lyapunov_covariant_vectors()
+    assert v.shape == (m, K + 1, m) == tuple(g['clv_shape'])
+    assert all(len(x) == K for x in (cp.G_dil, cp.g_dil)) and np.abs(np.array(cp.G_dil)).max() == 0.0

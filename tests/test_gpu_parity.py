@@ -316,3 +316,28 @@ def test_ill_conditioned_block_falls_back_to_two_passes():
     assert np.abs(Q @ Q.T - np.eye(m)).max() < 1e-13
     assert maxrel(R.T @ Q, W) < 1e-12
     eng.close()
+
+
+@gpu
+@pytest.mark.parametrize('N,m,cond', [(5, 5, 1e9), (300, 6, 1e11), (4096, 12, 1e11)])
+def test_numerically_singular_gram_takes_shifted_choleskyqr3(N, m, cond):
+    """A tangent block whose Gram is singular in fp64 (cond_2 of the block far beyond 1e8: CholeskyQR2 breaks down)
+    -- what m = N with a wide Lyapunov spectrum produces -- is still factored: shifted CholeskyQR3 agrees with
+    Householder QR (np.linalg.qr, what the reference calls at pascal_lite/operators/linalg.py:21) on R to
+    cond * u and orthonormalises to rounding."""
+    rng = np.random.RandomState(m)
+    U = np.linalg.qr(rng.randn(N, m))[0]
+    W = (np.linalg.qr(rng.randn(m, m))[0] * np.logspace(0, -np.log10(cond), m)) @ U.T         # (m, N), singular values 1 .. 1/cond
+    eng = fds_b200.L96(max(N, 4)).engine(m) if N >= 4 else None
+    eng.set_state(rng.rand(N))
+    eng.set_tangents(W, np.zeros(N))
+    eng.set_time_dilation(False)
+    R, b, _, _ = eng.boundary(0.0, 1e-4, from_ensemble=0, do_qr=1, build=0)
+    assert eng.ctx.last_qr_passes == 3
+    Q, _ = eng.get_tangents()
+    assert np.abs(Q @ Q.T - np.eye(m)).max() < 1e-12
+    assert maxrel(R.T @ Q, W) < 1e-12                                 # backward error of the factorisation
+    Rr = np.linalg.qr(W.T)[1]
+    sgn = np.sign(np.diag(Rr))
+    assert maxrel(R, sgn[:, None] * Rr) < 1e-4 * cond * 1e-12 + 1e-9   # forward error ~ cond * u
+    eng.close()
