@@ -140,7 +140,7 @@ double fds_last_condition(const fds_ctx*);
 /* split-phase API: after fds_boundary_factor, 1 if the certified single pass was accepted -- no second
  * Gram was launched, so the caller skips the second sum-reduce of FDS_BUF_GRAM                          */
 int    fds_single_pass_pending(const fds_ctx*);
-int    fds_last_qr_passes(const fds_ctx*);   /* 1 or 2: what the last boundary with QR took (after its results were read) */
+int    fds_last_qr_passes(const fds_ctx*);   /* 1, 2 or 3 (shifted CholeskyQR3): what the last boundary with QR took (after its results were read) */
 
 /* ---- the solver plugin itself: u1, J = run(u0, s, steps), fds/fds.py:184-200 -- */
 /* single trajectory on the context's primal array (world == 1; halos wrapped inside);
