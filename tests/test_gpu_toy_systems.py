@@ -104,3 +104,18 @@ def test_toy_restart_equivalence():
     np.random.seed(0)
     J1, G1 = fds_b200.shadowing(run, u0, 1.0, 1, 20, 100, 0)
     assert np.array_equal(J1, J2) and np.allclose(G1, G2)
+
+
+@gpu
+def test_lorenz63_gradient_over_rho():
+    """reference tests/test_lorenz.py:34-45 (test_gradient): rho = 28 .. 33, m = 2, 10 segments of 1000 steps, run-up
+    5000 -- the reference's own windows on J and dJ/drho at every rho."""
+    rho = np.linspace(28, 33, 6)
+    J, G = np.zeros([rho.size, 2]), np.zeros([rho.size, 2])
+    run = fds_b200.Lorenz63()
+    np.random.seed(0)
+    for i, r in enumerate(rho):
+        J[i], G[i] = fds_b200.shadowing(run, np.array([1.0, 1.0, 28.0]), r, 2, 10, 1000, 5000)
+    assert (np.abs(J[:, 1] - 100) < 1e-12).all() and (np.abs(G[:, 1]) < 1e-12).all()
+    assert (np.abs(J[:, 0] - ((rho - 31) ** 2 + 85)) < 20).all()
+    assert (np.abs(G[:, 0] - 2 * (rho - 31)) < 2).all()
