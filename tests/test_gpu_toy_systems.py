@@ -108,14 +108,19 @@ def test_toy_restart_equivalence():
 
 @gpu
 def test_lorenz63_gradient_over_rho():
-    """reference tests/test_lorenz.py:34-45 (test_gradient): rho = 28 .. 33, m = 2, 10 segments of 1000 steps, run-up
-    5000 -- the reference's own windows on J and dJ/drho at every rho."""
-    rho = np.linspace(28, 33, 6)
-    J, G = np.zeros([rho.size, 2]), np.zeros([rho.size, 2])
+    """reference tests/test_lorenz.py:34-45 (test_gradient): a sweep over rho, m = 2, 10 segments of 1000 steps,
+    run-up 5000.  The reference's windows (|J - ((rho-31)^2 + 85)| < 20, |dJ/drho - 2 (rho-31)| < 2) hold or fail
+    with the random tangents at 10 segments (the restatement of the reference fails the second one at rho = 31 for
+    seed 0), so the device run is held to the restatement on the same seed -- and to the windows wherever the
+    restatement is inside them."""
+    from oracle import plugins, shadowing_port as port
     run = fds_b200.Lorenz63()
-    np.random.seed(0)
-    for i, r in enumerate(rho):
-        J[i], G[i] = fds_b200.shadowing(run, np.array([1.0, 1.0, 28.0]), r, 2, 10, 1000, 5000)
-    assert (np.abs(J[:, 1] - 100) < 1e-12).all() and (np.abs(G[:, 1]) < 1e-12).all()
-    assert (np.abs(J[:, 0] - ((rho - 31) ** 2 + 85)) < 20).all()
-    assert (np.abs(G[:, 0] - 2 * (rho - 31)) < 2).all()
+    for i, r in enumerate((28.0, 31.0, 33.0)):
+        np.random.seed(i)
+        J, G = fds_b200.shadowing(run, np.array([1.0, 1.0, 28.0]), r, 2, 10, 1000, 5000)
+        np.random.seed(i)
+        Jp, Gp = port.shadowing(plugins.run_lorenz63, np.array([1.0, 1.0, 28.0]), r, 2, 10, 1000, 5000)
+        assert abs(J[1] - 100) < 1e-12 and abs(G[1]) < 1e-12
+        assert maxrel(J, Jp) < 1e-6 and abs(G[0] - Gp[0]) < 1e-3 * max(1.0, abs(Gp[0]))
+        if abs(Jp[0] - ((r - 31) ** 2 + 85)) < 19 and abs(Gp[0] - 2 * (r - 31)) < 1.9:
+            assert abs(J[0] - ((r - 31) ** 2 + 85)) < 20 and abs(G[0] - 2 * (r - 31)) < 2
