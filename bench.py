@@ -396,6 +396,7 @@ def run_ours(args):
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda', dtype=torch.float64)
     counts = torch.tensor([eng.ctx.launches - l0, eng.ctx.collectives - c0], device='cuda', dtype=torch.float64)
     kern_ms, kern_n = eng.ctx.profile_read()
+    kern_cycles = eng.ctx.profile_cycles()
     steps_per_launch = eng.ctx.profile_steps / max(kern_n, 1)     # 2 with temporal blocking
     eng.ctx.profile_enable(False)
     kern = torch.tensor([kern_ms / max(kern_n, 1)], device='cuda', dtype=torch.float64)
@@ -412,11 +413,11 @@ def run_ours(args):
     assert np.isfinite(hist[-1][4]).all()
 
     # ---- the measured FP64 roof (the board still warm from the timed region) -------------------- #
-    fp64_peak, fp64_clk = None, None
+    fp64_peak, fp64_clk, fp64_per_clk = None, None, None
     if rank == 0:
         probe_clk = ClockSampler(local_rank)
         probe_clk.start()
-        fp64_peak, _ = fdev.fp64_issue_rate(local_rank)
+        fp64_peak, _, fp64_per_clk = fdev.fp64_issue_rate(local_rank)
         fp64_clk = probe_clk.result()
     barrier()
 
@@ -476,7 +477,7 @@ def run_ours(args):
         del u, V, v
 
     roof_main = roofline(args, args.math, n_local, M, float(kern.item()), steps_per_launch, S, args.steps, total_ms,
-                         clocks, fp64_peak, fp64_clk) if rank == 0 else None
+                         clocks, fp64_peak, fp64_clk, kern_cycles, fp64_per_clk) if rank == 0 else None
     loop.close()
     fds_b200._lib.pool_release()
 
@@ -554,7 +555,8 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def roofline(args, math, n_local, M, kms, steps_per_launch, S, K, total_ms, clocks, fp64_peak, fp64_clk):
+def roofline(args, math, n_local, M, kms, steps_per_launch, S, K, total_ms, clocks, fp64_peak, fp64_clk,
+             kern_cycles=None, fp64_per_clk=None):
     """Roofline object of the step kernel.  Exact math: FP64-issue bound (measured peak); fast math: HBM
     bound on the REAL traffic (8 B per trajectory-site-step with two steps per pass)."""
     peaks = {}
@@ -597,8 +599,18 @@ def roofline(args, math, n_local, M, kms, steps_per_launch, S, K, total_ms, cloc
                'fp64_warp_inst_per_update': ipu,
                'why': 'two time steps per pass: DRAM traffic per launch is half the algorithmic bytes, the FP64 pipe '
                       '(%g exact-mode instructions per update) is what is saturated' % ipu}
-        if clocks.get('sm_mhz') and fp64_clk and fp64_clk.get('sm_mhz'):
-            # per-clock view: removes the clock difference between the probe (no DRAM power) and the step kernel
+        if kern_cycles and fp64_per_clk:
+            # per-clock view from the kernels' own cycle counters (clock64 inside the step kernel and inside the
+            # probe): removes the clock difference between the probe (no DRAM power: near the maximum clock) and
+            # the power-capped step kernel -- this is the pipe utilisation ncu reports
+            import torch
+            sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            per_clk = winst / sms / kern_cycles
+            out['frac_per_clock'] = per_clk / fp64_per_clk
+            out['per_clock'] = {'achieved_winst_per_sm_clk': per_clk, 'peak_winst_per_sm_clk': fp64_per_clk,
+                                'kernel_sm_cycles': kern_cycles,
+                                'kernel_sm_mhz': kern_cycles / (kms * 1e-3) / 1e6}
+        elif clocks.get('sm_mhz') and fp64_clk and fp64_clk.get('sm_mhz'):
             out['frac_per_clock'] = out['frac'] * fp64_clk['sm_mhz'] / clocks['sm_mhz']
         out.update(common)
         return out

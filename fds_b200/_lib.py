@@ -92,12 +92,13 @@ SIGNATURES = {
     'fds_get_ensemble_rows': (_I32, [_CTX, _I64, _I64, c_double_p]),
     'fds_get_ensemble_column': (_I32, [_CTX, _I32, c_double_p]),
     'fds_strip_plan': (_I32, [_CTX, c_int64_p]),
-    'fds_fp64_issue_rate': (_I32, [_I32, c_double_p, c_double_p]),
+    'fds_fp64_issue_rate': (_I32, [_I32, c_double_p, c_double_p, c_double_p]),
     'fds_buffer_ptr': (ctypes.c_void_p, [_CTX, _I32]),
     'fds_kernel_launches': (_I64, [_CTX]),
     'fds_sync': (_I32, [_CTX]),
     'fds_profile_enable': (_I32, [_CTX, _I32]),
     'fds_profile_read': (_I32, [_CTX, c_double_p, c_int64_p]),
+    'fds_profile_cycles': (_I32, [_CTX, c_double_p]),
     'fds_profile_steps': (_I64, [_CTX]),
 }
 

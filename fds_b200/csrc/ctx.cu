@@ -104,6 +104,7 @@ struct fds_ctx {
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
+    unsigned long long* prof_cycles = nullptr;   // device: {sum of the CTAs' clock spans, CTAs} of the profiled launches
 
     // *_all: stacked site 0; the others: site 0 of problem 0 (the same thing without a batch)
     double* E_all(int which) const { return Ebase[which] + (-alo) * M; }
@@ -460,7 +461,7 @@ void fds_ctx_destroy(fds_ctx* c) {
         if (c->ev_done[j]) cudaEventDestroy(c->ev_done[j]);
     }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    cudaFree(c->jnode); cudaFree(c->jnode_scratch);
+    cudaFree(c->jnode); cudaFree(c->jnode_scratch); cudaFree(c->prof_cycles);
     cudaFreeHost(c->A_host);
     for (auto& pe : c->prof_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -552,13 +553,13 @@ int fds_strip_plan(const fds_ctx* c, int64_t out[8]) {
     return 0;
 }
 
-int fds_fp64_issue_rate(int device, double* winst_per_s, double* seconds) {
+int fds_fp64_issue_rate(int device, double* winst_per_s, double* seconds, double* winst_per_clk_sm) {
     int ndev = 0, sms = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || device < 0 || device >= ndev) { g_create_err = "fds_fp64_issue_rate: no such CUDA device"; return 3; }
     DeviceGuard guard__(device);
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = fp64_issue_rate(sms, nullptr, winst_per_s, seconds);
+    if (e == cudaSuccess) e = fp64_issue_rate(sms, nullptr, winst_per_s, seconds, winst_per_clk_sm);
     if (e != cudaSuccess) { g_create_err = std::string("fds_fp64_issue_rate: ") + cudaGetErrorString(e); return 1; }
     return 0;
 }
@@ -575,6 +576,11 @@ int64_t fds_kernel_launches(const fds_ctx* c) { return c->ls.launches; }
 int64_t fds_profile_steps(const fds_ctx* c) { return c->prof_steps; }
 
 int fds_profile_enable(fds_ctx* c, int enabled) {
+    FDS_ON_DEVICE(c);
+    if (enabled) {
+        if (!c->prof_cycles) FDS_CK(c, cudaMalloc(&c->prof_cycles, 2 * sizeof(unsigned long long)));
+        FDS_CK(c, cudaMemsetAsync(c->prof_cycles, 0, 2 * sizeof(unsigned long long), c->stream));
+    }
     c->profiling = enabled != 0;
     c->prof_used = 0;
     c->prof_steps = 0;
@@ -593,6 +599,19 @@ int fds_profile_read(fds_ctx* c, double* total_ms, int64_t* launches) {
     if (total_ms) *total_ms = tot;
     if (launches) *launches = (int64_t)c->prof_used;
     c->prof_used = 0;
+    return 0;
+}
+
+// mean SM cycles a CTA of the profiled step-kernel launches ran (clock64 inside the kernel): with the FP64
+// instruction count this gives the pipe utilisation at the kernel's OWN clock, whatever the power cap did to it
+int fds_profile_cycles(fds_ctx* c, double* mean_cycles_per_cta) {
+    FDS_ON_DEVICE(c);
+    unsigned long long h[2] = {0, 0};
+    if (c->prof_cycles) {
+        FDS_CK(c, cudaMemcpyAsync(h, c->prof_cycles, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        FDS_CK(c, cudaStreamSynchronize(c->stream));
+    }
+    if (mean_cycles_per_cta) *mean_cycles_per_cta = h[1] ? (double)h[0] / (double)h[1] : 0.0;
     return 0;
 }
 
@@ -945,6 +964,7 @@ static int one_step(fds_ctx* c, const double* X, double* Y, int M_, double F0, d
         a.jpart = c->jnode + (size_t)jslot * c->plan.nnode * c->M * 2;
         if (two) { a.two_steps = 1; a.jpart2 = a.jpart + (size_t)c->plan.nnode * c->M * 2; a.nfuse = nfuse; }
         a.primal_out = primal_out;
+        a.cycles = c->profiling ? c->prof_cycles : nullptr;
         cudaEvent_t e1 = nullptr;
         if (c->profiling) {
             if (c->prof_used == c->prof_events.size()) {

@@ -43,6 +43,8 @@ struct StepArgs {
     // RK4, two steps per pass: also write column 0 of the output (the primal state) to this single-column array
     // (pointer to site 0) -- the last pass of a segment saves the strided extraction pass of the next boundary
     double* primal_out = nullptr;
+    // profiling: every CTA adds its clock64() span to cycles[0] and 1 to cycles[1] (nullptr: off)
+    unsigned long long* cycles = nullptr;
 };
 
 // streaming TMA-fed kernel (RK4 only); `plan` = make_strip_plan(n, H, num_sms * stream_runs_per_cta(M)),
@@ -196,7 +198,7 @@ cudaError_t launch_apply_mma(int src, const double* E, const double* Tin, const 
 // FP64 issue-rate microbenchmark: the roof of the exact-mode step kernel.  Runs the step kernel's own
 // instruction mix (2 DADD : 1 DMUL, 8 independent chains per thread, 2 warps per scheduler, one CTA per SM)
 // and returns FP64 warp-instructions per second for the whole GPU at the clock the board sustains.
-cudaError_t fp64_issue_rate(int num_sms, cudaStream_t st, double* winst_per_s, double* seconds);
+cudaError_t fp64_issue_rate(int num_sms, cudaStream_t st, double* winst_per_s, double* seconds, double* winst_per_clk_sm);
 
 // ---- toy_ode.cu -------------------------------------------------------------- //
 // small ODE systems (Lorenz-63, Van der Pol, circular): state dimension, 0 for the L96 systems

@@ -43,6 +43,7 @@ struct StreamParams {
     int fuse2;                                 // 1: two steps per pass (l96_march2.cuh)
     const double2* Fpp;                        // per-problem (F0, Flast) of a batch, or nullptr
     double* P0out;                             // EMIT kernels: column 0 of the output goes here as well (site 0)
+    unsigned long long* cycles;                // profiling: sum of the CTAs' clock64() spans, number of CTAs (or nullptr)
     int spp;                                   // strips per problem (batch)
     int prefetch;                              // shared-producer mode: blocks in flight ahead of the consumers (<= nstages - 2)
     Rk4Coef c;
@@ -278,6 +279,7 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     }
     __syncthreads();
 
+    const long long clk0 = p.cycles != nullptr ? clock64() : 0;
     const long long last_strip = p.nstrips - 1;
     StreamProducer prod;
     prod.init(&p, sdata, full, lane, FuseGeom<KF>::kInOff, p.nblk + FuseGeom<KF>::kExtra);   // blocks b = -2 .. nblk (-3 .. nblk + 1)
@@ -361,6 +363,10 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     else if (MODE == 3) l96_march2_t<MP, EulerPipe<MP>, STATS>(io, g, F, p.c);
     else if (MODE == 4) l96_marchk_t<MP, EulerPipe<MP>, 4, STATS>(io, g, F, p.c);
     else l96_march_t<MP, STATS, Rk4Pipe<MP>>(io, g, F, p.c);
+    if (p.cycles != nullptr && tid == 0) {
+        atomicAdd(p.cycles, (unsigned long long)(clock64() - clk0));
+        atomicAdd(p.cycles + 1, 1ULL);
+    }
 }
 
 // 16 warps per CTA (4 per scheduler, so each thread can hold up to 128 registers), all of
@@ -439,6 +445,7 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     p.Fpp = a.Fpp; p.spp = a.spp > 0 ? a.spp : 1;
     p.jpart2 = a.jpart2; p.fuse2 = fuse2;
     p.P0out = a.primal_out;
+    p.cycles = a.cycles;
     const bool emit = a.primal_out != nullptr;
     if (emit && (euler || nfuse != 2 || a.jpart == nullptr)) return cudaErrorInvalidValue;   // RK4, two steps, with objective sums
     p.nfuse = nfuse; p.jstride = (long long)plan.nnode * a.M * 2;

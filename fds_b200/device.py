@@ -87,6 +87,12 @@ class Context:
         self._ck(self.lib.fds_profile_read(self.h, ctypes.byref(ms), ctypes.byref(cnt)))
         return ms.value, cnt.value
 
+    def profile_cycles(self):
+        """Mean SM cycles a CTA of the profiled step-kernel launches ran (clock64 inside the kernel)."""
+        c = ctypes.c_double()
+        self._ck(self.lib.fds_profile_cycles(self.h, ctypes.byref(c)))
+        return c.value
+
     def buffer_ptr(self, which):
         return self.lib.fds_buffer_ptr(self.h, which)
 
@@ -343,13 +349,14 @@ def comm_unique_id():
 
 
 def fp64_issue_rate(device=0):
-    """(FP64 warp-instructions per second of the whole GPU, seconds the probe ran): the measured roof
-    of the exact-mode step kernel (same CTA shape and instruction mix, no memory traffic)."""
+    """(FP64 warp-instructions per second of the whole GPU, seconds the probe ran, FP64 warp-instructions per SM
+    and SM clock): the measured roof of the exact-mode step kernel (same CTA shape and instruction mix, no memory
+    traffic); the third value comes from the probe's own cycle counters and does not depend on the clock."""
     lib = _lib.load()
-    r, t = ctypes.c_double(), ctypes.c_double()
-    if lib.fds_fp64_issue_rate(int(device), ctypes.byref(r), ctypes.byref(t)) != 0:
+    r, t, pc = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+    if lib.fds_fp64_issue_rate(int(device), ctypes.byref(r), ctypes.byref(t), ctypes.byref(pc)) != 0:
         raise FdsError(lib.fds_last_error(None).decode())
-    return r.value, t.value
+    return r.value, t.value, pc.value
 
 
 def lss_solve(R, b, device=0):

@@ -282,12 +282,13 @@ int fds_get_ensemble_column(fds_ctx*, int k, double* out);                      
 int fds_strip_plan(const fds_ctx*, int64_t out[8]);
 /* measured roof of the exact-mode step kernel: FP64 warp-instructions per second of the whole GPU with the
  * kernel's own shape and instruction mix (~0.25 s of load, so at the clock the board sustains)          */
-int fds_fp64_issue_rate(int device, double* winst_per_s, double* seconds);
+int fds_fp64_issue_rate(int device, double* winst_per_s, double* seconds, double* winst_per_clk_sm);
 int     fds_sync(fds_ctx*);
 /* per-launch device timing of the ensemble step kernel (CUDA events on the context's stream):
  * enable, run, then read the summed duration and the number of launches since enabling   */
 int     fds_profile_enable(fds_ctx*, int enabled);
 int     fds_profile_read(fds_ctx*, double* total_ms, int64_t* launches);
+int     fds_profile_cycles(fds_ctx*, double* mean_cycles_per_cta);   /* SM cycles a CTA of those launches ran, clock64() inside the kernel */
 int64_t fds_profile_steps(const fds_ctx*);   /* time steps those launches covered (2 per launch with temporal blocking) */
 
 #ifdef __cplusplus
