@@ -11,6 +11,8 @@ small problem on its own GPU alone and compares:
   bit-identical, ``R_0`` to 1e-10 (the Gram is summed in a different order), dJ/ds to 1e-6;
 * both communication modes: the library's own NCCL communicator (one enqueue per boundary) and the
   host-driven ``torch.distributed`` ring;
+* the tensor-core, device-gated boundary (m = 16) over the library's communicator, with the adaptive single pass
+  and with CholeskyQR2 forced: objective histories and final state bit-identical, R and the tangents to 1e-10;
 * the batched parameter sweep split over the ranks (replicas only): bit-identical to one GPU.
 
 This is a consistency check of the product against itself on different device counts; parity with the
@@ -75,6 +77,33 @@ def sharded_vs_single(local_device, sites_per_rank=4096, m=6, steps=30, K=4, wit
                              r['R0_rel_err'] < 1e-10 and r['djds_rel_err'] < 1e-6 and
                              (coll > 0) == (comm == 'nccl'))
             res[comm] = r
+            ok = ok and r['pass']
+
+    # the tensor-core, device-gated boundary (m = 16: what the headline workload runs with m = 32) over the
+    # library's communicator: Gram all-reduce inside the enqueue-only boundary, including a forced CholeskyQR2
+    for passes in (0, 2):
+        mg, Kg, Sg = 16, 3, 10
+        cpg1 = None
+        if rank == 0:
+            e1 = Engine(N, mg, device=local_device, distributed=False, max_halo_steps=8)
+            e1.ctx.set_qr_passes(passes)
+
+            class _S1:
+                def engine(self, mm):
+                    return e1
+            cpg1 = fds_b200.shadowing(_S1(), u0, s, mg, Kg, Sg, 20, epsilon=eps, return_checkpoint=True, tangent_seed=3)
+            e1.close()
+        rung = fds_b200.L96(N, device=local_device, max_halo_steps=8, comm='nccl')
+        rung.engine(mg).ctx.set_qr_passes(passes)
+        cpg = fds_b200.shadowing(rung, u0, s, mg, Kg, Sg, 20, epsilon=eps, return_checkpoint=True, tangent_seed=3)
+        rung.close()
+        if rank == 0:
+            r = {'J_bitwise': bool(np.array_equal(np.array(cpg.J), np.array(cpg1.J))),
+                 'final_state_bitwise': bool(np.array_equal(cpg.u0, cpg1.u0)),
+                 'R_rel_err': _relerr(np.array(cpg.lss.Rs), np.array(cpg1.lss.Rs)),
+                 'V_rel_err': _relerr(cpg.V, cpg1.V)}
+            r['pass'] = bool(r['J_bitwise'] and r['final_state_bitwise'] and r['R_rel_err'] < 1e-10 and r['V_rel_err'] < 1e-9)
+            res['gated_m16_%s' % ('adaptive' if passes == 0 else 'choleskyqr2')] = r
             ok = ok and r['pass']
 
     if with_sweep:
