@@ -612,7 +612,7 @@ __device__ __forceinline__ double tree_rows(const double* __restrict__ in, long 
     }
     return v[0];
 }
-__global__ void __launch_bounds__(1024) tree_level_kernel(const double* __restrict__ in, long long n_in, int C,
+__global__ void __launch_bounds__(512, 2) tree_level_kernel(const double* __restrict__ in, long long n_in, int C,
                                                           int Q, double* __restrict__ out) {
     extern __shared__ double sm[];                 // [Q][C]
     const int c = threadIdx.x % C, q = threadIdx.x / C;
@@ -625,7 +625,7 @@ __global__ void __launch_bounds__(1024) tree_level_kernel(const double* __restri
         while ((1 << L) < per) ++L;
         const long long e0 = g * kLG + (long long)q * per;
         double r;
-        // 16 rows at a time (the kernel is compiled for up to 1024 threads = 64 registers per thread)
+        // 16 rows at a time (the kernel is compiled for up to 512 threads, two CTAs per SM = 64 registers per thread)
         if (per == 32) r = tree_rows<16>(in, e0, n_in, C, c) + tree_rows<16>(in, e0 + 16, n_in, C, c);
         else if (per == 16) r = tree_rows<16>(in, e0, n_in, C, c);
         else if (per == 64)
@@ -661,8 +661,10 @@ cudaError_t launch_tree_reduce(const double* in, long long n_in, int C, double* 
 cudaError_t launch_tree_reduce_batched(const double* in, long long n_in, int C, long long batch, double* out,
                                        double* scratch, cudaStream_t st, LaunchStats* ls) {
     int Q = 1;
-    while (Q * 2 * C <= 1024 && Q * 2 <= kLG) Q *= 2;
-    if (C > 1024) return cudaErrorInvalidValue;
+    // <= 512 threads at <= 64 registers: three CTAs of 272 threads per SM at C = 68 (one CTA of 544 before: the
+    // pass ran at 4.5 TB/s with 17 warps of loads in flight)
+    while (Q * 2 * C <= 512 && Q * 2 <= kLG) Q *= 2;
+    if (C > 512) return cudaErrorInvalidValue;
     const long long cap = (n_in + kLG - 1) / kLG;   // size of one scratch half, in rows
     const double* src = in;
     long long n = n_in;
