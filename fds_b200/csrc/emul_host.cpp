@@ -47,10 +47,12 @@ struct HostIO2 {
     long long a;
     int M, k;
     long long cs = 0, j0 = 0;
+    template <int H = -1>
     void begin_block(int b) {
         cs = a + 8LL * b + 4;
         j0 = a + 8LL * b - 11;
     }
+    template <int H = -1>
     void end_block(int) {}
     double load(int p) const { return X[(cs + p) * M + k]; }
     void store(int p, double v) { Y[(j0 + p) * M + k] = v; }
@@ -61,6 +63,7 @@ struct HostIO2 {
         }
     }
     bool all(bool v) const { return v; }
+    template <int H = -1>
     void mid_block() {}
     int warp_max(int v) const { return v; }
     int warp_min(int v) const { return v; }
@@ -86,10 +89,12 @@ struct HostIOK {
     long long a;
     int M, k;
     long long cs = 0, j0 = 0;
+    template <int H = -1>
     void begin_block(int b) {
         cs = a + 8LL * b + 4;
         j0 = a + 8LL * b - 3 - 8LL * (K - 1);
     }
+    template <int H = -1>
     void end_block(int) {}
     double load(int p) const { return X[(cs + p) * M + k]; }
     void store(int p, double v) { Y[(j0 + p) * M + k] = v; }
@@ -100,6 +105,7 @@ struct HostIOK {
         }
     }
     bool all(bool v) const { return v; }
+    template <int H = -1>
     void mid_block() {}
     int warp_max(int v) const { return v; }
     int warp_min(int v) const { return v; }

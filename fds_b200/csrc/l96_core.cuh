@@ -282,7 +282,8 @@ struct NodeCounter {
 // (l96_marchk.cuh) K - 1 blocks: the plan pads for kMaxFuse steps per pass.
 // --------------------------------------------------------------------------- //
 constexpr int kMaxFuse = 4;                          // most time steps one pass of the streaming kernel advances
-constexpr int kPlanPad = 12 + 8 * (kMaxFuse - 1);    // sites the arrays extend beyond the strips on either side
+constexpr int kPlanPad = 12 + 8 * (kMaxFuse - 1) + 8;   // sites the arrays extend beyond the strips on either side (+ 8: the
+                                                       // two-block ring of the fused kernels fetches one block ahead of a strip's first)
 
 struct StripPlan {
     long long a0;       // first strip starts here (multiple of the node size)

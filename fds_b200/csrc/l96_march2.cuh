@@ -160,7 +160,7 @@ FDS_HD void march2_block(IO& io, PIPE& p1, PIPE& p2, double& x1_prev, StepStats&
     }
     FDS_M2(3);
     FDS_M2(4);
-    io.mid_block();                // ring bookkeeping + early probe of the next block's input, hidden in the FP64 stream
+    io.template mid_block<BP>();   // ring bookkeeping + early probe of the next stage's input, hidden in the FP64 stream
     FDS_M2(5);
     FDS_M2(6);
     FDS_M2(7);
@@ -226,12 +226,13 @@ FDS_HD void l96_march2_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c)
             if (STATS) io.pl_cur_set(((b - 1) & 7) >> 1);
 #pragma unroll 1
             for (; b + 1 <= bfh; b += 2) {
-                io.begin_block(b);
+                // (block parity = which half of its ring stage the block is: the IO policy synchronises once per pair)
+                io.template begin_block<0>(b);
                 march2_block<MP, PIPE, true, STATS, 0>(io, p1, p2, x1_prev, sa, sb, g, b, slo, shi, jlo, jhi, F, c);
-                io.end_block(b);
-                io.begin_block(b + 1);
+                io.template end_block<0>(b);
+                io.template begin_block<1>(b + 1);
                 march2_block<MP, PIPE, true, STATS, 1>(io, p1, p2, x1_prev, sa, sb, g, b + 1, slo, shi, jlo, jhi, F, c);
-                io.end_block(b + 1);
+                io.template end_block<1>(b + 1);
                 if (STATS) {
                     io.pl_cur_next();
                     if ((b & 7) == 0) {

@@ -31,7 +31,7 @@ static_assert(FuseGeom<1>::kFirst == -2 && FuseGeom<1>::kExtra == 3 && FuseGeom<
               FuseGeom<1>::kOutOff == -19, "one step per pass");
 static_assert(FuseGeom<2>::kFirst == kFuse2First && FuseGeom<2>::kInOff == -20 && FuseGeom<2>::kOutOff == -35 &&
               FuseGeom<2>::kPad == 20, "two steps per pass");
-static_assert(FuseGeom<kMaxFuse>::kPad == kPlanPad, "the strip plan pads for the deepest pass");
+static_assert(FuseGeom<kMaxFuse>::kPad + 8 == kPlanPad, "the strip plan pads for the deepest pass");
 
 template <class MP, class PIPE, int K, int P, bool FAST, bool STATS, class IO>
 FDS_HD void marchk_site(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&st)[K], long long jb, long long slo,
@@ -95,7 +95,7 @@ FDS_HD void marchk_block(IO& io, PIPE (&p)[K], double (&xprev)[K], StepStats (&s
     }
     FDS_MK(3);
     FDS_MK(4);
-    io.mid_block();
+    io.template mid_block<BP>();
     FDS_MK(5);
     FDS_MK(6);
     FDS_MK(7);
@@ -156,12 +156,12 @@ FDS_HD void l96_marchk_t(IO& io, const MarchGeom& g, double F, const Rk4Coef& c)
         if (pass == 0) {
 #pragma unroll 1
             for (; b + 1 <= bfh; b += 2) {
-                io.begin_block(b);
+                io.template begin_block<0>(b);
                 marchk_block<MP, PIPE, K, true, STATS, 0>(io, p, xprev, st, g, b, slo, shi, jlo, jhi, F, c);
-                io.end_block(b);
-                io.begin_block(b + 1);
+                io.template end_block<0>(b);
+                io.template begin_block<1>(b + 1);
                 marchk_block<MP, PIPE, K, true, STATS, 1>(io, p, xprev, st, g, b + 1, slo, shi, jlo, jhi, F, c);
-                io.end_block(b + 1);
+                io.template end_block<1>(b + 1);
             }
         }
     }

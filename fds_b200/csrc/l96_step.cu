@@ -45,7 +45,9 @@ struct StreamParams {
     double* P0out;                             // EMIT kernels: column 0 of the output goes here as well (site 0)
     unsigned long long* cycles;                // profiling: sum of the CTAs' clock64() spans, number of CTAs (or nullptr)
     int spp;                                   // strips per problem (batch)
-    int prefetch;                              // shared-producer mode: blocks in flight ahead of the consumers (<= nstages - 2)
+    int prefetch;                              // shared-producer mode: stages in flight ahead of the consumers (<= nstages - 2)
+    int chunk;                                 // sites per strip and stage: 8 (one block), or 16 (two / four steps per pass: a
+                                               // stage holds TWO blocks, so the ring is synchronised once per pair of blocks)
     Rk4Coef c;
 };
 
@@ -87,23 +89,24 @@ struct StreamProducer {
         it = 0; st = 0; par = 0;
     }
     FDS_D bool done() const { return it >= nit; }
-    // fetch block `it` (8 input sites of every strip) into stage `st`
+    // fetch stage `it` (P->chunk input sites of every strip) into ring slot `st`
     FDS_D void issue() { issue_at(it, st, par); }
     FDS_D void issue_at(int it, int st, uint32_t par) {
         uint64_t* empty = full + kMaxStages;
         const int R = P->R, M = P->M, stage_stride = R * P->run_stride;
-        const uint32_t chunk_bytes = (uint32_t)(8 * M * sizeof(double));
+        const int CH = P->chunk;
+        const uint32_t chunk_bytes = (uint32_t)(CH * M * sizeof(double));
         if (it >= P->nstages) mbar_wait(&empty[st], par ^ 1u);
         if (lane == 0) mbar_expect_tx(&full[st], chunk_bytes * (uint32_t)rcta);
         __syncwarp();
-        if (lane < rcta) bulk_g2s(dst0 + (size_t)st * stage_stride, src + (long long)it * (8 * M), chunk_bytes, &full[st]);
+        if (lane < rcta) bulk_g2s(dst0 + (size_t)st * stage_stride, src + (long long)it * (CH * M), chunk_bytes, &full[st]);
         for (int r = lane + 32; r < rcta; r += 32) {         // more than 32 strips per CTA (tiny M; never packed)
             long long strip = (long long)blockIdx.x * R + r;
             strip = strip < P->nstrips - 1 ? strip : P->nstrips - 1;
             const long long off = (strip - ((long long)blockIdx.x * R + lane < P->nstrips - 1
                                                 ? (long long)blockIdx.x * R + lane : P->nstrips - 1)) * P->ls;
             bulk_g2s(dst0 + (size_t)st * stage_stride + (r - lane) * P->run_stride,
-                     src + (off + 8LL * it) * M, chunk_bytes, &full[st]);
+                     src + (off + (long long)CH * it) * M, chunk_bytes, &full[st]);
         }
     }
     FDS_D void advance() {
@@ -143,50 +146,64 @@ struct StreamIO {
     int st;
     uint32_t par;
     const double* cur;
-    // MID only: the ring position is carried as shared-window addresses (no index arithmetic, no generic->shared
-    // conversion in the loop)
-    uint32_t cur_s, nxt_s;   // this thread's slot in the current block's stage / in the next block's (set by mid_block)
+    // MID only: a ring stage holds TWO 8-site blocks of every strip, so the ring is synchronised (barrier wait, stage
+    // release, probe, copy duty) once per PAIR of blocks; the position is carried as shared-window addresses (no index
+    // arithmetic, no generic->shared conversion in the loop).  H = which half of its stage a block is (0 / 1) when
+    // known at compile time (the unchecked body: two blocks per iteration), -1: tracked in `half`.
+    uint32_t cur_s, nxt_s;   // this thread's slot for the current block / for the next one (set by mid_block)
+    uint32_t base_s;         // this thread's slot in the current stage (first half)
     uint32_t bar_s, bar_end; // `full` barrier of the current stage; one past the last stage's
-    uint32_t stage_bytes, ring_bytes;
-    uint32_t prev_empty;     // `empty` barrier of the previous block's stage, not yet released (first block: a sink)
-    int blk, ahead;          // blocks begun so far; blocks the copies run ahead of the consumers
-    int nit;                 // blocks per strip
-    int duty;                // the next block at whose end this warp issues copies (block duty + ahead), INT_MAX: none left
-    bool mine;               // this warp issues the copies of block blk - 1 + ahead at the end of the block
-    bool ready;              // this block's `full` phase was already seen complete by mid_block()
+    uint32_t stage_bytes, ring_bytes, half_bytes;
+    uint32_t prev_empty;     // `empty` barrier of the previous stage, not yet released (first stage: a sink)
+    int half;                // which half of its stage the next block to begin is (dynamic tracking)
+    bool need_wait;          // the next block to begin opens a new stage
+    int stg, ahead;          // stages begun so far; stages the copies run ahead of the consumers
+    int nit;                 // stages per strip
+    int duty;                // the next stage at whose end this warp issues copies (stage duty + ahead), INT_MAX: none left
+    bool mine;               // this warp issues the copies of stage stg - 1 + ahead at the end of the block
+    bool ready;              // the next stage's `full` phase was already seen complete by mid_block()
 
-    // MID: the ring bookkeeping of block c -- probe of block c + 1's `full` barrier, whose turn it is to fetch,
-    // position of the next block -- runs in the MIDDLE of block c (mid_block), inside straight-line code
-    // where its latencies hide behind the FP64 stream.
-    // The producer position is a function of the consumer's (block c + `ahead` goes into stage st + ahead), so
-    // no separate producer state is carried.  The other kernels keep everything at the block boundary.
+    template <int H = -1>
     FDS_D void begin_block(int) {
         if (MID) {
-            if (!ready) mbar_wait_s(bar_s, par);
-            // release the previous block's stage: EVERY lane arrives for itself (the barrier counts lanes), so no
-            // warp-wide sync is needed -- fewer instructions between the FP64 streams of two blocks
-            mbar_arrive_s(prev_empty);
+            if (H >= 0 ? H == 0 : need_wait) {
+                if (!ready) mbar_wait_s(bar_s, par);
+                // release the previous stage: EVERY lane arrives for itself (the barrier counts lanes), so no
+                // warp-wide sync is needed -- fewer instructions between the FP64 streams of two blocks
+                mbar_arrive_s(prev_empty);
+                need_wait = false;
+            }
             cur_s = nxt_s;
         } else {
             mbar_wait_s(full_s + 8u * (uint32_t)st, par);
             cur = sdata + (size_t)st * stage_stride;
         }
     }
+    // the ring bookkeeping runs in the MIDDLE of a block, inside straight-line code where its latencies hide behind
+    // the FP64 stream: in the second block of a stage the probe of the NEXT stage's `full` barrier, whose turn it
+    // is to fetch, and the position of the next stage.  The producer position is a function of the consumer's
+    // (stage c + `ahead` goes into slot st + ahead), so no separate producer state is carried.
+    template <int H = -1>
     FDS_D void mid_block() {
         if (!MID) return;
-        mine = blk == duty;          // copy duty of this block (block blk + ahead): every nwarps-th block, while any is left
-        ++blk;
-        // next block
-        prev_empty = bar_s + 8u * kMaxStages;
-        bar_s += 8u;
-        nxt_s = cur_s + stage_bytes;          // (the rest of THIS block still loads through cur_s)
-        if (bar_s == bar_end) {      // wrap: step back by the length of the ring (three predicated instructions)
-            bar_s -= 8u * (uint32_t)nstages;
-            nxt_s -= ring_bytes;
-            par ^= 1u;
+        if (H >= 0 ? H == 1 : half == 1) {
+            mine = stg == duty;          // copy duty at the end of this stage: every nwarps-th stage, while any is left
+            ++stg;
+            prev_empty = bar_s + 8u * kMaxStages;
+            bar_s += 8u;
+            base_s += stage_bytes;
+            if (bar_s == bar_end) {      // wrap: step back by the length of the ring
+                bar_s -= 8u * (uint32_t)nstages;
+                base_s -= ring_bytes;
+                par ^= 1u;
+            }
+            nxt_s = base_s;
+            // all lanes see the same phase: the vote makes the branch on it warp-uniform for the compiler as well
+            ready = __all_sync(0xffffffffu, mbar_test_s(bar_s, par));
+            need_wait = true;
+        } else {
+            nxt_s = base_s + half_bytes;      // (the rest of THIS block still loads through cur_s)
         }
-        // all lanes see the same phase: the vote makes the branch on it warp-uniform for the compiler as well
-        ready = __all_sync(0xffffffffu, mbar_test_s(bar_s, par));
     }
     FDS_D int warp_max(int v) const { return __reduce_max_sync(0xffffffffu, v); }
     FDS_D int warp_min(int v) const { return __reduce_min_sync(0xffffffffu, v); }
@@ -198,19 +215,21 @@ struct StreamIO {
         yrow[p * cols()] = v;
         if (EMIT && col0) prow[p] = v;
     }
+    template <int H = -1>
     FDS_D void end_block(int) {
         if (MID) {
-            if (mine) {
-                // this block (blk - 1) sat in the stage of prev_empty; mid_block() has moved on (and flipped the
+            if ((H >= 0 ? H == 1 : half == 1) && mine) {
+                // this stage (stg - 1) sat in the slot of prev_empty; mid_block() has moved on (and flipped the
                 // parity if it wrapped)
                 const int pst = (int)((prev_empty - full_s) >> 3) - kMaxStages;
                 const uint32_t cpar = bar_s == full_s ? par ^ 1u : par;
                 const int q = pst + ahead;
                 const bool w = q >= nstages;
-                prod->issue_at(blk - 1 + ahead, w ? q - nstages : q, w ? cpar ^ 1u : cpar);
+                prod->issue_at(stg - 1 + ahead, w ? q - nstages : q, w ? cpar ^ 1u : cpar);
                 duty += nwarps;
                 if (duty + ahead >= nit) duty = 0x7fffffff;
             }
+            if (H < 0) half ^= 1;
         } else {
             __syncwarp();
             if (lane == 0) mbar_arrive_s(full_s + 8u * (uint32_t)(kMaxStages + st));
@@ -282,7 +301,10 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     const long long clk0 = p.cycles != nullptr ? clock64() : 0;
     const long long last_strip = p.nstrips - 1;
     StreamProducer prod;
-    prod.init(&p, sdata, full, lane, FuseGeom<KF>::kInOff, p.nblk + FuseGeom<KF>::kExtra);   // blocks b = -2 .. nblk (-3 .. nblk + 1)
+    // two / four steps per pass: the strip's first block is the SECOND half of stage 0 (the stage boundaries then fall
+    // on even block indices, where the unchecked two-block body starts); the half before it is fetched, never read
+    prod.init(&p, sdata, full, lane, FuseGeom<KF>::kInOff - (MODE >= 2 ? 8 : 0),
+              MODE >= 2 ? (p.nblk + FuseGeom<KF>::kExtra + 1) / 2 : p.nblk + FuseGeom<KF>::kExtra);
     if (p.dedicated) {
         if (warp == nwarps) {
             while (!prod.done()) { prod.issue(); prod.advance(); }
@@ -344,12 +366,15 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.st = 0;
     io.par = 0;
     io.ready = false; io.mine = false;
-    io.blk = 0; io.ahead = p.prefetch; io.nit = prod.nit;
+    io.stg = 0; io.ahead = p.prefetch; io.nit = prod.nit;
     io.duty = warp + p.prefetch < prod.nit ? warp : 0x7fffffff;
     io.cur = io.sdata;
-    io.cur_s = smem_u32(io.sdata); io.nxt_s = io.cur_s;
     io.stage_bytes = (uint32_t)stage_stride * 8u;
     io.ring_bytes = io.stage_bytes * (uint32_t)p.nstages;
+    io.half_bytes = (uint32_t)(8 * p.M) * 8u;
+    io.base_s = smem_u32(io.sdata);
+    io.nxt_s = io.base_s + io.half_bytes; io.cur_s = io.nxt_s;      // the first block is the second half of stage 0
+    io.half = 1; io.need_wait = true;
     io.bar_s = io.full_s; io.bar_end = io.full_s + 8u * (uint32_t)p.nstages;
     io.prev_empty = smem_u32(sink);
 
@@ -427,9 +452,10 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
         p.nconsumer = 256;
         p.R = (256 + a.M - 1) / a.M + 1;
     }
+    p.chunk = fuse2 ? 16 : 8;
     int pad = (16 - (7 * a.M) % 16) % 16;
     if (pad & 1) pad += 1;
-    p.run_stride = 8 * a.M + pad;
+    p.run_stride = p.chunk * a.M + pad;
     const int cthreads = ((p.nconsumer + 31) / 32) * 32;
     const int block = cthreads + 32 * p.dedicated;
     const size_t stage_bytes = (size_t)p.R * p.run_stride * sizeof(double);
@@ -449,7 +475,8 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     const bool emit = a.primal_out != nullptr;
     if (emit && (euler || nfuse != 2 || a.jpart == nullptr)) return cudaErrorInvalidValue;   // RK4, two steps, with objective sums
     p.nfuse = nfuse; p.jstride = (long long)plan.nnode * a.M * 2;
-    p.prefetch = std::max(1, std::min(nst - 2, stream_prefetch()));
+    // (FDS_PREFETCH counts blocks; a stage of the two-block ring is two of them)
+    p.prefetch = std::max(1, std::min(nst - 2, fuse2 ? (stream_prefetch() + 1) / 2 : stream_prefetch()));
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = p.pack ? (int)((plan.nstrips * a.M + p.nconsumer - 1) / p.nconsumer)
                             : (int)((plan.nstrips + p.R - 1) / p.R);
