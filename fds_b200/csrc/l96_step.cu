@@ -187,7 +187,6 @@ struct StreamIO {
     FDS_D void mid_block() {
         if (!MID) return;
         if (H >= 0 ? H == 1 : half == 1) {
-            mine = stg == duty;          // copy duty at the end of this stage: every nwarps-th stage, while any is left
             ++stg;
             prev_empty = bar_s + 8u * kMaxStages;
             bar_s += 8u;
@@ -202,6 +201,9 @@ struct StreamIO {
             ready = __all_sync(0xffffffffu, mbar_test_s(bar_s, par));
             need_wait = true;
         } else {
+            // copy duty at the end of the FIRST block of this stage (every nwarps-th stage, while any is left): stage
+            // stg + ahead is then three blocks away, and the slot it reuses was left by every warp a block ago
+            mine = stg == duty;
             nxt_s = base_s + half_bytes;      // (the rest of THIS block still loads through cur_s)
         }
     }
@@ -218,14 +220,12 @@ struct StreamIO {
     template <int H = -1>
     FDS_D void end_block(int) {
         if (MID) {
-            if ((H >= 0 ? H == 1 : half == 1) && mine) {
-                // this stage (stg - 1) sat in the slot of prev_empty; mid_block() has moved on (and flipped the
-                // parity if it wrapped)
-                const int pst = (int)((prev_empty - full_s) >> 3) - kMaxStages;
-                const uint32_t cpar = bar_s == full_s ? par ^ 1u : par;
+            if ((H >= 0 ? H == 0 : half == 0) && mine) {
+                // this stage (stg) sits in the slot of bar_s with parity par; stage stg + ahead goes `ahead` slots on
+                const int pst = (int)((bar_s - full_s) >> 3);
                 const int q = pst + ahead;
                 const bool w = q >= nstages;
-                prod->issue_at(stg - 1 + ahead, w ? q - nstages : q, w ? cpar ^ 1u : cpar);
+                prod->issue_at(stg + ahead, w ? q - nstages : q, w ? par ^ 1u : par);
                 duty += nwarps;
                 if (duty + ahead >= nit) duty = 0x7fffffff;
             }
@@ -311,8 +311,9 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
             return;
         }
     } else {
-        // prologue: warp 0 fills all but two stages; every warp tracks the producer position
-        for (int j = 0; j < p.prefetch && !prod.done(); ++j) {
+        // prologue: warp 0 fills all but two stages; every warp tracks the producer position.  (Two-block stages:
+        // stage 0 has no first block -- a strip starts in its second half -- so its copy duty is done here.)
+        for (int j = 0; j < p.prefetch + (MODE >= 2 ? 1 : 0) && !prod.done(); ++j) {
             if (warp == 0) prod.issue();
             prod.advance();
         }
@@ -367,7 +368,8 @@ __global__ void __launch_bounds__(MODE >= 2 ? 256 : 512, 1) l96_rk4_stream_kerne
     io.par = 0;
     io.ready = false; io.mine = false;
     io.stg = 0; io.ahead = p.prefetch; io.nit = prod.nit;
-    io.duty = warp + p.prefetch < prod.nit ? warp : 0x7fffffff;
+    io.duty = warp == 0 ? nwarps : warp;              // stage 0's duty was done by the prologue
+    if (io.duty + p.prefetch >= prod.nit) io.duty = 0x7fffffff;
     io.cur = io.sdata;
     io.stage_bytes = (uint32_t)stage_stride * 8u;
     io.ring_bytes = io.stage_bytes * (uint32_t)p.nstages;
