@@ -478,7 +478,11 @@ cudaError_t launch_l96_rk4_stream(const StepArgs& a, const StripPlan& plan, cuda
     if (emit && (euler || nfuse != 2 || a.jpart == nullptr)) return cudaErrorInvalidValue;   // RK4, two steps, with objective sums
     p.nfuse = nfuse; p.jstride = (long long)plan.nnode * a.M * 2;
     // (FDS_PREFETCH counts blocks; a stage of the two-block ring is two of them)
-    p.prefetch = std::max(1, std::min(nst - 2, fuse2 ? (stream_prefetch() + 1) / 2 : stream_prefetch()));
+    // two-block stages: the copies of stage c + d are issued in the MIDDLE of stage c into the slot of stage c + d - nst,
+    // which every warp left when it began stage c + d - nst + 1: d = nst - 1 still leaves half a stage of slack
+    // (forward Euler, four steps per pass: three stages fit next to the pair-sum and node tables)
+    p.prefetch = fuse2 ? std::max(1, std::min(nst - 1, (stream_prefetch() + 1) / 2))
+                       : std::max(1, std::min(nst - 2, stream_prefetch()));
     p.c = Rk4Coef{0.5 * a.dt, a.dt, a.dt / 6.0};
     const int grid = p.pack ? (int)((plan.nstrips * a.M + p.nconsumer - 1) / p.nconsumer)
                             : (int)((plan.nstrips + p.R - 1) / p.R);
