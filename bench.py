@@ -18,7 +18,8 @@ metric = state-updates/s = N_total * (m+1) * steps_per_segment * K / time.
             stream back to back (no host round trip), results read once -- the product loop of
             fds_b200/fds.py:_segment_loop.
 `e2e`       the public API call continue_shadowing(run, s, checkpoint, ...) on HOST numpy buffers:
-            u0/V/v uploaded, K segments, u0/V/v + histories downloaded.
+            u0/V/v uploaded, K segments, u0/V/v + histories downloaded (`e2e_result_only`: the reference's default
+            return value (mean J, dJ/ds) instead of the checkpoint -- no download of the tangents).
 `roofline`  the ensemble step kernel.  Exact mode is bound by the FP64 pipe (two time steps per pass halve
             the HBM traffic): achieved FP64 warp-instructions/s vs the rate measured in this run by the
             library's probe (fds_fp64_issue_rate: same CTA shape and instruction mix, no memory traffic).
@@ -422,7 +423,7 @@ def run_ours(args):
     barrier()
 
     # ---- end to end through the public API on host buffers ----------------- #
-    e2e = per_seg = None
+    e2e = per_seg = e2e_jg = None
     if not args.no_e2e:
         from fds_b200.lsstan import LssTangent
         from fds_b200.checkpoint import Checkpoint
@@ -449,6 +450,20 @@ def run_ours(args):
         dt = float(tt.item())
         assert out.lss.K_segments() == args.steps and np.isfinite(out.V).all()
         del out
+        # the same call returning what the reference returns by default -- (mean J, dJ/ds), fds/fds.py:175-176 --
+        # instead of the full checkpoint: the upload stays, the download is KBs
+        def call_jg():
+            cp = Checkpoint(u, V, v, LssTangent(), [], [], [], [], [])
+            return fds_b200.continue_shadowing(plug, s, cp, args.steps, S, epsilon=eps)
+        barrier()
+        t0 = time.perf_counter()
+        Jm, Gm = call_jg()
+        barrier()
+        tt = torch.tensor([time.perf_counter() - t0], device='cuda', dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt_jg = float(tt.item())
+        assert np.isfinite(Jm).all() and np.isfinite(Gm).all()
         # strictest reading: the reference's run_segment(u0, V, v) -> (u0, V, v, J0, G, g) on host arrays, i.e.
         # the whole ensemble state crosses PCIe in both directions EVERY segment (single GPU only)
         bytes_in_1 = M * n_local * 8
@@ -470,6 +485,11 @@ def run_ours(args):
                        'call': 'segment.run_segment(run, u0, V, v, s, 0, %d, eps) on pinned host arrays, one call per segment' % S}
         bytes_in = (M * n_local * 8) * world
         small = args.steps * (m * m + m + m + 1 + S * M * 2) * 8
+        e2e_jg = {'value': N * (m + 1) * S * args.steps / dt_jg, 'unit': UNIT,
+                  'h2d_bytes_per_step': (M * n_local * 8) * world / args.steps,
+                  'd2h_bytes_per_step': (args.steps * (m * m + m + m + 1 + S * M * 2) * 8) / args.steps,
+                  'call': 'J, G = continue_shadowing(run, s, checkpoint(host u0,V,v), %d segments): the reference\'s default '
+                          'return value (fds/fds.py:175-176), no checkpoint download; %.3f s' % (args.steps, dt_jg)}
         e2e = {'value': N * (m + 1) * S * args.steps / dt, 'unit': UNIT,
                'h2d_bytes_per_step': bytes_in / args.steps, 'd2h_bytes_per_step': (bytes_in + small) / args.steps,
                'call': 'continue_shadowing(run, s, checkpoint(host u0,V,v), %d segments, return_checkpoint=True); '
@@ -534,6 +554,8 @@ def run_ours(args):
             line['e2e'] = e2e
             if per_seg is not None:
                 line['e2e_run_segment'] = per_seg
+            if e2e_jg is not None:
+                line['e2e_result_only'] = e2e_jg
         if dist_check is not None:
             line['dist_check'] = dist_check
         if fast is not None:
