@@ -634,6 +634,36 @@ __device__ double cta_eq_norm_after(const double* Li, int m, const double* sq, d
     return *out;
 }
 
+// |S|_2 of a symmetric m x m matrix S (in A, row stride m; B: scratch of the same size; both are overwritten) from
+// above: |S|_2^(2^k) = |S^(2^k)|_2 <= |S^(2^k)|_inf, so the 2^k-th root of the row-sum norm of S squared k times
+// over-estimates |S|_2 by at most m^(1/2^(k+1)) (1.11 for m = 32, k = 4) -- against sqrt(m) for |S|_inf itself.
+__device__ double cta_sym_norm2_bound(double* A, double* B, int m, int k, double* rs, double* out) {
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int it = 0; it < k; ++it) {
+        for (int e = tid; e < m * m; e += nthr) {
+            const int i = e / m, j = e % m;
+            double acc = 0.0;
+            for (int l = 0; l < m; ++l) acc += A[i * m + l] * A[l * m + j];      // (row i broadcast, row l at unit stride over the lanes)
+            B[e] = acc;
+        }
+        __syncthreads();
+        double* t = A; A = B; B = t;
+    }
+    for (int i = tid; i < m; i += nthr) {
+        double r = 0.0;
+        for (int j = 0; j < m; ++j) r += fabs(A[i * m + j]);
+        rs[i] = r;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0;
+        for (int i = 0; i < m; ++i) a = fmax(a, rs[i]);
+        *out = pow(a, 1.0 / (double)(1 << k)) * (1.0 + 1e-9);       // (rounding of the k products: far below this margin)
+    }
+    __syncthreads();
+    return *out;
+}
+
 // pass 1: G_dil/g_dil, projection, (optionally) first Cholesky factor; builds A1
 // shift_rel > 0: the projected Gram gets shift_rel * trace added to its diagonal before it is factored (first pass of
 // the shifted CholeskyQR3 below) -- the factor then exists for any numerically rank-deficient block
@@ -905,6 +935,35 @@ __global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, i
         B.A[e] = v;
     }
     __syncthreads();
+    // Tighten the certificate by repeated squaring (everything else has left shared memory: G and the factor's own
+    // storage are scratch now): H = D L L^T D and H^-1 = D^-1 L^-T L^-1 D^-1, each squared four times.  The plain
+    // row-sum / Frobenius bound over-estimates cond_2 by 2 - 4 at m = 32 and sent 2 of 30 well-conditioned
+    // boundaries at N = 2^24 through CholeskyQR2.
+    if (fail == 0) {
+        __shared__ double nrm2[2];
+        for (int e = tid; e < m * m; e += nthr) {
+            const int j = e / m, l = e % m, kk = j < l ? j : l;
+            double acc = 0.0;
+            for (int k = 0; k <= kk; ++k) acc += Gp[j * m + k] * Gp[l * m + k];      // (lanes read a column of L: bank conflicts, but m^3 / 3 once)
+            const double sc = sq[j] * sq[l];
+            G[e] = sc > 0.0 ? acc / sc : (j == l ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        cta_sym_norm2_bound(G, Gp, m, 4, fr, &nrm2[0]);
+        for (int e = tid; e < m * m; e += nthr) {
+            const int a = e / m, b = e % m;
+            double acc = 0.0;
+            for (int k = a > b ? a : b; k < m; ++k) acc += Li[k * m + a] * Li[k * m + b];
+            G[e] = acc * sq[a] * sq[b];
+        }
+        __syncthreads();
+        cta_sym_norm2_bound(G, Gp, m, 4, fr, &nrm2[1]);
+        if (tid == 0) {
+            if (nrm2[0] < nrm[0]) nrm[0] = nrm2[0];
+            if (nrm2[1] < nrm[1]) nrm[1] = nrm2[1];
+        }
+        __syncthreads();
+    }
     if (tid == 0) {
         const double cond = sqrt(nrm[0] * nrm[1]);
         *B.status = fail;
