@@ -18,9 +18,16 @@ def _filename(cp):
     return 'm{0}_segment{1}'.format(cp.lss.m_modes(), cp.lss.K_segments())
 
 
-def save_checkpoint(checkpoint_path, cp):
+def save_checkpoint(checkpoint_path, cp, reference_format=None):
     """Written to a temporary name and renamed, so that a concurrent load_last_checkpoint never sees a
-    truncated file (and never picks the temporary up: its name does not parse as m{m}_segment{K})."""
+    truncated file (and never picks the temporary up: its name does not parse as m{m}_segment{K}).
+    ``reference_format=True`` (or ``FDS_CHECKPOINT_FORMAT=reference`` in the environment) writes a file the
+    REFERENCE loads and continues from (refcheckpoint.dumps_reference_checkpoint); both kinds are read back here."""
+    if reference_format is None:
+        reference_format = os.environ.get('FDS_CHECKPOINT_FORMAT', '') == 'reference'
+    if reference_format:
+        from . import refcheckpoint
+        return refcheckpoint.save_reference_checkpoint(checkpoint_path, cp)
     final = os.path.join(checkpoint_path, _filename(cp))
     tmp = os.path.join(checkpoint_path, '.tmp_{0}_{1}'.format(_filename(cp), os.getpid()))
     with open(tmp, 'wb') as f:

@@ -123,6 +123,8 @@ class _Unpickler(pickle.Unpickler):
                 return super().find_class(module, name)
             raise ReferenceCheckpointError('unexpected numpy global %s.%s' % (module, name))
         if top in ('fds', 'pascal_lite'):
+            if (module, name) == ('fds.checkpoint', 'Checkpoint'):       # written by name (dumps_reference_checkpoint)
+                return Checkpoint
             return _stub_class(module, name)
         if module in ('dill._dill', 'dill.dill', 'dill'):
             return _DILL.get(name, _Inert)
@@ -137,7 +139,8 @@ class _Unpickler(pickle.Unpickler):
                         'bytes', 'str', 'object', 'range'):
                 return super().find_class(module, name)
             return _Inert
-        if (module, name) in (('collections', 'OrderedDict'), ('copyreg', '_reconstructor')):
+        if (module, name) in (('collections', 'OrderedDict'), ('copyreg', '_reconstructor'), ('copy_reg', '_reconstructor'),
+                              ('_codecs', 'encode')):           # (protocol <= 2 stores array bytes through _codecs.encode)
             return super().find_class(module, name)
         raise ReferenceCheckpointError('refusing global %s.%s in a checkpoint file' % (module, name))
 
@@ -275,6 +278,78 @@ def load_reference_checkpoint(checkpoint_file):
     if V.ndim != 2 or u0.ndim != 1 or v.shape != u0.shape or V.shape[1] != u0.shape[0]:
         raise ReferenceCheckpointError('unexpected shapes: u0 %s, V %s, v %s' % (u0.shape, V.shape, v.shape))
     return Checkpoint(u0, V, v, lss, G_lss, g_lss, J, G_dil, g_dil)
+
+
+# --------------------------------------------------------------------------- #
+# the other direction: a file the reference can load and continue from
+# --------------------------------------------------------------------------- #
+_REF_CLASSES = (('fds.checkpoint', 'Checkpoint'), ('fds.lsstan', 'LssTangent'),
+                ('pascal_lite.symbolic_variable', 'symbolic_array'),
+                ('pascal_lite.symbolic_value', 'symbolic_array_value'))
+
+
+def dumps_reference_checkpoint(cp):
+    """Bytes of a pickle that the REFERENCE's ``load_checkpoint`` (dill.load, fds/checkpoint.py:17-18) turns into ITS
+    ``Checkpoint``: ``u0, V, v`` as evaluated ``pascal_lite.symbolic_array``s (``value.field`` = the array, site axis
+    last: pascal_lite/symbolic_variable.py:47-60, symbolic_value.py:29-34), ``lss`` as its ``LssTangent`` with the
+    ``Rs, bs`` lists (fds/lsstan.py:9-12), the histories as lists of arrays.  The classes are written BY NAME (the
+    reference resolves them to its own on load); nothing of the reference is needed to write the file."""
+    import sys
+    import types
+    stubs = {}
+    for mod, name in _REF_CLASSES:
+        if name == 'Checkpoint':
+            cls = collections.namedtuple('Checkpoint', Checkpoint._fields)
+        else:
+            cls = type(name, (object,), {})
+        cls.__module__, cls.__qualname__ = mod, name
+        stubs[(mod, name)] = cls
+
+    def sym(field, shape):
+        val = stubs[('pascal_lite.symbolic_value', 'symbolic_array_value')]()
+        val.__dict__.update(shape=tuple(shape), owner=None, field=np.array(field, dtype=np.float64), is_distributed=True)
+        arr = stubs[('pascal_lite.symbolic_variable', 'symbolic_array')]()
+        arr.__dict__.update(value=val)
+        return arr
+
+    V = np.asarray(cp.V, dtype=np.float64)
+    lss = stubs[('fds.lsstan', 'LssTangent')]()
+    lss.__dict__.update(Rs=[np.array(R, dtype=np.float64) for R in cp.lss.Rs],
+                        bs=[np.array(b, dtype=np.float64) for b in cp.lss.bs])
+    out = stubs[('fds.checkpoint', 'Checkpoint')](
+        sym(cp.u0, ()), sym(V, (V.shape[0],)), sym(cp.v, ()), lss,
+        [[np.array(g, dtype=np.float64) for g in G] for G in cp.G_lss],
+        [np.array(g, dtype=np.float64) for g in cp.g_lss],
+        [np.array(J, dtype=np.float64) for J in cp.J],
+        [np.array(g, dtype=np.float64) for g in cp.G_dil],
+        [np.float64(g) for g in cp.g_dil])
+    # pickle writes classes as (module, name) after checking that the name resolves to the class: stand-in modules
+    # for the duration of the dump (whatever was there -- e.g. the real reference -- is put back)
+    names = sorted({m for m, _ in _REF_CLASSES} | {m.rsplit('.', 1)[0] for m, _ in _REF_CLASSES})
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for k in names:
+            sys.modules[k] = types.ModuleType(k)
+        for (mod, name), cls in stubs.items():
+            setattr(sys.modules[mod], name, cls)
+        return pickle.dumps(out, protocol=3)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def save_reference_checkpoint(checkpoint_path, cp):
+    """Write ``cp`` under the reference's file name ``m{m}_segment{K}`` (fds/checkpoint.py:8-15) in a form the
+    reference loads: a run continued here can go back."""
+    import os
+    name = 'm{0}_segment{1}'.format(cp.lss.m_modes(), cp.lss.K_segments())
+    tmp = os.path.join(checkpoint_path, '.tmp_{0}_{1}'.format(name, os.getpid()))
+    with open(tmp, 'wb') as f:
+        f.write(dumps_reference_checkpoint(cp))
+    os.replace(tmp, os.path.join(checkpoint_path, name))
 
 
 def is_reference_checkpoint(checkpoint_file):

@@ -85,3 +85,56 @@ def test_continue_shadowing_from_a_reference_checkpoint():
     eG = np.abs(G - want['cont_G']).max() / np.abs(want['cont_G']).max()
     print('R3 %.2e  R4,5 %.2e  dJ/ds %.2e' % (e3, e45, eG))
     assert e3 < 1e-12 and e45 < eps and eG < 0.1 * eps       # measured: 6e-17, 1e-5, 1e-7
+
+
+def _fixture_checkpoint():
+    from fds_b200.checkpoint import Checkpoint
+    from fds_b200.lsstan import LssTangent
+    g = golden('refcp_l96euler_expected')
+    return g, Checkpoint(g['u0'], g['V'], g['v'], LssTangent(list(g['file_Rs']), list(g['file_bs'])),
+                         list(g['file_G_lss']), list(g['file_g_lss']), list(g['file_J']), list(g['file_G_dil']),
+                         list(g['file_g_dil']))
+
+
+def test_reference_format_round_trip(tmp_path):
+    """save_reference_checkpoint writes the reference's classes by name; our own reader takes the file back."""
+    from fds_b200.refcheckpoint import save_reference_checkpoint, is_reference_checkpoint
+    from fds_b200.checkpoint import load_last_checkpoint, verify_checkpoint
+    g, cp = _fixture_checkpoint()
+    save_reference_checkpoint(str(tmp_path), cp)
+    f = tmp_path / 'm4_segment3'
+    assert f.exists() and is_reference_checkpoint(str(f))
+    assert 'pascal_lite' not in sys.modules and 'fds' not in sys.modules
+    back = load_last_checkpoint(str(tmp_path), 4)
+    assert verify_checkpoint(back)
+    assert np.array_equal(back.u0, cp.u0) and np.array_equal(back.V, cp.V) and np.array_equal(back.v, cp.v)
+    assert np.array_equal(np.array(back.lss.Rs), g['file_Rs']) and np.array_equal(np.array(back.J), g['file_J'])
+    assert np.array_equal(np.array(back.G_lss), g['file_G_lss']) and back.g_dil == list(g['file_g_dil'])
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/fds'), reason='needs the reference (build container only)')
+def test_the_reference_continues_from_a_file_written_here(tmp_path):
+    """The other direction of the restart protocol: a checkpoint written by save_reference_checkpoint is loaded by
+    the REFERENCE (dill) and continued by the reference's continue_shadowing -- and gives what the reference gets
+    from its own file (fixture), bit for bit: same evaluated V and v, same histories."""
+    from fds_b200.refcheckpoint import save_reference_checkpoint
+    g, cp = _fixture_checkpoint()
+    save_reference_checkpoint(str(tmp_path), cp)
+    code = ("import sys, io, contextlib, numpy as np\n"
+            "sys.dont_write_bytecode = True\n"
+            "sys.path.insert(0, '/root/reference'); sys.path.insert(0, %r)\n"
+            "import fds\n"
+            "from fds.checkpoint import load_last_checkpoint\n"
+            "from oracle import plugins\n"
+            "cp = load_last_checkpoint(%r, 4)\n"
+            "assert type(cp).__module__ == 'fds.checkpoint' and type(cp.lss).__module__ == 'fds.lsstan'\n"
+            "with contextlib.redirect_stdout(io.StringIO()):\n"
+            "    cp2 = fds.continue_shadowing(plugins.run_l96_euler, %r, cp, %d, %d, epsilon=%r, return_checkpoint=True)\n"
+            "np.savez(sys.argv[1], J=np.array(cp2.J), Rs=np.array(cp2.lss.Rs), G=fds.lss_gradient(cp2))\n"
+            % (ROOT, str(tmp_path), float(g['s']), int(g['K1']), int(g['steps']), float(g['eps'])))
+    out = str(tmp_path / 'cont.npz')
+    r = subprocess.run([sys.executable, '-W', 'ignore', '-c', code, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = np.load(out)
+    assert np.array_equal(got['J'], g['cont_J']) and np.array_equal(got['Rs'], g['cont_Rs'])
+    assert np.array_equal(got['G'], g['cont_G'])
