@@ -668,8 +668,8 @@ __device__ double cta_sym_norm2_bound(double* A, double* B, int m, int k, double
 // shift_rel > 0: the projected Gram gets shift_rel * trace added to its diagonal before it is factored (first pass of
 // the shifted CholeskyQR3 below) -- the factor then exists for any numerically rank-deficient block
 __global__ void __launch_bounds__(256) small1_kernel(SmallBufs B, int m, int use_d, int do_qr, long long bstride,
-                                                     const int* gate, int gate_want, double shift_rel) {
-    if (gate != nullptr && *gate != gate_want) return;
+                                                     const int* gate, int gate_want, double shift_rel, long long gate_stride) {
+    if (gate != nullptr && gate[(size_t)blockIdx.x * gate_stride] != gate_want) return;
     B = small_of(B, bstride, blockIdx.x);
     extern __shared__ __align__(16) double sm[];
     const int MX = m + 2, MO = m + 1, D = m + 1;
@@ -794,8 +794,8 @@ __global__ void __launch_bounds__(256) small_mid_kernel(SmallBufs B, int m, long
 
 // pass 2: second Cholesky factor on the Gram of [Q1; p_w], b, R = (L1 L2)^T; builds A2
 __global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long long bstride, const double* gram2,
-                                                     const int* gate, int gate_want) {
-    if (gate != nullptr && *gate != gate_want) return;
+                                                     const int* gate, int gate_want, long long gate_stride) {
+    if (gate != nullptr && gate[(size_t)blockIdx.x * gate_stride] != gate_want) return;
     if (gram2 != nullptr) gram2 += (size_t)blockIdx.x * bstride;
     B = small_of(B, bstride, blockIdx.x);
     if (gram2 != nullptr) B.gram = const_cast<double*>(gram2);
@@ -854,7 +854,8 @@ __global__ void __launch_bounds__(256) small2_kernel(SmallBufs B, int m, long lo
 // that condition number next to the status so that the two-pass CholeskyQR2 (small1 / small2) takes over
 // whenever it is not negligible.
 __global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, int use_d, long long bstride,
-                                                           int* two_pass_flag, int force_two) {
+                                                           int* two_pass_flag, int force_two, long long flag_stride) {
+    if (two_pass_flag != nullptr) two_pass_flag += (size_t)blockIdx.x * flag_stride;
     B = small_of(B, bstride, blockIdx.x);
     extern __shared__ __align__(16) double sm[];
     const int MX = m + 2, MO = m + 1, D = m + 1;
@@ -969,18 +970,21 @@ __global__ void __launch_bounds__(256) small_single_kernel(SmallBufs B, int m, i
         *B.status = fail;
         reinterpret_cast<double*>(B.status)[1] = cond;
         // one Cholesky pass loses orthogonality like cond^2 u: CholeskyQR2 takes over unless that is negligible
-        if (two_pass_flag != nullptr && (force_two || fail != 0 || !(cond * cond * 2.3e-16 < kSinglePassTol)))
-            atomicMax(two_pass_flag, 1);
+        if (two_pass_flag != nullptr) {
+            const int two = (force_two || fail != 0 || !(cond * cond * 2.3e-16 < kSinglePassTol)) ? 1 : 0;
+            if (flag_stride != 0) *two_pass_flag = two;          // this problem's own gate
+            else if (two) atomicMax(two_pass_flag, 1);          // one gate for all (zeroed by the caller)
+        }
     }
 }
 
 cudaError_t launch_small_single(const SmallBufs& B, int m, int use_d, cudaStream_t st, LaunchStats* ls,
-                                const BatchDesc* batch, int* two_pass_flag, int force_two) {
+                                const BatchDesc* batch, int* two_pass_flag, int force_two, long long flag_stride) {
     const size_t smem = small_smem_bytes(m);
     cudaError_t e = cudaFuncSetAttribute(small_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     small_single_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, batch ? batch->small_stride : 0,
-                                                                     two_pass_flag, force_two);
+                                                                     two_pass_flag, force_two, flag_stride);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
@@ -992,7 +996,7 @@ cudaError_t launch_small1(const SmallBufs& B, int m, int use_d, int do_qr, cudaS
     if (e != cudaSuccess) return e;
     small1_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, use_d, do_qr, batch ? batch->small_stride : 0,
                                                                batch ? batch->gate : nullptr, batch ? batch->gate_want : 0,
-                                                               shift_rel);
+                                                               shift_rel, batch ? batch->gate_stride : 0);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }
@@ -1010,7 +1014,8 @@ cudaError_t launch_small2(const SmallBufs& B, int m, cudaStream_t st, LaunchStat
     cudaError_t e = cudaFuncSetAttribute(small2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     small2_kernel<<<batch ? batch->count : 1, 256, smem, st>>>(B, m, batch ? batch->small_stride : 0, gram2,
-                                                               batch ? batch->gate : nullptr, batch ? batch->gate_want : 0);
+                                                               batch ? batch->gate : nullptr, batch ? batch->gate_want : 0,
+                                                               batch ? batch->gate_stride : 0);
     if (ls) ls->launches++;
     return cudaGetLastError();
 }

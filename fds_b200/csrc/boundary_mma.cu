@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(32 * (kMmaWarps + 1), 1) gram_mma_kernel(
     const double* __restrict__ E, const double* __restrict__ T, const double* __restrict__ d, int MX, double inv_eps,
     long long n, int nst, double* __restrict__ part, BatchDesc bd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (bd.gate != nullptr && *bd.gate != bd.gate_want) return;      // the untaken CholeskyQR variant
+    if (bd.gate != nullptr && bd.gate[(size_t)blockIdx.y * bd.gate_stride] != bd.gate_want) return;      // the untaken CholeskyQR variant
     constexpr int NP = NBK * (NBK + 1) / 2, S = kMmaSites, NC = 32 * kMmaWarps;
     const int W = SRC == SRC_ENSEMBLE ? MX : MX - 1;
     const int MO = MX - 1;
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(32 * (kMmaWarps + 1), 2) gram_mma2_kernel(
     const double* __restrict__ E, const double* __restrict__ T, const double* __restrict__ d, int MX, double inv_eps,
     long long n, int nst, double* __restrict__ part, BatchDesc bd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (bd.gate != nullptr && *bd.gate != bd.gate_want) return;      // the untaken CholeskyQR variant
+    if (bd.gate != nullptr && bd.gate[(size_t)blockIdx.y * bd.gate_stride] != bd.gate_want) return;      // the untaken CholeskyQR variant
     constexpr int NP = NBD * (NBD + 1) / 2, S = kMmaSites, NC = 32 * kMmaWarps, NS = NV * (NV + 1) / 2;
     const int W = SRC == SRC_ENSEMBLE ? MX : MX - 1;
     const int MO = MX - 1;
@@ -303,7 +303,7 @@ __global__ void sum_partials_mma_kernel(const double* __restrict__ part, int npa
                                         double* __restrict__ out, BatchDesc bd) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= len) return;
-    if (bd.gate != nullptr && *bd.gate != bd.gate_want) return;
+    if (bd.gate != nullptr && bd.gate[(size_t)blockIdx.y * bd.gate_stride] != bd.gate_want) return;
     part += (size_t)blockIdx.y * bd.part_stride;
     out += (size_t)blockIdx.y * bd.small_stride;
     double s = 0.0;
@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(32 * (kApplyMmaWarps + 1), 2) apply_mma_kernel
     double inv_eps, long long n, double* Tout, double* E_out, const double* __restrict__ u, double eps, int nst,
     BatchDesc bd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (bd.gate != nullptr && *bd.gate != bd.gate_want) return;      // the untaken CholeskyQR variant
+    if (bd.gate != nullptr && bd.gate[(size_t)blockIdx.y * bd.gate_stride] != bd.gate_want) return;      // the untaken CholeskyQR variant
     using SH = ApplyMmaShape<MX>;
     {   // problem blockIdx.y of a batch
         const size_t off = (size_t)blockIdx.y * bd.slot;
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(32 * (kApplyMmaWarps + 1), 2) apply_mma2_kerne
     double inv_eps, long long n, double* Tout, double* E_out, const double* __restrict__ u, double eps, int nst,
     BatchDesc bd) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    if (bd.gate != nullptr && *bd.gate != bd.gate_want) return;      // the untaken CholeskyQR variant
+    if (bd.gate != nullptr && bd.gate[(size_t)blockIdx.y * bd.gate_stride] != bd.gate_want) return;      // the untaken CholeskyQR variant
     {   // problem blockIdx.y of a batch
         const size_t off = (size_t)blockIdx.y * bd.slot;
         E += off * MX; Tin += off * (MX - 1);

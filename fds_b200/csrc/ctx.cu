@@ -1358,12 +1358,14 @@ static int gated_factor_finish(fds_ctx* c, int do_qr, int from_ensemble, double 
         c->tangents_implicit = false;
         if (ens) FDS_CK(c, launch_make_ensemble(c->P_all(0), c->T_alloc, c->M, eps, c->E_all(c->cur), c->nall, c->stream, &c->ls));
     } else {
-        int* flag = c->small.status + 1;          // one flag for the whole batch: the worst problem decides
-        FDS_CK(c, cudaMemsetAsync(flag, 0, sizeof(int), c->stream));
-        FDS_CK(c, launch_small_single(c->small, c->m, use_d, c->stream, &c->ls, c->batch(), flag, c->qr_mode == 2));
+        // every problem's own gate (the int next to its status word): small_single_kernel sets it to 0 or 1, so a
+        // well-conditioned problem of a sweep skips the CholeskyQR2 kernels that an ill-conditioned one needs
+        int* flag = c->small.status + 1;
+        const long long fstride = 2 * c->small_stride;        // ints between two problems' status blocks
+        FDS_CK(c, launch_small_single(c->small, c->m, use_d, c->stream, &c->ls, c->batch(), flag, c->qr_mode == 2, fstride));
         BatchDesc two = c->bd, one = c->bd;
-        two.gate = flag; two.gate_want = 1;
-        one.gate = flag; one.gate_want = 0;
+        two.gate = flag; two.gate_want = 1; two.gate_stride = fstride;
+        one.gate = flag; one.gate_want = 0; one.gate_stride = fstride;
         // CholeskyQR2 (gate = 1): pass 1 -> T, Gram of T -> gram2, pass 2
         FDS_CK(c, launch_small1(c->small, c->m, use_d, 1, c->stream, &c->ls, &two));
         FDS_CK(c, launch_apply_mma(src, c->Ecur(), c->T, c->d, c->small.A, c->m, inv_eps, c->n, c->T, nullptr, c->P(0),

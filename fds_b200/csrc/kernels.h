@@ -130,6 +130,7 @@ struct BatchDesc {
     // empty launch.
     const int* gate = nullptr;
     int gate_want = 0;
+    long long gate_stride = 0;   // ints between the gates of consecutive problems of a batch (0: one gate for all)
 };
 // Gram of X_i = [t_0..t_m, d_i]  (MX = m+2), t from the ensemble ((E_k - E_0) * inv_eps) or from T.
 // part: [grid][MX*MX] scratch; out: MX*MX (deterministic fixed-order sum of the partials)
@@ -162,12 +163,13 @@ cudaError_t launch_small_mid(const SmallBufs&, int m, cudaStream_t, LaunchStats*
 cudaError_t launch_small2(const SmallBufs&, int m, cudaStream_t, LaunchStats*, const BatchDesc* batch = nullptr,
                           const double* gram2 = nullptr);
 // single-pass CholeskyQR from one Gram; writes sqrt(|G|_inf |G^-1|_inf) >= cond_2 to ((double*)status)[1].
-// two_pass_flag (optional, zeroed by the caller): raised to 1 (atomicMax, so the worst problem of a batch
-// decides) when the factor failed or cond^2 u >= kSinglePassTol, or when force_two is set -- the gate of
-// the CholeskyQR2 kernels enqueued behind it.
+// two_pass_flag (optional): problem p's flag, two_pass_flag[p * flag_stride], is set to 1 when its factor failed or
+// cond^2 u >= kSinglePassTol, or when force_two is set, else to 0 -- the gate of the CholeskyQR2 kernels enqueued
+// behind it, problem by problem (a well-conditioned problem of a sweep does not pay for an ill-conditioned one).
 constexpr double kSinglePassTol = 2e-13;
 cudaError_t launch_small_single(const SmallBufs&, int m, int use_d, cudaStream_t, LaunchStats*,
-                                const BatchDesc* batch = nullptr, int* two_pass_flag = nullptr, int force_two = 0);
+                                const BatchDesc* batch = nullptr, int* two_pass_flag = nullptr, int force_two = 0,
+                                long long flag_stride = 0);
 size_t small_smem_bytes(int m);
 
 // ---- boundary_fast.cu ---------------------------------------------------------- //
