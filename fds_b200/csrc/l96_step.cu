@@ -801,8 +801,15 @@ __global__ void __launch_bounds__(128) batch_jreduce_kernel(const double* __rest
     while ((1LL << L) < leaves_pp) ++L;
     TreeAcc<24> acc;
     acc.reset();
-    for (long long j = 0; j < (1LL << L); ++j) acc.push(j < leaves_pp ? in[(size_t)j * C] : 0.0);
-    out[idx] = acc.result(L);
+    if (L >= 4) {
+        // 16 leaves at a time, all loads issued before the first add (tree_rows); the binary counter then only
+        // combines the 16-leaf subtrees -- the same canonical tree, without one dependent load per leaf
+        for (long long j = 0; j < (1LL << L); j += 16) acc.push(tree_rows<16>(in, j, leaves_pp, C, 0));
+        out[idx] = acc.result(L - 4);
+    } else {
+        for (long long j = 0; j < (1LL << L); ++j) acc.push(j < leaves_pp ? in[(size_t)j * C] : 0.0);
+        out[idx] = acc.result(L);
+    }
 }
 
 cudaError_t launch_batch_jreduce(const double* leaves, long long nleaf_total, long long leaf0, long long slot_leaves,
