@@ -105,7 +105,27 @@ def _create_array(f, args, state, npdict=None):
     return array
 
 
+_SAFE_TYPES = {'SliceType': slice, 'NoneType': type(None), 'EllipsisType': type(Ellipsis), 'TupleType': tuple,
+               'ListType': list, 'DictType': dict, 'IntType': int, 'FloatType': float, 'BooleanType': bool,
+               'StringType': str, 'BytesType': bytes,
+               # (the spelling depends on the dill version: 0.3.x writes 'slice')
+               'slice': slice, 'ellipsis': type(Ellipsis), 'tuple': tuple, 'list': list, 'dict': dict, 'int': int,
+               'float': float, 'bool': bool, 'str': str, 'bytes': bytes}
+
+
+def _load_type(name):
+    """dill writes builtin types through _load_type (a slice index of a getitem operator arrives this way,
+    pascal_lite/operators/indexing.py:9-13); everything that is not plain data (code, functions, cells) is inert."""
+    return _SAFE_TYPES.get(name, _Inert)
+
+
+def _eval_repr(text):
+    return {'Ellipsis': Ellipsis, 'NotImplemented': NotImplemented}.get(text, _Inert())
+
+
 _DILL = {
+    '_load_type': _load_type,
+    '_eval_repr': _eval_repr,
     '_create_namedtuple': _create_namedtuple,
     '_create_array': _create_array,
     '_setattr': _safe_setattr,

@@ -226,6 +226,45 @@ def reference_checkpoint_fixture():
     print('reference checkpoint fixture: file', name, 'continued to', cp2.lss.K_segments(), 'segments, G =', out['cont_G'])
 
 
+def reference_graph_ops_fixture():
+    """A reference-format checkpoint whose lazy V and v go through every operator family of pascal_lite
+    (neg, transpose, sum over an axis, pow, div, outer, getitem, setitem, reshape / ravel, norm, dot, qr_transpose;
+    pascal_lite/operators/*.py), dill-dumped as the reference does, next to what the reference's executor computes:
+    pins the by-name evaluation of fds_b200/refcheckpoint.py operator by operator."""
+    import dill
+    from fds.checkpoint import Checkpoint as RefCheckpoint
+    from fds.compute import run_compute
+    rng = np.random.RandomState(21)
+    N, m = 6, 3
+    A = pascal.symbolic_array(field=rng.rand(m, N))
+    A.value.shape = (m,)
+    B = pascal.symbolic_array(field=rng.rand(2, m, N))
+    B.value.shape = (2, m)
+    x = pascal.symbolic_array(field=rng.rand(N))
+    Bt = B.T                                        # transpose -> (m, 2)
+    s1 = Bt.sum(1)                                  # sum over an axis -> (m,)
+    d = pascal.dot(A, x)                            # ReduceSum -> (m,), not distributed
+    V1 = A * 2.0 + s1 / (pascal.norm(x) + 1.0) - pascal.outer(d, x)      # broadcast, div, pow 0.5, reshape inside outer
+    V2 = V1.copy()
+    V2[1] = x ** 2.0                                # setitem, pow
+    V3 = V2 + (-Bt).ravel()[1:4] * 0.25             # neg, reshape (ravel), getitem with a slice
+    Q, R = pascal.qr_transpose(V3)
+    b = pascal.dot(Q, x)
+    vf = x - pascal.dot(b, Q)                       # (b * Q).sum(): sum over all axes of a distributed product
+    run_compute([R, b])                             # what continue_shadowing evaluates at its last boundary
+    lss = RefLss()
+    lss.Rs.append(R.field)
+    lss.bs.append(b.field)
+    cp = RefCheckpoint(x, Q, vf, lss, [[rng.rand(2) for _ in range(m)]], [rng.rand(2)], [rng.rand(5, 2)],
+                       [rng.rand(m)], [float(rng.rand())])
+    with open(os.path.join(GOLD, 'refcp_ops_m3_segment1'), 'wb') as f:
+        dill.dump(cp, f)
+    run_compute([Q, vf])
+    np.savez_compressed(os.path.join(GOLD, 'refcp_ops_expected.npz'), u0=x.field, V=Q.field, v=vf.field,
+                        R=lss.Rs[0], b=lss.bs[0])
+    print('reference graph-ops fixture: V', Q.field.shape, 'v', vf.field.shape)
+
+
 def lorenz_vdp_dudt(u, s):
     """The reference's only pure-Python plugin (tests/test_lyapunov_vector.py:13-22): a Lorenz-63 system driving
     a Van der Pol-type oscillator."""
@@ -260,6 +299,9 @@ def lyapunov_plugin_fixture():
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ['refops']:
+        reference_graph_ops_fixture()
+        return
     if sys.argv[1:] == ['lyap']:
         lyapunov_plugin_fixture()
         return
@@ -299,6 +341,7 @@ def main():
              20, 50000, 2000, 1e-6, 0, pin_tol=1e-6)
     clv_fixture()
     reference_checkpoint_fixture()
+    reference_graph_ops_fixture()
     lyapunov_plugin_fixture()
 
 

@@ -138,3 +138,16 @@ def test_the_reference_continues_from_a_file_written_here(tmp_path):
     got = np.load(out)
     assert np.array_equal(got['J'], g['cont_J']) and np.array_equal(got['Rs'], g['cont_Rs'])
     assert np.array_equal(got['G'], g['cont_G'])
+
+
+def test_every_operator_family_of_a_stored_graph():
+    """tests/golden/refcp_ops_m3_segment1: a reference-format checkpoint whose lazy V and v run through neg,
+    transpose, sum over an axis, pow, div, outer (reshape + broadcast), getitem with a slice, setitem, ravel, norm,
+    dot and qr_transpose (oracle/gen_golden.py reference_graph_ops_fixture): the by-name evaluation gives what the
+    reference's executor gives, bit for bit."""
+    from fds_b200.refcheckpoint import load_reference_checkpoint
+    want = golden('refcp_ops_expected')
+    cp = load_reference_checkpoint(os.path.join(ROOT, 'tests', 'golden', 'refcp_ops_m3_segment1'))
+    assert np.array_equal(cp.u0, want['u0']) and np.array_equal(cp.V, want['V']) and np.array_equal(cp.v, want['v'])
+    assert np.array_equal(cp.lss.Rs[0], want['R']) and np.array_equal(cp.lss.bs[0], want['b'])
+    assert np.abs(cp.V @ cp.V.T - np.eye(3)).max() < 1e-14
