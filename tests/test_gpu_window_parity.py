@@ -44,9 +44,9 @@ def _windows(plan, N, M, width=64):
 
 
 @gpu
-@pytest.mark.parametrize('steps', [2, 9])
-def test_baseline_size_windows_bitwise_vs_oracle(steps):
-    N, m = 1 << 24, 32
+@pytest.mark.parametrize('logn,steps', [(24, 2), (24, 9), (26, 2)])     # 2^26 x 34 = 2.3e9 elements: 64-bit indexing
+def test_baseline_size_windows_bitwise_vs_oracle(logn, steps):
+    N, m = 1 << logn, 32
     M = m + 2
     eps, s = 1e-6 * np.sqrt(N), 0.1
     run = fds_b200.L96(N)
