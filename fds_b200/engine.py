@@ -288,17 +288,32 @@ class Engine:
         self.ctx.close()
 
 
+class _FieldFile:
+    """A state the solver returned as a file: its name and the ``/field`` read from it."""
+    def __init__(self, path, data):
+        self.path, self.data = path, data
+
+
 class HostSolverEngine(Engine):
     """Engine for a solver that lives on the host (reference SURVEY 8f-4): the user's own
     ``run(u0, parameter, steps[, run_id][, interprocess])`` advances the m+2 trajectories, everything
     else of the segment loop -- time-dilation algebra, projection, Gram, CholeskyQR, ``R``, ``b``,
     ``G_dil``, the next perturbed ensemble, the LSS solve -- runs on the device.  Per segment the
     ensemble crosses PCIe once in each direction, as it would cross the reference's process pool.
-    The run_id strings are the reference's (fds/segment.py:38-49, fds/fds.py:109,131)."""
+    The run_id strings are the reference's (fds/segment.py:38-49, fds/fds.py:109,131).
 
-    def __init__(self, run, m, math='exact', device=None, simultaneous_runs=None):
+    File mode (the reference's MPI mode, fds/compute.py:59-132): when the initial state is the NAME of an HDF5 file
+    (or ``field_files=True``), states travel to and from the solver as files holding one dataset ``/field``
+    (``h5field.py``): the baseline run gets the file the previous baseline run returned, every perturbed
+    trajectory its own ``<get_host_dir(run_id)>/input.h5`` (fds/segment.py:46,51), and ``run`` answers with
+    ``(name of the file it wrote, J)`` (tests/test_fun3d_mpi.py:82-122)."""
+
+    def __init__(self, run, m, math='exact', device=None, simultaneous_runs=None, field_files=False):
         import threading
         self.user_run = run
+        self.field_files = bool(field_files)
+        self.get_host_dir = None
+        self._state_path, self._field_shape = None, None
         self.m, self.M = int(m), int(m) + 2
         self.kw = dict(math=math, device=0 if device is None else int(device))
         self.device = self.kw['device']
@@ -328,13 +343,50 @@ class HostSolverEngine(Engine):
     # -- the reference's RunWrapper (fds/fds.py:53-90): 3-, 4- or 5-argument plugins -------------- #
     def _call(self, u0, parameter, steps, run_id):
         run, last, ip = self.user_run, None, self.interprocess
+        if self.field_files and not isinstance(u0, str):
+            u0 = self._write_input(u0, run_id)
         for kw in (dict(run_id=run_id, interprocess=ip), dict(run_id=run_id), dict(interprocess=ip), {}):
             try:
-                u1, J = run(np.array(u0), parameter, steps, **kw)
-                return np.asarray(u1, dtype=np.float64), np.array(J, dtype=np.float64).reshape([steps, -1])
+                u1, J = run(u0 if isinstance(u0, str) else np.array(u0), parameter, steps, **kw)
             except TypeError as e:
                 last = e
+                continue
+            J = np.array(J, dtype=np.float64).reshape([steps, -1])
+            if isinstance(u1, str):
+                return _FieldFile(u1, self._read_field(u1)), J
+            return np.asarray(u1, dtype=np.float64), J
         raise last
+
+    # -- file mode: /field datasets in place of arrays (fds/compute.py:91-106) ------------------------- #
+    def set_host_dir(self, get_host_dir):
+        """``get_host_dir(run_id)`` of the reference (fds/segment.py:32-33): where the input of a run is put."""
+        self.get_host_dir = get_host_dir
+
+    def _read_field(self, path):
+        from .h5field import read_field
+        a = read_field(path)
+        if self._field_shape is None:
+            self._field_shape = a.shape
+        return np.asarray(a, dtype=np.float64).ravel()
+
+    def _write_input(self, u, run_id):
+        from .h5field import write_field
+        import os
+        d = self.get_host_dir(run_id) if self.get_host_dir is not None else run_id
+        os.makedirs(d, exist_ok=True)                     # fds/compute.py:123-125
+        path = os.path.join(d, 'input.h5')
+        u = np.asarray(u, dtype=np.float64)
+        write_field(path, u.reshape(self._field_shape) if self._field_shape is not None else u)
+        return path
+
+    def _baseline(self):
+        """What the baseline run starts from: the file that holds the device's primal state when there is one
+        (the reference passes ``u0.field``, the name the previous run returned), else the state itself."""
+        return self._state_path if self._state_path is not None else self.ctx.get_state()
+
+    def _ran_baseline(self, u1):
+        self._state_path = u1.path if isinstance(u1, _FieldFile) else None
+        return u1.data if isinstance(u1, _FieldFile) else u1
 
     def _map(self, jobs):
         if self.simultaneous_runs == 1 or len(jobs) == 1:
@@ -360,13 +412,22 @@ class HostSolverEngine(Engine):
             self.ctx.set_dxdt_weights(self._weights)
 
     def set_state(self, u):
+        self._state_path = None
+        if isinstance(u, str):                            # the reference's file mode: u0 is a file name
+            self.field_files, path = True, u
+            u = self._read_field(path)
+            self._state_path = path
         u = np.asarray(u, dtype=np.float64).ravel()
         self._ensure(u.size)
         self.ctx.set_state(u)
 
+    def get_state_ref(self):
+        """The primal state as the reference's driver would hold it: the file name in file mode."""
+        return self._state_path if self._state_path is not None else self.ctx.get_state()
+
     def run(self, s, steps, want_J=True):
-        u1, J = self._call(self.ctx.get_state(), s, int(steps), 'runup')       # fds/fds.py:207
-        self.ctx.set_state(u1)
+        u1, J = self._call(self._baseline(), s, int(steps), 'runup')           # fds/fds.py:207
+        self.ctx.set_state(self._ran_baseline(u1))
         return J if want_J else None
 
     def boundary(self, s, eps, from_ensemble, do_qr, build, keep_tangents=True):
@@ -376,11 +437,11 @@ class HostSolverEngine(Engine):
         if self.run_ddt is not None:
             c.set_dxdt(np.asarray(self.run_ddt(c.get_state(), s), dtype=np.float64))
         elif self.time_dilation:
-            u0 = c.get_state()
+            u0 = self._baseline()
             rid = 'time_dilation_{0:02d}'.format(self.i_segment)
             res = self._map([(u0, s, k, rid + '_{0}steps'.format(k)) for k in (1, 2, 3)])
             for k, (uk, _) in zip((1, 2, 3), res):
-                c.set_primal_history(k, uk)
+                c.set_primal_history(k, uk.data if isinstance(uk, _FieldFile) else uk)
         c.boundary_dxdt(s, from_ensemble, eps)
         c.boundary_factor(do_qr, from_ensemble, eps)
         c.boundary_finish(do_qr, eps, flags)
@@ -394,9 +455,12 @@ class HostSolverEngine(Engine):
               ['segment{0:02d}_init_perturb{1:03d}'.format(i, j) for j in range(m)] + \
               ['segment{0:02d}_param_perturb{1:03d}'.format(i, m)]
         jobs = [(E[k], s + eps if k == m + 1 else s, int(steps), ids[k]) for k in range(m + 2)]
+        if self._state_path is not None:
+            jobs[0] = (self._state_path,) + jobs[0][1:]
         res = self._map(jobs)
         for k, (uk, _) in enumerate(res):
-            E[k] = uk
+            E[k] = uk.data if isinstance(uk, _FieldFile) else uk
+        self._ran_baseline(res[0][0])
         c.set_ensemble(E, eps)
         self.i_segment += 1
         J = np.stack([r[1] for r in res], axis=1)

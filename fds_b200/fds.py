@@ -80,13 +80,17 @@ def continue_shadowing(run, parameter, checkpoint, num_segments, steps_per_segme
     callable ``run_ddt(u0, parameter) -> du per step`` (the reference's TimeDilationExact, whose upstream
     implementation raises NameError at fds/timedilation.py:58).
     ``simultaneous_runs`` sets the worker count of a ``HostSolver`` (fds/segment.py:37) and is inert for
-    device plugins; ``get_host_dir``, ``spawn_compute_job`` are inert."""
+    device plugins; ``get_host_dir(run_id)`` says where a ``HostSolver`` in file mode puts the ``input.h5`` of a
+    run (fds/segment.py:32-33,46,51); ``spawn_compute_job`` is inert (the algebra it would spawn MPI ranks for
+    runs on the device)."""
     assert verify_checkpoint(checkpoint)
     u0, V, v, lss, G_lss, g_lss, J_hist, G_dil, g_dil = checkpoint
     V = np.asarray(V)
     eng = _engine_of(run, V.shape[0])
     eng.set_time_dilation(_dilation_mode(run_ddt))
     eng.set_dxdt_weights(stencil_weights(timedilation.ORDER_OF_ACCURACY))
+    if hasattr(eng, 'set_host_dir'):
+        eng.set_host_dir(get_host_dir)
     eng.set_state(u0)
     eng.set_tangents(V, v)
     if hasattr(eng, 'i_segment'):
@@ -185,6 +189,8 @@ def shadowing(run, u0, parameter, subspace_dimension, num_segments, steps_per_se
     eng = _engine_of(run, m)
     eng.set_time_dilation(_dilation_mode(run_ddt))
     eng.set_dxdt_weights(stencil_weights(timedilation.ORDER_OF_ACCURACY))
+    if hasattr(eng, 'set_host_dir'):
+        eng.set_host_dir(get_host_dir)
     eng.set_state(u0)
     if hasattr(eng, 'i_segment'):
         eng.i_segment = 0                      # run_id numbering of a host solver starts over (fds/segment.py:38-49)

@@ -73,11 +73,16 @@ class HostSolver:
     ``run(u0, parameter, steps[, run_id][, interprocess]) -> (u1, J)`` (reference fds/fds.py:184-200) to
     ``shadowing`` / ``continue_shadowing``; the trajectories are advanced by that solver on the host, the
     algebra of the segment loop runs on the device (``HostSolverEngine``).  A bare Python callable is
-    still rejected: nothing in this package runs the hot path on the CPU behind the user's back."""
+    still rejected: nothing in this package runs the hot path on the CPU behind the user's back.
 
-    def __init__(self, run, math='exact', device=None, simultaneous_runs=None):
+    File mode of the reference (fds/compute.py:59-132, tests/test_fun3d_mpi.py): pass the NAME of an HDF5 file
+    with one dataset ``/field`` as ``u0`` (or ``field_files=True`` when continuing from a checkpoint) and ``run``
+    is called with file names and answers ``(name of the file it wrote, J)``; ``get_host_dir`` of ``shadowing``
+    says where the ``input.h5`` of each run goes."""
+
+    def __init__(self, run, math='exact', device=None, simultaneous_runs=None, field_files=False):
         self.user_run = run
-        self.kw = dict(math=math, device=device, simultaneous_runs=simultaneous_runs)
+        self.kw = dict(math=math, device=device, simultaneous_runs=simultaneous_runs, field_files=field_files)
         self._engines = {}
 
     def engine(self, m):

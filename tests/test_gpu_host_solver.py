@@ -119,3 +119,63 @@ def test_lyapunov_spectrum_of_a_python_plugin():
     v = cp.lss.lyapunov_covariant_vectors()
     assert v.shape == (m, K + 1, m) == tuple(g['clv_shape'])
     assert all(len(x) == K for x in (cp.G_dil, cp.g_dil)) and np.abs(np.array(cp.G_dil)).max() == 0.0
+
+
+@gpu
+def test_file_mode_of_the_reference_mpi_path(tmp_path):
+    """The reference's tests/test_fun3d_mpi.py:82-154 with its mock solver (forward-Euler Lorenz-96): the initial
+    state is the NAME of an HDF5 file, ``solve`` reads ``/field`` of the file it is given and answers with the
+    name of the ``output.h5`` it wrote into ``get_host_dir(run_id)``; the perturbed initial conditions arrive as
+    ``<get_host_dir(run_id)>/input.h5`` (fds/segment.py:46,51).  Same numbers as the in-memory mode."""
+    import os
+    from fds_b200 import h5field
+    base = str(tmp_path)
+    inputs = {}
+
+    def get_host_dir(run_id):
+        return os.path.join(base, run_id)
+
+    def solve(u0, s, nsteps, run_id, interprocess):
+        assert isinstance(u0, str)
+        inputs[run_id] = u0
+        u1, J = plugins.run_l96_euler(h5field.read_field(u0), s, nsteps)
+        os.makedirs(get_host_dir(run_id), exist_ok=True)
+        path = os.path.join(get_host_dir(run_id), 'output.h5')
+        h5field.write_field(path, u1)
+        return path, J
+
+    N, m, K, steps, eps, s = 40, 4, 3, 25, 1e-4, 0.1
+    u0 = plugins.run_l96_euler(np.random.RandomState(5).rand(N), s, 200)[0]
+    u0_file = os.path.join(base, 'u0.h5')
+    h5field.write_field(u0_file, u0)
+
+    np.random.seed(11)
+    a = fds_b200.shadowing(fds_b200.HostSolver(solve, simultaneous_runs=2), u0_file, s, m, K, steps, 10,
+                           epsilon=eps, checkpoint_path=base, get_host_dir=get_host_dir, return_checkpoint=True)
+    np.random.seed(11)
+    b = fds_b200.shadowing(fds_b200.HostSolver(plugins.run_l96_euler), u0, s, m, K, steps, 10, epsilon=eps,
+                           return_checkpoint=True)
+    assert np.array_equal(np.array(a.J), np.array(b.J)) and np.array_equal(a.u0, b.u0)
+    assert np.array_equal(a.V, b.V) and np.array_equal(np.array(a.lss.Rs), np.array(b.lss.Rs))
+    assert np.array_equal(fds_b200.lss_gradient(a), fds_b200.lss_gradient(b))
+    # who got which file: the run-up the user's file, the baseline the previous baseline's output, every
+    # perturbed trajectory its own input.h5
+    assert inputs['runup'] == u0_file
+    assert inputs['segment00_baseline'] == os.path.join(base, 'runup', 'output.h5')
+    assert inputs['segment01_baseline'] == os.path.join(base, 'segment00_baseline', 'output.h5')
+    assert inputs['time_dilation_01_2steps'] == os.path.join(base, 'segment00_baseline', 'output.h5')
+    for rid in ('segment00_init_perturb003', 'segment02_param_perturb004'):
+        assert inputs[rid] == os.path.join(base, rid, 'input.h5')
+    w = h5field.read_field(inputs['segment00_init_perturb000'])
+    assert w.shape == (N,) and w.dtype == np.float64
+
+    # continue from the checkpoint on disk (arrays): the solver still gets files
+    cp = ckpt.load_last_checkpoint(base, m)
+    inputs.clear()
+    c = fds_b200.continue_shadowing(fds_b200.HostSolver(solve, field_files=True), s, cp, K + 2, steps,
+                                    epsilon=eps, get_host_dir=get_host_dir, return_checkpoint=True)
+    d = fds_b200.continue_shadowing(fds_b200.HostSolver(plugins.run_l96_euler), s, b, K + 2, steps, epsilon=eps,
+                                    return_checkpoint=True)
+    assert np.array_equal(np.array(c.J), np.array(d.J)) and np.array_equal(c.V, d.V)
+    assert inputs['segment03_baseline'] == os.path.join(base, 'segment03_baseline', 'input.h5')
+    assert inputs['segment04_baseline'] == os.path.join(base, 'segment03_baseline', 'output.h5')
