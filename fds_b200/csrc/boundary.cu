@@ -60,10 +60,14 @@ constexpr int kDilThreads = 256;
 constexpr int kDilRun = 8;
 constexpr int kDilWindow = kDilThreads * kDilRun;
 
-template <class MP, int EULER>
+//
+// STATE = 1 is the same march used as the single-column solver (run-up, fds/fds.py:207): it writes the state after
+// `order` steps for the sites [lo, hi) -- lo < 0 / hi > n reach into the halo cells of the array, which a multi-step
+// advance consumes at 8 sites on the left and 4 on the right per step like the one-step kernel does -- instead of d.
+template <class MP, int EULER, int STATE>
 __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const double* __restrict__ P0, double* __restrict__ d,
-                                                                     long long n, DilationStencil st, double F0, Rk4Coef c,
-                                                                     const double2* __restrict__ Fpp, long long slot) {
+                                                                     long long lo, long long n, DilationStencil st, double F0,
+                                                                     Rk4Coef c, const double2* __restrict__ Fpp, long long slot) {
     constexpr int GL = EULER ? 2 : 8, GR = EULER ? 1 : 4, L = kDilRun, W = kDilWindow;
     // window position j lives at sm[.][j + (j >> 3) + 3]: one unused slot per run of 8, so that the lanes of a warp
     // (runs 8 positions apart) hit different banks -- with the plain layout every exchange was an 8-way bank conflict
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
     __shared__ __align__(16) double sm[2][SMW];
     const int p = st.order;
     const int tile = W - p * (GL + GR);
-    const long long t0 = (long long)blockIdx.x * tile;                  // first site this CTA writes d for
+    const long long t0 = lo + (long long)blockIdx.x * tile;             // first site this CTA writes d for
     const long long w0 = t0 - (long long)p * GL;                        // site of window position 0
     const int tid = threadIdx.x, j0 = tid * L;
     if (tid < 2) { sm[0][tid] = 0.0; sm[1][tid] = 0.0; }               // positions -2, -1
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
     for (int q = 0; q < L; ++q) {
         const long long site = w0 + j0 + q;
         u[q] = site < n + (long long)p * GR ? P0[site] : 0.0;          // (the left halo always exists: site >= -p GL)
-        dacc[q] = __dmul_rn(st.c[0], u[q]);
+        dacc[q] = STATE ? 0.0 : __dmul_rn(st.c[0], u[q]);
         F[q] = F0;
         if (Fpp != nullptr) {
             long long pr = site / slot;                                  // ghosts left of stacked site 0 belong to problem 0
@@ -138,14 +142,16 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
                 u[q] = MP::muladd(c.h6, MP::add(acc[q], k4), u[q]);
             }
         }
+        if (!STATE) {
 #pragma unroll
-        for (int q = 0; q < L; ++q) dacc[q] = __dadd_rn(dacc[q], __dmul_rn(st.c[k], u[q]));
+            for (int q = 0; q < L; ++q) dacc[q] = __dadd_rn(dacc[q], __dmul_rn(st.c[k], u[q]));
+        }
     }
 #pragma unroll
     for (int q = 0; q < L; ++q) {
         const int j = j0 + q;
         const long long site = w0 + j;
-        if (j >= p * GL && j < p * GL + tile && site < n) d[site] = dacc[q];
+        if (j >= p * GL && j < p * GL + tile && site < n) d[site] = STATE ? u[q] : dacc[q];
     }
 }
 
@@ -156,10 +162,29 @@ cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, cons
     const int tile = kDilWindow - st.order * (euler ? 3 : 12);
     const unsigned grid = (unsigned)((n + tile - 1) / tile);
     const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
-#define FDS_DIL(MP, E) dilation_fused_kernel<MP, E><<<grid, kDilThreads, 0, stream>>>(P0, d, n, st, F0, c, Fpp, slot)
+#define FDS_DIL(MP, E) dilation_fused_kernel<MP, E, 0><<<grid, kDilThreads, 0, stream>>>(P0, d, 0, n, st, F0, c, Fpp, slot)
     if (exact) { if (euler) FDS_DIL(ExactMath, 1); else FDS_DIL(ExactMath, 0); }
     else       { if (euler) FDS_DIL(FastMath, 1);  else FDS_DIL(FastMath, 0); }
 #undef FDS_DIL
+    if (ls) ls->launches++;
+    return cudaGetLastError();
+}
+
+// Y[lo, hi) = X advanced by `steps` (1 .. kMaxDilationOrder) time steps; X must be valid on
+// [lo - 8 steps, hi + 4 steps) (2 / 1 per step for forward Euler).  Single problem (the batch keeps the one-step kernel).
+cudaError_t launch_primal_multi(const double* X, double* Y, long long lo, long long hi, int steps, double F0, double dt,
+                                int exact, int euler, cudaStream_t stream, LaunchStats* ls) {
+    if (steps < 1 || steps > kMaxDilationOrder) return cudaErrorInvalidValue;
+    if (hi <= lo) return cudaSuccess;
+    DilationStencil st{};
+    st.order = steps;
+    const int tile = kDilWindow - steps * (euler ? 3 : 12);
+    const unsigned grid = (unsigned)((hi - lo + tile - 1) / tile);
+    const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
+#define FDS_PRI(MP, E) dilation_fused_kernel<MP, E, 1><<<grid, kDilThreads, 0, stream>>>(X, Y, lo, hi, st, F0, c, nullptr, 1)
+    if (exact) { if (euler) FDS_PRI(ExactMath, 1); else FDS_PRI(ExactMath, 0); }
+    else       { if (euler) FDS_PRI(FastMath, 1);  else FDS_PRI(FastMath, 0); }
+#undef FDS_PRI
     if (ls) ls->launches++;
     return cudaGetLastError();
 }

@@ -341,3 +341,24 @@ def test_numerically_singular_gram_takes_shifted_choleskyqr3(N, m, cond):
     sgn = np.sign(np.diag(Rr))
     assert maxrel(R, sgn[:, None] * Rr) < 1e-4 * cond * 1e-12 + 1e-9   # forward error ~ cond * u
     eng.close()
+
+
+@gpu
+@pytest.mark.parametrize('scheme,run', [('rk4', plugins.run_l96_rk4), ('euler', plugins.run_l96_euler)])
+@pytest.mark.parametrize('N,steps', [(40, 1), (40, 37), (1000, 8), (4099, 9), (50000, 23), (50000, 300)])
+def test_unrecorded_primal_march_is_the_oracle_run(scheme, run, N, steps):
+    """Run-up (fds/fds.py:207: solver call whose J is dropped) goes through the fused multi-step single-column
+    kernel, up to 8 steps per pass; with J it goes one step per launch.  Same bits either way, and the oracle's."""
+    s = 0.1
+    u0 = np.random.RandomState(N + steps).rand(N) * 2 - 0.5
+    eng = fds_b200.L96(N, scheme=scheme).engine(2)
+    eng.set_state(u0)
+    eng.run(s, steps, want_J=False)
+    a = eng.get_state().copy()
+    eng.set_state(u0)
+    J = eng.run(s, steps, want_J=True)
+    b = eng.get_state().copy()
+    eng.close()
+    u1, Jo = run(u0, s, steps)
+    assert np.array_equal(a, b) and np.array_equal(a, u1)
+    assert J.shape == Jo.shape
