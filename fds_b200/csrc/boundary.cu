@@ -64,20 +64,33 @@ constexpr int kDilWindow = kDilThreads * kDilRun;
 // STATE = 1 is the same march used as the single-column solver (run-up, fds/fds.py:207): it writes the state after
 // `order` steps for the sites [lo, hi) -- lo < 0 / hi > n reach into the halo cells of the array, which a multi-step
 // advance consumes at 8 sites on the left and 4 on the right per step like the one-step kernel does -- instead of d.
+// STATE = 2 also records the objective of every step (the solver call u1, J = run(u0, s, steps)): the windows then
+// start at multiples of 64 sites, a thread's run is an aligned group of 8, eight neighbouring lanes a 64-site leaf of
+// the canonical tree, and the leaf sums [sum x, sum x^2] of step k go to jp[k - 1][leaf][2] (sites >= sites count as
+// zero, as in stats_leaf_kernel); the levels above the leaves are reduced by tree_level_kernel, all steps at once.
+struct DilationGeom {
+    int glw, tile;             // window positions [glw, glw + tile) are the ones this CTA writes
+    long long lo, hi;          // sites written: [lo, hi); read: [rlo, hi + order * GR)
+    long long t00, rlo;        // first site of CTA 0's tile; lowest site that may be read
+    long long sites, nleaf;    // STATE = 2: sites of the state proper, 64-site leaves
+};
+
 template <class MP, int EULER, int STATE>
 __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const double* __restrict__ P0, double* __restrict__ d,
-                                                                     long long lo, long long n, DilationStencil st, double F0,
-                                                                     Rk4Coef c, const double2* __restrict__ Fpp, long long slot) {
-    constexpr int GL = EULER ? 2 : 8, GR = EULER ? 1 : 4, L = kDilRun, W = kDilWindow;
+                                                                     DilationGeom g, DilationStencil st, double F0,
+                                                                     Rk4Coef c, const double2* __restrict__ Fpp, long long slot,
+                                                                     double* __restrict__ jp) {
+    constexpr int GR = EULER ? 1 : 4, L = kDilRun, W = kDilWindow;
     // window position j lives at sm[.][j + (j >> 3) + 3]: one unused slot per run of 8, so that the lanes of a warp
     // (runs 8 positions apart) hit different banks -- with the plain layout every exchange was an 8-way bank conflict
     // and the kernel spent its time in the shared-memory pipe (0.37 ms at N = 2^24)
     constexpr int SMW = W + W / L + 4;
     __shared__ __align__(16) double sm[2][SMW];
     const int p = st.order;
-    const int tile = W - p * (GL + GR);
-    const long long t0 = lo + (long long)blockIdx.x * tile;             // first site this CTA writes d for
-    const long long w0 = t0 - (long long)p * GL;                        // site of window position 0
+    const int tile = g.tile;
+    const long long n = g.hi;
+    const long long t0 = g.t00 + (long long)blockIdx.x * tile;          // first site this CTA writes d for
+    const long long w0 = t0 - g.glw;                                    // site of window position 0
     const int tid = threadIdx.x, j0 = tid * L;
     if (tid < 2) { sm[0][tid] = 0.0; sm[1][tid] = 0.0; }               // positions -2, -1
     if (tid == 2) { sm[0][W + W / L + 3] = 0.0; sm[1][W + W / L + 3] = 0.0; }   // position W
@@ -85,7 +98,7 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
 #pragma unroll
     for (int q = 0; q < L; ++q) {
         const long long site = w0 + j0 + q;
-        u[q] = site < n + (long long)p * GR ? P0[site] : 0.0;          // (the left halo always exists: site >= -p GL)
+        u[q] = site >= g.rlo && site < n + (long long)p * GR ? P0[site] : 0.0;
         dacc[q] = STATE ? 0.0 : __dmul_rn(st.c[0], u[q]);
         F[q] = F0;
         if (Fpp != nullptr) {
@@ -146,12 +159,35 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
 #pragma unroll
             for (int q = 0; q < L; ++q) dacc[q] = __dadd_rn(dacc[q], __dmul_rn(st.c[k], u[q]));
         }
+        if (STATE == 2) {
+            // canonical tree over the 8 sites of the run, then over the 8 runs of the leaf (adjacent pairs first)
+            double a[L], b[L];
+#pragma unroll
+            for (int q = 0; q < L; ++q) {
+                const long long site = w0 + j0 + q;
+                a[q] = site >= 0 && site < g.sites ? u[q] : 0.0;
+                b[q] = __dmul_rn(a[q], a[q]);
+            }
+#pragma unroll
+            for (int h = 1; h < L; h <<= 1) {
+#pragma unroll
+                for (int q = 0; q < L; q += 2 * h) { a[q] = __dadd_rn(a[q], a[q + h]); b[q] = __dadd_rn(b[q], b[q + h]); }
+            }
+#pragma unroll
+            for (int h = 1; h < 8; h <<= 1) {
+                a[0] = __dadd_rn(a[0], __shfl_xor_sync(0xffffffffu, a[0], h));
+                b[0] = __dadd_rn(b[0], __shfl_xor_sync(0xffffffffu, b[0], h));
+            }
+            const long long site0 = w0 + j0;
+            if ((tid & 7) == 0 && j0 >= g.glw && j0 < g.glw + tile && site0 >= 0 && site0 < g.sites)
+                reinterpret_cast<double2*>(jp)[(size_t)(k - 1) * g.nleaf + (site0 >> 6)] = make_double2(a[0], b[0]);
+        }
     }
 #pragma unroll
     for (int q = 0; q < L; ++q) {
         const int j = j0 + q;
         const long long site = w0 + j;
-        if (j >= p * GL && j < p * GL + tile && site < n) d[site] = STATE ? u[q] : dacc[q];
+        if (j >= g.glw && j < g.glw + tile && site >= g.lo && site < n) d[site] = STATE ? u[q] : dacc[q];
     }
 }
 
@@ -162,7 +198,9 @@ cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, cons
     const int tile = kDilWindow - st.order * (euler ? 3 : 12);
     const unsigned grid = (unsigned)((n + tile - 1) / tile);
     const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
-#define FDS_DIL(MP, E) dilation_fused_kernel<MP, E, 0><<<grid, kDilThreads, 0, stream>>>(P0, d, 0, n, st, F0, c, Fpp, slot)
+    // the left halo always exists: the lowest site read is -order * GL
+    const DilationGeom g{st.order * (euler ? 2 : 8), tile, 0, n, 0, -(long long)st.order * (euler ? 2 : 8), 0, 0};
+#define FDS_DIL(MP, E) dilation_fused_kernel<MP, E, 0><<<grid, kDilThreads, 0, stream>>>(P0, d, g, st, F0, c, Fpp, slot, nullptr)
     if (exact) { if (euler) FDS_DIL(ExactMath, 1); else FDS_DIL(ExactMath, 0); }
     else       { if (euler) FDS_DIL(FastMath, 1);  else FDS_DIL(FastMath, 0); }
 #undef FDS_DIL
@@ -172,16 +210,34 @@ cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, cons
 
 // Y[lo, hi) = X advanced by `steps` (1 .. kMaxDilationOrder) time steps; X must be valid on
 // [lo - 8 steps, hi + 4 steps) (2 / 1 per step for forward Euler).  Single problem (the batch keeps the one-step kernel).
+// jp != nullptr: also the 64-site leaf sums of the objective of every step, jp[steps][nleaf][2], for the `sites`
+// sites of the state proper (lo <= 0, hi >= sites).
 cudaError_t launch_primal_multi(const double* X, double* Y, long long lo, long long hi, int steps, double F0, double dt,
-                                int exact, int euler, cudaStream_t stream, LaunchStats* ls) {
+                                int exact, int euler, double* jp, long long sites, long long nleaf, cudaStream_t stream,
+                                LaunchStats* ls) {
     if (steps < 1 || steps > kMaxDilationOrder) return cudaErrorInvalidValue;
     if (hi <= lo) return cudaSuccess;
+    if (jp != nullptr && (lo > 0 || hi < sites)) return cudaErrorInvalidValue;
     DilationStencil st{};
     st.order = steps;
-    const int tile = kDilWindow - steps * (euler ? 3 : 12);
-    const unsigned grid = (unsigned)((hi - lo + tile - 1) / tile);
+    const int gl = euler ? 2 : 8, gr = euler ? 1 : 4;
+    DilationGeom g{};
+    g.lo = lo; g.hi = hi; g.rlo = lo - (long long)steps * gl; g.sites = sites; g.nleaf = nleaf;
+    if (jp != nullptr) {
+        // leaf-aligned windows: margins of 64 sites (>= 8 steps * 8 and 8 steps * 4) and a whole number of leaves
+        g.glw = 64;
+        g.tile = kDilWindow - 128;
+        g.t00 = -(((-lo) + 63) / 64) * 64;
+    } else {
+        g.glw = steps * gl;
+        g.tile = kDilWindow - steps * (gl + gr);
+        g.t00 = lo;
+    }
+    const unsigned grid = (unsigned)((hi - g.t00 + g.tile - 1) / g.tile);
     const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
-#define FDS_PRI(MP, E) dilation_fused_kernel<MP, E, 1><<<grid, kDilThreads, 0, stream>>>(X, Y, lo, hi, st, F0, c, nullptr, 1)
+#define FDS_PRI(MP, E)                                                                                              \
+    do { if (jp) dilation_fused_kernel<MP, E, 2><<<grid, kDilThreads, 0, stream>>>(X, Y, g, st, F0, c, nullptr, 1, jp); \
+         else dilation_fused_kernel<MP, E, 1><<<grid, kDilThreads, 0, stream>>>(X, Y, g, st, F0, c, nullptr, 1, nullptr); } while (0)
     if (exact) { if (euler) FDS_PRI(ExactMath, 1); else FDS_PRI(ExactMath, 0); }
     else       { if (euler) FDS_PRI(FastMath, 1);  else FDS_PRI(FastMath, 0); }
 #undef FDS_PRI

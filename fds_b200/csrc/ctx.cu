@@ -1065,17 +1065,25 @@ int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int 
     if (c->nb > 1 && record) return fail(c, "fds_primal_advance: objective recording is not available for a batch");
     if (int r = upload_forcing(c, s, 0.0)) return r;
     const bool euler = c->cfg.system == FDS_SYS_L96_EULER;
-    // run-up and other unrecorded marches of a single problem: up to kMaxDilationOrder steps per pass in registers
-    // (the fused time-dilation march writing the state); FDS_PRIMAL_FUSED=0 keeps the one-step kernel
+    // primal marches of a single problem (run-up; the plugin called as u1, J = run(u0, s, steps)): up to
+    // kMaxDilationOrder steps per pass in registers (the fused time-dilation march writing the state and, when J is
+    // wanted, the leaf sums of every step); FDS_PRIMAL_FUSED=0 keeps the one-step kernel
     static const bool fused_ok = [] { const char* e = getenv("FDS_PRIMAL_FUSED"); return !(e && e[0] == '0'); }();
     for (long long j = 0; j < nsteps;) {
         if (c->pri_halo_valid < 1) return fail(c, "fds_primal_advance: primal halo exhausted; refresh it first");
         long long k = 1;
-        if (!record && c->nb <= 1 && fused_ok) {
+        if (c->nb <= 1 && fused_ok) {
             const long long v = c->pri_halo_valid;
             k = std::min<long long>(std::min<long long>(nsteps - j, v), kMaxDilationOrder);
+            // recorded: the leaf sums of the k steps share the leaf buffer sized for one step of the M-column ensemble
+            if (record) k = std::min<long long>(k, c->M);
+            const long long nl = (c->n + 63) / 64;
             FDS_CK(c, launch_primal_multi(c->P_all(0), c->P_all(1), -8 * (v - k), c->n + 4 * (v - k), (int)k, s + 8.0,
-                                          c->cfg.dt, c->cfg.math == FDS_MATH_EXACT, euler, c->stream, &c->ls));
+                                          c->cfg.dt, c->cfg.math == FDS_MATH_EXACT, euler, record ? c->jpart : nullptr,
+                                          c->n, nl, c->stream, &c->ls));
+            if (record)
+                FDS_CK(c, launch_tree_reduce_batched(c->jpart, nl, 2, k, c->jsum + (size_t)(step0 + j) * 2, c->jscratch,
+                                                     c->stream, &c->ls));
         } else {
             // the one-thread-per-element kernel (single column), one step
             StepArgs a;

@@ -345,13 +345,15 @@ def test_numerically_singular_gram_takes_shifted_choleskyqr3(N, m, cond):
 
 @gpu
 @pytest.mark.parametrize('scheme,run', [('rk4', plugins.run_l96_rk4), ('euler', plugins.run_l96_euler)])
-@pytest.mark.parametrize('N,steps', [(40, 1), (40, 37), (1000, 8), (4099, 9), (50000, 23), (50000, 300)])
-def test_unrecorded_primal_march_is_the_oracle_run(scheme, run, N, steps):
-    """Run-up (fds/fds.py:207: solver call whose J is dropped) goes through the fused multi-step single-column
-    kernel, up to 8 steps per pass; with J it goes one step per launch.  Same bits either way, and the oracle's."""
+@pytest.mark.parametrize('N,steps,m', [(40, 1, 2), (40, 37, 2), (1000, 8, 6), (4099, 9, 6), (50000, 23, 1),
+                                       (50000, 300, 16), (1 << 20, 11, 8)])
+def test_primal_march_is_the_oracle_run(scheme, run, N, steps, m):
+    """The solver call ``u1, J = run(u0, s, steps)`` and the run-up (fds/fds.py:207, J dropped) go through the fused
+    multi-step single-column kernel, up to 8 steps per pass, the recorded one with the 64-site leaf sums of the
+    objective of every step: the state and J are the oracle's bit for bit."""
     s = 0.1
     u0 = np.random.RandomState(N + steps).rand(N) * 2 - 0.5
-    eng = fds_b200.L96(N, scheme=scheme).engine(2)
+    eng = fds_b200.L96(N, scheme=scheme).engine(m)
     eng.set_state(u0)
     eng.run(s, steps, want_J=False)
     a = eng.get_state().copy()
@@ -361,4 +363,4 @@ def test_unrecorded_primal_march_is_the_oracle_run(scheme, run, N, steps):
     eng.close()
     u1, Jo = run(u0, s, steps)
     assert np.array_equal(a, b) and np.array_equal(a, u1)
-    assert J.shape == Jo.shape
+    assert np.array_equal(J, Jo)

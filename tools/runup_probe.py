@@ -17,3 +17,4 @@ for want in (False, True):
     dt = time.perf_counter() - t0
     print('N=2^24 %d steps, J %s: %.4f s = %.4f ms/step (fused=%s)' % (steps, 'recorded' if want else 'dropped', dt, dt / steps * 1e3,
                                                               os.environ.get('FDS_PRIMAL_FUSED', '1')))
+eng.close()
