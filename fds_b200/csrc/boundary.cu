@@ -70,8 +70,8 @@ constexpr int kDilWindow = kDilThreads * kDilRun;
 // zero, as in stats_leaf_kernel); the levels above the leaves are reduced by tree_level_kernel, all steps at once.
 struct DilationGeom {
     int glw, tile;             // window positions [glw, glw + tile) are the ones this CTA writes
-    long long lo, hi;          // sites written: [lo, hi); read: [rlo, hi + order * GR)
-    long long t00, rlo;        // first site of CTA 0's tile; lowest site that may be read
+    long long lo, hi;          // sites written: [lo, hi)
+    long long t00, rlo, rhi;   // first site of CTA 0's tile; sites that may be read: [rlo, rhi), zero outside
     long long sites, nleaf;    // STATE = 2: sites of the state proper, 64-site leaves
 };
 
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
                                                                      DilationGeom g, DilationStencil st, double F0,
                                                                      Rk4Coef c, const double2* __restrict__ Fpp, long long slot,
                                                                      double* __restrict__ jp) {
-    constexpr int GR = EULER ? 1 : 4, L = kDilRun, W = kDilWindow;
+    constexpr int L = kDilRun, W = kDilWindow;
     // window position j lives at sm[.][j + (j >> 3) + 3]: one unused slot per run of 8, so that the lanes of a warp
     // (runs 8 positions apart) hit different banks -- with the plain layout every exchange was an 8-way bank conflict
     // and the kernel spent its time in the shared-memory pipe (0.37 ms at N = 2^24)
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kDilThreads) dilation_fused_kernel(const doubl
 #pragma unroll
     for (int q = 0; q < L; ++q) {
         const long long site = w0 + j0 + q;
-        u[q] = site >= g.rlo && site < n + (long long)p * GR ? P0[site] : 0.0;
+        u[q] = site >= g.rlo && site < g.rhi ? P0[site] : 0.0;
         dacc[q] = STATE ? 0.0 : __dmul_rn(st.c[0], u[q]);
         F[q] = F0;
         if (Fpp != nullptr) {
@@ -199,7 +199,8 @@ cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, cons
     const unsigned grid = (unsigned)((n + tile - 1) / tile);
     const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
     // the left halo always exists: the lowest site read is -order * GL
-    const DilationGeom g{st.order * (euler ? 2 : 8), tile, 0, n, 0, -(long long)st.order * (euler ? 2 : 8), 0, 0};
+    const DilationGeom g{st.order * (euler ? 2 : 8), tile, 0, n, 0, -(long long)st.order * (euler ? 2 : 8),
+                         n + (long long)st.order * (euler ? 1 : 4), 0, 0};
 #define FDS_DIL(MP, E) dilation_fused_kernel<MP, E, 0><<<grid, kDilThreads, 0, stream>>>(P0, d, g, st, F0, c, Fpp, slot, nullptr)
     if (exact) { if (euler) FDS_DIL(ExactMath, 1); else FDS_DIL(ExactMath, 0); }
     else       { if (euler) FDS_DIL(FastMath, 1);  else FDS_DIL(FastMath, 0); }
@@ -209,12 +210,14 @@ cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, cons
 }
 
 // Y[lo, hi) = X advanced by `steps` (1 .. kMaxDilationOrder) time steps; X must be valid on
-// [lo - 8 steps, hi + 4 steps) (2 / 1 per step for forward Euler).  Single problem (the batch keeps the one-step kernel).
+// [lo - 8 steps, hi + 4 steps) (2 / 1 per step for forward Euler).
 // jp != nullptr: also the 64-site leaf sums of the objective of every step, jp[steps][nleaf][2], for the `sites`
 // sites of the state proper (lo <= 0, hi >= sites).
+// Fpp != nullptr: a batch -- [lo, hi) = all stacked sites, site i belongs to problem i / slot and takes its forcing;
+// nothing is read below lo (the cells that would need it are ghost cells of problem 0 that the march gives up anyway).
 cudaError_t launch_primal_multi(const double* X, double* Y, long long lo, long long hi, int steps, double F0, double dt,
-                                int exact, int euler, double* jp, long long sites, long long nleaf, cudaStream_t stream,
-                                LaunchStats* ls) {
+                                int exact, int euler, double* jp, long long sites, long long nleaf,
+                                const double2* Fpp, long long slot, cudaStream_t stream, LaunchStats* ls) {
     if (steps < 1 || steps > kMaxDilationOrder) return cudaErrorInvalidValue;
     if (hi <= lo) return cudaSuccess;
     if (jp != nullptr && (lo > 0 || hi < sites)) return cudaErrorInvalidValue;
@@ -222,7 +225,10 @@ cudaError_t launch_primal_multi(const double* X, double* Y, long long lo, long l
     st.order = steps;
     const int gl = euler ? 2 : 8, gr = euler ? 1 : 4;
     DilationGeom g{};
-    g.lo = lo; g.hi = hi; g.rlo = lo - (long long)steps * gl; g.sites = sites; g.nleaf = nleaf;
+    g.lo = lo; g.hi = hi; g.sites = sites; g.nleaf = nleaf;
+    g.rlo = Fpp ? lo : lo - (long long)steps * gl;
+    g.rhi = Fpp ? hi : hi + (long long)steps * gr;
+    if (jp != nullptr && Fpp != nullptr) return cudaErrorInvalidValue;
     if (jp != nullptr) {
         // leaf-aligned windows: margins of 64 sites (>= 8 steps * 8 and 8 steps * 4) and a whole number of leaves
         g.glw = 64;
@@ -237,7 +243,7 @@ cudaError_t launch_primal_multi(const double* X, double* Y, long long lo, long l
     const Rk4Coef c{0.5 * dt, dt, dt / 6.0};
 #define FDS_PRI(MP, E)                                                                                              \
     do { if (jp) dilation_fused_kernel<MP, E, 2><<<grid, kDilThreads, 0, stream>>>(X, Y, g, st, F0, c, nullptr, 1, jp); \
-         else dilation_fused_kernel<MP, E, 1><<<grid, kDilThreads, 0, stream>>>(X, Y, g, st, F0, c, nullptr, 1, nullptr); } while (0)
+         else dilation_fused_kernel<MP, E, 1><<<grid, kDilThreads, 0, stream>>>(X, Y, g, st, F0, c, Fpp, Fpp ? slot : 1, nullptr); } while (0)
     if (exact) { if (euler) FDS_PRI(ExactMath, 1); else FDS_PRI(ExactMath, 0); }
     else       { if (euler) FDS_PRI(FastMath, 1);  else FDS_PRI(FastMath, 0); }
 #undef FDS_PRI

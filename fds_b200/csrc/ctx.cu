@@ -1072,15 +1072,20 @@ int fds_primal_advance(fds_ctx* c, double s, int64_t step0, int64_t nsteps, int 
     for (long long j = 0; j < nsteps;) {
         if (c->pri_halo_valid < 1) return fail(c, "fds_primal_advance: primal halo exhausted; refresh it first");
         long long k = 1;
-        if (c->nb <= 1 && fused_ok) {
+        if (fused_ok) {
             const long long v = c->pri_halo_valid;
             k = std::min<long long>(std::min<long long>(nsteps - j, v), kMaxDilationOrder);
             // recorded: the leaf sums of the k steps share the leaf buffer sized for one step of the M-column ensemble
             if (record) k = std::min<long long>(k, c->M);
             const long long nl = (c->n + 63) / 64;
+            if (c->nb > 1)       // every stacked site, ghost cells included: what k passes of the one-step kernel leave valid
+                FDS_CK(c, launch_primal_multi(c->P_all(0), c->P_all(1), 0, c->nall, (int)k, s + 8.0, c->cfg.dt,
+                                              c->cfg.math == FDS_MATH_EXACT, euler, nullptr, 0, 0, c->Fpp, c->slot,
+                                              c->stream, &c->ls));
+            else
             FDS_CK(c, launch_primal_multi(c->P_all(0), c->P_all(1), -8 * (v - k), c->n + 4 * (v - k), (int)k, s + 8.0,
                                           c->cfg.dt, c->cfg.math == FDS_MATH_EXACT, euler, record ? c->jpart : nullptr,
-                                          c->n, nl, c->stream, &c->ls));
+                                          c->n, nl, nullptr, 1, c->stream, &c->ls));
             if (record)
                 FDS_CK(c, launch_tree_reduce_batched(c->jpart, nl, 2, k, c->jsum + (size_t)(step0 + j) * 2, c->jscratch,
                                                      c->stream, &c->ls));

@@ -103,8 +103,8 @@ cudaError_t launch_dilation_fused(const double* P0, double* d, long long n, cons
                                   double dt, int exact, int euler, const double2* Fpp, long long slot,
                                   cudaStream_t, LaunchStats*);
 cudaError_t launch_primal_multi(const double* X, double* Y, long long lo, long long hi, int steps, double F0, double dt,
-                                int exact, int euler, double* jp, long long sites, long long nleaf, cudaStream_t,
-                                LaunchStats*);
+                                int exact, int euler, double* jp, long long sites, long long nleaf,
+                                const double2* Fpp, long long slot, cudaStream_t, LaunchStats*);
 cudaError_t launch_diff_tangents(const double* E, int M, double eps, double* T, long long n,
                                  cudaStream_t, LaunchStats*);
 cudaError_t launch_make_ensemble(const double* u, const double* T, int M, double eps, double* E,

@@ -147,3 +147,22 @@ def test_batched_fast_math_is_close_to_exact():
     (ue, Ve, ve, Je), (uf, Vf, vf, Jf) = out
     assert maxrel(uf, ue) < 1e-13 and maxrel(Jf, Je) < 1e-13 and not np.array_equal(uf, ue)
     assert maxrel(Vf, Ve) < 1e-6            # FD tangents amplify rounding by 1 / eps
+
+
+@gpu
+@pytest.mark.parametrize('scheme,run', [('rk4', plugins.run_l96_rk4), ('euler', plugins.run_l96_euler)])
+@pytest.mark.parametrize('B,N,steps,hs', [(3, 64, 29, 8), (7, 4096, 50, 16), (2, 192, 5, 3)])
+def test_batched_run_up_is_the_oracle_run_of_every_problem(scheme, run, B, N, steps, hs):
+    """Run-up of a sweep (shadowing_batch(..., runup_steps)): all problems in one fused multi-step march over the
+    stacked sites, ghost cells included; problem p ends where the oracle's run at parameter s + ds[p] ends."""
+    rng = np.random.RandomState(B + N)
+    params = np.linspace(-0.3, 0.6, B)
+    U = rng.rand(B, N) * 2 - 0.5
+    bc = Context(N, 2, batch=B, scheme=scheme, max_halo_steps=hs)
+    bc.set_batch_params(params)
+    bc.set_state(U)
+    bc.run(0.05, steps, want_J=False)
+    Ub = bc.get_state()
+    bc.close()
+    for p in range(B):
+        assert np.array_equal(Ub[p], run(U[p], 0.05 + params[p], steps)[0])
