@@ -232,7 +232,9 @@ class _File:
     def dataset(self, addr):
         shape = dtype = None
         layout = None
-        for t, _fl, body in self.messages(addr):
+        for t, fl, body in self.messages(addr):
+            if fl & 0x02 and t in (0x01, 0x03, 0x05, 0x08):
+                raise H5FormatError('%s: shared (committed) header messages are not supported' % self.path)
             if t == 0x01:
                 shape = _dataspace(body, self.path)
             elif t == 0x03:
