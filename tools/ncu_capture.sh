@@ -10,5 +10,9 @@ ncu --set full --clock-control none --import-source on -k 'regex:gram_mma|apply_
 F="$B --math fast"
 $F > $O/${TAG}_plain_fast.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:l96_rk4_stream -s 160 -c 1 -o $O/${TAG}_step_fast $F > $O/${TAG}_ncu_stepf.log 2>&1
-for r in step boundary step_fast; do ncu -i $O/${TAG}_$r.ncu-rep --page raw --csv > $O/${TAG}_${r}_raw.csv 2>/dev/null; done
+# the primal marches (run-up, recorded solver call): outside the bench's timed region, captured from the probe
+ncu --set full --clock-control none --import-source on -k regex:dilation_fused -s 8 -c 1 -o $O/${TAG}_runup python tools/runup_probe.py > $O/${TAG}_ncu_runup.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:dilation_fused -s 140 -c 1 -o $O/${TAG}_recorded python tools/runup_probe.py > $O/${TAG}_ncu_rec.log 2>&1
+# gpurun brings back at most 64 MiB: keep the raw-page exports (what tools/summarize_profiles.py reads), drop the reports
+for r in step boundary step_fast runup recorded; do ncu -i $O/${TAG}_$r.ncu-rep --page raw --csv > $O/${TAG}_${r}_raw.csv 2>/dev/null && rm -f $O/${TAG}_$r.ncu-rep; done
 du -sh $O; ls -la $O

@@ -1,6 +1,6 @@
 """Turn gpurun_out ncu artefacts into the committed summaries under profiles/ (development aid).
 
-    python tools/summarize_profiles.py <round-tag> <launches.csv> <name>=<prof.ncu-rep> [...]
+    python tools/summarize_profiles.py <round-tag> <launches.csv> <name>=<prof.ncu-rep | raw-page export .csv> [...]
 """
 import collections
 import csv
@@ -58,7 +58,8 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 traffic, fp64 = {}, {}
 for spec in reps:
     name, rep = spec.split('=')
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    raw = open(rep).read() if rep.endswith('.csv') else \
+        subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index('Kernel Name')
