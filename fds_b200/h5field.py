@@ -282,8 +282,8 @@ class _File:
     def _raw(self, data, nbytes):
         if nbytes == 0:
             return b''
-        if data == _UNDEF:
-            raise H5FormatError('%s: storage of the dataset was never allocated' % self.path)
+        if data == _UNDEF:                              # never written: the library hands out the fill value (default 0)
+            return bytes(nbytes)
         pos = data + self.base
         if pos + nbytes > self.size:
             raise H5FormatError('%s: truncated (%d bytes of data missing)' % (self.path, pos + nbytes - self.size))

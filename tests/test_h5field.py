@@ -91,6 +91,18 @@ def test_refusals(tmp_path):
         h5field.write_field(p, np.array(['a', 'b']))
 
 
+def test_unallocated_storage_reads_as_the_default_fill_value(tmp_path):
+    """create_dataset('field', shape, dtype) that was never written (fds/compute.py:104 before the collective write):
+    late allocation leaves the address undefined and the library returns zeros."""
+    head, eof = h5field.field_file_header((5,), np.float64)
+    raw = bytearray(head)
+    at = raw.index(struct.pack('<BBQ', 3, 1, len(head)))          # the layout message: version 3, contiguous, address
+    raw[at + 2:at + 10] = struct.pack('<Q', h5field._UNDEF)
+    p = str(tmp_path / 'empty.h5')
+    open(p, 'wb').write(bytes(raw) + b'\0' * 40)
+    assert np.array_equal(h5field.read_field(p), np.zeros(5))
+
+
 def test_new_style_file(tmp_path):
     """libver='latest' files: superblock v2, v2 object headers (OHDR), a compact group of link messages,
     dataspace v2, layout v4 -- assembled here by hand from the format specification."""
