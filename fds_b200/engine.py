@@ -421,10 +421,6 @@ class HostSolverEngine(Engine):
         self._ensure(u.size)
         self.ctx.set_state(u)
 
-    def get_state_ref(self):
-        """The primal state as the reference's driver would hold it: the file name in file mode."""
-        return self._state_path if self._state_path is not None else self.ctx.get_state()
-
     def run(self, s, steps, want_J=True):
         u1, J = self._call(self._baseline(), s, int(steps), 'runup')           # fds/fds.py:207
         self.ctx.set_state(self._ran_baseline(u1))
