@@ -10,8 +10,9 @@ wrote.  Neither h5py nor libhdf5 is in this image, so the two functions below sp
 ``read_field(path)``   finds ``/field`` in a file written by libhdf5 -- superblock versions 0-3, old-style groups
                        (symbol table: B-tree v1 + local heap + symbol-table nodes) and new-style compact groups
                        (link messages), object headers v1 and v2, dataspace v1/v2, fixed-point and IEEE types
-                       of either byte order, layout v1-v4 contiguous or compact -- and returns a numpy array.
-                       Chunked, filtered or externally stored data is refused by name, never guessed at.
+                       of either byte order, layout v1-v4 contiguous or compact, v1-v3 chunked (B-tree v1 of
+                       chunks; deflate, shuffle, fletcher32 filters) -- and returns a numpy array.  Version-4
+                       chunk indices, other filters and externally stored data are refused by name.
 ``write_field(path, a)`` writes what ``h5py.File(path, 'w').create_dataset('field', data=a)`` writes with the
                        library's default (earliest) format bounds: superblock v0, the root group as a symbol
                        table, one v1 object header (dataspace v1, datatype v1, fill value v2, layout v3,
@@ -232,6 +233,7 @@ class _File:
     def dataset(self, addr):
         shape = dtype = None
         layout = None
+        filters = []
         for t, fl, body in self.messages(addr):
             if fl & 0x02 and t in (0x01, 0x03, 0x05, 0x08):
                 raise H5FormatError('%s: shared (committed) header messages are not supported' % self.path)
@@ -241,8 +243,8 @@ class _File:
                 dtype = _datatype(body, self.path)
             elif t == 0x08:
                 layout = body
-            elif t == 0x0B and body[1]:
-                raise H5FormatError('%s: filtered (compressed) data is not supported' % self.path)
+            elif t == 0x0B:
+                filters = _filters(body, self.path)
             elif t == 0x07:
                 raise H5FormatError('%s: externally stored data is not supported' % self.path)
         if shape is None or dtype is None or layout is None:
@@ -260,7 +262,8 @@ class _File:
                 n = struct.unpack_from('<I', layout, p)[0]
                 raw = layout[p + 4:p + 4 + n]
             else:
-                raise H5FormatError('%s: chunked data is not supported' % self.path)
+                dims = struct.unpack_from('<%dI' % rank, layout, 16)
+                return self._chunked(struct.unpack_from('<Q', layout, 8)[0], shape, dtype, dims[:-1], filters)
         elif ver in (3, 4):
             cls = layout[1]
             if cls == 1:
@@ -271,13 +274,54 @@ class _File:
             elif cls == 0:
                 n = struct.unpack_from('<H', layout, 2)[0]
                 raw = layout[4:4 + n]
+            elif cls == 2 and ver == 3:
+                rank = layout[2]                           # dataset rank + 1: the last "dimension" is the element size
+                dims = struct.unpack_from('<%dI' % rank, layout, 11)
+                return self._chunked(struct.unpack_from('<Q', layout, 3)[0], shape, dtype, dims[:-1], filters)
             else:
-                raise H5FormatError('%s: chunked or virtual data is not supported' % self.path)
+                raise H5FormatError('%s: version-4 chunk indices and virtual datasets are not supported' % self.path)
         else:
             raise H5FormatError('%s: data layout version %d' % (self.path, ver))
         if len(raw) < nbytes:
             raise H5FormatError('%s: %d bytes stored, %d expected' % (self.path, len(raw), nbytes))
         return np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)
+
+    # -- chunked storage: B-tree v1 of raw-data chunks (spec III.A.1, node type 1) ------------------------ #
+    def _chunked(self, btree, shape, dtype, chunk, filters):
+        if len(chunk) != len(shape) or not shape:
+            raise H5FormatError('%s: chunk rank %d for a dataset of rank %d' % (self.path, len(chunk), len(shape)))
+        out = np.zeros(shape, dtype=dtype)                 # chunks that were never written hold the fill value
+        csize = int(np.prod(chunk, dtype=np.int64)) * dtype.itemsize
+        rank = len(shape)
+
+        def walk(node):
+            h = self.at(node, 24)
+            if h[:4] != b'TREE' or h[4] != 1:
+                raise H5FormatError('%s: no chunk B-tree node at %#x' % (self.path, node))
+            level, used = h[5], struct.unpack_from('<H', h, 6)[0]
+            ksz = 8 + 8 * (rank + 1)
+            body = self.at(node + 24, used * (ksz + 8) + ksz)
+            for i in range(used):
+                q = i * (ksz + 8)
+                nbytes, mask = struct.unpack_from('<II', body, q)
+                offs = struct.unpack_from('<%dQ' % rank, body, q + 8)
+                child = struct.unpack_from('<Q', body, q + ksz)[0]
+                if level:
+                    walk(child)
+                    continue
+                raw = bytes(self.at(child, nbytes))
+                for k in range(len(filters) - 1, -1, -1):  # undo the pipeline back to front, skipping masked filters
+                    if not mask >> k & 1:
+                        raw = filters[k](raw)
+                if len(raw) != csize:
+                    raise H5FormatError('%s: chunk of %d bytes, %d expected' % (self.path, len(raw), csize))
+                block = np.frombuffer(raw, dtype=dtype).reshape(chunk)
+                sel = tuple(slice(o, min(o + c, n)) for o, c, n in zip(offs, chunk, shape))
+                out[sel] = block[tuple(slice(0, t.stop - t.start) for t in sel)]   # edge chunks are stored whole
+
+        if btree != _UNDEF:
+            walk(btree)
+        return out
 
     def _raw(self, data, nbytes):
         if nbytes == 0:
@@ -288,6 +332,37 @@ class _File:
         if pos + nbytes > self.size:
             raise H5FormatError('%s: truncated (%d bytes of data missing)' % (self.path, pos + nbytes - self.size))
         return np.fromfile(self.path, dtype=np.uint8, count=nbytes, offset=pos)
+
+
+def _filters(body, path):
+    """The filter pipeline message (spec IV.A.2.l) as a list of inverse transforms, in pipeline order."""
+    import zlib
+    ver, n = body[0], body[1]
+    p = 8 if ver == 1 else 2
+    out = []
+    for _ in range(n):
+        fid = struct.unpack_from('<H', body, p)[0]
+        if ver == 1 or fid >= 256:
+            nlen = struct.unpack_from('<H', body, p + 2)[0]
+            p += 4
+        else:
+            nlen = 0
+            p += 2
+        _flags, ncd = struct.unpack_from('<HH', body, p)
+        p += 4 + (nlen + (-nlen % 8 if ver == 1 else 0))
+        cd = struct.unpack_from('<%dI' % ncd, body, p)
+        p += 4 * ncd + (4 if ver == 1 and ncd % 2 else 0)
+        if fid == 1:
+            out.append(zlib.decompress)
+        elif fid == 2:
+            size = cd[0]
+            out.append(lambda raw, size=size: np.frombuffer(raw, np.uint8).reshape(size, -1).T.tobytes()
+                       if size > 1 and len(raw) % size == 0 else raw)
+        elif fid == 3:
+            out.append(lambda raw: raw[:-4])               # Fletcher-32 checksum behind the data (not verified)
+        else:
+            raise H5FormatError('%s: filter %d is not supported (deflate, shuffle and fletcher32 are)' % (path, fid))
+    return out
 
 
 def _dataspace(body, path):

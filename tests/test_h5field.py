@@ -129,3 +129,75 @@ def test_new_style_file(tmp_path):
     p = str(tmp_path / 'latest.h5')
     open(p, 'wb').write(bytes(raw))
     assert np.array_equal(h5field.read_field(p), data)
+
+
+def test_chunked_compressed_dataset(tmp_path):
+    """A 2-D /field stored in chunks behind a two-level chunk B-tree, shuffle + deflate (what
+    create_dataset(..., chunks=(4, 3), shuffle=True, compression='gzip') stores): edge chunks stored whole, one
+    chunk with the deflate filter masked out, one chunk never written (fill value) -- assembled by hand from the
+    format specification."""
+    import zlib
+    U = h5field._UNDEF
+    data = np.arange(10 * 7, dtype='<f8').reshape(10, 7) * 0.5 - 3
+    chunk = (4, 3)
+    want = data.copy()
+    want[8:10, 6:7] = 0.0                                           # the chunk at (8, 6) is left out below
+
+    def ohdr(msgs):
+        body = b''.join(struct.pack('<BHB', t, len(m), 0) + m for t, m in msgs)
+        return b'OHDR' + struct.pack('<BB', 2, 1) + struct.pack('<H', len(body)) + body + b'\0\0\0\0'
+
+    blob = bytearray(4096)
+    pos = [1024]
+
+    def put(b):
+        a = pos[0]
+        blob[a:a + len(b)] = b
+        pos[0] = a + len(b) + (-len(b) % 8)
+        return a
+
+    def key(nbytes, mask, offs):
+        return struct.pack('<II', nbytes, mask) + struct.pack('<3Q', offs[0], offs[1], 0)
+
+    def shuffle(raw):
+        return np.frombuffer(raw, np.uint8).reshape(-1, 8).T.tobytes()
+
+    entries = []
+    for i in range(0, 10, 4):
+        for j in range(0, 7, 3):
+            if (i, j) == (8, 6):
+                continue
+            full = np.zeros(chunk)
+            part = data[i:i + 4, j:j + 3]
+            full[:part.shape[0], :part.shape[1]] = part
+            raw = shuffle(full.astype('<f8').tobytes())
+            mask = 0
+            if (i, j) == (4, 3):
+                mask = 2                                            # second filter (deflate) skipped for this chunk
+            else:
+                raw = zlib.compress(raw)
+            entries.append((key(len(raw), mask, (i, j)), put(raw)))
+
+    def node(level, ents, last):
+        b = b'TREE' + struct.pack('<BBH', 1, level, len(ents)) + struct.pack('<QQ', U, U)
+        for k, child in ents:
+            b += k + struct.pack('<Q', child)
+        return put(b + last)
+    end = key(0, 0, (12, 9))
+    leaf0 = node(0, entries[:5], entries[5][0])
+    leaf1 = node(0, entries[5:], end)
+    root_node = node(1, [(entries[0][0], leaf0), (entries[5][0], leaf1)], end)
+
+    space = struct.pack('<BBBB', 2, 2, 0, 1) + struct.pack('<QQ', 10, 7)
+    layout = struct.pack('<BBB', 3, 2, 3) + struct.pack('<Q', root_node) + struct.pack('<III', 4, 3, 8)
+    pipeline = struct.pack('<BB', 2, 2) + struct.pack('<HHHI', 2, 0, 1, 8) + struct.pack('<HHHI', 1, 0, 1, 4)
+    dset = put(ohdr([(0x01, space), (0x03, h5field._float_type(np.dtype('<f8'))), (0x0B, pipeline), (0x08, layout)]))
+    link = struct.pack('<BB', 1, 0) + struct.pack('<B', 5) + b'field' + struct.pack('<Q', dset)
+    root = ohdr([(0x02, struct.pack('<BBQQ', 0, 0, U, U)), (0x06, link)])
+    blob[48:48 + len(root)] = root
+    sb = h5field._SIG + struct.pack('<BBBB', 2, 8, 8, 0) + struct.pack('<4Q', 0, U, len(blob), 48) + b'\0' * 4
+    blob[:len(sb)] = sb
+    p = str(tmp_path / 'chunked.h5')
+    open(p, 'wb').write(bytes(blob))
+    got = h5field.read_field(p)
+    assert got.shape == (10, 7) and np.array_equal(got, want)
