@@ -5,7 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import fds_b200
 
 B, N, m, steps, eps = 4096, 4096, 16, 100, 1e-4
-run = fds_b200.L96(N, distributed=False)
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+run = fds_b200.L96(N, distributed=False, max_halo_steps=H)
+print('max_halo_steps', H or 'default (16)')
 eng = run.batch_engine(m, B)
 eng.ctx.set_batch_params(np.linspace(-2.0, 2.0, B))
 eng.set_state(np.random.RandomState(0).rand(B, N))
