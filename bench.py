@@ -614,10 +614,17 @@ def roofline(args, math, n_local, M, kms, steps_per_launch, S, K, total_ms, cloc
     if math == 'exact' and ipu and fp64_peak:
         winst = n_local * M * steps_per_launch * ipu / 32.0
         ach = winst / (kms * 1e-3)
+        # the clock the probe ran at, from its own cycle counter (without DRAM traffic it stays near the maximum
+        # clock, the power-capped step kernel does not: frac_per_clock below removes that difference)
+        probe_mhz = '%s MHz (nvidia-smi sample)' % (fp64_clk or {}).get('sm_mhz')
+        if fp64_per_clk:
+            import torch
+            nsm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+            probe_mhz = '%.0f MHz (its own cycle counter)' % (fp64_peak / (fp64_per_clk * nsm) / 1e6)
         out = {'bound': 'fp64', 'achieved': ach / 1e9, 'peak': fp64_peak / 1e9, 'unit': 'G FP64 warp-inst/s',
                'frac': ach / fp64_peak,
                'peak_source': 'fds_fp64_issue_rate() measured in this run (one 256-thread CTA per SM, 2 DADD : 1 DMUL, '
-                              '8 chains per thread, no memory traffic) at %s MHz' % (fp64_clk or {}).get('sm_mhz'),
+                              '8 chains per thread, no memory traffic, 0.25 s) at %s' % probe_mhz,
                'fp64_warp_inst_per_update': ipu,
                'why': 'two time steps per pass: DRAM traffic per launch is half the algorithmic bytes, the FP64 pipe '
                       '(%g exact-mode instructions per update) is what is saturated' % ipu}
